@@ -1,0 +1,502 @@
+// bp_oracle.cpp -- CPU oracle: a from-scratch C++ restatement of the broadphase-rs hot path.
+//
+// TEST INFRASTRUCTURE ONLY (see bp_oracle.h).  Never linked into or called by the product.
+//
+// PARITY STATUS: codec/quantiser pinned by the reference's in-source KATs; extend/sort/scan
+// end-to-end "parity unpinned" (no Rust toolchain, LFS-stub fixtures) -- cross-checked against
+// the independent numpy restatement in oracle/pyref.py.
+//
+// Every function cites the reference file:line (relative to /root/reference) that it follows.
+// Build: g++ -O3 -march=x86-64-v3 -fopenmp -ffp-contract=off (never -ffast-math), see Makefile.
+
+#include "bp_oracle.h"
+
+#include <omp.h>
+
+#include <algorithm>
+#include <cstring>
+#include <parallel/algorithm>
+#include <utility>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Index codec -- src/index.rs:65-295
+// ---------------------------------------------------------------------------------------------
+
+// Spread the low 21 bits of v so that bit i lands on bit 3*i.  Equivalent (bit for bit) to the
+// three-step octal-mask spread of src/index.rs:193-207; checked exhaustively against the
+// bit-by-bit definition in tests/test_oracle.py.
+inline uint64_t spread3(uint64_t v) {
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x001f00000000ffffull;
+    v = (v | (v << 16)) & 0x001f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+// Spread the low 32 bits of v so that bit i lands on bit 2*i (src/index.rs:155-172).
+inline uint64_t spread2(uint64_t v) {
+    v &= 0xffffffffull;
+    v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+    v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+    v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+    v = (v | (v << 2)) & 0x3333333333333333ull;
+    v = (v | (v << 1)) & 0x5555555555555555ull;
+    return v;
+}
+
+inline uint32_t compact_bits(uint64_t v, int stride, int nbits) {
+    uint32_t out = 0;
+    for (int i = 0; i < nbits; ++i) out |= (uint32_t)((v >> (stride * i)) & 1u) << i;
+    return out;
+}
+
+// index_impl!{index: $name, $dim, $bits, $depth_bits, $axis_bits} -- src/index.rs:65-123, 293-295
+template <class K, int DIM_, int DEPTH_BITS_, int AXIS_BITS_> struct IndexT {
+    typedef K key_t;
+    static const int DIM = DIM_;
+    static const int DEPTH_BITS = DEPTH_BITS_;
+    static const int AXIS_BITS = AXIS_BITS_;
+    static const int ORIGIN_BITS = DIM_ * AXIS_BITS_; // src/index.rs:75
+    static const int ORIGIN_SHIFT = DEPTH_BITS_;      // src/index.rs:76 (DEPTH_SHIFT = 0)
+    static K depth_mask() { return (K)(((K)1 << DEPTH_BITS) - 1); }                       // :73
+    static K origin_mask() { return (K)((((K)1 << ORIGIN_BITS) - 1) << ORIGIN_SHIFT); }   // :77
+
+    // encode_axis -- src/index.rs:155-172 (2D), :193-207 (3D): the top AXIS_BITS bits of the u32
+    // coordinate, bit i -> origin bit DIM*i.
+    static K encode_axis(uint32_t v) {
+        uint64_t top = (uint64_t)(v >> (32 - AXIS_BITS));
+        return (K)(DIM == 2 ? spread2(top) : spread3(top));
+    }
+    // decode_axis -- src/index.rs:134-151 (2D), :176-190 (3D)
+    static uint32_t decode_axis(K origin_bits) {
+        return compact_bits((uint64_t)origin_bits, DIM, AXIS_BITS) << (32 - AXIS_BITS);
+    }
+    // clamp_depth -- src/index.rs:93-95
+    static uint32_t clamp_depth(uint32_t d) { return std::min<uint32_t>(d, AXIS_BITS); }
+    // depth -- src/index.rs:99-102
+    static uint32_t depth(K k) { return (uint32_t)(k & depth_mask()); }
+    // Index::default().set_depth(depth).set_origin(p) -- src/index.rs:106-112, 230-250
+    static K make(uint32_t d, const uint32_t *p) {
+        K origin = 0;
+        for (int a = 0; a < DIM; ++a) origin |= (K)(encode_axis(p[a]) << a);
+        K k = (K)(depth_mask() & (K)clamp_depth(d));
+        k |= (K)(origin_mask() & (K)(origin << ORIGIN_SHIFT));
+        return k;
+    }
+    // level_mask -- src/index.rs:82-86
+    static K level_mask(uint32_t d) {
+        if (d == 0) return 0;
+        return (K)((((K)1 << (DIM * d)) - 1) << (ORIGIN_BITS + ORIGIN_SHIFT - DIM * d));
+    }
+    // same_cell_at_depth -- src/index.rs:120-122
+    static bool same_cell_at_depth(K a, K b, uint32_t d) { return ((a ^ b) & level_mask(d)) == 0; }
+    // overlaps -- src/index.rs:116-118
+    static bool overlaps(K a, K b) { return same_cell_at_depth(a, b, std::min(depth(a), depth(b))); }
+};
+
+typedef IndexT<uint32_t, 2, 4, 14> Index32_2D; // src/index.rs:293
+typedef IndexT<uint64_t, 2, 5, 29> Index64_2D; // src/index.rs:294
+typedef IndexT<uint64_t, 3, 5, 19> Index64_3D; // src/index.rs:295
+
+// ---------------------------------------------------------------------------------------------
+// Quantiser + index generator -- src/geom.rs:40-61, 104-128, 148-163, 189-304
+// ---------------------------------------------------------------------------------------------
+
+// Rust `f32 as u32`: truncate toward zero, saturate, NaN -> 0.
+inline uint32_t f32_as_u32(float x) {
+    if (!(x == x)) return 0u;
+    if (x <= 0.0f) return 0u;
+    if (x >= 4294967296.0f) return 0xffffffffu;
+    return (uint32_t)x;
+}
+
+// SystemBounds::to_local, one scalar -- src/geom.rs:148-156.  Separate IEEE roundings for the
+// subtract, divide, multiply and add (the file is compiled with -ffp-contract=off).
+inline uint32_t to_local_scalar(float g, float sys_min, float sys_size) {
+    const float MIN_VALUE = 0.0f;
+    const float MAX_VALUE = 4294967040.0f; // 0xffff_ff00u32 as f32
+    const float RANGE = MAX_VALUE - MIN_VALUE;
+    const float t = g - sys_min;
+    const float q = t / sys_size;
+    const float m = q * RANGE;
+    const float r = m + MIN_VALUE;
+    return f32_as_u32(r);
+}
+
+// SystemBounds::to_global, one scalar -- src/geom.rs:165-174
+inline float to_global_scalar(uint32_t l, float sys_min, float sys_size) {
+    const float RANGE = 4294967040.0f;
+    const float a = (float)l - 0.0f;
+    const float q = a / RANGE;
+    const float m = q * sys_size;
+    const float r = sys_min + m;
+    return r;
+}
+
+// Bounds::contains -- src/geom.rs:121-128 (NaN passes: both comparisons are false)
+template <int DIM> inline bool contains(const float *sys, const float *b) {
+    for (int i = 0; i < DIM; ++i)
+        if (sys[i] > b[i] || sys[DIM + i] < b[DIM + i]) return false;
+    return true;
+}
+
+inline uint32_t leading_zeros32(uint32_t v) { return v == 0 ? 32u : (uint32_t)__builtin_clz(v); }
+
+// scale_at_depth / truncate_to_depth -- src/geom.rs:48-61 (depth >= 1 here)
+inline uint32_t scale_at_depth(uint32_t depth) { return 1u << (32 - depth); }
+inline uint32_t truncate_to_depth(uint32_t x, uint32_t depth) {
+    return depth == 0 ? x : (x & ~(scale_at_depth(depth) - 1u));
+}
+
+// IndexGenerator::indices + indices_at_depth -- src/geom.rs:189-238 (2D), :247-304 (3D).
+// Appends (index, id) for every cell, z outermost, then y, x innermost.
+template <class Ix, class ID>
+inline void gen_indices(const uint32_t *lmin, const uint32_t *lmax, uint32_t min_depth, ID id,
+                        std::vector<std::pair<typename Ix::key_t, ID>> &tree) {
+    const int DIM = Ix::DIM;
+    // max_axis(sizei) -- src/geom.rs:40-46, 104-110; u32 wrapping arithmetic as in a release build
+    uint32_t max_axis = 0;
+    for (int i = 0; i < DIM; ++i) max_axis = std::max(max_axis, (uint32_t)(lmax[i] - lmin[i] + 1u));
+    uint32_t depth = leading_zeros32(max_axis - 1u);
+    if (depth < min_depth) depth = min_depth;
+    depth = Ix::clamp_depth(depth);
+
+    if (depth == 0) { // src/geom.rs:203-205, :261-263 -- Index::default()
+        tree.emplace_back((typename Ix::key_t)0, id);
+        return;
+    }
+    uint32_t tmin[3] = {0, 0, 0}, tmax[3] = {0, 0, 0};
+    for (int i = 0; i < DIM; ++i) {
+        tmin[i] = truncate_to_depth(lmin[i], depth);
+        tmax[i] = truncate_to_depth(lmax[i], depth);
+    }
+    const uint32_t step = scale_at_depth(depth);
+    uint32_t p[3];
+    p[2] = tmin[2];
+    for (;;) { // z loop (single trip for 2D)
+        p[1] = tmin[1];
+        for (;;) {
+            p[0] = tmin[0];
+            for (;;) {
+                tree.emplace_back(Ix::make(depth, p), id);
+                if (p[0] >= tmax[0]) break;
+                p[0] += step;
+            }
+            if (p[1] >= tmax[1]) break;
+            p[1] += step;
+        }
+        if (DIM < 3 || p[2] >= tmax[2]) break;
+        p[2] += step;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Filters (device functors on the GPU side; plain functors here)
+// ---------------------------------------------------------------------------------------------
+struct Filter {
+    int kind;
+    uint64_t arg;
+    const uint32_t *table;
+    size_t n_table;
+    inline bool operator()(uint64_t a, uint64_t b) const {
+        switch (kind) {
+        case BPO_FILTER_NONE: return true;
+        case BPO_FILTER_ID_PARITY: return ((a ^ b) & 1u) == 1u;
+        case BPO_FILTER_XOR_MASK: return ((a ^ b) & arg) != 0;
+        case BPO_FILTER_CATEGORY: {
+            uint32_t ca = 0xffffffffu, ma = 0xffffffffu, cb = 0xffffffffu, mb = 0xffffffffu;
+            if (a < n_table) { ca = table[2 * a]; ma = table[2 * a + 1]; }
+            if (b < n_table) { cb = table[2 * b]; mb = table[2 * b + 1]; }
+            return (ca & mb) != 0 && (cb & ma) != 0;
+        }
+        default: return true;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Layer -- src/layer.rs:40-165, 448-573
+// ---------------------------------------------------------------------------------------------
+struct LayerBase {
+    virtual ~LayerBase() {}
+    virtual void clear() = 0;
+    virtual void extend(const float *sys, const float *bounds, const void *ids, size_t n) = 0;
+    virtual void merge(const LayerBase *other) = 0;
+    virtual void sort(bool par) = 0;
+    virtual size_t scan(const Filter &f, bool par) = 0;
+    virtual size_t len() const = 0;
+    virtual size_t num_collisions() const = 0;
+    virtual void records(uint64_t *keys, uint64_t *ids) const = 0;
+    virtual void collisions_out(uint64_t *a, uint64_t *b) const = 0;
+    virtual void set_records(const uint64_t *keys, const uint64_t *ids, size_t n, bool sorted) = 0;
+    int kind = 0, id_bytes = 0;
+    uint32_t min_depth = 0;
+    bool sorted = true; // LayerBuilder::build starts with sorted = true -- src/layer.rs:681
+    size_t raw_collisions = 0;
+};
+
+template <class Ix, class ID> struct LayerT : LayerBase {
+    typedef typename Ix::key_t K;
+    typedef std::pair<K, ID> Rec;   // (Index, ID): derived lexicographic Ord -- src/index.rs:67
+    typedef std::pair<ID, ID> Pair; // (ID, ID)
+    std::vector<Rec> tree;
+    std::vector<Pair> collisions;
+    std::vector<ID> invalid;
+    std::vector<std::vector<Pair>> collisions_tls; // CachedThreadLocal -- src/layer.rs:67
+
+    // Layer::clear -- src/layer.rs:84-88
+    void clear() override {
+        tree.clear();
+        sorted = true;
+    }
+
+    // Layer::extend -- src/layer.rs:94-121 (sequential, like the reference)
+    void extend(const float *sys, const float *bounds, const void *ids_, size_t n) override {
+        const int DIM = Ix::DIM;
+        const ID *ids = (const ID *)ids_;
+        tree.reserve(tree.size() + n); // size_hint upper bound -- src/layer.rs:103-105
+        float size[3];
+        for (int i = 0; i < DIM; ++i) { // sizef -- src/geom.rs:97-102
+            const float s = sys[DIM + i] - sys[i];
+            size[i] = s;
+        }
+        for (size_t o = 0; o < n; ++o) {
+            const float *b = bounds + o * 2 * DIM;
+            if (!contains<DIM>(sys, b)) { // src/layer.rs:108-111
+                invalid.push_back(ids[o]);
+                continue;
+            }
+            uint32_t lmin[3] = {0, 0, 0}, lmax[3] = {0, 0, 0};
+            for (int i = 0; i < DIM; ++i) { // to_local -- src/geom.rs:148-163
+                lmin[i] = to_local_scalar(b[i], sys[i], size[i]);
+                lmax[i] = to_local_scalar(b[DIM + i], sys[i], size[i]);
+            }
+            gen_indices<Ix, ID>(lmin, lmax, min_depth, ids[o], tree);
+            sorted = false; // src/layer.rs:119
+        }
+    }
+
+    // Layer::merge -- src/layer.rs:127-138
+    void merge(const LayerBase *other_) override {
+        const LayerT *other = static_cast<const LayerT *>(other_);
+        if (other->min_depth < min_depth) min_depth = other->min_depth;
+        tree.insert(tree.end(), other->tree.begin(), other->tree.end());
+        sorted = false;
+    }
+
+    // Layer::sort / par_sort -- src/layer.rs:146-165
+    void sort(bool par) override {
+        if (sorted) return;
+        if (par)
+            __gnu_parallel::sort(tree.begin(), tree.end());
+        else
+            std::sort(tree.begin(), tree.end());
+        sorted = true;
+    }
+
+    // Layer::scan_impl -- src/layer.rs:550-573 (the literal stack sweep)
+    static void scan_impl(const Rec *tree, size_t n, std::vector<Pair> &out, const Filter &filter) {
+        std::vector<Rec> stack;
+        stack.reserve(256);
+        for (size_t t = 0; t < n; ++t) {
+            const K index = tree[t].first;
+            const ID id = tree[t].second;
+            while (!stack.empty()) {
+                if (Ix::overlaps(index, stack.back().first)) break;
+                stack.pop_back();
+            }
+            bool same = false;
+            for (const Rec &s : stack)
+                if (s.second == id) { same = true; break; }
+            if (same) continue;
+            for (const Rec &s : stack)
+                if (id != s.second && filter((uint64_t)id, (uint64_t)s.second)) out.emplace_back(id, s.second);
+            stack.push_back(tree[t]);
+        }
+    }
+
+    // Layer::par_scan_impl -- src/layer.rs:523-548 (rayon::join -> OpenMP tasks)
+    void par_scan_impl(size_t threads, const Rec *t, size_t n, const Filter &filter) {
+        const size_t SPLIT_THRESHOLD = 64;
+        if (threads <= 1 || n <= SPLIT_THRESHOLD) {
+            scan_impl(t, n, collisions_tls[omp_get_thread_num()], filter);
+            return;
+        }
+        size_t i = n / 2;
+        while (i < n) {
+            if (!Ix::same_cell_at_depth(t[i - 1].first, t[i].first, min_depth)) break;
+            ++i;
+        }
+#pragma omp task default(shared) firstprivate(threads, t, i)
+        par_scan_impl(threads >> 1, t, i, filter);
+#pragma omp task default(shared) firstprivate(threads, t, i, n)
+        par_scan_impl(threads >> 1, t + i, n - i, filter);
+#pragma omp taskwait
+    }
+
+    // Layer::scan_filtered -- src/layer.rs:456-477; par_scan_filtered -- :489-520
+    size_t scan(const Filter &filter, bool par) override {
+        sort(par);
+        collisions.clear();
+        invalid.clear();
+        if (!par) {
+            scan_impl(tree.data(), tree.size(), collisions, filter);
+            raw_collisions = collisions.size();
+            std::sort(collisions.begin(), collisions.end());
+        } else {
+            const int nt = omp_get_max_threads();
+            collisions_tls.resize(nt);
+            for (auto &v : collisions_tls) v.clear();
+#pragma omp parallel
+#pragma omp single
+            par_scan_impl((size_t)nt, tree.data(), tree.size(), filter);
+            for (auto &v : collisions_tls) collisions.insert(collisions.end(), v.begin(), v.end());
+            raw_collisions = collisions.size();
+            __gnu_parallel::sort(collisions.begin(), collisions.end());
+        }
+        collisions.erase(std::unique(collisions.begin(), collisions.end()), collisions.end()); // dedup()
+        return collisions.size();
+    }
+
+    size_t len() const override { return tree.size(); }
+    size_t num_collisions() const override { return collisions.size(); }
+    void records(uint64_t *keys, uint64_t *ids) const override {
+        for (size_t i = 0; i < tree.size(); ++i) {
+            keys[i] = (uint64_t)tree[i].first;
+            ids[i] = (uint64_t)tree[i].second;
+        }
+    }
+    void collisions_out(uint64_t *a, uint64_t *b) const override {
+        for (size_t i = 0; i < collisions.size(); ++i) {
+            a[i] = (uint64_t)collisions[i].first;
+            b[i] = (uint64_t)collisions[i].second;
+        }
+    }
+    void set_records(const uint64_t *keys, const uint64_t *ids, size_t n, bool sorted_) override {
+        tree.resize(n);
+        for (size_t i = 0; i < n; ++i) tree[i] = Rec((K)keys[i], (ID)ids[i]);
+        sorted = sorted_;
+    }
+};
+
+LayerBase *make_layer(int kind, int id_bytes) {
+    if (id_bytes == 4) {
+        if (kind == BPO_INDEX32_2D) return new LayerT<Index32_2D, uint32_t>();
+        if (kind == BPO_INDEX64_2D) return new LayerT<Index64_2D, uint32_t>();
+        if (kind == BPO_INDEX64_3D) return new LayerT<Index64_3D, uint32_t>();
+    } else if (id_bytes == 8) {
+        if (kind == BPO_INDEX32_2D) return new LayerT<Index32_2D, uint64_t>();
+        if (kind == BPO_INDEX64_2D) return new LayerT<Index64_2D, uint64_t>();
+        if (kind == BPO_INDEX64_3D) return new LayerT<Index64_3D, uint64_t>();
+    }
+    return nullptr;
+}
+
+} // namespace
+
+struct bpo_layer {
+    LayerBase *impl;
+};
+
+extern "C" {
+
+bpo_layer *bpo_layer_new(int kind, int id_bytes, uint32_t min_depth) {
+    LayerBase *impl = make_layer(kind, id_bytes);
+    if (!impl) return nullptr;
+    impl->kind = kind;
+    impl->id_bytes = id_bytes;
+    impl->min_depth = min_depth;
+    bpo_layer *l = new bpo_layer;
+    l->impl = impl;
+    return l;
+}
+void bpo_layer_free(bpo_layer *l) {
+    if (!l) return;
+    delete l->impl;
+    delete l;
+}
+void bpo_layer_clear(bpo_layer *l) { l->impl->clear(); }
+void bpo_layer_extend(bpo_layer *l, const float *sys, const float *bounds, const void *ids, size_t n) {
+    l->impl->extend(sys, bounds, ids, n);
+}
+void bpo_layer_merge(bpo_layer *l, const bpo_layer *other) { l->impl->merge(other->impl); }
+void bpo_layer_sort(bpo_layer *l) { l->impl->sort(false); }
+void bpo_layer_par_sort(bpo_layer *l) { l->impl->sort(true); }
+size_t bpo_layer_scan(bpo_layer *l, int filter, uint64_t arg, const uint32_t *table, size_t n_table) {
+    Filter f = {filter, arg, table, n_table};
+    return l->impl->scan(f, false);
+}
+size_t bpo_layer_par_scan(bpo_layer *l, int filter, uint64_t arg, const uint32_t *table, size_t n_table) {
+    Filter f = {filter, arg, table, n_table};
+    return l->impl->scan(f, true);
+}
+size_t bpo_layer_len(const bpo_layer *l) { return l->impl->len(); }
+int bpo_layer_sorted(const bpo_layer *l) { return l->impl->sorted ? 1 : 0; }
+uint32_t bpo_layer_min_depth(const bpo_layer *l) { return l->impl->min_depth; }
+size_t bpo_layer_num_collisions(const bpo_layer *l) { return l->impl->num_collisions(); }
+size_t bpo_layer_num_raw_collisions(const bpo_layer *l) { return l->impl->raw_collisions; }
+void bpo_layer_records(const bpo_layer *l, uint64_t *keys, uint64_t *ids) { l->impl->records(keys, ids); }
+void bpo_layer_collisions(const bpo_layer *l, uint64_t *a, uint64_t *b) { l->impl->collisions_out(a, b); }
+void bpo_layer_set_records(bpo_layer *l, const uint64_t *keys, const uint64_t *ids, size_t n, int sorted) {
+    l->impl->set_records(keys, ids, n, sorted != 0);
+}
+
+uint64_t bpo_encode_axis(int kind, uint32_t v) {
+    switch (kind) {
+    case BPO_INDEX32_2D: return Index32_2D::encode_axis(v);
+    case BPO_INDEX64_2D: return Index64_2D::encode_axis(v);
+    default: return Index64_3D::encode_axis(v);
+    }
+}
+uint32_t bpo_decode_axis(int kind, uint64_t o) {
+    switch (kind) {
+    case BPO_INDEX32_2D: return Index32_2D::decode_axis((uint32_t)o);
+    case BPO_INDEX64_2D: return Index64_2D::decode_axis(o);
+    default: return Index64_3D::decode_axis(o);
+    }
+}
+uint64_t bpo_make_index(int kind, uint32_t depth, const uint32_t *origin) {
+    switch (kind) {
+    case BPO_INDEX32_2D: return Index32_2D::make(depth, origin);
+    case BPO_INDEX64_2D: return Index64_2D::make(depth, origin);
+    default: return Index64_3D::make(depth, origin);
+    }
+}
+uint64_t bpo_level_mask(int kind, uint32_t depth) {
+    switch (kind) {
+    case BPO_INDEX32_2D: return Index32_2D::level_mask(depth);
+    case BPO_INDEX64_2D: return Index64_2D::level_mask(depth);
+    default: return Index64_3D::level_mask(depth);
+    }
+}
+int bpo_overlaps(int kind, uint64_t a, uint64_t b) {
+    switch (kind) {
+    case BPO_INDEX32_2D: return Index32_2D::overlaps((uint32_t)a, (uint32_t)b);
+    case BPO_INDEX64_2D: return Index64_2D::overlaps(a, b);
+    default: return Index64_3D::overlaps(a, b);
+    }
+}
+void bpo_to_local(int dim, const float *sys, const float *b, uint32_t *out) {
+    for (int i = 0; i < dim; ++i) {
+        const float s = sys[dim + i] - sys[i];
+        out[i] = to_local_scalar(b[i], sys[i], s);
+        out[dim + i] = to_local_scalar(b[dim + i], sys[i], s);
+    }
+}
+void bpo_to_global(int dim, const float *sys, const uint32_t *local, float *out) {
+    for (int i = 0; i < dim; ++i) {
+        const float s = sys[dim + i] - sys[i];
+        out[i] = to_global_scalar(local[i], sys[i], s);
+        out[dim + i] = to_global_scalar(local[dim + i], sys[i], s);
+    }
+}
+
+int bpo_max_threads(void) { return omp_get_max_threads(); }
+void bpo_set_threads(int n) { omp_set_num_threads(n); }
+
+} // extern "C"

@@ -1,0 +1,76 @@
+/*
+ * bp_oracle.h -- C ABI of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a CPU restatement of the broadphase-rs hot path
+ * (extend / sort / par_sort / merge / scan / par_scan / scan_filtered).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it;
+ * the product (libbroadphase_b200.so) never links, loads or calls anything in oracle/.
+ *
+ * PARITY STATUS: the codec and quantiser are pinned by the reference's in-source
+ * known-answer tests (src/index.rs:343-374, src/geom.rs:696-706).  The end-to-end
+ * extend/sort/scan results are "parity unpinned": the reference's golden fixtures are
+ * Git-LFS pointer stubs and no Rust toolchain exists in this image, so they are pinned only by
+ * agreement between this restatement and an independent numpy restatement (oracle/pyref.py).
+ */
+#ifndef BP_ORACLE_H
+#define BP_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* index kinds -- src/index.rs:293-295 */
+enum { BPO_INDEX32_2D = 0, BPO_INDEX64_2D = 1, BPO_INDEX64_3D = 2 };
+
+/* filters for scan_filtered (src/layer.rs:456-477); (a, b) = (later id, earlier id) */
+enum {
+    BPO_FILTER_NONE = 0,      /* |_, _| true                                  */
+    BPO_FILTER_ID_PARITY = 1, /* ((a ^ b) & 1) == 1                           */
+    BPO_FILTER_XOR_MASK = 2,  /* ((a ^ b) & arg) != 0                         */
+    BPO_FILTER_CATEGORY = 3   /* (cat[a] & msk[b]) != 0 && (cat[b] & msk[a]) != 0,
+                                 table = n_table x {u32 cat, u32 msk}; ids >= n_table act as all-ones */
+};
+
+typedef struct bpo_layer bpo_layer;
+
+bpo_layer *bpo_layer_new(int kind, int id_bytes, uint32_t min_depth);
+void bpo_layer_free(bpo_layer *);
+void bpo_layer_clear(bpo_layer *);
+/* sys_bounds: 2*D floats (min.., max..); bounds: n x 2*D floats; ids: n x id_bytes */
+void bpo_layer_extend(bpo_layer *, const float *sys_bounds, const float *bounds, const void *ids, size_t n);
+void bpo_layer_merge(bpo_layer *, const bpo_layer *other);
+void bpo_layer_sort(bpo_layer *);
+void bpo_layer_par_sort(bpo_layer *);
+size_t bpo_layer_scan(bpo_layer *, int filter, uint64_t arg, const uint32_t *table, size_t n_table);
+size_t bpo_layer_par_scan(bpo_layer *, int filter, uint64_t arg, const uint32_t *table, size_t n_table);
+
+size_t bpo_layer_len(const bpo_layer *);
+int bpo_layer_sorted(const bpo_layer *);
+uint32_t bpo_layer_min_depth(const bpo_layer *);
+size_t bpo_layer_num_collisions(const bpo_layer *);
+size_t bpo_layer_num_raw_collisions(const bpo_layer *); /* pairs before sort+dedup in the last scan */
+/* copies widened to u64 */
+void bpo_layer_records(const bpo_layer *, uint64_t *keys, uint64_t *ids);
+void bpo_layer_collisions(const bpo_layer *, uint64_t *a, uint64_t *b);
+/* loads records directly (keys/ids widened to u64) -- used to test sort/scan on arbitrary trees */
+void bpo_layer_set_records(bpo_layer *, const uint64_t *keys, const uint64_t *ids, size_t n, int sorted);
+
+/* codec + quantiser, exposed for the known-answer tests */
+uint64_t bpo_encode_axis(int kind, uint32_t v);
+uint32_t bpo_decode_axis(int kind, uint64_t origin_bits);
+uint64_t bpo_make_index(int kind, uint32_t depth, const uint32_t *origin);
+uint64_t bpo_level_mask(int kind, uint32_t depth);
+int bpo_overlaps(int kind, uint64_t a, uint64_t b);
+void bpo_to_local(int dim, const float *sys_bounds, const float *bounds, uint32_t *out_local);
+void bpo_to_global(int dim, const float *sys_bounds, const uint32_t *local, float *out_bounds);
+
+int bpo_max_threads(void);
+void bpo_set_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

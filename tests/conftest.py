@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def bp():
+    """The product package (loads libbroadphase_b200.so; raises if it was not built)."""
+    import _loadpkg
+    return _loadpkg.load()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import cpu_oracle
+    cpu_oracle.lib()
+    return cpu_oracle
