@@ -1,0 +1,18 @@
+"""broadphase-rs_b200 -- the B200-native (sm_100a CUDA) implementation of broadphase-rs's hot path
+(Layer::extend / sort / merge / scan) behind the C ABI of include/bp.h.
+
+Importing this package loads libbroadphase_b200.so; it raises ImportError when the library has not
+been built.  There is no CPU fallback and no alternative backend.
+"""
+from . import _lib
+from ._lib import BpError, lib
+
+lib()  # fail loudly, at import time, if the CUDA library is missing
+
+from .layer import (FILTER_CATEGORY, FILTER_ID_PARITY, FILTER_NONE, FILTER_XOR_MASK, Index32_2D, Index64_2D,  # noqa: E402
+                    Index64_3D, Layer, LayerBuilder, ScanFilter, device_count, plan_radix_passes)
+from . import scenes  # noqa: E402
+
+__all__ = ["Layer", "LayerBuilder", "ScanFilter", "Index32_2D", "Index64_2D", "Index64_3D", "BpError",
+           "FILTER_NONE", "FILTER_ID_PARITY", "FILTER_XOR_MASK", "FILTER_CATEGORY", "device_count",
+           "plan_radix_passes", "scenes", "lib"]

@@ -1,0 +1,99 @@
+"""ctypes binding of libbroadphase_b200.so (include/bp.h).  Fails loudly if the library is missing:
+there is no CPU fallback and no other backend."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libbroadphase_b200.so")
+
+BP_OK = 0
+STATUS = {0: "BP_OK", 1: "BP_ERR_INVALID_ARG", 2: "BP_ERR_CUDA", 3: "BP_ERR_OOM", 4: "BP_ERR_TOO_LARGE",
+          5: "BP_ERR_INTERNAL", 6: "BP_ERR_MISMATCH"}
+BP_K_COUNT = 10
+KERNEL_CLASSES = ["encode", "sort_hist", "sort_pass", "merge", "scan_runs", "scan_emit", "pair_hist", "pair_pass",
+                  "pair_unique", "misc"]
+
+
+class BpError(RuntimeError):
+    def __init__(self, status, message=""):
+        self.status = status
+        super().__init__("%s: %s" % (STATUS.get(status, status), message))
+
+
+class LayerConfig(ctypes.Structure):
+    _fields_ = [("index_kind", ctypes.c_int32), ("id_bytes", ctypes.c_int32), ("min_depth", ctypes.c_uint32),
+                ("device", ctypes.c_int32), ("index_capacity", ctypes.c_size_t),
+                ("collision_capacity", ctypes.c_size_t), ("test_capacity", ctypes.c_size_t)]
+
+
+class Filter(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("table_on_device", ctypes.c_int32), ("arg", ctypes.c_uint64),
+                ("table", ctypes.c_void_p), ("n_table", ctypes.c_size_t)]
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [("n_records", ctypes.c_uint64), ("n_invalid", ctypes.c_uint64), ("n_work_items", ctypes.c_uint64),
+                ("n_raw_pairs", ctypes.c_uint64), ("n_pairs", ctypes.c_uint64), ("sort_passes", ctypes.c_uint32),
+                ("pair_sort_passes", ctypes.c_uint32), ("merged", ctypes.c_uint32), ("rescans", ctypes.c_uint32),
+                ("launches_total", ctypes.c_uint64), ("launches", ctypes.c_uint64 * BP_K_COUNT),
+                ("kernel_ms", ctypes.c_double * BP_K_COUNT), ("algo_bytes", ctypes.c_double * BP_K_COUNT)]
+
+
+# every symbol include/bp.h declares: name -> (restype, argtypes)
+_vp, _sz, _i, _u32, _u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64
+_P = ctypes.POINTER
+SYMBOLS = {
+    "bp_layer_create": (_i, [_P(LayerConfig), _P(_vp)]),
+    "bp_layer_destroy": (_i, [_vp]),
+    "bp_layer_set_stream": (_i, [_vp, _vp]),
+    "bp_layer_clear": (_i, [_vp]),
+    "bp_layer_extend_host": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "bp_layer_extend_device": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "bp_layer_merge": (_i, [_vp, _vp]),
+    "bp_layer_sort": (_i, [_vp]),
+    "bp_layer_scan": (_i, [_vp, _P(Filter), _P(_vp), _P(_sz)]),
+    "bp_layer_scan_device": (_i, [_vp, _P(Filter), _P(_vp), _P(_sz)]),
+    "bp_layer_records": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
+    "bp_layer_records_device": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
+    "bp_layer_set_records": (_i, [_vp, _vp, _vp, _sz, _i, _i]),
+    "bp_layer_len": (_i, [_vp, _P(_sz)]),
+    "bp_layer_is_sorted": (_i, [_vp, _P(_i)]),
+    "bp_layer_min_depth": (_i, [_vp, _P(_u32)]),
+    "bp_layer_set_profiling": (_i, [_vp, _i]),
+    "bp_layer_reset_stats": (_i, [_vp]),
+    "bp_layer_stats": (_i, [_vp, _P(Stats)]),
+    "bp_layer_last_error": (ctypes.c_char_p, [_vp]),
+    "bp_status_string": (ctypes.c_char_p, [_i]),
+    "bp_version": (_i, []),
+    "bp_device_count": (_i, [_P(_i)]),
+    "bp_plan_radix_passes": (_i, [_u64, _P(_u32), _P(_u32), _i]),
+}
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library.  Raises if it has not been built (python __graft_entry__.py build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(
+            "libbroadphase_b200.so is missing at %s: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'`.  There is no CPU fallback." % SO_PATH)
+    L = ctypes.CDLL(SO_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def check(status, handle=None):
+    if status != BP_OK:
+        msg = ""
+        if handle:
+            m = lib().bp_layer_last_error(handle)
+            msg = m.decode() if m else ""
+        raise BpError(status, msg)

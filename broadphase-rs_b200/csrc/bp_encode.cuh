@@ -1,0 +1,301 @@
+// bp_encode.cuh -- K1: fused contains + quantise + depth choice + cell enumeration + Morton encode.
+//
+// Replaces the sequential loop of Layer::extend (src/layer.rs:94-121) and everything it calls:
+// Bounds::contains (src/geom.rs:121-128), SystemBounds::to_local (src/geom.rs:148-163),
+// IndexGenerator::indices / indices_at_depth (src/geom.rs:189-304), set_depth / set_origin /
+// encode_axis (src/index.rs:106-112, 155-172, 193-207, 230-250).
+//
+// One pass over the objects: a CTA stages a tile of AABBs in shared memory with 16-byte loads,
+// every thread quantises its objects with explicitly rounded IEEE ops (sub, div, mul, add -- never
+// fused, never a reciprocal), counts its cells, the tile's record range comes from a block scan + a
+// decoupled look-back over the preceding tiles, and the records are staged in shared memory and
+// written in the reference's order (object order; z outermost, then y, x innermost) with coalesced
+// stores.  The kernel also folds in the reductions the sort planner needs (OR / AND of all keys
+// and IDs, "IDs ascending" check), so no extra pass over the records is required.
+#pragma once
+
+#include "bp_common.cuh"
+
+namespace bp {
+
+struct ExtendResult {
+    unsigned long long total_records; // records this call produced (all of them, even if capacity ran out)
+    unsigned long long n_invalid;     // objects rejected by contains()
+    unsigned long long key_or, key_and, id_or, id_and;
+    unsigned int nonmono;  // 1 if an ID smaller than its predecessor was seen
+    unsigned int too_many; // 1 if one object wanted more than ENCODE_MAX_CELLS cells
+};
+
+constexpr uint32_t ENCODE_MAX_CELLS = 1u << 20;
+constexpr int ENCODE_THREADS = 256;
+constexpr int ENCODE_OPT = 4; // objects per thread
+constexpr int ENCODE_TILE = ENCODE_THREADS * ENCODE_OPT;
+constexpr int ENCODE_WINDOW = 4096; // records staged per write-out round
+
+template <class T, class IdT> struct EncodeArgs {
+    const float *bounds; // n x 2*DIM
+    const IdT *ids;      // n
+    uint32_t n;
+    float sys_min[3], sys_max[3], sys_size[3];
+    uint32_t min_depth;
+    typename T::key_t *keys_out; // tree arrays
+    IdT *ids_out;
+    uint64_t out_base;     // records already in the tree
+    uint64_t capacity;     // records the tree arrays can hold
+    uint64_t *status;      // look-back status, one per tile, zeroed
+    uint32_t *tile_counter; // zeroed
+    ExtendResult *result;  // initialised by the host (sums 0, and-masks ~0)
+    const IdT *prev_last_id; // last ID of the previous extend since the tail began (or null)
+    IdT *next_last_id;
+    int *err;
+};
+
+template <class T, class IdT> struct EncodeSmem {
+    static constexpr size_t BOUNDS_BYTES = (size_t)ENCODE_TILE * 2 * T::DIM * sizeof(float);
+    static constexpr size_t STAGE_BYTES = (size_t)ENCODE_WINDOW * (sizeof(typename T::key_t) + sizeof(IdT));
+    static constexpr size_t UNION_BYTES = BOUNDS_BYTES > STAGE_BYTES ? BOUNDS_BYTES : STAGE_BYTES;
+    static constexpr size_t BYTES = UNION_BYTES + (size_t)ENCODE_TILE * sizeof(uint32_t) + 64 * sizeof(uint64_t);
+};
+
+// SystemBounds::to_local for one scalar (src/geom.rs:148-156): ((g - min) / size * RANGE + 0) as u32
+// with one IEEE rounding per operation; the cast truncates, saturates and maps NaN to 0 exactly like
+// Rust's `as u32` (cvt.rzi.u32.f32).
+__device__ __forceinline__ uint32_t quantise(float g, float mn, float size) {
+    const float t = __fsub_rn(g, mn);
+    const float q = __fdiv_rn(t, size);
+    const float m = __fmul_rn(q, 4294967040.0f);
+    const float r = __fadd_rn(m, 0.0f);
+    return __float2uint_rz(r);
+}
+
+template <class T, class IdT>
+__global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs<T, IdT> a) {
+    typedef typename T::key_t K;
+    constexpr int DIM = T::DIM;
+    constexpr int FPO = 2 * DIM; // floats per object
+    typedef EncodeSmem<T, IdT> S;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *sbounds = (float *)smem_raw;
+    K *skeys = (K *)smem_raw;
+    IdT *sids = (IdT *)(smem_raw + (size_t)ENCODE_WINDOW * sizeof(K));
+    uint32_t *scnt = (uint32_t *)(smem_raw + S::UNION_BYTES);                                   // [ENCODE_TILE]
+    uint64_t *sred = (uint64_t *)(smem_raw + S::UNION_BYTES + ENCODE_TILE * sizeof(uint32_t)); // scratch
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) *(uint32_t *)sred = atomicAdd(a.tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = *(uint32_t *)sred;
+    __syncthreads();
+    const uint32_t obj0 = tile * ENCODE_TILE;
+    if (obj0 >= a.n) return;
+    const uint32_t tile_objs = min((uint32_t)ENCODE_TILE, a.n - obj0);
+
+    // ---- stage the tile's AABBs with 16-byte loads ------------------------------------------------
+    {
+        const float *src = a.bounds + (size_t)obj0 * FPO;
+        const uint32_t nfl = tile_objs * FPO;
+        if ((((uintptr_t)src) & 15u) == 0) {
+            const uint32_t nv = nfl >> 2;
+            const float4 *src4 = (const float4 *)src;
+            float4 *dst4 = (float4 *)sbounds;
+            for (uint32_t i = tid; i < nv; i += ENCODE_THREADS) dst4[i] = __ldcs(src4 + i);
+            for (uint32_t i = (nv << 2) + tid; i < nfl; i += ENCODE_THREADS) sbounds[i] = src[i];
+        } else {
+            for (uint32_t i = tid; i < nfl; i += ENCODE_THREADS) sbounds[i] = src[i];
+        }
+    }
+    __syncthreads();
+
+    // ---- per object: contains, quantise, depth, cell grid ----------------------------------------
+    uint32_t depth[ENCODE_OPT], tmin[ENCODE_OPT][3], ncell[ENCODE_OPT][3], count[ENCODE_OPT];
+    IdT id[ENCODE_OPT];
+    uint32_t n_invalid = 0, nonmono = 0, too_many = 0;
+    unsigned long long id_or = 0, id_and = ~0ull;
+#pragma unroll
+    for (int k = 0; k < ENCODE_OPT; ++k) {
+        const uint32_t o = k * ENCODE_THREADS + tid; // striped: conflict-light shared reads, coalesced ID loads
+        count[k] = 0;
+        depth[k] = 0;
+        id[k] = 0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            tmin[k][i] = 0;
+            ncell[k][i] = 1;
+        }
+        if (o >= tile_objs) continue;
+        const uint32_t g = obj0 + o;
+        id[k] = a.ids[g];
+        // IDs ascending in object order => records enter the sort in ascending ID order, so a stable
+        // sort on the key alone yields the (Index, ID) order of src/layer.rs:146-165.
+        if (g > 0) {
+            if (a.ids[g - 1] > id[k]) nonmono = 1;
+        } else if (a.prev_last_id) {
+            if (*a.prev_last_id > id[k]) nonmono = 1;
+        }
+        const float *b = sbounds + o * FPO;
+        bool valid = true;
+        uint32_t lmin[3] = {0, 0, 0}, lmax[3] = {0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) {
+            const float bmin = b[i], bmax = b[DIM + i];
+            // Bounds::contains -- src/geom.rs:121-128 (NaN passes both tests)
+            if (a.sys_min[i] > bmin || a.sys_max[i] < bmax) valid = false;
+            lmin[i] = quantise(bmin, a.sys_min[i], a.sys_size[i]);
+            lmax[i] = quantise(bmax, a.sys_min[i], a.sys_size[i]);
+        }
+        if (!valid) {
+            ++n_invalid;
+            continue;
+        }
+        id_or |= (unsigned long long)id[k];
+        id_and &= (unsigned long long)id[k];
+        // indices(): depth = leading_zeros(max_axis(sizei) - 1), raised to min_depth, clamped
+        uint32_t max_axis = 0;
+#pragma unroll
+        for (int i = 0; i < DIM; ++i) max_axis = max(max_axis, lmax[i] - lmin[i] + 1u);
+        uint32_t d = (uint32_t)__clz((int)(max_axis - 1u));
+        d = max(d, a.min_depth);
+        d = min(d, (uint32_t)T::AXIS_BITS);
+        depth[k] = d;
+        uint64_t cells = 1;
+        if (d != 0) { // indices_at_depth(): truncate to the depth grid, count cells per axis
+            const uint32_t sh = 32u - d;
+#pragma unroll
+            for (int i = 0; i < DIM; ++i) {
+                const uint32_t lo = (lmin[i] >> sh) << sh, hi = (lmax[i] >> sh) << sh;
+                tmin[k][i] = lo;
+                ncell[k][i] = hi > lo ? ((hi - lo) >> sh) + 1u : 1u;
+                cells *= ncell[k][i];
+            }
+        }
+        if (cells > ENCODE_MAX_CELLS) {
+            too_many = 1;
+            cells = 0;
+        }
+        count[k] = (uint32_t)cells;
+    }
+    __syncthreads(); // sbounds is dead from here on (its space becomes the staging window)
+
+    // ---- exclusive scan of the counts in object order ---------------------------------------------
+#pragma unroll
+    for (int k = 0; k < ENCODE_OPT; ++k) scnt[k * ENCODE_THREADS + tid] = count[k];
+    __syncthreads();
+    uint32_t c4[ENCODE_OPT], tsum = 0;
+#pragma unroll
+    for (int k = 0; k < ENCODE_OPT; ++k) {
+        c4[k] = scnt[tid * ENCODE_OPT + k];
+        tsum += c4[k];
+    }
+    uint32_t tile_total;
+    uint32_t ex = block_exclusive_sum<ENCODE_THREADS, uint32_t>(tsum, (uint32_t *)sred, &tile_total);
+#pragma unroll
+    for (int k = 0; k < ENCODE_OPT; ++k) {
+        scnt[tid * ENCODE_OPT + k] = ex;
+        ex += c4[k];
+    }
+    __syncthreads();
+
+    // ---- tile offset: decoupled look-back -----------------------------------------------------------
+    if (warp == 0) {
+        const uint64_t excl = lookback_exclusive(a.status, tile, (uint64_t)tile_total, a.err);
+        if (lane == 0) sred[32] = excl;
+    }
+    __syncthreads();
+    const uint64_t tile_base = sred[32];
+    const uint64_t gout = a.out_base + tile_base;
+
+    // ---- generate the records through a shared-memory window, write them coalesced --------------
+    unsigned long long key_or = 0, key_and = ~0ull;
+    uint32_t off[ENCODE_OPT];
+#pragma unroll
+    for (int k = 0; k < ENCODE_OPT; ++k) off[k] = scnt[k * ENCODE_THREADS + tid];
+    for (uint32_t w0 = 0; w0 < tile_total; w0 += ENCODE_WINDOW) {
+        const uint32_t w1 = min(tile_total, w0 + (uint32_t)ENCODE_WINDOW);
+#pragma unroll
+        for (int k = 0; k < ENCODE_OPT; ++k) {
+            if (count[k] == 0) continue;
+            const uint32_t lo = off[k] > w0 ? off[k] : w0;
+            const uint32_t hi = min(off[k] + count[k], w1);
+            if (lo >= hi) continue;
+            const uint32_t d = depth[k];
+            const uint32_t step = d ? (1u << (32u - d)) : 0u;
+            const uint32_t nx = ncell[k][0], nxy = ncell[k][0] * ncell[k][1];
+            for (uint32_t p = lo; p < hi; ++p) {
+                const uint32_t c = p - off[k];
+                const uint32_t iz = c / nxy, r = c - iz * nxy;
+                const uint32_t iy = r / nx, ix = r - iy * nx;
+                uint64_t origin = encode_axis<T>(tmin[k][0] + ix * step) | (encode_axis<T>(tmin[k][1] + iy * step) << 1);
+                if (DIM == 3) origin |= encode_axis<T>(tmin[k][2] + iz * step) << 2;
+                const K key = d ? make_key<T>(d, origin) : (K)0; // depth 0 -> Index::default()
+                key_or |= (unsigned long long)key;
+                key_and &= (unsigned long long)key;
+                skeys[p - w0] = key;
+                sids[p - w0] = id[k];
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < w1 - w0; i += ENCODE_THREADS) {
+            const uint64_t gi = gout + w0 + i;
+            if (gi < a.capacity) {
+                a.keys_out[gi] = skeys[i];
+                a.ids_out[gi] = sids[i];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- block-level reductions for the sort planner ------------------------------------------------
+    key_or = warp_or(key_or);
+    key_and = warp_and(key_and);
+    id_or = warp_or(id_or);
+    id_and = warp_and(id_and);
+    n_invalid = warp_sum(n_invalid);
+    nonmono = warp_or(nonmono);
+    too_many = warp_or(too_many);
+    if (lane == 0) {
+        if (key_or) atomicOr(&a.result->key_or, key_or);
+        if (key_and != ~0ull) atomicAnd(&a.result->key_and, key_and);
+        if (id_or) atomicOr(&a.result->id_or, id_or);
+        if (id_and != ~0ull) atomicAnd(&a.result->id_and, id_and);
+        if (n_invalid) atomicAdd(&a.result->n_invalid, (unsigned long long)n_invalid);
+        if (nonmono) atomicOr(&a.result->nonmono, 1u);
+        if (too_many) atomicOr(&a.result->too_many, 1u);
+    }
+    if (obj0 + tile_objs == a.n && tid == 0) { // last tile: totals + the tail's last ID
+        a.result->total_records = tile_base + tile_total;
+        if (a.next_last_id) *a.next_last_id = a.ids[a.n - 1];
+    }
+}
+
+// OR / AND of keys and IDs + "IDs ascending" for a tree that did not come from encode_kernel
+// (bp_layer_set_records).  result must be pre-initialised like for encode_kernel.
+template <class K, class IdT>
+__global__ void __launch_bounds__(256) record_masks_kernel(const K *__restrict__ keys, const IdT *__restrict__ ids,
+                                                           uint32_t n, ExtendResult *result) {
+    unsigned long long key_or = 0, key_and = ~0ull, id_or = 0, id_and = ~0ull;
+    unsigned nonmono = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long k = (unsigned long long)keys[i], v = (unsigned long long)ids[i];
+        key_or |= k;
+        key_and &= k;
+        id_or |= v;
+        id_and &= v;
+        if (i > 0 && ids[i - 1] > ids[i]) nonmono = 1;
+    }
+    key_or = warp_or(key_or);
+    key_and = warp_and(key_and);
+    id_or = warp_or(id_or);
+    id_and = warp_and(id_and);
+    nonmono = warp_or(nonmono);
+    if ((threadIdx.x & 31) == 0) {
+        if (key_or) atomicOr(&result->key_or, key_or);
+        if (key_and != ~0ull) atomicAnd(&result->key_and, key_and);
+        if (id_or) atomicOr(&result->id_or, id_or);
+        if (id_and != ~0ull) atomicAnd(&result->id_and, id_and);
+        if (nonmono) atomicOr(&result->nonmono, 1u);
+    }
+}
+
+} // namespace bp

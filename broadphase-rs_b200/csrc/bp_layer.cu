@@ -1,0 +1,1192 @@
+// bp_layer.cu -- host runtime + C ABI (include/bp.h) of libbroadphase_b200.so.
+//
+// Mirrors the reference's Layer<Index, ID> (src/layer.rs:42-68): a device-resident tree of
+// (Index, ID) records in SoA form (keys[], ids[]) with the reference's "sorted" flag, plus the
+// scratch the kernels need.  All work is enqueued on one CUDA stream per layer; the host only
+// synchronises where a size has to come back (record count after extend, work-item / pair counts
+// in scan).  There is no CPU fallback: every entry point fails if CUDA does.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "bp_common.cuh"
+#include "bp_encode.cuh"
+#include "bp_merge.cuh"
+#include "bp_radix.cuh"
+#include "bp_scan.cuh"
+
+using namespace bp;
+
+namespace {
+
+// ---- tunables -------------------------------------------------------------------------------------
+template <class K, class V> struct PassTune { // threads, items per thread of radix_pass_kernel
+    static constexpr int THREADS = 384, ITEMS = 12;
+};
+template <> struct PassTune<uint32_t, uint32_t> { static constexpr int THREADS = 512, ITEMS = 16; };
+template <> struct PassTune<uint64_t, NoVal> { static constexpr int THREADS = 384, ITEMS = 12; };
+template <> struct PassTune<uint64_t, uint64_t> { static constexpr int THREADS = 256, ITEMS = 12; };
+
+constexpr uint64_t MAX_RECORDS = (1ull << 30) - 1;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct ProfEvent {
+    cudaEvent_t start, stop;
+    int cls;
+};
+
+} // namespace
+
+struct bp_layer {
+    bp_layer_config cfg;
+    int kind, id_bytes, key_bytes, dim, device;
+    uint32_t min_depth;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    // tree: ping-pong SoA buffers
+    DevBuf keys[2], ids[2];
+    int cur = 0;
+    size_t cap_records = 0;
+    uint64_t n_records = 0;
+    bool dirty = false;       // !sorted flag of the reference
+    uint64_t prefix = 0;      // records [0, prefix) are sorted (meaningful while dirty)
+    bool tail_sorted = false; // records [prefix, n) form one sorted run
+    bool tail_nonmono = false; // tail IDs not known to ascend in record order
+    bool tail_has_last = false;
+    int last_slot = 0;
+    uint64_t key_or = 0, key_and = ~0ull, id_or = 0, id_and = ~0ull;
+    uint64_t n_invalid = 0;
+
+    // pending extend result
+    bool pending = false;
+    uint64_t pending_base = 0;
+    cudaEvent_t ev_sync = nullptr;
+    ExtendResult *h_res = nullptr; // pinned
+    ExtendResult *d_res = nullptr;
+    void *d_last = nullptr;        // 2 x u64 slots
+    ScanTotals *h_tot = nullptr;   // pinned
+    ScanTotals *d_tot = nullptr;
+    int *d_err = nullptr;
+    int *h_err = nullptr; // pinned
+
+    DevBuf scratch;                // look-back status words, tile counters, histograms
+    DevBuf stage_bounds, stage_ids; // extend_host staging
+    DevBuf src_idx, src_off, chunk_src, inactive;
+    DevBuf praw[2], praw_b[2];     // raw pairs, ping-pong (u32 IDs: packed; u64 IDs: later / earlier)
+    DevBuf pout;                   // final pairs
+    DevBuf filter_table;
+    void *h_pairs = nullptr;
+    size_t h_pairs_cap = 0;
+    void *h_keys = nullptr, *h_ids = nullptr;
+    size_t h_keys_cap = 0, h_ids_cap = 0;
+    uint64_t n_pairs = 0;
+
+    bool profiling = false;
+    std::vector<ProfEvent> prof_events;
+    std::vector<ProfEvent> prof_pool;
+    bp_stats stats;
+    std::string last_error;
+};
+
+namespace {
+
+int fail(bp_layer *L, int status, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (L) L->last_error = buf;
+    return status;
+}
+
+#define CU(L, call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) {                                                                             \
+            cudaGetLastError();                                                                              \
+            return fail((L), e_ == cudaErrorMemoryAllocation ? BP_ERR_OOM : BP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                         \
+        }                                                                                                    \
+    } while (0)
+
+#define TRY(expr)                   \
+    do {                            \
+        int s_ = (expr);            \
+        if (s_ != BP_OK) return s_; \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+int ensure(bp_layer *L, DevBuf &b, size_t bytes, bool preserve = false, size_t preserve_bytes = 0) {
+    if (bytes <= b.cap) return BP_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    want = (want + 255) & ~(size_t)255;
+    void *np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = (bytes + 255) & ~(size_t)255;
+        e = cudaMalloc(&np, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(L, BP_ERR_OOM, "cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        }
+    }
+    if (preserve && b.p && preserve_bytes) {
+        CU(L, cudaMemcpyAsync(np, b.p, preserve_bytes, cudaMemcpyDeviceToDevice, L->stream));
+    }
+    if (b.p) {
+        CU(L, cudaStreamSynchronize(L->stream));
+        CU(L, cudaFree(b.p));
+    }
+    b.p = np;
+    b.cap = want;
+    return BP_OK;
+}
+
+void release(DevBuf &b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+// ---- launch bookkeeping -------------------------------------------------------------------------------
+struct LaunchScope {
+    bp_layer *L;
+    int cls;
+    ProfEvent pe;
+    bool timed;
+    LaunchScope(bp_layer *L_, int cls_, double bytes) : L(L_), cls(cls_), timed(false) {
+        L->stats.launches[cls] += 1;
+        L->stats.launches_total += 1;
+        L->stats.algo_bytes[cls] += bytes;
+        if (L->profiling) {
+            if (!L->prof_pool.empty()) {
+                pe = L->prof_pool.back();
+                L->prof_pool.pop_back();
+            } else {
+                cudaEventCreate(&pe.start);
+                cudaEventCreate(&pe.stop);
+            }
+            pe.cls = cls;
+            cudaEventRecord(pe.start, L->stream);
+            timed = true;
+        }
+    }
+    ~LaunchScope() {
+        if (timed) {
+            cudaEventRecord(pe.stop, L->stream);
+            L->prof_events.push_back(pe);
+        }
+    }
+};
+
+int check_launch(bp_layer *L, const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(L, BP_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+    return BP_OK;
+}
+
+void collect_profile(bp_layer *L) {
+    for (ProfEvent &pe : L->prof_events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pe.start, pe.stop) == cudaSuccess) L->stats.kernel_ms[pe.cls] += ms;
+        L->prof_pool.push_back(pe);
+    }
+    L->prof_events.clear();
+}
+
+template <class T> inline T *ptr(DevBuf &b, size_t off = 0) { return (T *)b.p + off; }
+
+// ---- radix planning --------------------------------------------------------------------------------------
+int plan_passes(uint64_t mask, RadixPlan &plan, int first = 0) {
+    int np = first;
+    while (mask && np < RADIX_MAX_PASSES) {
+        const int shift = __builtin_ctzll(mask);
+        uint64_t window = shift + 8 >= 64 ? (mask >> shift) : ((mask >> shift) & 0xffull);
+        window &= 0xffull;
+        const int bits = 64 - __builtin_clzll(window);
+        plan.shift[np] = (unsigned char)shift;
+        plan.bits[np] = (unsigned char)bits;
+        ++np;
+        if (shift + 8 >= 64)
+            mask = 0;
+        else
+            mask &= ~(0xffull << shift);
+    }
+    plan.npasses = np;
+    return np;
+}
+
+// scratch layout for one radix sort: [hist 16*256 u32][counters 16 u32][status passes*tiles*256 u32]
+struct RadixScratch {
+    uint32_t *hist, *counters, *status;
+    size_t bytes;
+};
+
+template <class K, class V>
+int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32_t *n_dev, uint64_t mask, int cls_hist,
+               int cls_pass, int *out_passes, bool *out_in_alt, size_t elem_bytes) {
+    typedef PassTune<K, V> Tune;
+    typedef RadixPassCfg<K, V, Tune::THREADS, Tune::ITEMS> Cfg;
+    *out_in_alt = false;
+    *out_passes = 0;
+    RadixPlan plan;
+    memset(&plan, 0, sizeof plan);
+    const int np = plan_passes(mask, plan);
+    if (np == 0 || n < 2) return BP_OK;
+    const uint32_t tiles = (n + Cfg::TILE - 1) / Cfg::TILE;
+    const size_t hist_bytes = (size_t)RADIX_MAX_PASSES * RADIX * sizeof(uint32_t);
+    const size_t ctr_bytes = 64 * sizeof(uint32_t);
+    const size_t status_bytes = (size_t)np * tiles * RADIX * sizeof(uint32_t);
+    const size_t total = hist_bytes + ctr_bytes + status_bytes;
+    TRY(ensure(L, L->scratch, total));
+    uint32_t *hist = (uint32_t *)L->scratch.p;
+    uint32_t *counters = hist + RADIX_MAX_PASSES * RADIX;
+    uint32_t *status = counters + 64;
+    CU(L, cudaMemsetAsync(L->scratch.p, 0, total, L->stream));
+    {
+        LaunchScope ls(L, cls_hist, (double)n * sizeof(K));
+        const int blocks = (int)std::min<size_t>((n + 512 * 8 - 1) / (512 * 8), 148 * 8);
+        radix_hist_kernel<K><<<std::max(blocks, 1), 512, 0, L->stream>>>(k0, n, n_dev, plan, hist);
+    }
+    TRY(check_launch(L, "radix_hist_kernel"));
+    {
+        LaunchScope ls(L, BP_K_MISC, 0);
+        radix_scan_hist_kernel<<<np, RADIX, 0, L->stream>>>(hist);
+    }
+    TRY(check_launch(L, "radix_scan_hist_kernel"));
+    auto kern = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS>;
+    CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    K *kin = k0, *kout = k1;
+    V *vin = v0, *vout = v1;
+    for (int p = 0; p < np; ++p) {
+        RadixPassArgs<K, V> a;
+        a.kin = kin;
+        a.kout = kout;
+        a.vin = vin;
+        a.vout = vout;
+        a.n_host = n;
+        a.n_dev = n_dev;
+        a.ghist_excl = hist + (size_t)p * RADIX;
+        a.status = status + (size_t)p * tiles * RADIX;
+        a.tile_counter = counters + p;
+        a.shift = plan.shift[p];
+        a.bits = plan.bits[p];
+        a.err = L->d_err;
+        {
+            LaunchScope ls(L, cls_pass, 2.0 * (double)n * (double)elem_bytes);
+            kern<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
+        }
+        TRY(check_launch(L, "radix_pass_kernel"));
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
+    *out_passes = np;
+    *out_in_alt = (np & 1) != 0;
+    return BP_OK;
+}
+
+// ---- per (index kind, id type) implementation ------------------------------------------------------------
+template <int KIND, class IdT> struct Impl {
+    typedef IndexTraits<KIND> T;
+    typedef typename T::key_t K;
+
+    static K *keys(bp_layer *L, int which) { return (K *)L->keys[which].p; }
+    static IdT *ids(bp_layer *L, int which) { return (IdT *)L->ids[which].p; }
+
+    static int ensure_tree(bp_layer *L, uint64_t records) {
+        if (records <= L->cap_records) return BP_OK;
+        if (records > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "tree would exceed 2^30 records");
+        uint64_t want = std::max<uint64_t>(records, L->cap_records + L->cap_records / 2);
+        want = std::min<uint64_t>(want, MAX_RECORDS);
+        const size_t live = (size_t)L->n_records;
+        TRY(ensure(L, L->keys[L->cur], want * sizeof(K), true, live * sizeof(K)));
+        TRY(ensure(L, L->ids[L->cur], want * sizeof(IdT), true, live * sizeof(IdT)));
+        TRY(ensure(L, L->keys[L->cur ^ 1], want * sizeof(K)));
+        TRY(ensure(L, L->ids[L->cur ^ 1], want * sizeof(IdT)));
+        L->cap_records = want;
+        return BP_OK;
+    }
+
+    // ---- extend ------------------------------------------------------------------------------------------
+    static int launch_encode(bp_layer *L, const float *sysb, const float *d_bounds, const IdT *d_ids, uint32_t n) {
+        EncodeArgs<T, IdT> a;
+        a.bounds = d_bounds;
+        a.ids = d_ids;
+        a.n = n;
+        for (int i = 0; i < 3; ++i) a.sys_min[i] = a.sys_max[i] = a.sys_size[i] = 0.f;
+        for (int i = 0; i < T::DIM; ++i) {
+            a.sys_min[i] = sysb[i];
+            a.sys_max[i] = sysb[T::DIM + i];
+            volatile float s = sysb[T::DIM + i] - sysb[i]; // sizef -- src/geom.rs:97-102, one f32 rounding
+            a.sys_size[i] = s;
+        }
+        a.min_depth = L->min_depth;
+        a.keys_out = keys(L, L->cur);
+        a.ids_out = ids(L, L->cur);
+        a.out_base = L->n_records;
+        a.capacity = L->cap_records;
+        const uint32_t tiles = (n + ENCODE_TILE - 1) / ENCODE_TILE;
+        const size_t sbytes = (size_t)tiles * sizeof(uint64_t) + 64;
+        TRY(ensure(L, L->scratch, sbytes));
+        CU(L, cudaMemsetAsync(L->scratch.p, 0, sbytes, L->stream));
+        a.tile_counter = (uint32_t *)L->scratch.p;
+        a.status = (uint64_t *)((char *)L->scratch.p + 64);
+        // result accumulators: sums 0, and-masks all ones
+        ExtendResult init;
+        memset(&init, 0, sizeof init);
+        init.key_and = ~0ull;
+        init.id_and = ~0ull;
+        *L->h_res = init;
+        CU(L, cudaMemcpyAsync(L->d_res, L->h_res, sizeof init, cudaMemcpyHostToDevice, L->stream));
+        a.result = L->d_res;
+        IdT *slots = (IdT *)L->d_last; // two 8-byte slots
+        a.prev_last_id = L->tail_has_last ? (const IdT *)((char *)slots + 8 * L->last_slot) : nullptr;
+        a.next_last_id = (IdT *)((char *)slots + 8 * (L->last_slot ^ 1));
+        a.err = L->d_err;
+        typedef EncodeSmem<T, IdT> S;
+        auto kern = encode_kernel<T, IdT>;
+        CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
+        {
+            // algorithmic bytes: input AABBs + IDs; the record bytes are added when the count is known
+            LaunchScope ls(L, BP_K_ENCODE, (double)n * (2 * T::DIM * 4 + sizeof(IdT)));
+            kern<<<tiles, ENCODE_THREADS, S::BYTES, L->stream>>>(a);
+        }
+        TRY(check_launch(L, "encode_kernel"));
+        CU(L, cudaMemcpyAsync(L->h_res, L->d_res, sizeof(ExtendResult), cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaEventRecord(L->ev_sync, L->stream));
+        L->pending = true;
+        L->pending_base = L->n_records;
+        return BP_OK;
+    }
+
+    static int extend_device(bp_layer *L, const float *sysb, const float *d_bounds, const void *d_ids, size_t n) {
+        if (n == 0) return BP_OK;
+        if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "too many objects in one extend");
+        const uint64_t per_obj = 1ull << T::DIM;
+        TRY(ensure_tree(L, std::min<uint64_t>(L->n_records + n * per_obj, MAX_RECORDS)));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            TRY(launch_encode(L, sysb, d_bounds, (const IdT *)d_ids, (uint32_t)n));
+            if (L->min_depth == 0 && L->n_records + n * per_obj <= L->cap_records) return BP_OK; // cannot overflow: stays async
+            // min_depth can push objects below their natural depth: the record count is only
+            // known after the kernel, so check it now and redo the call once with enough room
+            CU(L, cudaEventSynchronize(L->ev_sync));
+            const uint64_t total = L->h_res->total_records;
+            if (L->pending_base + total <= L->cap_records) return BP_OK;
+            L->pending = false;
+            TRY(ensure_tree(L, L->pending_base + total));
+        }
+        return fail(L, BP_ERR_INTERNAL, "extend did not converge");
+    }
+
+    // ---- sort --------------------------------------------------------------------------------------------------
+    // Sorts records [off, off + cnt) of the current buffer by (key, id); the result is left in the
+    // current buffer.
+    static int sort_range(bp_layer *L, uint64_t off, uint64_t cnt, bool need_id_passes) {
+        const int c = L->cur, o = c ^ 1;
+        K *k0 = keys(L, c) + off, *k1 = keys(L, o) + off;
+        IdT *v0 = ids(L, c) + off, *v1 = ids(L, o) + off;
+        const uint64_t kmask = L->key_or & ~L->key_and, imask = L->id_or & ~L->id_and;
+        bool in_alt = false;
+        int passes = 0, total_passes = 0;
+        if (need_id_passes && imask) { // secondary key first (LSD): IDs as the sort key, Index as the payload
+            TRY((radix_sort<IdT, K>(L, v0, k0, v1, k1, (uint32_t)cnt, nullptr, imask, BP_K_SORT_HIST, BP_K_SORT_PASS,
+                                    &passes, &in_alt, sizeof(K) + sizeof(IdT))));
+            total_passes += passes;
+            if (in_alt) {
+                std::swap(k0, k1);
+                std::swap(v0, v1);
+            }
+        }
+        bool in_alt2 = false;
+        TRY((radix_sort<K, IdT>(L, k0, v0, k1, v1, (uint32_t)cnt, nullptr, kmask, BP_K_SORT_HIST, BP_K_SORT_PASS, &passes,
+                                &in_alt2, sizeof(K) + sizeof(IdT))));
+        total_passes += passes;
+        const bool final_in_alt = in_alt != in_alt2;
+        L->stats.sort_passes = (uint32_t)total_passes;
+        if (final_in_alt) {
+            if (off == 0 && cnt == L->n_records) {
+                L->cur = o; // whole tree: just flip the buffers
+            } else {
+                CU(L, cudaMemcpyAsync(keys(L, c) + off, keys(L, o) + off, cnt * sizeof(K), cudaMemcpyDeviceToDevice, L->stream));
+                CU(L, cudaMemcpyAsync(ids(L, c) + off, ids(L, o) + off, cnt * sizeof(IdT), cudaMemcpyDeviceToDevice, L->stream));
+            }
+        }
+        return BP_OK;
+    }
+
+    static int merge_runs(bp_layer *L, uint64_t na, uint64_t nb) {
+        const int c = L->cur, o = c ^ 1;
+        MergeArgs<K, IdT> a;
+        a.ka = keys(L, c);
+        a.va = ids(L, c);
+        a.na = (uint32_t)na;
+        a.kb = keys(L, c) + na;
+        a.vb = ids(L, c) + na;
+        a.nb = (uint32_t)nb;
+        a.kout = keys(L, o);
+        a.vout = ids(L, o);
+        const uint32_t tiles = (uint32_t)((na + nb + MERGE_TILE - 1) / MERGE_TILE);
+        TRY(ensure(L, L->scratch, (size_t)(tiles + 1) * sizeof(uint32_t)));
+        a.partition = (uint32_t *)L->scratch.p;
+        const double bytes = 2.0 * (double)(na + nb) * (sizeof(K) + sizeof(IdT));
+        {
+            LaunchScope ls(L, BP_K_MISC, 0);
+            merge_partition_kernel<K, IdT><<<(tiles + 1 + 255) / 256, 256, 0, L->stream>>>(a, tiles);
+        }
+        TRY(check_launch(L, "merge_partition_kernel"));
+        {
+            LaunchScope ls(L, BP_K_MERGE, bytes);
+            merge_tiles_kernel<K, IdT><<<tiles, MERGE_THREADS, 0, L->stream>>>(a);
+        }
+        TRY(check_launch(L, "merge_tiles_kernel"));
+        L->cur = o;
+        L->stats.merged = 1;
+        return BP_OK;
+    }
+
+    static int sort(bp_layer *L) {
+        if (!L->dirty) return BP_OK;
+        const uint64_t R = L->n_records;
+        L->stats.sort_passes = 0;
+        L->stats.merged = 0;
+        uint64_t prefix = std::min(L->prefix, R);
+        const uint64_t tail = R - prefix;
+        if (R >= 2 && tail > 0) {
+            if (prefix == 0) {
+                if (!L->tail_sorted) TRY(sort_range(L, 0, R, L->tail_nonmono));
+            } else if (prefix * 8 >= R) {
+                if (!L->tail_sorted) TRY(sort_range(L, prefix, tail, L->tail_nonmono));
+                TRY(merge_runs(L, prefix, tail));
+            } else {
+                TRY(sort_range(L, 0, R, true)); // short sorted prefix: cheaper to re-sort everything
+            }
+        }
+        L->dirty = false;
+        L->prefix = 0;
+        L->tail_sorted = false;
+        L->tail_nonmono = false;
+        L->tail_has_last = false;
+        return BP_OK;
+    }
+
+    // ---- scan ---------------------------------------------------------------------------------------------------
+    template <int FK> static int launch_emit(bp_layer *L, EmitArgs<IdT> &a, uint32_t chunks, double bytes) {
+        LaunchScope ls(L, BP_K_SCAN_EMIT, bytes);
+        scan_emit_kernel<IdT, FK><<<chunks, EMIT_THREADS, 0, L->stream>>>(a);
+        return BP_OK;
+    }
+    static int emit(bp_layer *L, EmitArgs<IdT> &a, int fk, uint32_t chunks, double bytes) {
+        switch (fk) {
+        case BP_FILTER_NONE: launch_emit<BP_FILTER_NONE>(L, a, chunks, bytes); break;
+        case BP_FILTER_ID_PARITY: launch_emit<BP_FILTER_ID_PARITY>(L, a, chunks, bytes); break;
+        case BP_FILTER_XOR_MASK: launch_emit<BP_FILTER_XOR_MASK>(L, a, chunks, bytes); break;
+        case BP_FILTER_CATEGORY: launch_emit<BP_FILTER_CATEGORY>(L, a, chunks, bytes); break;
+        default: return fail(L, BP_ERR_INVALID_ARG, "unknown filter kind %d", fk);
+        }
+        return check_launch(L, "scan_emit_kernel");
+    }
+
+    static int fetch_totals(bp_layer *L) {
+        CU(L, cudaMemcpyAsync(L->h_tot, L->d_tot, sizeof(ScanTotals), cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaMemcpyAsync(L->h_err, L->d_err, sizeof(int), cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaStreamSynchronize(L->stream));
+        if (*L->h_err) {
+            cudaMemsetAsync(L->d_err, 0, sizeof(int), L->stream);
+            return fail(L, BP_ERR_INTERNAL, "a kernel reported a look-back time-out");
+        }
+        return BP_OK;
+    }
+
+    static int scan(bp_layer *L, const bp_filter *f) {
+        TRY(sort(L));
+        L->n_pairs = 0;
+        L->stats.n_work_items = L->stats.n_raw_pairs = L->stats.n_pairs = 0;
+        L->stats.pair_sort_passes = 0;
+        L->stats.rescans = 0;
+        L->n_invalid = 0; // `self.invalid.clear()` -- src/layer.rs:468, :502
+        const uint64_t R = L->n_records;
+        if (R < 2) return BP_OK;
+        const int fk = f ? f->kind : BP_FILTER_NONE;
+        FilterArgs fa;
+        fa.arg = f ? f->arg : 0;
+        fa.table = nullptr;
+        fa.n_table = 0;
+        if (fk == BP_FILTER_CATEGORY) {
+            if (!f->table && f->n_table) return fail(L, BP_ERR_INVALID_ARG, "category filter without a table");
+            fa.n_table = f->n_table;
+            if (f->table_on_device) {
+                fa.table = f->table;
+            } else if (f->n_table) {
+                TRY(ensure(L, L->filter_table, f->n_table * 8));
+                CU(L, cudaMemcpyAsync(L->filter_table.p, f->table, f->n_table * 8, cudaMemcpyHostToDevice, L->stream));
+                fa.table = (const uint32_t *)L->filter_table.p;
+            }
+        }
+
+        // ---- runs ----
+        const uint32_t rtiles = (uint32_t)((R + RUNS_TILE - 1) / RUNS_TILE);
+        const size_t sbytes = 64 + 2 * (size_t)rtiles * sizeof(uint64_t);
+        TRY(ensure(L, L->scratch, sbytes));
+        TRY(ensure(L, L->src_idx, R * sizeof(uint32_t)));
+        TRY(ensure(L, L->src_off, (R + 1) * sizeof(uint64_t)));
+        CU(L, cudaMemsetAsync(L->scratch.p, 0, sbytes, L->stream));
+        CU(L, cudaMemsetAsync(L->d_tot, 0, sizeof(ScanTotals), L->stream));
+        RunsArgs<T> ra;
+        ra.keys = keys(L, L->cur);
+        ra.n = (uint32_t)R;
+        ra.src_idx = (uint32_t *)L->src_idx.p;
+        ra.src_off = (uint64_t *)L->src_off.p;
+        ra.tile_counter = (uint32_t *)L->scratch.p;
+        ra.status_cnt = (uint64_t *)((char *)L->scratch.p + 64);
+        ra.status_work = ra.status_cnt + rtiles;
+        ra.totals = L->d_tot;
+        ra.err = L->d_err;
+        {
+            LaunchScope ls(L, BP_K_SCAN_RUNS, (double)R * sizeof(K));
+            scan_runs_kernel<T><<<rtiles, RUNS_THREADS, 0, L->stream>>>(ra);
+        }
+        TRY(check_launch(L, "scan_runs_kernel"));
+        TRY(fetch_totals(L));
+        const uint64_t C = L->h_tot->n_sources, W = L->h_tot->n_work;
+        L->stats.n_work_items = W;
+        L->stats.algo_bytes[BP_K_SCAN_RUNS] += (double)C * 12.0;
+        if (W == 0) return BP_OK;
+        if (W > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "scan would visit %llu record pairs (limit 2^30)", (unsigned long long)W);
+
+        // ---- chunk partition + emit ----
+        const uint32_t chunks = (uint32_t)((W + EMIT_CHUNK - 1) / EMIT_CHUNK);
+        const bool wide = sizeof(IdT) == 8;
+        TRY(ensure(L, L->chunk_src, (size_t)chunks * sizeof(uint32_t)));
+        for (int i = 0; i < 2; ++i) {
+            TRY(ensure(L, L->praw[i], W * sizeof(uint64_t)));
+            if (wide) TRY(ensure(L, L->praw_b[i], W * sizeof(uint64_t)));
+        }
+        TRY(ensure(L, L->pout, W * 2 * sizeof(IdT)));
+        {
+            LaunchScope ls(L, BP_K_MISC, 0);
+            scan_chunks_kernel<<<(uint32_t)((C + 255) / 256), 256, 0, L->stream>>>((const uint64_t *)L->src_off.p, (uint32_t)C,
+                                                                                  (uint32_t *)L->chunk_src.p);
+        }
+        TRY(check_launch(L, "scan_chunks_kernel"));
+        const size_t ebytes = 64 + (size_t)chunks * sizeof(uint64_t);
+        TRY(ensure(L, L->scratch, ebytes));
+        EmitArgs<IdT> ea;
+        ea.ids = ids(L, L->cur);
+        ea.src_idx = (const uint32_t *)L->src_idx.p;
+        ea.src_off = (const uint64_t *)L->src_off.p;
+        ea.chunk_src = (const uint32_t *)L->chunk_src.p;
+        ea.n_work = W;
+        ea.n_sources = (uint32_t)C;
+        ea.inactive = nullptr;
+        ea.out_packed = wide ? nullptr : (uint64_t *)L->praw[0].p;
+        ea.out_a = wide ? (uint64_t *)L->praw[0].p : nullptr;
+        ea.out_b = wide ? (uint64_t *)L->praw_b[0].p : nullptr;
+        ea.capacity = W;
+        ea.tile_counter = (uint32_t *)L->scratch.p;
+        ea.status = (uint64_t *)((char *)L->scratch.p + 64);
+        ea.totals = L->d_tot;
+        ea.filter = fa;
+        ea.err = L->d_err;
+        // algorithmic bytes of one emission: both IDs of every work item + the pair it writes
+        const double emit_bytes = (double)W * (2.0 * sizeof(IdT) + 2.0 * sizeof(IdT)) + (double)C * 12.0;
+        CU(L, cudaMemsetAsync(L->scratch.p, 0, ebytes, L->stream));
+        ea.mode = EMIT_MODE_FIRST;
+        TRY(emit(L, ea, fk, chunks, emit_bytes));
+        TRY(fetch_totals(L));
+        if (L->h_tot->any_same_id) {
+            // some ID owns nested bounds: the reference skips such records entirely (src/layer.rs:562-564),
+            // so mark them and emit again without them
+            L->stats.rescans = 1;
+            TRY(ensure(L, L->inactive, R));
+            CU(L, cudaMemsetAsync(L->inactive.p, 0, R, L->stream));
+            ea.inactive = (unsigned char *)L->inactive.p;
+            CU(L, cudaMemsetAsync(L->scratch.p, 0, ebytes, L->stream));
+            ea.mode = EMIT_MODE_FLAG;
+            TRY(emit(L, ea, fk, chunks, (double)W * 2.0 * sizeof(IdT)));
+            CU(L, cudaMemsetAsync(L->scratch.p, 0, ebytes, L->stream));
+            ea.mode = EMIT_MODE_ACTIVE;
+            TRY(emit(L, ea, fk, chunks, emit_bytes));
+            TRY(fetch_totals(L));
+        }
+        const uint64_t P_raw = L->h_tot->n_raw_pairs;
+        L->stats.n_raw_pairs = P_raw;
+        if (P_raw == 0) return BP_OK;
+
+        // ---- sort the raw pairs (src/layer.rs:473, :516) ----
+        const uint64_t imask = L->id_or & ~L->id_and;
+        uint64_t *sorted_a = nullptr, *sorted_b = nullptr;
+        int passes = 0, total_passes = 0;
+        bool in_alt = false;
+        if (!wide) {
+            const uint64_t pmask = (imask << 32) | (imask & 0xffffffffull);
+            TRY((radix_sort<uint64_t, NoVal>(L, (uint64_t *)L->praw[0].p, (NoVal *)nullptr, (uint64_t *)L->praw[1].p,
+                                             (NoVal *)nullptr, (uint32_t)P_raw, nullptr, pmask, BP_K_PAIR_HIST, BP_K_PAIR_PASS,
+                                             &passes, &in_alt, 8)));
+            total_passes = passes;
+            sorted_a = (uint64_t *)L->praw[in_alt ? 1 : 0].p;
+        } else {
+            uint64_t *a0 = (uint64_t *)L->praw[0].p, *a1 = (uint64_t *)L->praw[1].p;
+            uint64_t *b0 = (uint64_t *)L->praw_b[0].p, *b1 = (uint64_t *)L->praw_b[1].p;
+            TRY((radix_sort<uint64_t, uint64_t>(L, b0, a0, b1, a1, (uint32_t)P_raw, nullptr, imask, BP_K_PAIR_HIST,
+                                                BP_K_PAIR_PASS, &passes, &in_alt, 16)));
+            total_passes = passes;
+            if (in_alt) {
+                std::swap(a0, a1);
+                std::swap(b0, b1);
+            }
+            TRY((radix_sort<uint64_t, uint64_t>(L, a0, b0, a1, b1, (uint32_t)P_raw, nullptr, imask, BP_K_PAIR_HIST,
+                                                BP_K_PAIR_PASS, &passes, &in_alt, 16)));
+            total_passes += passes;
+            if (in_alt) {
+                std::swap(a0, a1);
+                std::swap(b0, b1);
+            }
+            sorted_a = a0;
+            sorted_b = b0;
+        }
+        L->stats.pair_sort_passes = (uint32_t)total_passes;
+
+        // ---- dedup (src/layer.rs:474, :517) ----
+        const uint32_t utiles = (uint32_t)((P_raw + UNIQ_TILE - 1) / UNIQ_TILE);
+        const size_t ubytes = 64 + (size_t)utiles * sizeof(uint64_t);
+        TRY(ensure(L, L->scratch, ubytes));
+        CU(L, cudaMemsetAsync(L->scratch.p, 0, ubytes, L->stream));
+        UniqueArgs<IdT> ua;
+        ua.in_packed = wide ? nullptr : sorted_a;
+        ua.in_a = wide ? sorted_a : nullptr;
+        ua.in_b = sorted_b;
+        ua.n_host = (uint32_t)P_raw;
+        ua.n_dev = nullptr;
+        ua.out = (IdT *)L->pout.p;
+        ua.tile_counter = (uint32_t *)L->scratch.p;
+        ua.status = (uint64_t *)((char *)L->scratch.p + 64);
+        ua.totals = L->d_tot;
+        ua.err = L->d_err;
+        {
+            LaunchScope ls(L, BP_K_PAIR_UNIQUE, (double)P_raw * 2.0 * sizeof(IdT));
+            pair_unique_kernel<IdT><<<utiles, UNIQ_THREADS, 0, L->stream>>>(ua);
+        }
+        TRY(check_launch(L, "pair_unique_kernel"));
+        TRY(fetch_totals(L));
+        L->n_pairs = L->h_tot->n_pairs;
+        L->stats.n_pairs = L->n_pairs;
+        L->stats.algo_bytes[BP_K_PAIR_UNIQUE] += (double)L->n_pairs * 2.0 * sizeof(IdT);
+        return BP_OK;
+    }
+
+    static int masks_from_records(bp_layer *L, uint64_t n) {
+        ExtendResult init;
+        memset(&init, 0, sizeof init);
+        init.key_and = ~0ull;
+        init.id_and = ~0ull;
+        *L->h_res = init;
+        CU(L, cudaMemcpyAsync(L->d_res, L->h_res, sizeof init, cudaMemcpyHostToDevice, L->stream));
+        if (n) {
+            LaunchScope ls(L, BP_K_MISC, 0);
+            const int blocks = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+            record_masks_kernel<K, IdT><<<blocks, 256, 0, L->stream>>>(keys(L, L->cur), ids(L, L->cur), (uint32_t)n, L->d_res);
+        }
+        TRY(check_launch(L, "record_masks_kernel"));
+        CU(L, cudaMemcpyAsync(L->h_res, L->d_res, sizeof(ExtendResult), cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaStreamSynchronize(L->stream));
+        return BP_OK;
+    }
+};
+
+// ---- runtime dispatch over (kind, id_bytes) ----------------------------------------------------------------
+#define DISPATCH(L, CALL)                                                              \
+    do {                                                                               \
+        if ((L)->id_bytes == 4) {                                                      \
+            switch ((L)->kind) {                                                       \
+            case BP_INDEX32_2D: return Impl<BP_INDEX32_2D, uint32_t>::CALL;            \
+            case BP_INDEX64_2D: return Impl<BP_INDEX64_2D, uint32_t>::CALL;            \
+            default: return Impl<BP_INDEX64_3D, uint32_t>::CALL;                       \
+            }                                                                          \
+        } else {                                                                       \
+            switch ((L)->kind) {                                                       \
+            case BP_INDEX32_2D: return Impl<BP_INDEX32_2D, uint64_t>::CALL;            \
+            case BP_INDEX64_2D: return Impl<BP_INDEX64_2D, uint64_t>::CALL;            \
+            default: return Impl<BP_INDEX64_3D, uint64_t>::CALL;                       \
+            }                                                                          \
+        }                                                                              \
+    } while (0)
+
+int do_ensure_tree(bp_layer *L, uint64_t records) { DISPATCH(L, ensure_tree(L, records)); }
+int do_extend_device(bp_layer *L, const float *sysb, const float *b, const void *ids, size_t n) {
+    DISPATCH(L, extend_device(L, sysb, b, ids, n));
+}
+int do_sort(bp_layer *L) { DISPATCH(L, sort(L)); }
+int do_scan(bp_layer *L, const bp_filter *f) { DISPATCH(L, scan(L, f)); }
+int do_masks(bp_layer *L, uint64_t n) { DISPATCH(L, masks_from_records(L, n)); }
+
+// Folds the result of the last (still asynchronous) extend into the host-side state.
+int resolve_pending(bp_layer *L) {
+    if (!L->pending) return BP_OK;
+    CU(L, cudaEventSynchronize(L->ev_sync));
+    L->pending = false;
+    const ExtendResult &r = *L->h_res;
+    L->n_invalid += r.n_invalid;
+    L->stats.n_invalid = L->n_invalid;
+    L->tail_has_last = true;
+    L->last_slot ^= 1;
+    const uint64_t room = L->cap_records - L->pending_base;
+    const uint64_t added = std::min<uint64_t>(r.total_records, room);
+    if (added > 0) {
+        L->stats.algo_bytes[BP_K_ENCODE] += (double)added * (L->key_bytes + L->id_bytes);
+        if (!L->dirty) { // first append onto a sorted tree: everything before it stays a sorted prefix
+            L->dirty = true;
+            L->prefix = L->pending_base;
+            L->tail_nonmono = false;
+        }
+        L->tail_sorted = false;
+        if (r.nonmono) L->tail_nonmono = true;
+        L->n_records = L->pending_base + added;
+        L->key_or |= r.key_or;
+        L->key_and &= r.key_and;
+        L->id_or |= r.id_or;
+        L->id_and &= r.id_and;
+    }
+    L->stats.n_records = L->n_records;
+    if (r.too_many) return fail(L, BP_ERR_TOO_LARGE, "an object wanted more than 2^20 cells (min_depth too high for its size); it was skipped");
+    if (r.total_records > room) return fail(L, BP_ERR_INTERNAL, "record capacity exceeded");
+    return BP_OK;
+}
+
+int pinned_ensure(bp_layer *L, void **p, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return BP_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    want += want / 4;
+    cudaError_t e = cudaMallocHost(p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(L, BP_ERR_OOM, "cudaMallocHost of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    }
+    *cap = want;
+    return BP_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int bp_version(void) { return BP_VERSION; }
+
+const char *bp_status_string(int s) {
+    switch (s) {
+    case BP_OK: return "ok";
+    case BP_ERR_INVALID_ARG: return "invalid argument";
+    case BP_ERR_CUDA: return "CUDA error";
+    case BP_ERR_OOM: return "out of memory";
+    case BP_ERR_TOO_LARGE: return "too large";
+    case BP_ERR_INTERNAL: return "internal error";
+    case BP_ERR_MISMATCH: return "layer type mismatch";
+    default: return "unknown status";
+    }
+}
+
+int bp_device_count(int *out) {
+    if (!out) return BP_ERR_INVALID_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *out = 0;
+        return BP_ERR_CUDA;
+    }
+    *out = n;
+    return BP_OK;
+}
+
+int bp_plan_radix_passes(uint64_t varying_mask, uint32_t *out_shift, uint32_t *out_bits, int max_passes) {
+    RadixPlan plan;
+    memset(&plan, 0, sizeof plan);
+    const int np = plan_passes(varying_mask, plan);
+    for (int i = 0; i < np && i < max_passes; ++i) {
+        if (out_shift) out_shift[i] = plan.shift[i];
+        if (out_bits) out_bits[i] = plan.bits[i];
+    }
+    return np;
+}
+
+const char *bp_layer_last_error(const bp_layer *L) { return L ? L->last_error.c_str() : "null layer"; }
+
+int bp_layer_create(const bp_layer_config *cfg, bp_layer **out) {
+    if (!cfg || !out) return BP_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->index_kind < BP_INDEX32_2D || cfg->index_kind > BP_INDEX64_3D) return BP_ERR_INVALID_ARG;
+    if (cfg->id_bytes != 4 && cfg->id_bytes != 8) return BP_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return BP_ERR_CUDA; // no CPU fallback by design
+    }
+    int dev = cfg->device;
+    if (dev < 0) {
+        if (cudaGetDevice(&dev) != cudaSuccess) return BP_ERR_CUDA;
+    }
+    if (dev >= ndev) return BP_ERR_INVALID_ARG;
+    bp_layer *L = new bp_layer();
+    L->cfg = *cfg;
+    L->kind = cfg->index_kind;
+    L->id_bytes = cfg->id_bytes;
+    L->key_bytes = cfg->index_kind == BP_INDEX32_2D ? 4 : 8;
+    L->dim = cfg->index_kind == BP_INDEX64_3D ? 3 : 2;
+    L->device = dev;
+    L->min_depth = cfg->min_depth;
+    memset(&L->stats, 0, sizeof L->stats);
+    DeviceGuard g(dev);
+    auto bail = [&](int st) {
+        bp_layer_destroy(L);
+        return st;
+    };
+    if (cudaStreamCreateWithFlags(&L->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(BP_ERR_CUDA);
+    L->own_stream = true;
+    if (cudaEventCreateWithFlags(&L->ev_sync, cudaEventDisableTiming) != cudaSuccess) return bail(BP_ERR_CUDA);
+    if (cudaMallocHost((void **)&L->h_res, sizeof(ExtendResult)) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaMallocHost((void **)&L->h_tot, sizeof(ScanTotals)) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaMallocHost((void **)&L->h_err, sizeof(int)) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaMalloc((void **)&L->d_res, sizeof(ExtendResult)) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaMalloc((void **)&L->d_tot, sizeof(ScanTotals)) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaMalloc((void **)&L->d_err, sizeof(int)) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaMalloc((void **)&L->d_last, 16) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaMemsetAsync(L->d_err, 0, sizeof(int), L->stream) != cudaSuccess) return bail(BP_ERR_CUDA);
+    if (cudaStreamSynchronize(L->stream) != cudaSuccess) return bail(BP_ERR_CUDA);
+    *L->h_err = 0;
+    if (cfg->index_capacity) {
+        int st = do_ensure_tree(L, std::min<uint64_t>(cfg->index_capacity, MAX_RECORDS));
+        if (st != BP_OK) return bail(st);
+    }
+    if (cfg->collision_capacity) {
+        const size_t c = std::min<uint64_t>(cfg->collision_capacity, MAX_RECORDS);
+        int st = ensure(L, L->pout, c * 2 * L->id_bytes);
+        for (int i = 0; i < 2 && st == BP_OK; ++i) st = ensure(L, L->praw[i], c * 8);
+        if (st != BP_OK) return bail(st);
+    }
+    *out = L;
+    return BP_OK;
+}
+
+int bp_layer_destroy(bp_layer *L) {
+    if (!L) return BP_OK;
+    DeviceGuard g(L->device);
+    if (L->stream) cudaStreamSynchronize(L->stream);
+    for (int i = 0; i < 2; ++i) {
+        release(L->keys[i]);
+        release(L->ids[i]);
+        release(L->praw[i]);
+        release(L->praw_b[i]);
+    }
+    release(L->scratch);
+    release(L->stage_bounds);
+    release(L->stage_ids);
+    release(L->src_idx);
+    release(L->src_off);
+    release(L->chunk_src);
+    release(L->inactive);
+    release(L->pout);
+    release(L->filter_table);
+    if (L->h_pairs) cudaFreeHost(L->h_pairs);
+    if (L->h_keys) cudaFreeHost(L->h_keys);
+    if (L->h_ids) cudaFreeHost(L->h_ids);
+    if (L->h_res) cudaFreeHost(L->h_res);
+    if (L->h_tot) cudaFreeHost(L->h_tot);
+    if (L->h_err) cudaFreeHost(L->h_err);
+    if (L->d_res) cudaFree(L->d_res);
+    if (L->d_tot) cudaFree(L->d_tot);
+    if (L->d_err) cudaFree(L->d_err);
+    if (L->d_last) cudaFree(L->d_last);
+    for (ProfEvent &pe : L->prof_events) {
+        cudaEventDestroy(pe.start);
+        cudaEventDestroy(pe.stop);
+    }
+    for (ProfEvent &pe : L->prof_pool) {
+        cudaEventDestroy(pe.start);
+        cudaEventDestroy(pe.stop);
+    }
+    if (L->ev_sync) cudaEventDestroy(L->ev_sync);
+    if (L->own_stream && L->stream) cudaStreamDestroy(L->stream);
+    cudaGetLastError();
+    delete L;
+    return BP_OK;
+}
+
+int bp_layer_set_stream(bp_layer *L, void *stream) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    CU(L, cudaStreamSynchronize(L->stream));
+    if (L->own_stream) cudaStreamDestroy(L->stream);
+    L->stream = (cudaStream_t)stream;
+    L->own_stream = false;
+    return BP_OK;
+}
+
+int bp_layer_clear(bp_layer *L) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    if (L->pending) { // the result of an extend nobody looked at is discarded with the tree
+        CU(L, cudaEventSynchronize(L->ev_sync));
+        L->pending = false;
+        L->n_invalid += L->h_res->n_invalid;
+    }
+    L->n_records = 0;
+    L->dirty = false;
+    L->prefix = 0;
+    L->tail_sorted = false;
+    L->tail_nonmono = false;
+    L->tail_has_last = false;
+    L->key_or = L->id_or = 0;
+    L->key_and = L->id_and = ~0ull;
+    L->stats.n_records = 0;
+    return BP_OK;
+}
+
+int bp_layer_extend_device(bp_layer *L, const float *sysb, const float *d_bounds, const void *d_ids, size_t n) {
+    if (!L || !sysb || (n && (!d_bounds || !d_ids))) return fail(L, BP_ERR_INVALID_ARG, "null argument to extend");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_extend_device(L, sysb, d_bounds, d_ids, n);
+}
+
+int bp_layer_extend_host(bp_layer *L, const float *sysb, const float *bounds, const void *ids, size_t n) {
+    if (!L || !sysb || (n && (!bounds || !ids))) return fail(L, BP_ERR_INVALID_ARG, "null argument to extend");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    if (n == 0) return BP_OK;
+    const size_t bbytes = n * 2 * L->dim * sizeof(float), ibytes = n * L->id_bytes;
+    TRY(ensure(L, L->stage_bounds, bbytes));
+    TRY(ensure(L, L->stage_ids, ibytes));
+    CU(L, cudaMemcpyAsync(L->stage_bounds.p, bounds, bbytes, cudaMemcpyHostToDevice, L->stream));
+    CU(L, cudaMemcpyAsync(L->stage_ids.p, ids, ibytes, cudaMemcpyHostToDevice, L->stream));
+    TRY(do_extend_device(L, sysb, (const float *)L->stage_bounds.p, L->stage_ids.p, n));
+    // the caller may reuse its buffers as soon as we return
+    return resolve_pending(L);
+}
+
+int bp_layer_merge(bp_layer *L, const bp_layer *O_) {
+    bp_layer *O = const_cast<bp_layer *>(O_);
+    if (!L || !O) return BP_ERR_INVALID_ARG;
+    if (L == O) return fail(L, BP_ERR_INVALID_ARG, "cannot merge a layer into itself");
+    if (L->kind != O->kind || L->id_bytes != O->id_bytes || L->device != O->device)
+        return fail(L, BP_ERR_MISMATCH, "layers differ in index kind, ID width or device");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    TRY(resolve_pending(O));
+    if (O->min_depth < L->min_depth) L->min_depth = O->min_depth; // src/layer.rs:131-134
+    const uint64_t base = L->n_records, add = O->n_records;
+    if (add) {
+        TRY(do_ensure_tree(L, base + add));
+        // order the copy after everything queued on the other layer's stream
+        if (O->stream != L->stream) {
+            CU(L, cudaEventRecord(O->ev_sync, O->stream));
+            CU(L, cudaStreamWaitEvent(L->stream, O->ev_sync, 0));
+        }
+        CU(L, cudaMemcpyAsync((char *)L->keys[L->cur].p + base * L->key_bytes, O->keys[O->cur].p, add * L->key_bytes,
+                              cudaMemcpyDeviceToDevice, L->stream));
+        CU(L, cudaMemcpyAsync((char *)L->ids[L->cur].p + base * L->id_bytes, O->ids[O->cur].p, add * L->id_bytes,
+                              cudaMemcpyDeviceToDevice, L->stream));
+        if (O->stream != L->stream) { // and keep the other layer from overwriting its tree before the copy ran
+            CU(L, cudaEventRecord(L->ev_sync, L->stream));
+            CU(L, cudaStreamWaitEvent(O->stream, L->ev_sync, 0));
+        }
+        L->stats.launches_total += 0;
+    }
+    if (!L->dirty) {
+        L->prefix = base;
+        L->tail_sorted = !O->dirty; // a sorted tree appended to a sorted tree: two runs -> merge path
+        L->tail_nonmono = true;
+    } else {
+        L->tail_sorted = false;
+        L->tail_nonmono = true;
+    }
+    L->tail_has_last = false;
+    L->dirty = true; // `*sorted = false` even when `other` is empty -- src/layer.rs:137
+    L->n_records = base + add;
+    L->key_or |= O->key_or;
+    L->key_and &= O->key_and;
+    L->id_or |= O->id_or;
+    L->id_and &= O->id_and;
+    L->stats.n_records = L->n_records;
+    return BP_OK;
+}
+
+int bp_layer_sort(bp_layer *L) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_sort(L);
+}
+
+int bp_layer_scan_device(bp_layer *L, const bp_filter *f, const void **out_pairs, size_t *out_count) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    TRY(do_scan(L, f));
+    if (out_pairs) *out_pairs = L->n_pairs ? L->pout.p : nullptr;
+    if (out_count) *out_count = (size_t)L->n_pairs;
+    return BP_OK;
+}
+
+int bp_layer_scan(bp_layer *L, const bp_filter *f, const void **out_pairs, size_t *out_count) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    TRY(do_scan(L, f));
+    const size_t bytes = (size_t)L->n_pairs * 2 * L->id_bytes;
+    if (bytes) {
+        TRY(pinned_ensure(L, &L->h_pairs, &L->h_pairs_cap, bytes));
+        CU(L, cudaMemcpyAsync(L->h_pairs, L->pout.p, bytes, cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaStreamSynchronize(L->stream));
+    }
+    if (out_pairs) *out_pairs = bytes ? L->h_pairs : nullptr;
+    if (out_count) *out_count = (size_t)L->n_pairs;
+    return BP_OK;
+}
+
+int bp_layer_records_device(bp_layer *L, const void **out_keys, const void **out_ids, size_t *out_n, int *out_sorted) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    if (out_keys) *out_keys = L->keys[L->cur].p;
+    if (out_ids) *out_ids = L->ids[L->cur].p;
+    if (out_n) *out_n = (size_t)L->n_records;
+    if (out_sorted) *out_sorted = L->dirty ? 0 : 1;
+    return BP_OK;
+}
+
+int bp_layer_records(bp_layer *L, const void **out_keys, const void **out_ids, size_t *out_n, int *out_sorted) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    const size_t n = (size_t)L->n_records;
+    if (n) {
+        TRY(pinned_ensure(L, &L->h_keys, &L->h_keys_cap, n * L->key_bytes));
+        TRY(pinned_ensure(L, &L->h_ids, &L->h_ids_cap, n * L->id_bytes));
+        CU(L, cudaMemcpyAsync(L->h_keys, L->keys[L->cur].p, n * L->key_bytes, cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaMemcpyAsync(L->h_ids, L->ids[L->cur].p, n * L->id_bytes, cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaMemcpyAsync(L->h_err, L->d_err, sizeof(int), cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaStreamSynchronize(L->stream));
+        if (*L->h_err) {
+            cudaMemsetAsync(L->d_err, 0, sizeof(int), L->stream);
+            return fail(L, BP_ERR_INTERNAL, "a kernel reported a look-back time-out");
+        }
+    }
+    if (out_keys) *out_keys = n ? L->h_keys : nullptr;
+    if (out_ids) *out_ids = n ? L->h_ids : nullptr;
+    if (out_n) *out_n = n;
+    if (out_sorted) *out_sorted = L->dirty ? 0 : 1;
+    return BP_OK;
+}
+
+int bp_layer_set_records(bp_layer *L, const void *keys, const void *ids, size_t n, int sorted, int on_device) {
+    if (!L || (n && (!keys || !ids))) return fail(L, BP_ERR_INVALID_ARG, "null argument to set_records");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
+    DeviceGuard g(L->device);
+    TRY(bp_layer_clear(L));
+    if (n) {
+        TRY(do_ensure_tree(L, n));
+        const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        CU(L, cudaMemcpyAsync(L->keys[L->cur].p, keys, n * L->key_bytes, kind, L->stream));
+        CU(L, cudaMemcpyAsync(L->ids[L->cur].p, ids, n * L->id_bytes, kind, L->stream));
+    }
+    L->n_records = n;
+    TRY(do_masks(L, n));
+    L->key_or = L->h_res->key_or;
+    L->key_and = L->h_res->key_and;
+    L->id_or = L->h_res->id_or;
+    L->id_and = L->h_res->id_and;
+    L->dirty = !sorted;
+    L->prefix = 0;
+    L->tail_sorted = false;
+    L->tail_nonmono = L->h_res->nonmono != 0;
+    L->stats.n_records = n;
+    return BP_OK;
+}
+
+int bp_layer_len(bp_layer *L, size_t *out_n) {
+    if (!L || !out_n) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    *out_n = (size_t)L->n_records;
+    return BP_OK;
+}
+
+int bp_layer_is_sorted(bp_layer *L, int *out_sorted) {
+    if (!L || !out_sorted) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    *out_sorted = L->dirty ? 0 : 1;
+    return BP_OK;
+}
+
+int bp_layer_min_depth(const bp_layer *L, uint32_t *out) {
+    if (!L || !out) return BP_ERR_INVALID_ARG;
+    *out = L->min_depth;
+    return BP_OK;
+}
+
+int bp_layer_set_profiling(bp_layer *L, int enabled) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    L->profiling = enabled != 0;
+    return BP_OK;
+}
+
+int bp_layer_reset_stats(bp_layer *L) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    if (!L->prof_events.empty()) {
+        CU(L, cudaStreamSynchronize(L->stream));
+        collect_profile(L);
+    }
+    const uint64_t total = L->stats.launches_total;
+    memset(&L->stats, 0, sizeof L->stats);
+    L->stats.launches_total = total;
+    L->stats.n_records = L->n_records;
+    return BP_OK;
+}
+
+int bp_layer_stats(bp_layer *L, bp_stats *out) {
+    if (!L || !out) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    if (!L->prof_events.empty()) {
+        CU(L, cudaStreamSynchronize(L->stream));
+        collect_profile(L);
+    }
+    L->stats.n_records = L->n_records;
+    L->stats.n_invalid = L->n_invalid;
+    *out = L->stats;
+    return BP_OK;
+}
+
+} // extern "C"

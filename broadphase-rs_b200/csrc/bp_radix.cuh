@@ -1,0 +1,257 @@
+// bp_radix.cuh -- LSD radix sort ("onesweep": one histogram read, then one read + one write per
+// digit) of key arrays with an optional payload array, for sm_100a.
+//
+// Replaces the reference's `tree.par_sort_unstable()` (src/layer.rs:149, :162) and
+// `collisions.par_sort_unstable()` (src/layer.rs:473, :516).  Both sort a total order, so any
+// correct sort reproduces the reference's sequence exactly.
+//
+// Per pass, each CTA takes a tile (atomic ticket), ranks its keys by digit with warp-level
+// match-any multisplit into per-warp shared-memory counters, publishes its per-digit counts, resolves
+// its global digit offsets by a decoupled look-back over the preceding tiles, stages the tile in shared
+// memory in digit order and writes each digit run to its final place with coalesced stores.
+#pragma once
+
+#include <type_traits>
+
+#include "bp_common.cuh"
+
+namespace bp {
+
+struct NoVal {};
+
+constexpr int RADIX_MAX_PASSES = 16;
+constexpr int RADIX = 256;
+
+struct RadixPlan {
+    int npasses;
+    unsigned char shift[RADIX_MAX_PASSES];
+    unsigned char bits[RADIX_MAX_PASSES];
+};
+
+// ---- histograms for every planned digit in one read of the keys ---------------------------------
+template <class K>
+__global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ keys, uint32_t n_host,
+                                                          const uint32_t *__restrict__ n_dev, RadixPlan plan,
+                                                          uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t sh[RADIX_MAX_PASSES * RADIX];
+    const int np = plan.npasses;
+    for (int i = threadIdx.x; i < np * RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const uint32_t n = n_dev ? *n_dev : n_host;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    constexpr int UNROLL = 4;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < n; i += UNROLL * stride) {
+        K k[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) k[u] = ld_stream(keys + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            for (int p = 0; p < np; ++p)
+                atomicAdd(&sh[p * RADIX + (uint32_t)((k[u] >> plan.shift[p]) & (K)((1u << plan.bits[p]) - 1))], 1u);
+    }
+    for (; i < n; i += stride) {
+        const K k = ld_stream(keys + i);
+        for (int p = 0; p < np; ++p)
+            atomicAdd(&sh[p * RADIX + (uint32_t)((k >> plan.shift[p]) & (K)((1u << plan.bits[p]) - 1))], 1u);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < np * RADIX; j += blockDim.x) {
+        const uint32_t c = sh[j];
+        if (c) atomicAdd(&ghist[j], c);
+    }
+}
+
+// ---- exclusive scan of each pass's 256-bin histogram (one CTA of 256 threads per pass) -----------
+__global__ void __launch_bounds__(RADIX) radix_scan_hist_kernel(uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t wt[RADIX / 32 + 1];
+    uint32_t *h = ghist + (size_t)blockIdx.x * RADIX;
+    const uint32_t c = h[threadIdx.x];
+    uint32_t total;
+    const uint32_t ex = block_exclusive_sum<RADIX, uint32_t>(c, wt, &total);
+    h[threadIdx.x] = ex;
+}
+
+// ---- one onesweep pass --------------------------------------------------------------------------------
+template <class K, class V> struct RadixPassArgs {
+    const K *kin;
+    K *kout;
+    const V *vin;
+    V *vout;
+    uint32_t n_host;
+    const uint32_t *n_dev;      // optional: element count in device memory (grid sized by n_host >= *n_dev)
+    const uint32_t *ghist_excl; // [RADIX] exclusive digit offsets of this pass
+    uint32_t *status;           // [tiles][RADIX], zeroed; bits 31..30 flag, 29..0 count
+    uint32_t *tile_counter;     // zeroed
+    uint32_t shift, bits;
+    int *err;
+};
+
+constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_INC = 2u << 30, RS_VALUE_MASK = (1u << 30) - 1;
+
+template <class K, class V, int THREADS, int ITEMS> struct RadixPassCfg {
+    static constexpr bool HAS_V = !std::is_same<V, NoVal>::value;
+    static constexpr int TILE = THREADS * ITEMS;
+    static constexpr int WARPS = THREADS / 32;
+    static constexpr size_t ELEM = HAS_V ? (sizeof(K) > sizeof(V) ? sizeof(K) : sizeof(V)) : sizeof(K);
+    static constexpr size_t STAGE_BYTES = (size_t)TILE * ELEM;
+    static constexpr size_t SMEM_BYTES = STAGE_BYTES + (size_t)(WARPS * RADIX + 2 * RADIX + 16) * sizeof(uint32_t);
+    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
+    static_assert(TILE < 65536, "ranks are packed in 16 bits");
+};
+
+template <class K, class V, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs<K, V> a) {
+    typedef RadixPassCfg<K, V, THREADS, ITEMS> Cfg;
+    constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS;
+    constexpr bool HAS_V = Cfg::HAS_V;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned char *stage = smem_raw;
+    uint32_t *whist = (uint32_t *)(smem_raw + Cfg::STAGE_BYTES); // [WARPS][RADIX]
+    uint32_t *dstart = whist + WARPS * RADIX;                    // [RADIX] first block rank of each digit
+    uint32_t *gbase = dstart + RADIX;                            // [RADIX] global offset minus dstart
+    uint32_t *misc = gbase + RADIX;                              // [0] tile, [1..9] warp totals
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+
+    if (tid == 0) misc[0] = atomicAdd(a.tile_counter, 1u);
+    for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
+    __syncthreads();
+    const uint32_t tile = misc[0];
+    const uint32_t n = a.n_dev ? *a.n_dev : a.n_host;
+    const uint64_t tile_begin = (uint64_t)tile * TILE;
+    if (tile_begin >= n) return;
+    const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, (uint64_t)n - tile_begin);
+
+    // ---- load keys, warp-striped: item k of lane l of warp w is tile element w*32*ITEMS + k*32 + l
+    const K *kin = a.kin + tile_begin;
+    const uint32_t base_i = warp * (32 * ITEMS) + lane;
+    K key[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t i = base_i + k * 32;
+        key[k] = (i < tile_n) ? ld_stream(kin + i) : (K) ~(K)0; // pads rank last within the tile
+    }
+
+    // ---- rank within the warp: match-any groups + one shared counter per (warp, digit) ----------
+    const K dmask = (K)((1u << a.bits) - 1u);
+    const uint32_t shift = a.shift;
+    volatile uint32_t *wrow = whist + warp * RADIX;
+    const unsigned lt = lanemask_lt();
+    uint32_t rd[ITEMS]; // low 16 bits: rank, high 16 bits: digit
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t d = (uint32_t)((key[k] >> shift) & dmask);
+        const unsigned m = __match_any_sync(BP_FULL_MASK, d);
+        const int leader = __ffs(m) - 1;
+        uint32_t old = 0;
+        if ((int)lane == leader) {
+            old = wrow[d];
+            wrow[d] = old + __popc(m);
+        }
+        old = __shfl_sync(BP_FULL_MASK, old, leader);
+        rd[k] = (old + __popc(m & lt)) | (d << 16);
+        __syncwarp();
+    }
+
+    // payload loads are issued now so that their latency overlaps the look-back
+    V val[HAS_V ? ITEMS : 1];
+    if constexpr (HAS_V) {
+        const V *vin = a.vin + tile_begin;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t i = base_i + k * 32;
+            if (i < tile_n) val[k] = ld_stream(vin + i);
+        }
+    }
+    __syncthreads();
+
+    // ---- per digit: exclusive scan over the warps, publish the tile count, look back -------------
+    uint32_t count_full = 0, incl = 0;
+    if (tid < RADIX) {
+        uint32_t sum = 0;
+#pragma unroll 4
+        for (int w = 0; w < WARPS; ++w) {
+            const uint32_t c = whist[w * RADIX + tid];
+            whist[w * RADIX + tid] = sum;
+            sum += c;
+        }
+        count_full = sum;
+        uint32_t count = sum;
+        if (tid == (uint32_t)dmask) count -= (uint32_t)(TILE - tile_n); // pads carry the all-ones digit
+        uint32_t *st = a.status + (size_t)tile * RADIX + tid;
+        st_volatile_u32(st, (tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG) | count);
+        incl = warp_inclusive_sum(count_full);
+        if (lane == 31) misc[1 + warp] = incl;
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+        uint32_t off = 0;
+        for (unsigned w = 0; w < warp; ++w) off += misc[1 + w];
+        const uint32_t ds = off + incl - count_full;
+        dstart[tid] = ds;
+        uint32_t excl = 0;
+        if (tile != 0) {
+            uint32_t count = count_full;
+            if (tid == (uint32_t)dmask) count -= (uint32_t)(TILE - tile_n);
+            for (int64_t t = (int64_t)tile - 1; t >= 0; --t) {
+                const uint32_t *ps = a.status + (size_t)t * RADIX + tid;
+                uint32_t s = ld_volatile_u32(ps);
+                uint32_t spins = 0;
+                while ((s >> 30) == 0) {
+                    if (++spins > BP_SPIN_LIMIT) {
+                        *a.err = 1;
+                        s = RS_FLAG_INC;
+                        break;
+                    }
+                    s = ld_volatile_u32(ps);
+                }
+                excl += s & RS_VALUE_MASK;
+                if ((s >> 30) == 2) break;
+            }
+            st_volatile_u32(a.status + (size_t)tile * RADIX + tid, RS_FLAG_INC | ((excl + count) & RS_VALUE_MASK));
+        }
+        gbase[tid] = a.ghist_excl[tid] + excl - ds;
+    }
+    __syncthreads();
+
+    // ---- stage the keys in digit order, then write each digit run with coalesced stores ----------
+    K *skeys = (K *)stage;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t d = rd[k] >> 16;
+        const uint32_t r = (rd[k] & 0xffffu) + whist[warp * RADIX + d] + dstart[d];
+        rd[k] = r;
+        skeys[r] = key[k];
+    }
+    __syncthreads();
+    uint32_t dst[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t i = k * THREADS + tid;
+        if (i < tile_n) {
+            const K kk = skeys[i];
+            const uint32_t d = (uint32_t)((kk >> shift) & dmask);
+            dst[k] = gbase[d] + i;
+            a.kout[dst[k]] = kk;
+        }
+    }
+    if constexpr (HAS_V) {
+        __syncthreads();
+        V *svals = (V *)stage;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t i = base_i + k * 32;
+            if (i < tile_n) svals[rd[k]] = val[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t i = k * THREADS + tid;
+            if (i < tile_n) a.vout[dst[k]] = svals[i];
+        }
+    }
+}
+
+} // namespace bp

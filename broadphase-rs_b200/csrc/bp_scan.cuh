@@ -1,0 +1,447 @@
+// bp_scan.cuh -- K3/K4: the stack-free, load-balanced reformulation of Layer::scan.
+//
+// Replaces scan_impl (src/layer.rs:550-573) and the sort + dedup that follows it in scan_filtered /
+// par_scan_filtered (src/layer.rs:473-474, 516-517).
+//
+// The reference sweeps the sorted tree with a stack of "open" ancestor cells.  In the sorted
+// (Index, ID) order every cell's descendants-or-equals form one contiguous run that starts at the
+// cell's own record, so the stack at record j is exactly the set of earlier *pushed* records i whose
+// run contains j.  With
+//     anc(i, j)   <=>  i < j  and  key_j <= key_i | ~level_mask(depth_i)
+//     inactive(j) <=>  exists i: anc(i, j) and id_i == id_j     (the "same ID already on the stack" skip)
+// the reference's output multiset is { (id_j, id_i) : anc(i, j), !inactive(i), !inactive(j),
+// filter(id_j, id_i) }.  (DESIGN.md has the proof; tests/test_oracle.py checks the closed form
+// against the literal stack sweep.)
+//
+// Kernels:
+//   scan_runs_kernel   one thread per record: galloping search for the end of its run, compaction of
+//                      the non-empty runs and exclusive scan of their lengths (single pass, two
+//                      decoupled look-back chains), plus the first source of every work chunk.
+//   scan_emit_kernel   one CTA per chunk of 2048 (ancestor, descendant) work items regardless of
+//                      how they are distributed over the runs; applies the filter functor, compacts
+//                      the surviving pairs (look-back) and writes them coalesced.
+//   pair_unique_kernel adjacent-difference dedup of the sorted pairs + final (later, earlier) layout.
+#pragma once
+
+#include "bp_common.cuh"
+
+namespace bp {
+
+// ---------------------------------------------------------------------------------------------
+// filter functors -- scan_filtered's F: FnMut(ID, ID) -> bool (src/layer.rs:456-460)
+// ---------------------------------------------------------------------------------------------
+struct FilterArgs {
+    uint64_t arg;
+    const uint32_t *table; // device, n_table x {cat, msk}
+    uint64_t n_table;
+};
+
+template <int FK> struct FilterFn;
+template <> struct FilterFn<BP_FILTER_NONE> {
+    template <class IdT> __device__ __forceinline__ static bool pass(const FilterArgs &, IdT, IdT) { return true; }
+};
+template <> struct FilterFn<BP_FILTER_ID_PARITY> {
+    template <class IdT> __device__ __forceinline__ static bool pass(const FilterArgs &, IdT a, IdT b) {
+        return ((a ^ b) & (IdT)1) == (IdT)1;
+    }
+};
+template <> struct FilterFn<BP_FILTER_XOR_MASK> {
+    template <class IdT> __device__ __forceinline__ static bool pass(const FilterArgs &f, IdT a, IdT b) {
+        return (((uint64_t)(a ^ b)) & f.arg) != 0;
+    }
+};
+template <> struct FilterFn<BP_FILTER_CATEGORY> {
+    template <class IdT> __device__ __forceinline__ static bool pass(const FilterArgs &f, IdT a, IdT b) {
+        uint32_t ca = 0xffffffffu, ma = 0xffffffffu, cb = 0xffffffffu, mb = 0xffffffffu;
+        if ((uint64_t)a < f.n_table) {
+            const uint2 t = __ldg((const uint2 *)f.table + (uint64_t)a);
+            ca = t.x;
+            ma = t.y;
+        }
+        if ((uint64_t)b < f.n_table) {
+            const uint2 t = __ldg((const uint2 *)f.table + (uint64_t)b);
+            cb = t.x;
+            mb = t.y;
+        }
+        return (ca & mb) != 0 && (cb & ma) != 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// scan_runs_kernel
+// ---------------------------------------------------------------------------------------------
+constexpr int RUNS_THREADS = 256;
+constexpr int RUNS_IPT = 4;
+constexpr int RUNS_TILE = RUNS_THREADS * RUNS_IPT;
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_IPT = 8;
+constexpr int EMIT_CHUNK = EMIT_THREADS * EMIT_IPT;
+
+struct ScanTotals {
+    unsigned long long n_sources;   // records with a non-empty descendant run
+    unsigned long long n_work;      // sum of run lengths = (ancestor, descendant) record pairs
+    unsigned long long n_raw_pairs; // pairs emitted by scan_emit_kernel
+    unsigned long long n_pairs;     // unique pairs
+    unsigned int any_same_id;       // an (i, j) work item with id_i == id_j exists -> inactive records exist
+    unsigned int pad;
+};
+
+template <class T> struct RunsArgs {
+    const typename T::key_t *keys; // sorted
+    uint32_t n;
+    uint32_t *src_idx;   // [n]   compacted: record index of each non-empty run
+    uint64_t *src_off;   // [n+1] compacted: exclusive prefix of run lengths (+ total at [n_sources])
+    uint64_t *status_cnt; // look-back chains, one status word per tile each, zeroed
+    uint64_t *status_work;
+    uint32_t *tile_counter; // zeroed
+    ScanTotals *totals;
+    int *err;
+};
+
+template <class T>
+__global__ void __launch_bounds__(RUNS_THREADS) scan_runs_kernel(const RunsArgs<T> a) {
+    typedef typename T::key_t K;
+    __shared__ K skeys[RUNS_TILE + 1];
+    __shared__ uint64_t sscratch[RUNS_THREADS / 32 + 2];
+    __shared__ uint64_t sbase[2];
+    __shared__ uint32_t stile;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) stile = atomicAdd(a.tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = stile;
+    const uint32_t r0 = tile * RUNS_TILE;
+    if (r0 >= a.n) return;
+    const uint32_t tile_n = min((uint32_t)RUNS_TILE, a.n - r0);
+
+    // keys of the tile plus the first key of the next one, coalesced
+    for (uint32_t i = tid; i < tile_n + 1; i += RUNS_THREADS)
+        if (r0 + i < a.n) skeys[i] = a.keys[r0 + i];
+    __syncthreads();
+
+    uint32_t len[RUNS_IPT];
+    uint32_t nz = 0;
+    uint64_t work = 0;
+#pragma unroll
+    for (int q = 0; q < RUNS_IPT; ++q) {
+        const uint32_t li = tid * RUNS_IPT + q; // blocked: a thread owns consecutive records
+        len[q] = 0;
+        if (li >= tile_n) continue;
+        const uint32_t i = r0 + li;
+        if (i + 1 >= a.n) continue;
+        const K hi = run_upper_key<T>(skeys[li]);
+        if (skeys[li + 1] > hi) continue; // the common case: no later record inside this cell
+        // gallop, then bisect, for the first index whose key exceeds hi
+        uint32_t lo = i + 1, step = 1;
+        while (lo + step < a.n && a.keys[lo + step] <= hi) {
+            lo += step;
+            step <<= 1;
+        }
+        uint32_t end = min(lo + step, a.n); // keys[lo] <= hi, (end == n or keys[end] > hi)
+        while (lo + 1 < end) {
+            const uint32_t mid = lo + ((end - lo) >> 1);
+            if (a.keys[mid] <= hi)
+                lo = mid;
+            else
+                end = mid;
+        }
+        len[q] = lo - i;
+        ++nz;
+        work += len[q];
+    }
+
+    // block scans of (non-empty count, work)
+    uint32_t nz_total;
+    uint64_t work_total;
+    const uint32_t nz_ex = block_exclusive_sum<RUNS_THREADS, uint32_t>(nz, (uint32_t *)sscratch, &nz_total);
+    __syncthreads();
+    const uint64_t work_ex = block_exclusive_sum<RUNS_THREADS, uint64_t>(work, sscratch, &work_total);
+    __syncthreads();
+    // two look-back chains, walked by two different warps at the same time
+    if (warp == 0) {
+        const uint64_t e = lookback_exclusive(a.status_cnt, tile, (uint64_t)nz_total, a.err);
+        if (lane == 0) sbase[0] = e;
+    } else if (warp == 1) {
+        const uint64_t e = lookback_exclusive(a.status_work, tile, work_total, a.err);
+        if (lane == 0) sbase[1] = e;
+    }
+    __syncthreads();
+    uint32_t c = (uint32_t)sbase[0] + nz_ex;
+    uint64_t w = sbase[1] + work_ex;
+#pragma unroll
+    for (int q = 0; q < RUNS_IPT; ++q) {
+        if (len[q] == 0) continue;
+        a.src_idx[c] = r0 + tid * RUNS_IPT + q;
+        a.src_off[c] = w;
+        ++c;
+        w += len[q];
+    }
+    if (r0 + tile_n == a.n && tid == 0) { // last tile: totals and the sentinel offset
+        const uint64_t ns = sbase[0] + nz_total, nw = sbase[1] + work_total;
+        a.totals->n_sources = ns;
+        a.totals->n_work = nw;
+        a.src_off[ns] = nw;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan_chunks_kernel: one thread per non-empty run; every chunk boundary m*EMIT_CHUNK that falls
+// inside the run's work range [off, off + len) records this run as the chunk's first source.  The
+// ranges tile [0, n_work), so every chunk_src[m] is written exactly once and the emit CTAs need no
+// global binary search.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scan_chunks_kernel(const uint64_t *__restrict__ src_off, uint32_t n_sources,
+                                                          uint32_t *__restrict__ chunk_src) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_sources) return;
+    const uint64_t w = src_off[c], e = src_off[c + 1];
+    for (uint64_t m = (w + EMIT_CHUNK - 1) / EMIT_CHUNK; m * EMIT_CHUNK < e; ++m) chunk_src[m] = c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scan_emit_kernel
+// ---------------------------------------------------------------------------------------------
+enum { EMIT_MODE_FIRST = 0, EMIT_MODE_FLAG = 1, EMIT_MODE_ACTIVE = 2 };
+
+template <class IdT> struct EmitArgs {
+    const IdT *ids; // sorted tree IDs
+    const uint32_t *src_idx;
+    const uint64_t *src_off;
+    const uint32_t *chunk_src;
+    uint64_t n_work;
+    uint32_t n_sources;
+    int mode;               // FIRST: emit assuming no inactive records, report same-ID items;
+                            // FLAG: only mark inactive[j]; ACTIVE: emit, skipping inactive records
+    unsigned char *inactive; // [n records] (FLAG / ACTIVE)
+    uint64_t *out_packed;   // u32 IDs: (later << 32) | earlier
+    uint64_t *out_a;        // u64 IDs: later
+    uint64_t *out_b;        //          earlier
+    uint64_t capacity;      // pairs the output arrays can hold
+    uint64_t *status;       // look-back, one per chunk, zeroed
+    uint32_t *tile_counter; // zeroed
+    ScanTotals *totals;
+    FilterArgs filter;
+    int *err;
+};
+
+template <class IdT, int FK>
+__global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<IdT> a) {
+    constexpr bool WIDE = sizeof(IdT) == 8;
+    __shared__ uint64_t soff[EMIT_CHUNK + 2];
+    // sidx holds the source record indices during the walk; for u64 IDs it is sized so that it can
+    // stage the `earlier` half of the output afterwards
+    __shared__ uint64_t sidx_raw[WIDE ? EMIT_CHUNK : (EMIT_CHUNK + 2) / 2];
+    __shared__ uint64_t sscratch[EMIT_THREADS / 32 + 2];
+    __shared__ uint64_t sbase;
+    __shared__ uint32_t stile;
+    uint32_t *sidx = (uint32_t *)sidx_raw;
+    // the staged output reuses soff / sidx: every thread has finished its walk before the first
+    // barrier inside block_exclusive_sum, and staging starts after it
+    uint64_t *spa = soff;     // packed pair, or `later`
+    uint64_t *spb = sidx_raw; // `earlier` (u64 IDs only)
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) stile = atomicAdd(a.tile_counter, 1u);
+    __syncthreads();
+    const uint32_t chunk = stile;
+    const uint64_t w0 = (uint64_t)chunk * EMIT_CHUNK;
+    if (w0 >= a.n_work) return;
+    const uint32_t chunk_n = (uint32_t)min((uint64_t)EMIT_CHUNK, a.n_work - w0);
+
+    // the sources whose runs intersect this chunk: at most chunk_n of them (every run is non-empty)
+    const uint32_t c0 = a.chunk_src[chunk];
+    const uint32_t nsrc = min(a.n_sources - c0, chunk_n);
+    for (uint32_t i = tid; i < nsrc + 1; i += EMIT_THREADS) soff[i] = a.src_off[c0 + i]; // src_off[n_sources] = n_work
+    for (uint32_t i = tid; i < nsrc; i += EMIT_THREADS) sidx[i] = a.src_idx[c0 + i];
+    __syncthreads();
+
+    // each thread owns EMIT_IPT consecutive work items: one bisection, then a linear walk
+    const uint32_t first = tid * EMIT_IPT;
+    uint32_t npass = 0;
+    uint64_t pa[EMIT_IPT], pb[EMIT_IPT];
+    if (first < chunk_n) {
+        const uint64_t w = w0 + first;
+        uint32_t lo = 0, hi = nsrc; // largest s with soff[s] <= w
+        while (lo + 1 < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (soff[mid] <= w)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        uint32_t s = lo;
+        bool same_seen = false;
+#pragma unroll
+        for (int q = 0; q < EMIT_IPT; ++q) {
+            if (first + q >= chunk_n) break;
+            const uint64_t wq = w + q;
+            while (wq >= soff[s + 1]) ++s;
+            const uint32_t i = sidx[s];
+            const uint32_t j = i + 1u + (uint32_t)(wq - soff[s]);
+            const IdT id_i = a.ids[i], id_j = a.ids[j];
+            bool emit;
+            if (a.mode == EMIT_MODE_FIRST) {
+                const bool same = id_i == id_j;
+                same_seen |= same;
+                emit = !same && FilterFn<FK>::pass(a.filter, id_j, id_i);
+            } else if (a.mode == EMIT_MODE_FLAG) {
+                if (id_i == id_j) a.inactive[j] = 1;
+                emit = false;
+            } else {
+                emit = !a.inactive[i] && !a.inactive[j] && FilterFn<FK>::pass(a.filter, id_j, id_i);
+            }
+            if (emit) {
+                pa[npass] = (uint64_t)id_j; // (later, earlier) -- src/layer.rs:567
+                pb[npass] = (uint64_t)id_i;
+                ++npass;
+            }
+        }
+        if (same_seen) a.totals->any_same_id = 1u;
+    }
+    if (a.mode == EMIT_MODE_FLAG) return;
+
+    uint32_t chunk_pass;
+    const uint32_t ex = block_exclusive_sum<EMIT_THREADS, uint32_t>(npass, (uint32_t *)sscratch, &chunk_pass);
+    if (warp == 0) {
+        const uint64_t e = lookback_exclusive(a.status, chunk, (uint64_t)chunk_pass, a.err);
+        if (lane == 0) sbase = e;
+    }
+    // stage, then write coalesced
+#pragma unroll
+    for (int q = 0; q < EMIT_IPT; ++q) {
+        if (q < (int)npass) {
+            if (WIDE) {
+                spa[ex + q] = pa[q];
+                spb[ex + q] = pb[q];
+            } else {
+                spa[ex + q] = (pa[q] << 32) | pb[q];
+            }
+        }
+    }
+    __syncthreads();
+    const uint64_t base = sbase;
+    for (uint32_t i = tid; i < chunk_pass; i += EMIT_THREADS) {
+        const uint64_t g = base + i;
+        if (g < a.capacity) {
+            if (WIDE) {
+                a.out_a[g] = spa[i];
+                a.out_b[g] = spb[i];
+            } else {
+                a.out_packed[g] = spa[i];
+            }
+        }
+    }
+    if (w0 + chunk_n == a.n_work && tid == 0) a.totals->n_raw_pairs = base + chunk_pass;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair_unique_kernel -- `collisions.dedup()` (src/layer.rs:474, :517) + the (ID, ID) memory layout
+// ---------------------------------------------------------------------------------------------
+constexpr int UNIQ_THREADS = 256;
+constexpr int UNIQ_IPT = 8;
+constexpr int UNIQ_TILE = UNIQ_THREADS * UNIQ_IPT;
+
+template <class IdT> struct UniqueArgs {
+    const uint64_t *in_packed; // u32 IDs: sorted packed pairs
+    const uint64_t *in_a;      // u64 IDs: sorted (a, b) as two arrays
+    const uint64_t *in_b;
+    uint32_t n_host;
+    const unsigned long long *n_dev; // optional device-side count (n_raw_pairs)
+    IdT *out;                        // [2 * n] (later, earlier) interleaved
+    uint64_t *status;                // zeroed
+    uint32_t *tile_counter;          // zeroed
+    ScanTotals *totals;
+    int *err;
+};
+
+template <class IdT>
+__global__ void __launch_bounds__(UNIQ_THREADS) pair_unique_kernel(const UniqueArgs<IdT> a) {
+    constexpr bool WIDE = sizeof(IdT) == 8;
+    constexpr int WARPS = UNIQ_THREADS / 32;
+    __shared__ uint32_t swtot[WARPS + 1];
+    __shared__ uint64_t sbase;
+    __shared__ uint32_t stile;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) stile = atomicAdd(a.tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = stile;
+    const uint64_t n = a.n_dev ? (uint64_t)*a.n_dev : (uint64_t)a.n_host;
+    const uint64_t t0 = (uint64_t)tile * UNIQ_TILE;
+    if (n == 0) {
+        if (tile == 0 && tid == 0) a.totals->n_pairs = 0;
+        return;
+    }
+    if (t0 >= n) return;
+    const uint32_t tile_n = (uint32_t)min((uint64_t)UNIQ_TILE, n - t0);
+
+    // warp-striped: warp w owns tile elements [w*32*IPT, (w+1)*32*IPT); item q of lane l is element
+    // w*32*IPT + q*32 + l, so loads are coalesced and the order inside a warp is (q, lane)
+    const uint32_t wseg = warp * (32 * UNIQ_IPT);
+    const unsigned lt = lanemask_lt();
+    uint64_t xa[UNIQ_IPT], xb[UNIQ_IPT];
+    uint32_t pos[UNIQ_IPT];
+    uint32_t keepbits = 0, cnt = 0;
+    uint64_t last_a = 0, last_b = 0; // lane 31's element of the previous q
+#pragma unroll
+    for (int q = 0; q < UNIQ_IPT; ++q) {
+        const uint32_t li = wseg + q * 32 + lane;
+        const bool valid = li < tile_n;
+        const uint64_t g = t0 + li;
+        xa[q] = valid ? (WIDE ? a.in_a[g] : a.in_packed[g]) : 0;
+        xb[q] = (valid && WIDE) ? a.in_b[g] : 0;
+        uint64_t pa = __shfl_up_sync(BP_FULL_MASK, xa[q], 1);
+        uint64_t pb = __shfl_up_sync(BP_FULL_MASK, xb[q], 1);
+        if (lane == 0) {
+            if (q == 0) {
+                if (valid && g > 0) {
+                    pa = WIDE ? a.in_a[g - 1] : a.in_packed[g - 1];
+                    pb = WIDE ? a.in_b[g - 1] : 0;
+                }
+            } else {
+                pa = last_a;
+                pb = last_b;
+            }
+        }
+        const bool keep = valid && (g == 0 || xa[q] != pa || (WIDE && xb[q] != pb));
+        const unsigned m = __ballot_sync(BP_FULL_MASK, keep);
+        pos[q] = cnt + __popc(m & lt);
+        cnt += __popc(m);
+        if (keep) keepbits |= 1u << q;
+        last_a = __shfl_sync(BP_FULL_MASK, xa[q], 31);
+        last_b = __shfl_sync(BP_FULL_MASK, xb[q], 31);
+    }
+    if (lane == 0) swtot[warp] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t t = lane < WARPS ? swtot[lane] : 0;
+        const uint32_t ti = warp_inclusive_sum(t);
+        if (lane < WARPS) swtot[lane] = ti - t;
+        const uint32_t tile_keep = __shfl_sync(BP_FULL_MASK, ti, 31);
+        if (lane == 0) swtot[WARPS] = tile_keep;
+        const uint64_t e = lookback_exclusive(a.status, tile, (uint64_t)tile_keep, a.err);
+        if (lane == 0) sbase = e;
+    }
+    __syncthreads();
+    const uint64_t base = sbase + swtot[warp];
+#pragma unroll
+    for (int q = 0; q < UNIQ_IPT; ++q) {
+        if (keepbits & (1u << q)) {
+            const uint64_t g = base + pos[q];
+            if (WIDE) {
+                ulonglong2 p;
+                p.x = xa[q]; // later
+                p.y = xb[q]; // earlier
+                ((ulonglong2 *)a.out)[g] = p;
+            } else {
+                uint2 p;
+                p.x = (uint32_t)(xa[q] >> 32); // later
+                p.y = (uint32_t)xa[q];         // earlier
+                ((uint2 *)a.out)[g] = p;
+            }
+        }
+    }
+    if (t0 + tile_n == n && tid == 0) a.totals->n_pairs = sbase + swtot[WARPS];
+}
+
+} // namespace bp

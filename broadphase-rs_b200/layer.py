@@ -1,0 +1,258 @@
+"""Python mirror of the reference's `Layer<Index, ID>` / `LayerBuilder` API over the C ABI.
+
+Same method names, argument meaning and implicit behaviour as the crate (src/layer.rs):
+    LayerBuilder().with_min_depth(4).build(Index32_2D, "u32")   # src/layer.rs:620-696
+    layer.clear(); layer.extend(system_bounds, bounds, ids)     # :84-88, :94-121
+    layer.par_sort(); layer.par_scan(); layer.scan_filtered(f)  # :146-165, :449-520
+    layer.merge(other); layer.iter()                            # :127-138, :79-81
+Host arrays are numpy; device arrays are anything exposing `data_ptr()` (torch tensors) or raw
+integer device pointers.  Compute never happens on the host: every method calls the CUDA library.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import BpError, Filter, LayerConfig, Stats, check, lib
+
+Index32_2D, Index64_2D, Index64_3D = 0, 1, 2
+INDEX_DIM = {Index32_2D: 2, Index64_2D: 2, Index64_3D: 3}
+INDEX_KEY_DTYPE = {Index32_2D: np.uint32, Index64_2D: np.uint64, Index64_3D: np.uint64}
+
+FILTER_NONE, FILTER_ID_PARITY, FILTER_XOR_MASK, FILTER_CATEGORY = 0, 1, 2, 3
+
+
+class ScanFilter:
+    """A device functor standing in for scan_filtered's closure (include/bp.h, bp_filter_kind)."""
+
+    def __init__(self, kind=FILTER_NONE, arg=0, table=None):
+        self.kind, self.arg = kind, arg
+        self.table = None if table is None else np.ascontiguousarray(table, dtype=np.uint32).reshape(-1, 2)
+
+    @staticmethod
+    def none():
+        return ScanFilter(FILTER_NONE)
+
+    @staticmethod
+    def id_parity():
+        return ScanFilter(FILTER_ID_PARITY)
+
+    @staticmethod
+    def xor_mask(mask):
+        return ScanFilter(FILTER_XOR_MASK, mask)
+
+    @staticmethod
+    def category(table):
+        return ScanFilter(FILTER_CATEGORY, 0, table)
+
+    def _c(self):
+        f = Filter()
+        f.kind, f.arg, f.table_on_device = self.kind, self.arg, 0
+        if self.table is not None:
+            f.table = self.table.ctypes.data
+            f.n_table = self.table.shape[0]
+        return f
+
+
+def _dev_ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    return x.data_ptr()
+
+
+class Layer:
+    """A group of collision data resident on one B200 (reference: src/layer.rs:42-68)."""
+
+    def __init__(self, index=Index64_3D, id_type="u32", min_depth=0, index_capacity=0, collision_capacity=0,
+                 test_capacity=0, device=-1):
+        self.index = index
+        self.dim = INDEX_DIM[index]
+        self.id_bytes = {"u32": 4, "u64": 8, 4: 4, 8: 8}[id_type]
+        self.id_dtype = np.uint32 if self.id_bytes == 4 else np.uint64
+        self.key_dtype = INDEX_KEY_DTYPE[index]
+        cfg = LayerConfig(index, self.id_bytes, min_depth, device, index_capacity, collision_capacity, test_capacity)
+        h = ctypes.c_void_p()
+        check(lib().bp_layer_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().bp_layer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, status):
+        check(status, self._h)
+
+    # ---- Layer API ------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream):
+        self._ck(lib().bp_layer_set_stream(self._h, ctypes.c_void_p(cuda_stream)))
+
+    def clear(self):
+        self._ck(lib().bp_layer_clear(self._h))
+
+    def extend(self, system_bounds, bounds, ids):
+        """Layer::extend from host (numpy) arrays: bounds (n, 2*D) f32 as (min.., max..), ids (n,)."""
+        sysb = np.ascontiguousarray(system_bounds, dtype=np.float32).reshape(2 * self.dim)
+        b = np.ascontiguousarray(bounds, dtype=np.float32).reshape(-1, 2 * self.dim)
+        i = np.ascontiguousarray(ids, dtype=self.id_dtype).reshape(-1)
+        if i.shape[0] != b.shape[0]:
+            raise ValueError("bounds and ids differ in length")
+        self._ck(lib().bp_layer_extend_host(self._h, sysb.ctypes.data, b.ctypes.data, i.ctypes.data, b.shape[0]))
+
+    def extend_device(self, system_bounds, d_bounds, d_ids, n):
+        """Layer::extend from device-resident arrays (torch tensors or raw pointers)."""
+        sysb = np.ascontiguousarray(system_bounds, dtype=np.float32).reshape(2 * self.dim)
+        self._ck(lib().bp_layer_extend_device(self._h, sysb.ctypes.data, _dev_ptr(d_bounds), _dev_ptr(d_ids), n))
+
+    def merge(self, other):
+        self._ck(lib().bp_layer_merge(self._h, other._h))
+
+    def sort(self):
+        self._ck(lib().bp_layer_sort(self._h))
+
+    par_sort = sort  # src/layer.rs:146-151: same result, the device sort is always parallel
+
+    def _scan(self, flt, device):
+        f = None if flt is None else flt._c()
+        out, cnt = ctypes.c_void_p(), ctypes.c_size_t()
+        fn = lib().bp_layer_scan_device if device else lib().bp_layer_scan
+        self._ck(fn(self._h, None if f is None else ctypes.byref(f), ctypes.byref(out), ctypes.byref(cnt)))
+        return out.value, cnt.value
+
+    def scan_filtered(self, flt=None):
+        """Returns the sorted, unique (later_id, earlier_id) pairs as an (P, 2) numpy array (a view of
+        the layer's pinned result buffer, valid until the next call -- like the reference's borrow)."""
+        p, n = self._scan(flt, device=False)
+        if n == 0:
+            return np.zeros((0, 2), dtype=self.id_dtype)
+        buf = (ctypes.c_char * (n * 2 * self.id_bytes)).from_address(p)
+        return np.frombuffer(buf, dtype=self.id_dtype).reshape(n, 2)
+
+    def scan(self):
+        return self.scan_filtered(None)
+
+    par_scan = scan
+    par_scan_filtered = scan_filtered
+
+    def scan_device(self, flt=None):
+        """Like scan_filtered but leaves the pairs on the device: returns (device pointer, count)."""
+        return self._scan(flt, device=True)
+
+    def iter(self):
+        """Layer::iter: (keys, ids) numpy copies of the tree in its current order."""
+        k, i, n, s = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int()
+        self._ck(lib().bp_layer_records(self._h, ctypes.byref(k), ctypes.byref(i), ctypes.byref(n), ctypes.byref(s)))
+        if n.value == 0:
+            return np.zeros(0, dtype=self.key_dtype), np.zeros(0, dtype=self.id_dtype)
+        kb = (ctypes.c_char * (n.value * np.dtype(self.key_dtype).itemsize)).from_address(k.value)
+        ib = (ctypes.c_char * (n.value * self.id_bytes)).from_address(i.value)
+        return np.frombuffer(kb, dtype=self.key_dtype).copy(), np.frombuffer(ib, dtype=self.id_dtype).copy()
+
+    records = iter
+
+    def records_device(self):
+        k, i, n, s = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int()
+        self._ck(lib().bp_layer_records_device(self._h, ctypes.byref(k), ctypes.byref(i), ctypes.byref(n), ctypes.byref(s)))
+        return k.value, i.value, n.value, bool(s.value)
+
+    def set_records(self, keys, ids, sorted_=False, on_device=False, n=None):
+        if on_device:
+            self._ck(lib().bp_layer_set_records(self._h, _dev_ptr(keys), _dev_ptr(ids), n, int(sorted_), 1))
+        else:
+            k = np.ascontiguousarray(keys, dtype=self.key_dtype)
+            i = np.ascontiguousarray(ids, dtype=self.id_dtype)
+            self._ck(lib().bp_layer_set_records(self._h, k.ctypes.data, i.ctypes.data, k.shape[0], int(sorted_), 0))
+
+    def __len__(self):
+        n = ctypes.c_size_t()
+        self._ck(lib().bp_layer_len(self._h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def sorted(self):
+        s = ctypes.c_int()
+        self._ck(lib().bp_layer_is_sorted(self._h, ctypes.byref(s)))
+        return bool(s.value)
+
+    @property
+    def min_depth(self):
+        d = ctypes.c_uint32()
+        self._ck(lib().bp_layer_min_depth(self._h, ctypes.byref(d)))
+        return d.value
+
+    # ---- instrumentation ------------------------------------------------------------------------
+    def set_profiling(self, enabled):
+        self._ck(lib().bp_layer_set_profiling(self._h, int(enabled)))
+
+    def reset_stats(self):
+        self._ck(lib().bp_layer_reset_stats(self._h))
+
+    def stats(self):
+        s = Stats()
+        self._ck(lib().bp_layer_stats(self._h, ctypes.byref(s)))
+        d = {k: getattr(s, k) for k in ("n_records", "n_invalid", "n_work_items", "n_raw_pairs", "n_pairs",
+                                        "sort_passes", "pair_sort_passes", "merged", "rescans", "launches_total")}
+        d["launches"] = {c: s.launches[i] for i, c in enumerate(_lib.KERNEL_CLASSES)}
+        d["kernel_ms"] = {c: s.kernel_ms[i] for i, c in enumerate(_lib.KERNEL_CLASSES)}
+        d["algo_bytes"] = {c: s.algo_bytes[i] for i, c in enumerate(_lib.KERNEL_CLASSES)}
+        return d
+
+
+class LayerBuilder:
+    """src/layer.rs:620-696."""
+
+    def __init__(self):
+        self._min_depth = 0
+        self._index_capacity = 0
+        self._collision_capacity = 0
+        self._test_capacity = 0
+        self._device = -1
+
+    @staticmethod
+    def new():
+        return LayerBuilder()
+
+    def with_min_depth(self, depth):
+        self._min_depth = depth
+        return self
+
+    def with_index_capacity(self, capacity):
+        self._index_capacity = capacity
+        return self
+
+    def with_collision_capacity(self, capacity):
+        self._collision_capacity = capacity
+        return self
+
+    def with_test_capacity(self, capacity):
+        self._test_capacity = capacity
+        return self
+
+    def with_device(self, device):
+        self._device = device
+        return self
+
+    def build(self, index=Index64_3D, id_type="u32"):
+        return Layer(index, id_type, self._min_depth, self._index_capacity, self._collision_capacity,
+                     self._test_capacity, self._device)
+
+
+def plan_radix_passes(mask):
+    sh = (ctypes.c_uint32 * 16)()
+    bt = (ctypes.c_uint32 * 16)()
+    n = lib().bp_plan_radix_passes(mask, sh, bt, 16)
+    return [(sh[i], bt[i]) for i in range(n)]
+
+
+def device_count():
+    n = ctypes.c_int()
+    st = lib().bp_device_count(ctypes.byref(n))
+    return n.value if st == 0 else 0

@@ -1,0 +1,181 @@
+/*
+ * bp.h -- C ABI of libbroadphase_b200.so, the B200-native (sm_100a CUDA) implementation of the
+ * broadphase-rs hot path: Layer::{clear, extend, merge, sort/par_sort, scan/par_scan,
+ * scan_filtered/par_scan_filtered, iter} for Index32_2D / Index64_2D / Index64_3D.
+ *
+ * The reference (zvxryb/broadphase-rs, crate zvxryb-broadphase 0.1.2) has no FFI of its own; its
+ * boundary is the generic Rust type Layer<Index, ID> (src/layer.rs:42-47, re-exported at
+ * src/lib.rs:80-82).  Each entry point below names the reference method it replaces (file:line
+ * relative to the reference root).  A Rust `Layer<Index, ID>` shim binds exactly these symbols
+ * (see INTEGRATION.md); the C++ mirror is broadphase-rs_b200/cpp/broadphase/layer.hpp and the
+ * Python mirror (used by the tests) is broadphase-rs_b200/layer.py.
+ *
+ * Conventions
+ *  - Every function returns a bp_status (0 = BP_OK).  The reference never returns errors: it
+ *    drops out-of-bounds objects silently (src/layer.rs:108-111) and aborts on allocation failure;
+ *    here allocation/CUDA failures are status codes and bp_layer_last_error() has the text.
+ *  - A layer is single-caller (`&mut self` in the reference): no internal locking.
+ *  - Result pointers (records, pairs) are owned by the layer and stay valid until the next
+ *    mutating call on it, like the `&'a Vec<(ID, ID)>` the reference returns.
+ *  - There is no CPU fallback: without a CUDA device bp_layer_create fails with BP_ERR_CUDA.
+ *  - Limits: fewer than 2^30 records per layer and fewer than 2^30 raw pairs per scan.
+ */
+#ifndef BP_H
+#define BP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BP_VERSION 100 /* 0.1.0 */
+
+typedef enum bp_status {
+    BP_OK = 0,
+    BP_ERR_INVALID_ARG = 1,
+    BP_ERR_CUDA = 2,      /* a CUDA runtime call failed (including "no device") */
+    BP_ERR_OOM = 3,       /* device or pinned-host allocation failed */
+    BP_ERR_TOO_LARGE = 4, /* more than 2^30 records / raw pairs */
+    BP_ERR_INTERNAL = 5,  /* a kernel reported an inconsistency (e.g. look-back time-out) */
+    BP_ERR_MISMATCH = 6   /* layers of different Index / ID types or devices */
+} bp_status;
+
+/* Index types -- src/index.rs:293-295 */
+typedef enum bp_index_kind {
+    BP_INDEX32_2D = 0, /* u32 key: 4 depth bits,  2 x 14 origin bits; bounds are 4 floats */
+    BP_INDEX64_2D = 1, /* u64 key: 5 depth bits,  2 x 29 origin bits; bounds are 4 floats */
+    BP_INDEX64_3D = 2  /* u64 key: 5 depth bits,  3 x 19 origin bits; bounds are 6 floats */
+} bp_index_kind;
+
+/* Device functors standing in for scan_filtered's `F: FnMut(ID, ID) -> bool` (src/layer.rs:456-460).
+ * The filter is called as filter(later_id, earlier_id) before duplicate removal, like the reference.
+ * Rust closures cannot cross the ABI; stateful filters are unsupported. */
+typedef enum bp_filter_kind {
+    BP_FILTER_NONE = 0,      /* |_, _| true  (scan / par_scan) */
+    BP_FILTER_ID_PARITY = 1, /* ((a ^ b) & 1) == 1 */
+    BP_FILTER_XOR_MASK = 2,  /* ((a ^ b) & arg) != 0 */
+    BP_FILTER_CATEGORY = 3   /* (cat[a] & msk[b]) != 0 && (cat[b] & msk[a]) != 0; table = n_table x {u32 cat, u32 msk}
+                                indexed by ID; IDs >= n_table act as all-ones */
+} bp_filter_kind;
+
+typedef struct bp_filter {
+    int32_t kind;          /* bp_filter_kind */
+    int32_t table_on_device; /* 1: `table` is a device pointer; 0: host pointer (copied per call) */
+    uint64_t arg;
+    const uint32_t *table;
+    size_t n_table;
+} bp_filter;
+
+/* LayerBuilder -- src/layer.rs:620-696 */
+typedef struct bp_layer_config {
+    int32_t index_kind;        /* bp_index_kind */
+    int32_t id_bytes;          /* 4 (u32 IDs) or 8 (u64 IDs) -- ObjectID, src/traits.rs:6-16 */
+    uint32_t min_depth;        /* with_min_depth         src/layer.rs:646-649 */
+    int32_t device;            /* CUDA device ordinal; -1 = current device */
+    size_t index_capacity;     /* with_index_capacity    src/layer.rs:652-655 (records) */
+    size_t collision_capacity; /* with_collision_capacity src/layer.rs:658-661 (pairs) */
+    size_t test_capacity;      /* with_test_capacity     src/layer.rs:664-667 (accepted, unused: queries are out of scope) */
+} bp_layer_config;
+
+typedef struct bp_layer bp_layer;
+
+/* kernel classes for bp_stats */
+enum {
+    BP_K_ENCODE = 0,    /* fused quantise + encode (extend) */
+    BP_K_SORT_HIST = 1, /* record sort: digit histograms */
+    BP_K_SORT_PASS = 2, /* record sort: one onesweep pass */
+    BP_K_MERGE = 3,     /* merge-path merge of two sorted runs */
+    BP_K_SCAN_RUNS = 4, /* scan: descendant-run lengths + compaction */
+    BP_K_SCAN_EMIT = 5, /* scan: load-balanced pair emission */
+    BP_K_PAIR_HIST = 6, /* pair sort: digit histograms */
+    BP_K_PAIR_PASS = 7, /* pair sort: one onesweep pass */
+    BP_K_PAIR_UNIQUE = 8, /* dedup + final pair layout */
+    BP_K_MISC = 9,      /* small helpers (histogram scans, masks, gathers) */
+    BP_K_COUNT = 10
+};
+
+typedef struct bp_stats {
+    uint64_t n_records;       /* tree length */
+    uint64_t n_invalid;       /* objects rejected by contains() since the last scan (src/layer.rs:108-111) */
+    uint64_t n_work_items;    /* (ancestor, descendant) record pairs visited by the last scan */
+    uint64_t n_raw_pairs;     /* pairs emitted before sort + dedup in the last scan */
+    uint64_t n_pairs;         /* unique pairs returned by the last scan */
+    uint32_t sort_passes;     /* radix passes of the last record sort (0 if merge-only / clean) */
+    uint32_t pair_sort_passes;
+    uint32_t merged;          /* 1 if the last sort finished with a merge-path merge */
+    uint32_t rescans;         /* 1 if the last scan needed the same-ID (inactive) re-emission */
+    uint64_t launches_total;  /* kernels launched by this layer since creation */
+    /* per kernel class, accumulated since bp_layer_reset_stats(); times only when profiling is on */
+    uint64_t launches[BP_K_COUNT];
+    double kernel_ms[BP_K_COUNT];
+    double algo_bytes[BP_K_COUNT]; /* algorithmic bytes summed over those launches */
+} bp_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* LayerBuilder::build -- src/layer.rs:670-695.  Starts empty with the sorted flag set (:681). */
+int bp_layer_create(const bp_layer_config *config, bp_layer **out);
+int bp_layer_destroy(bp_layer *layer);
+/* Run this layer's work on a caller-owned cudaStream_t (default: a stream the layer creates). */
+int bp_layer_set_stream(bp_layer *layer, void *cuda_stream);
+
+/* ---- Layer methods ---------------------------------------------------------------------------- */
+
+/* Layer::clear -- src/layer.rs:84-88: empties the tree, sets the sorted flag. */
+int bp_layer_clear(bp_layer *layer);
+
+/* Layer::extend -- src/layer.rs:94-121.  system_bounds: 2*D floats (min.., max..) on the host;
+ * bounds: n x 2*D floats (min.., max.. like Bounds{min, max}, src/geom.rs:84-87); ids: n x id_bytes.
+ * Appends, for every object inside system_bounds, one record per cell in the reference's order
+ * (object order; z outermost, then y, x innermost).  _host takes host pointers (copied to the
+ * device inside the call), _device takes device pointers (bounds 16-byte aligned). */
+int bp_layer_extend_host(bp_layer *layer, const float *system_bounds, const float *bounds, const void *ids, size_t n);
+int bp_layer_extend_device(bp_layer *layer, const float *system_bounds, const float *d_bounds, const void *d_ids, size_t n);
+
+/* Layer::merge -- src/layer.rs:127-138: min_depth = min(self, other); appends other's tree
+ * verbatim; clears the sorted flag.  When both trees were sorted the next sort is a merge-path
+ * merge instead of a full re-sort. */
+int bp_layer_merge(bp_layer *layer, const bp_layer *other);
+
+/* Layer::sort and Layer::par_sort -- src/layer.rs:146-165: no-op when the flag is set, else sorts
+ * the tree by (Index, ID) and sets the flag. */
+int bp_layer_sort(bp_layer *layer);
+
+/* Layer::scan / scan_filtered / par_scan / par_scan_filtered -- src/layer.rs:449-520: sorts if
+ * needed, then returns the sorted, duplicate-free vector of (later_id, earlier_id) pairs, each pair
+ * stored as two consecutive IDs of id_bytes.  filter == NULL means BP_FILTER_NONE.
+ * bp_layer_scan copies the pairs to pinned host memory; _device leaves them on the device. */
+int bp_layer_scan(bp_layer *layer, const bp_filter *filter, const void **out_pairs, size_t *out_count);
+int bp_layer_scan_device(bp_layer *layer, const bp_filter *filter, const void **out_d_pairs, size_t *out_count);
+
+/* Layer::iter -- src/layer.rs:79-81, and the state PartialEq compares (src/layer.rs:582-585):
+ * keys (4 or 8 bytes each) and ids as separate arrays + the sorted flag. */
+int bp_layer_records(bp_layer *layer, const void **out_keys, const void **out_ids, size_t *out_n, int *out_sorted);
+int bp_layer_records_device(bp_layer *layer, const void **out_d_keys, const void **out_d_ids, size_t *out_n, int *out_sorted);
+/* Replaces the tree (the serde Deserialize path of Layer, src/layer.rs:41; also how a
+ * multi-GPU exchange hands a shard its records).  Host or device pointers per `on_device`. */
+int bp_layer_set_records(bp_layer *layer, const void *keys, const void *ids, size_t n, int sorted, int on_device);
+
+int bp_layer_len(bp_layer *layer, size_t *out_n);
+int bp_layer_is_sorted(bp_layer *layer, int *out_sorted);
+int bp_layer_min_depth(const bp_layer *layer, uint32_t *out_min_depth);
+
+/* ---- instrumentation -------------------------------------------------------------------------- */
+int bp_layer_set_profiling(bp_layer *layer, int enabled); /* CUDA-event timing of every kernel launch */
+int bp_layer_reset_stats(bp_layer *layer);
+int bp_layer_stats(bp_layer *layer, bp_stats *out);
+const char *bp_layer_last_error(const bp_layer *layer);
+const char *bp_status_string(int status);
+int bp_version(void);
+int bp_device_count(int *out_count);
+
+/* Host-side radix planning, exposed for tests: given the mask of key bits that differ between
+ * any two records, writes up to 16 (shift, bits) digit descriptors and returns how many. */
+int bp_plan_radix_passes(uint64_t varying_mask, uint32_t *out_shift, uint32_t *out_bits, int max_passes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BP_H */

@@ -1,0 +1,89 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/bp.h declares, fails loudly without a GPU, and the host-side radix planner behaves."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "bp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bp_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(bp):
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    L = bp.lib()
+    for name in declared:
+        assert hasattr(L, name), "libbroadphase_b200.so does not export %s" % name
+    # and the ctypes table binds exactly the declared set
+    from broadphase_rs_b200 import _lib
+    assert sorted(_lib.SYMBOLS) == declared
+
+
+def test_version_and_status_strings(bp):
+    L = bp.lib()
+    assert L.bp_version() == 100
+    assert L.bp_status_string(0) == b"ok"
+    assert L.bp_status_string(2) == b"CUDA error"
+
+
+def test_no_cpu_fallback(bp):
+    """Without a CUDA device layer creation must fail with BP_ERR_CUDA (never compute on the host)."""
+    if bp.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(bp.BpError) as e:
+        bp.Layer(bp.Index64_3D, "u32")
+    assert e.value.status == 2
+
+
+def test_invalid_arguments(bp):
+    from broadphase_rs_b200._lib import LayerConfig
+    L = bp.lib()
+    h = ctypes.c_void_p()
+    assert L.bp_layer_create(None, ctypes.byref(h)) == 1
+    cfg = LayerConfig(7, 4, 0, -1, 0, 0, 0)
+    assert L.bp_layer_create(ctypes.byref(cfg), ctypes.byref(h)) == 1
+    cfg = LayerConfig(2, 3, 0, -1, 0, 0, 0)
+    assert L.bp_layer_create(ctypes.byref(cfg), ctypes.byref(h)) == 1
+    assert L.bp_layer_destroy(None) == 0
+
+
+def test_radix_planner(bp):
+    plan = bp.plan_radix_passes
+    assert plan(0) == []
+    assert plan(0xFF) == [(0, 8)]
+    assert plan(0x1) == [(0, 1)]
+    # Index64_3D, every record at depth 7: only the top 21 origin bits vary -> 3 passes, not 8
+    mask = ((1 << 21) - 1) << (5 + 57 - 21)
+    p = plan(mask)
+    assert len(p) == 3 and p[0][0] == 41 and sum(b for _, b in p) == 21
+    # multi-depth keys: depth bits + top origin bits, with a gap in between
+    mask = 0xF | (((1 << 39) - 1) << 23)
+    p = plan(mask)
+    assert p[0] == (0, 4) and len(p) == 6
+    covered = 0
+    for s, b in p:
+        assert 1 <= b <= 8
+        covered |= ((1 << b) - 1) << s
+    assert covered & mask == mask
+    # full 62-bit key: 8 passes
+    assert len(plan((1 << 62) - 1)) == 8
+    assert len(plan((1 << 64) - 1)) == 8
+    for s, b in plan((1 << 64) - 1):
+        assert s + b <= 64
+
+
+def test_scene_recipes_are_deterministic(bp):
+    a = bp.scenes.uniform_cubes(1000, 2)
+    b = bp.scenes.uniform_cubes(1000, 2)
+    assert (a["bounds"] == b["bounds"]).all() and a["bounds"].dtype.name == "float32"
+    c = bp.scenes.lognormal_cubes(1000, 3)
+    assert (c["bounds"][:, 3:] >= c["bounds"][:, :3]).all() and (c["bounds"][:, 3:] <= 1.0).all()
+    d = bp.scenes.example_circles(1000, 1)
+    assert d["kind"] == 0 and d["min_depth"] == 4 and d["bounds"].shape == (1000, 4)

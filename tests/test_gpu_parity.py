@@ -1,0 +1,355 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Integer/byte work: the bar is bit-exact equality of the record sequence after extend, of the
+record sequence after sort, and of the pair sequence after scan (tests/test_layer.rs:25-124 of the
+reference make the same three comparisons against golden files)."""
+import numpy as np
+import pytest
+
+from oracle import cpu_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+KINDS = [0, 1, 2]
+
+
+def _random_scene(kind, n, seed, multi_bounds=False, span=0.05, shuffle_ids=True):
+    rng = np.random.Generator(np.random.Philox(seed))
+    dim = co.DIM[kind]
+    sysb = np.concatenate([np.full(dim, -3.0), np.full(dim, 5.0)]).astype(np.float32)
+    size = (8.0 * span * rng.random((n, dim)) ** 3).astype(np.float32)
+    mn = (-3.0 + rng.random((n, dim)) * (8.0 - size)).astype(np.float32)
+    mx = (mn + size).astype(np.float32)
+    bounds = np.concatenate([mn, mx], axis=1).astype(np.float32)
+    bounds[::97, 0] = -3.5                       # outside the system -> dropped
+    bounds[5::89, dim:] = bounds[5::89, :dim]    # zero extent
+    if multi_bounds:
+        ids = rng.integers(0, max(2, n // 3), size=n).astype(np.uint32)
+    elif shuffle_ids:
+        ids = rng.permutation(n).astype(np.uint32)
+    else:
+        ids = np.arange(n, dtype=np.uint32)
+    return sysb, bounds, ids
+
+
+def _pair(bp, kind, id_bytes, min_depth):
+    g = bp.LayerBuilder().with_min_depth(min_depth).build(kind, "u32" if id_bytes == 4 else "u64")
+    o = co.OracleLayer(kind, id_bytes, min_depth)
+    return g, o
+
+
+def _assert_records_equal(g, o):
+    gk, gi = g.iter()
+    ok, oi = o.records()
+    assert gk.shape == ok.shape, (gk.shape, ok.shape)
+    assert (gk.astype(np.uint64) == ok).all(), "keys differ at %s" % np.flatnonzero(gk.astype(np.uint64) != ok)[:5]
+    assert (gi.astype(np.uint64) == oi).all(), "ids differ at %s" % np.flatnonzero(gi.astype(np.uint64) != oi)[:5]
+    assert g.sorted == o.sorted
+    assert len(g) == len(o)
+
+
+def _assert_pairs_equal(gp, op):
+    assert gp.shape == op.shape, (gp.shape, op.shape)
+    assert (gp.astype(np.uint64) == op).all()
+
+
+def _is_strictly_increasing(p):
+    if p.shape[0] < 2:
+        return True
+    a, b = p[:, 0].astype(np.uint64), p[:, 1].astype(np.uint64)
+    return bool(((a[1:] > a[:-1]) | ((a[1:] == a[:-1]) & (b[1:] > b[:-1]))).all())
+
+
+# ---- extend -> sort -> scan, every index kind / ID width ----------------------------------------------
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("id_bytes", [4, 8])
+@pytest.mark.parametrize("min_depth", [0, 3])
+def test_extend_sort_scan_small(bp, kind, id_bytes, min_depth):
+    sysb, bounds, ids = _random_scene(kind, 5000, 100 + kind, span=0.06)
+    if id_bytes == 8:
+        ids = ids.astype(np.uint64) * np.uint64(0x100000001) + np.uint64(1 << 41)
+    g, o = _pair(bp, kind, id_bytes, min_depth)
+    g.extend(sysb, bounds, ids)
+    o.extend(sysb, bounds, ids)
+    _assert_records_equal(g, o)          # tests/test_layer.rs:25-40 `extend`
+    g.sort()
+    o.sort()
+    _assert_records_equal(g, o)          # tests/test_layer.rs:56-90 `sort` / `par_sort`
+    gp = g.scan()
+    op = o.scan()
+    _assert_pairs_equal(gp, op)          # tests/test_layer.rs:92-124 `scan` / `par_scan`
+    assert gp.shape[0] > 0 and _is_strictly_increasing(gp)
+    st = g.stats()
+    assert st["n_raw_pairs"] == o.num_raw_collisions
+    assert st["n_pairs"] == gp.shape[0]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_filters(bp, kind):
+    sysb, bounds, ids = _random_scene(kind, 4000, 7, span=0.08)
+    g, o = _pair(bp, kind, 4, 0)
+    g.extend(sysb, bounds, ids)
+    o.extend(sysb, bounds, ids)
+    rng = np.random.Generator(np.random.Philox(5))
+    table = rng.integers(0, 16, size=(3000, 2)).astype(np.uint32)  # ids >= 3000 act as all-ones
+    for gf, of in [(bp.ScanFilter.id_parity(), (co.FILTER_ID_PARITY, 0, None)),
+                   (bp.ScanFilter.xor_mask(6), (co.FILTER_XOR_MASK, 6, None)),
+                   (bp.ScanFilter.category(table), (co.FILTER_CATEGORY, 0, table)),
+                   (None, (co.FILTER_NONE, 0, None))]:
+        gp = g.scan_filtered(gf).copy()
+        op = o.scan(*of)
+        _assert_pairs_equal(gp, op)
+        assert _is_strictly_increasing(gp)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("id_bytes", [4, 8])
+def test_multi_bounds_ids_trigger_inactive_records(bp, kind, id_bytes):
+    """Several bounds per ID (static geometry, src/layer.rs:92-93): nested bounds of one ID make
+    records the reference skips entirely (src/layer.rs:562-564)."""
+    sysb, bounds, ids = _random_scene(kind, 6000, 21, multi_bounds=True, span=0.15)
+    ids = ids.astype(np.uint64 if id_bytes == 8 else np.uint32)
+    g, o = _pair(bp, kind, id_bytes, 0)
+    g.extend(sysb, bounds, ids)
+    o.extend(sysb, bounds, ids)
+    for flt, of in [(None, (co.FILTER_NONE, 0, None)), (bp.ScanFilter.id_parity(), (co.FILTER_ID_PARITY, 0, None))]:
+        gp = g.scan_filtered(flt).copy()
+        op = o.scan(*of)
+        _assert_pairs_equal(gp, op)
+    _assert_records_equal(g, o)
+    assert g.stats()["rescans"] == 1
+
+
+def test_edge_case_boxes(bp):
+    sc = bp.scenes.edge_cases_3d()
+    for min_depth in (0, 2):
+        g, o = _pair(bp, sc["kind"], 4, min_depth)
+        g.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+        o.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+        _assert_records_equal(g, o)
+        _assert_pairs_equal(g.scan(), o.scan())
+        _assert_records_equal(g, o)
+        assert g.stats()["n_invalid"] == 0  # cleared by scan, like self.invalid (src/layer.rs:468)
+
+
+def test_empty_and_flags(bp):
+    g, o = _pair(bp, 2, 4, 0)
+    assert g.sorted and len(g) == 0                       # src/layer.rs:681
+    assert g.scan().shape == (0, 2)
+    sc = bp.scenes.uniform_cubes(300, 1)
+    g.extend(sc["sys_bounds"], sc["bounds"][:0], sc["ids"][:0])
+    assert g.sorted and len(g) == 0                       # nothing appended: flag untouched
+    outside = sc["bounds"][:4] + 10.0
+    g.extend(sc["sys_bounds"], outside, sc["ids"][:4])
+    assert g.sorted and len(g) == 0                       # every object rejected (src/layer.rs:108-111)
+    g.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    o.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    assert not g.sorted
+    _assert_records_equal(g, o)
+    g.clear()
+    assert g.sorted and len(g) == 0                       # src/layer.rs:84-88
+    g.extend(sc["sys_bounds"], sc["bounds"][:1], sc["ids"][:1])
+    assert g.scan().shape == (0, 2) or len(g) > 1         # a single object has no pairs
+
+
+def test_multiple_extends_and_ragged_sizes(bp):
+    """Ragged batch sizes around the tile sizes of the kernels (1024 objects, 2048/4608-record tiles)."""
+    sysb, bounds, ids = _random_scene(2, 9000, 33, span=0.05, shuffle_ids=False)
+    g, o = _pair(bp, 2, 4, 0)
+    cuts = [0, 1, 2, 1023, 1024, 1025, 3071, 4097, 9000]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        g.extend(sysb, bounds[a:b], ids[a:b])
+        o.extend(sysb, bounds[a:b], ids[a:b])
+    _assert_records_equal(g, o)
+    _assert_pairs_equal(g.scan(), o.scan())
+    _assert_records_equal(g, o)
+
+
+def test_extend_after_sort_uses_prefix_merge(bp):
+    sysb, bounds, ids = _random_scene(2, 8000, 34, span=0.05)
+    g, o = _pair(bp, 2, 4, 0)
+    g.extend(sysb, bounds[:5000], ids[:5000])
+    o.extend(sysb, bounds[:5000], ids[:5000])
+    g.sort()
+    o.sort()
+    g.extend(sysb, bounds[5000:], ids[5000:])
+    o.extend(sysb, bounds[5000:], ids[5000:])
+    _assert_records_equal(g, o)           # sorted prefix followed by the new unsorted tail
+    g.sort()
+    o.sort()
+    _assert_records_equal(g, o)
+    assert g.stats()["merged"] == 1
+    _assert_pairs_equal(g.scan(), o.scan())
+    # a short sorted prefix followed by a long tail takes the full re-sort path instead
+    g2, o2 = _pair(bp, 2, 4, 0)
+    g2.extend(sysb, bounds[:300], ids[:300]); o2.extend(sysb, bounds[:300], ids[:300])
+    g2.sort(); o2.sort()
+    g2.extend(sysb, bounds[300:], ids[300:]); o2.extend(sysb, bounds[300:], ids[300:])
+    g2.sort(); o2.sort()
+    _assert_records_equal(g2, o2)
+    assert g2.stats()["merged"] == 0
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("id_bytes", [4, 8])
+def test_merge_static_into_dynamic(bp, kind, id_bytes):
+    """Layer::merge (src/layer.rs:127-138): appended verbatim, min_depth lowered, flag cleared; the
+    following sort + scan equal the oracle's full re-sort."""
+    sysb, bounds, ids = _random_scene(kind, 12000, 55, span=0.05)
+    ids = ids.astype(np.uint64 if id_bytes == 8 else np.uint32)
+    gs, os_ = _pair(bp, kind, id_bytes, 2)
+    gs.extend(sysb, bounds[:9000], ids[:9000]); os_.extend(sysb, bounds[:9000], ids[:9000])
+    gs.sort(); os_.sort()
+    gd, od = _pair(bp, kind, id_bytes, 3)
+    gd.extend(sysb, bounds[9000:], ids[9000:]); od.extend(sysb, bounds[9000:], ids[9000:])
+    gd.sort(); od.sort()
+    gd.merge(gs); od.merge(os_)
+    assert gd.min_depth == 2 and not gd.sorted
+    _assert_records_equal(gd, od)
+    gd.sort(); od.sort()
+    _assert_records_equal(gd, od)
+    assert gd.stats()["merged"] == 1
+    _assert_pairs_equal(gd.scan(), od.scan())
+    _assert_records_equal(gs, os_)        # the static layer is untouched
+    # merging an unsorted layer, and merging into an unsorted layer
+    ga, oa = _pair(bp, kind, id_bytes, 0)
+    gb, ob = _pair(bp, kind, id_bytes, 0)
+    ga.extend(sysb, bounds[:2000], ids[:2000]); oa.extend(sysb, bounds[:2000], ids[:2000])
+    gb.extend(sysb, bounds[2000:5000], ids[2000:5000]); ob.extend(sysb, bounds[2000:5000], ids[2000:5000])
+    ga.merge(gb); oa.merge(ob)
+    _assert_records_equal(ga, oa)
+    _assert_pairs_equal(ga.scan(), oa.scan())
+    _assert_records_equal(ga, oa)
+    # merging an empty layer still clears the flag (src/layer.rs:137)
+    ge, _ = _pair(bp, kind, id_bytes, 0)
+    ga.merge(ge)
+    assert not ga.sorted
+    ga.sort()
+    assert ga.sorted
+
+
+def test_set_records_roundtrip_and_scan(bp):
+    sysb, bounds, ids = _random_scene(2, 3000, 77, span=0.08)
+    o = co.OracleLayer(2, 4, 0)
+    o.extend(sysb, bounds, ids)
+    k, i = o.records()
+    g = bp.Layer(2, "u32")
+    g.set_records(k, i.astype(np.uint32), sorted_=False)
+    gk, gi = g.iter()
+    assert (gk == k).all() and (gi == i).all() and not g.sorted
+    _assert_pairs_equal(g.scan(), o.scan())
+    _assert_records_equal(g, o)
+
+
+# ---- BASELINE.json configs at sizes the oracle finishes in seconds --------------------------------------
+
+def _run_scene(bp, sc, id_type="u32", flt=None, oflt=(0, 0, None), check_unsorted=True):
+    g = bp.LayerBuilder().with_min_depth(sc["min_depth"]).build(sc["kind"], id_type)
+    o = co.OracleLayer(sc["kind"], 4 if id_type == "u32" else 8, sc["min_depth"])
+    g.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    o.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    if check_unsorted:
+        _assert_records_equal(g, o)
+    g.par_sort()
+    o.par_sort()
+    _assert_records_equal(g, o)
+    gp = g.par_scan_filtered(flt)
+    op = o.par_scan(*oflt)
+    _assert_pairs_equal(gp, op)
+    assert _is_strictly_increasing(gp)
+    return g, o, gp
+
+
+def test_config1_example_circles(bp):
+    """BASELINE config 1: 10,000 circles, Index32_2D, min_depth 4, par_scan."""
+    g, o, gp = _run_scene(bp, bp.scenes.example_circles(10_000, 1))
+    assert gp.shape[0] > 1000
+
+
+def test_config2_uniform_1m(bp):
+    """BASELINE config 2 at full size: 2^20 uniform cubes, Index64_3D."""
+    g, o, gp = _run_scene(bp, bp.scenes.uniform_cubes(1 << 20, 2))
+    st = g.stats()
+    assert st["sort_passes"] <= 4          # all keys at one depth: 21 varying origin bits
+    assert 3.0 < st["n_records"] / (1 << 20) < 4.0
+
+
+def test_config3_lognormal_parity_filter(bp):
+    """BASELINE config 3 recipe at 2^19 objects (multi-depth keys, skewed run lengths), ID-parity filter."""
+    sc = bp.scenes.lognormal_cubes(1 << 19, 3)
+    g, o, gp = _run_scene(bp, sc, flt=bp.ScanFilter.id_parity(), oflt=(co.FILTER_ID_PARITY, 0, None))
+    assert ((gp[:, 0] ^ gp[:, 1]) & 1).all()
+
+
+def test_gen_boxes_reference_test_scene(bp):
+    """The reference's own test-scene recipe (tests/gen_test_scenes.py: density 1/1000, sizes 1-10)."""
+    for n in (100, 1000, 10_000, 100_000):
+        _run_scene(bp, bp.scenes.gen_boxes(n, 0))
+
+
+def test_config4_static_plus_dynamic_frames(bp):
+    """BASELINE config 4 shape at reduced size: a static layer sorted once, a fresh dynamic layer per
+    frame merged with it."""
+    ns, nd = 1 << 18, 1 << 14
+    st = bp.scenes.uniform_cubes(ns, 4)
+    gs = bp.Layer(2, "u32"); os_ = co.OracleLayer(2, 4, 0)
+    gs.extend(st["sys_bounds"], st["bounds"], st["ids"]); os_.extend(st["sys_bounds"], st["bounds"], st["ids"])
+    gs.sort(); os_.par_sort()
+    gd = bp.Layer(2, "u32"); od = co.OracleLayer(2, 4, 0)
+    for frame in range(3):
+        dy = bp.scenes.uniform_cubes(nd, 5 + frame, id_base=ns, edge_factor=0.4 * (ns / nd) ** (-1.0 / 3.0))
+        gd.clear(); od.clear()
+        gd.extend(dy["sys_bounds"], dy["bounds"], dy["ids"]); od.extend(dy["sys_bounds"], dy["bounds"], dy["ids"])
+        gd.sort(); od.par_sort()
+        gd.merge(gs); od.merge(os_)
+        gp = gd.par_scan(); op = od.par_scan()
+        _assert_pairs_equal(gp, op)
+        _assert_records_equal(gd, od)
+        assert gd.stats()["merged"] == 1
+
+
+def test_non_ascending_ids_need_id_passes(bp):
+    """IDs in random order: the sort must order equal keys by ID (derived Ord of (Index, ID))."""
+    sc = bp.scenes.uniform_cubes(200_000, 9)
+    rng = np.random.Generator(np.random.Philox(1))
+    sc["ids"] = rng.permutation(200_000).astype(np.uint32)
+    sc["bounds"][:, 3:] = np.minimum(sc["bounds"][:, :3] + 0.02, 1.0)  # bigger cubes: many equal keys
+    g, o, gp = _run_scene(bp, sc)
+    assert g.stats()["sort_passes"] >= 4
+
+
+# ---- full-size properties (no oracle): BASELINE config 3 at 2^24 objects -----------------------------
+
+def test_config3_full_size_properties(bp):
+    import torch
+    n = 1 << 24
+    sc = bp.scenes.lognormal_cubes(n, 3)
+    g = bp.Layer(2, "u32")
+    db = torch.from_numpy(sc["bounds"]).cuda()
+    di = torch.from_numpy(sc["ids"].astype(np.int32)).cuda()
+    g.extend_device(sc["sys_bounds"], db, di, n)
+    g.par_sort()
+    kp, ip, nrec, is_sorted = g.records_device()
+    assert is_sorted and nrec > 4 * n
+    keys, ids = g.iter()
+    k64 = keys.astype(np.uint64)
+    nondecreasing = (k64[1:] > k64[:-1]) | ((k64[1:] == k64[:-1]) & (ids[1:] >= ids[:-1]))
+    assert nondecreasing.all()                              # tests/test_layer.rs:42-54, unique = false
+    # the multiset of records is preserved by the sort: order-independent checksums
+    g2 = bp.Layer(2, "u32")
+    g2.extend_device(sc["sys_bounds"], db, di, n)
+    k2, i2 = g2.iter()
+    assert k2.shape == keys.shape
+    assert int(k2.sum(dtype=np.uint64)) == int(keys.sum(dtype=np.uint64))
+    assert int((k2 ^ (i2.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15))).sum(dtype=np.uint64)) == \
+        int((keys ^ (ids.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15))).sum(dtype=np.uint64))
+    p1 = g.par_scan_filtered(bp.ScanFilter.id_parity()).copy()
+    assert p1.shape[0] > 0 and _is_strictly_increasing(p1)   # sorted + unique
+    assert ((p1[:, 0] ^ p1[:, 1]) & 1).all()                 # filter applied
+    p2 = g.par_scan_filtered(bp.ScanFilter.id_parity())
+    assert p1.shape == p2.shape and (p1 == p2).all()         # idempotent
+    # the filtered result is exactly the subset of the unfiltered one that passes the filter
+    pall = g.par_scan()
+    sub = pall[((pall[:, 0] ^ pall[:, 1]) & 1) == 1]
+    assert sub.shape == p1.shape and (sub == p1).all()
