@@ -1,0 +1,165 @@
+// broadphase/layer.hpp -- C++ host-side mirror of the reference crate's public interface for the hot
+// path, over the C ABI of include/bp.h.  (The reference is Rust; no Rust toolchain exists in this
+// image, so the host side above the C ABI is written in C++ with the crate's names, argument
+// meaning and implicit behaviour.  The equivalent Rust shim is in INTEGRATION.md.)
+//
+//   reference (Rust)                                       here (C++)
+//   ------------------------------------------------------------------------------------------------
+//   broadphase::Index32_2D / Index64_2D / Index64_3D       broadphase::Index32_2D / Index64_2D / Index64_3D
+//   broadphase::Bounds<Point3<f32>>{min, max}              broadphase::Bounds<3>{min, max}
+//   LayerBuilder::new().with_min_depth(4).build()          LayerBuilder().with_min_depth(4).build<Index, ID>()
+//   layer.clear()                          src/layer.rs:84  layer.clear()
+//   layer.extend(system_bounds, iter)      src/layer.rs:94  layer.extend(system_bounds, first, last) / (bounds*, ids*, n)
+//   layer.merge(&other)                    src/layer.rs:127 layer.merge(other)
+//   layer.sort() / par_sort()              src/layer.rs:146 layer.sort() / par_sort()
+//   layer.scan() / par_scan()              src/layer.rs:449 layer.scan() / par_scan()   -> const std::vector-like view
+//   layer.scan_filtered(f) / par_..        src/layer.rs:456 layer.scan_filtered(Filter) / par_scan_filtered(Filter)
+//   layer.iter()                           src/layer.rs:79  layer.iter()
+//
+// Errors: the reference never returns errors from these methods; allocation failure aborts.  Here a
+// failed C-ABI call throws broadphase::Error (status + message).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../../include/bp.h"
+
+namespace broadphase {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string &m) : std::runtime_error(std::string(bp_status_string(s)) + ": " + m), status(s) {}
+};
+
+// index tags -- src/index.rs:293-295
+struct Index32_2D { static constexpr int KIND = BP_INDEX32_2D, DIM = 2; typedef uint32_t key_type; };
+struct Index64_2D { static constexpr int KIND = BP_INDEX64_2D, DIM = 2; typedef uint64_t key_type; };
+struct Index64_3D { static constexpr int KIND = BP_INDEX64_3D, DIM = 3; typedef uint64_t key_type; };
+
+// Bounds -- src/geom.rs:84-87: min and max are inclusive; memory layout = 2*DIM floats (min.., max..)
+template <int DIM> struct Bounds {
+    float min[DIM];
+    float max[DIM];
+};
+
+// device functors for scan_filtered -- include/bp.h bp_filter_kind
+struct Filter {
+    bp_filter f{BP_FILTER_NONE, 0, 0, nullptr, 0};
+    static Filter none() { return Filter(); }
+    static Filter id_parity() { Filter r; r.f.kind = BP_FILTER_ID_PARITY; return r; }
+    static Filter xor_mask(uint64_t m) { Filter r; r.f.kind = BP_FILTER_XOR_MASK; r.f.arg = m; return r; }
+    static Filter category(const uint32_t *table, size_t n, bool on_device = false) {
+        Filter r; r.f.kind = BP_FILTER_CATEGORY; r.f.table = table; r.f.n_table = n; r.f.table_on_device = on_device; return r;
+    }
+};
+
+// a borrowed view of the layer's result buffer (the reference returns &Vec<(ID, ID)>)
+template <class ID> struct PairView {
+    const std::pair<ID, ID> *data_ = nullptr;
+    size_t size_ = 0;
+    const std::pair<ID, ID> *begin() const { return data_; }
+    const std::pair<ID, ID> *end() const { return data_ + size_; }
+    size_t size() const { return size_; }
+    bool empty() const { return size_ == 0; }
+    const std::pair<ID, ID> &operator[](size_t i) const { return data_[i]; }
+};
+
+template <class Index, class ID> class Layer {
+    static_assert(sizeof(ID) == 4 || sizeof(ID) == 8, "ObjectID must be a 32- or 64-bit integer (src/traits.rs:6-16)");
+    static_assert(sizeof(std::pair<ID, ID>) == 2 * sizeof(ID), "pair layout");
+    bp_layer *h_ = nullptr;
+    void ck(int st) const {
+        if (st != BP_OK) throw Error(st, h_ ? bp_layer_last_error(h_) : "");
+    }
+    friend class LayerBuilder;
+    explicit Layer(const bp_layer_config &cfg) {
+        int st = bp_layer_create(&cfg, &h_);
+        if (st != BP_OK) throw Error(st, "bp_layer_create");
+    }
+
+public:
+    typedef typename Index::key_type key_type;
+    Layer(Layer &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    Layer &operator=(Layer &&o) noexcept { std::swap(h_, o.h_); return *this; }
+    Layer(const Layer &) = delete;
+    Layer &operator=(const Layer &) = delete;
+    ~Layer() { if (h_) bp_layer_destroy(h_); }
+
+    bp_layer *handle() const { return h_; }
+
+    void clear() { ck(bp_layer_clear(h_)); }                                             // src/layer.rs:84-88
+
+    // extend from parallel host arrays
+    void extend(const Bounds<Index::DIM> &system_bounds, const Bounds<Index::DIM> *bounds, const ID *ids, size_t n) {
+        ck(bp_layer_extend_host(h_, system_bounds.min, bounds ? bounds[0].min : nullptr, ids, n)); // src/layer.rs:94-121
+    }
+    // extend from an iterator of (Bounds, ID), like the reference's `objects: Iter`
+    template <class It> void extend(const Bounds<Index::DIM> &system_bounds, It first, It last) {
+        std::vector<Bounds<Index::DIM>> b;
+        std::vector<ID> ids;
+        for (; first != last; ++first) {
+            b.push_back(first->first);
+            ids.push_back(first->second);
+        }
+        extend(system_bounds, b.data(), ids.data(), b.size());
+    }
+    // extend from device-resident arrays (no host round trip)
+    void extend_device(const Bounds<Index::DIM> &system_bounds, const float *d_bounds, const ID *d_ids, size_t n) {
+        ck(bp_layer_extend_device(h_, system_bounds.min, d_bounds, d_ids, n));
+    }
+
+    void merge(const Layer &other) { ck(bp_layer_merge(h_, other.h_)); }                 // src/layer.rs:127-138
+    void sort() { ck(bp_layer_sort(h_)); }                                               // src/layer.rs:157-165
+    void par_sort() { ck(bp_layer_sort(h_)); }                                           // src/layer.rs:146-152
+
+    PairView<ID> scan_filtered(const Filter &filter) {                                   // src/layer.rs:456-477
+        const void *p = nullptr;
+        size_t n = 0;
+        ck(bp_layer_scan(h_, &filter.f, &p, &n));
+        return PairView<ID>{static_cast<const std::pair<ID, ID> *>(p), n};
+    }
+    PairView<ID> scan() { return scan_filtered(Filter::none()); }                        // src/layer.rs:449-453
+    PairView<ID> par_scan() { return scan_filtered(Filter::none()); }                    // src/layer.rs:482-487
+    PairView<ID> par_scan_filtered(const Filter &f) { return scan_filtered(f); }         // src/layer.rs:489-520
+
+    // Layer::iter -- src/layer.rs:79-81
+    std::vector<std::pair<key_type, ID>> iter() {
+        const void *k = nullptr, *i = nullptr;
+        size_t n = 0;
+        int sorted = 0;
+        ck(bp_layer_records(h_, &k, &i, &n, &sorted));
+        std::vector<std::pair<key_type, ID>> out(n);
+        for (size_t r = 0; r < n; ++r) out[r] = {static_cast<const key_type *>(k)[r], static_cast<const ID *>(i)[r]};
+        return out;
+    }
+    size_t len() { size_t n = 0; ck(bp_layer_len(h_, &n)); return n; }
+    bool is_sorted() { int s = 0; ck(bp_layer_is_sorted(h_, &s)); return s != 0; }
+    uint32_t min_depth() const { uint32_t d = 0; bp_layer_min_depth(h_, &d); return d; }
+    bp_stats stats() { bp_stats s; ck(bp_layer_stats(h_, &s)); return s; }
+};
+
+// LayerBuilder -- src/layer.rs:620-696
+class LayerBuilder {
+    bp_layer_config cfg_{};
+
+public:
+    LayerBuilder() { cfg_.device = -1; }
+    LayerBuilder &with_min_depth(uint32_t depth) { cfg_.min_depth = depth; return *this; }
+    LayerBuilder &with_index_capacity(size_t c) { cfg_.index_capacity = c; return *this; }
+    LayerBuilder &with_collision_capacity(size_t c) { cfg_.collision_capacity = c; return *this; }
+    LayerBuilder &with_test_capacity(size_t c) { cfg_.test_capacity = c; return *this; }
+    LayerBuilder &with_device(int device) { cfg_.device = device; return *this; }
+    template <class Index, class ID> Layer<Index, ID> build() const {
+        bp_layer_config c = cfg_;
+        c.index_kind = Index::KIND;
+        c.id_bytes = (int32_t)sizeof(ID);
+        return Layer<Index, ID>(c);
+    }
+};
+
+} // namespace broadphase

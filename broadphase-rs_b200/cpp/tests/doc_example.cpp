@@ -1,0 +1,28 @@
+// The reference's crate-level doc example (src/lib.rs:24-47) written against the C++ mirror.
+// Built by tests/test_cpp_mirror.py; exits 0 when the scan finds the one expected pair.
+#include <cstdio>
+
+#include "../broadphase/layer.hpp"
+
+using namespace broadphase;
+
+int main() {
+    try {
+        auto layer = LayerBuilder().with_min_depth(0).build<Index64_3D, uint64_t>();
+        Bounds<3> system_bounds{{-10.f, -10.f, -10.f}, {10.f, 10.f, 10.f}};
+        std::vector<std::pair<Bounds<3>, uint64_t>> objects = {
+            {Bounds<3>{{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}}, 7},
+            {Bounds<3>{{0.5f, 0.5f, 0.5f}, {1.5f, 1.5f, 1.5f}}, 9},
+            {Bounds<3>{{-9.f, -9.f, -9.f}, {-8.f, -8.f, -8.f}}, 11},
+        };
+        layer.clear();
+        layer.extend(system_bounds, objects.begin(), objects.end());
+        auto pairs = layer.scan();
+        std::printf("records=%zu pairs=%zu\n", layer.len(), pairs.size());
+        for (const auto &p : pairs) std::printf("(%llu, %llu)\n", (unsigned long long)p.first, (unsigned long long)p.second);
+        return (pairs.size() == 1 && pairs[0].first == 9 && pairs[0].second == 7) ? 0 : 1;
+    } catch (const Error &e) {
+        std::printf("error: %s\n", e.what());
+        return e.status == BP_ERR_CUDA ? 77 : 2; // 77: no GPU here
+    }
+}

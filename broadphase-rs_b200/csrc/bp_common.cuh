@@ -82,7 +82,10 @@ template <class T> __host__ __device__ __forceinline__ typename T::key_t level_m
 // Largest key a descendant-or-equal of `k` can have: every record j > i with key_j <= this value
 // lies in cell(i) (the contiguity lemma of DESIGN.md; reference semantics src/layer.rs:550-573).
 template <class T> __host__ __device__ __forceinline__ typename T::key_t run_upper_key(typename T::key_t k) {
-    return (typename T::key_t)(k | ~level_mask<T>(key_depth<T>(k)));
+    typedef typename T::key_t K;
+    constexpr int total = T::DIM * T::AXIS_BITS + T::DEPTH_BITS; // bits a key uses (the rest are always 0)
+    const K used = total >= (int)(8 * sizeof(K)) ? (K) ~(K)0 : (K)((((uint64_t)1) << (total & 63)) - 1);
+    return (K)(k | (~level_mask<T>(key_depth<T>(k)) & used));
 }
 
 // ---------------------------------------------------------------------------------------------

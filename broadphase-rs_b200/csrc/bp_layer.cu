@@ -478,7 +478,9 @@ template <int KIND, class IdT> struct Impl {
         if (R >= 2 && tail > 0) {
             if (prefix == 0) {
                 if (!L->tail_sorted) TRY(sort_range(L, 0, R, L->tail_nonmono));
-            } else if (prefix * 8 >= R) {
+            } else if (L->tail_sorted || prefix * 8 >= R) {
+                // two sorted runs: one linear merge.  An unsorted tail is radix-sorted on its own first,
+                // unless the sorted prefix is so short that re-sorting everything is cheaper.
                 if (!L->tail_sorted) TRY(sort_range(L, prefix, tail, L->tail_nonmono));
                 TRY(merge_runs(L, prefix, tail));
             } else {
