@@ -26,12 +26,14 @@ using namespace bp;
 namespace {
 
 // ---- tunables -------------------------------------------------------------------------------------
-template <class K, class V> struct PassTune { // threads, items per thread of radix_pass_kernel
-    static constexpr int THREADS = 384, ITEMS = 12;
+template <class K, class V> struct PassTune { // threads, items per thread, min CTAs/SM of radix_pass_kernel
+    static constexpr int THREADS = 384, ITEMS = 12, MINB = 2;
 };
-template <> struct PassTune<uint32_t, uint32_t> { static constexpr int THREADS = 512, ITEMS = 16; };
-template <> struct PassTune<uint64_t, NoVal> { static constexpr int THREADS = 384, ITEMS = 12; };
-template <> struct PassTune<uint64_t, uint64_t> { static constexpr int THREADS = 256, ITEMS = 12; };
+// tuned with tools/sort_bench on B200 (profiles/r1_sort_tuning.md)
+template <> struct PassTune<uint64_t, uint32_t> { static constexpr int THREADS = 384, ITEMS = 12, MINB = 3; };
+template <> struct PassTune<uint32_t, uint32_t> { static constexpr int THREADS = 512, ITEMS = 16, MINB = 2; };
+template <> struct PassTune<uint64_t, NoVal> { static constexpr int THREADS = 384, ITEMS = 12, MINB = 3; };
+template <> struct PassTune<uint64_t, uint64_t> { static constexpr int THREADS = 256, ITEMS = 12, MINB = 3; };
 
 constexpr uint64_t MAX_RECORDS = (1ull << 30) - 1;
 
@@ -278,7 +280,7 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
         radix_scan_hist_kernel<<<np, RADIX, 0, L->stream>>>(hist);
     }
     TRY(check_launch(L, "radix_scan_hist_kernel"));
-    auto kern = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS>;
+    auto kern = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS, Tune::MINB>;
     CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     K *kin = k0, *kout = k1;
     V *vin = v0, *vout = v1;

@@ -87,6 +87,30 @@ template <class K, class V> struct RadixPassArgs {
     int *err;
 };
 
+// Lanes of the warp holding the same 8-bit digit.  Eight ballots instead of one MATCH.ANY: on
+// sm_100a MATCH runs on the ADU pipe at a rate that drops with the number of distinct values in
+// the warp -- the ncu capture profiles/r1_sortpass_before.txt shows it at 56% of peak, the top
+// unit, on high-entropy digits -- while VOTE does not depend on the data.
+__device__ __forceinline__ unsigned match_digit(uint32_t d) {
+    unsigned m = BP_FULL_MASK;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        // m &= (bit b of d) ? ballot : ~ballot, as  m & ~(ballot ^ e)  with e = all-ones iff the bit is set
+        asm("{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b32 t, v, e;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+            "selp.b32 e, 0xffffffff, 0, p;\n\t"
+            "lop3.b32 %0, %0, v, e, 0x90;\n\t"
+            "}"
+            : "+r"(m)
+            : "r"(d), "r"(1u << b));
+    }
+    return m;
+}
+
 constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_INC = 2u << 30, RS_VALUE_MASK = (1u << 30) - 1;
 
 template <class K, class V, int THREADS, int ITEMS> struct RadixPassCfg {
@@ -100,13 +124,14 @@ template <class K, class V, int THREADS, int ITEMS> struct RadixPassCfg {
     static_assert(TILE < 65536, "ranks are packed in 16 bits");
 };
 
-template <class K, class V, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs<K, V> a) {
+// The body of one tile.  FULL = the tile has exactly TILE elements: every bounds check disappears.
+template <class K, class V, int THREADS, int ITEMS, bool FULL>
+__device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V> &a, unsigned char *smem_raw, const uint32_t tile,
+                                                const uint32_t tile_n) {
     typedef RadixPassCfg<K, V, THREADS, ITEMS> Cfg;
     constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS;
     constexpr bool HAS_V = Cfg::HAS_V;
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned char *stage = smem_raw;
     uint32_t *whist = (uint32_t *)(smem_raw + Cfg::STAGE_BYTES); // [WARPS][RADIX]
     uint32_t *dstart = whist + WARPS * RADIX;                    // [RADIX] first block rank of each digit
@@ -114,15 +139,7 @@ __global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs
     uint32_t *misc = gbase + RADIX;                              // [0] tile, [1..9] warp totals
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-
-    if (tid == 0) misc[0] = atomicAdd(a.tile_counter, 1u);
-    for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
-    __syncthreads();
-    const uint32_t tile = misc[0];
-    const uint32_t n = a.n_dev ? *a.n_dev : a.n_host;
     const uint64_t tile_begin = (uint64_t)tile * TILE;
-    if (tile_begin >= n) return;
-    const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, (uint64_t)n - tile_begin);
 
     // ---- load keys, warp-striped: item k of lane l of warp w is tile element w*32*ITEMS + k*32 + l
     const K *kin = a.kin + tile_begin;
@@ -131,28 +148,40 @@ __global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t i = base_i + k * 32;
-        key[k] = (i < tile_n) ? ld_stream(kin + i) : (K) ~(K)0; // pads rank last within the tile
+        if (FULL)
+            key[k] = ld_stream(kin + i);
+        else
+            key[k] = (i < tile_n) ? ld_stream(kin + i) : (K) ~(K)0; // pads rank last within the tile
     }
 
-    // ---- rank within the warp: match-any groups + one shared counter per (warp, digit) ----------
+    // ---- rank within the warp: match groups + one shared counter per (warp, digit) --------------
+    // Three software-pipelined sweeps instead of one dependent chain per item: (1) all match
+    // votes, (2) one shared-memory atomic per group leader (same-address atomics of a warp retire in
+    // program order, so earlier items get the lower ranks: the sort stays stable), (3) the leaders'
+    // old counter values are broadcast with shuffles.
     const K dmask = (K)((1u << a.bits) - 1u);
     const uint32_t shift = a.shift;
-    volatile uint32_t *wrow = whist + warp * RADIX;
+    uint32_t *wrow = whist + warp * RADIX;
     const unsigned lt = lanemask_lt();
+    unsigned mm[ITEMS];
     uint32_t rd[ITEMS]; // low 16 bits: rank, high 16 bits: digit
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t d = (uint32_t)((key[k] >> shift) & dmask);
-        const unsigned m = __match_any_sync(BP_FULL_MASK, d);
-        const int leader = __ffs(m) - 1;
+        mm[k] = match_digit(d);
+        rd[k] = d;
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
         uint32_t old = 0;
-        if ((int)lane == leader) {
-            old = wrow[d];
-            wrow[d] = old + __popc(m);
-        }
-        old = __shfl_sync(BP_FULL_MASK, old, leader);
-        rd[k] = (old + __popc(m & lt)) | (d << 16);
-        __syncwarp();
+        if ((mm[k] & lt) == 0) old = atomicAdd(&wrow[rd[k]], (uint32_t)__popc(mm[k])); // lowest lane of its group
+        rd[k] |= old << 16; // parked in the high half until the broadcast below
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t d = rd[k] & 0xffffu;
+        const uint32_t old = __shfl_sync(BP_FULL_MASK, rd[k] >> 16, __ffs(mm[k]) - 1);
+        rd[k] = (old + __popc(mm[k] & lt)) | (d << 16);
     }
 
     // payload loads are issued now so that their latency overlaps the look-back
@@ -162,7 +191,7 @@ __global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
             const uint32_t i = base_i + k * 32;
-            if (i < tile_n) val[k] = ld_stream(vin + i);
+            if (FULL || i < tile_n) val[k] = ld_stream(vin + i);
         }
     }
     __syncthreads();
@@ -171,7 +200,7 @@ __global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs
     uint32_t count_full = 0, incl = 0;
     if (tid < RADIX) {
         uint32_t sum = 0;
-#pragma unroll 4
+#pragma unroll
         for (int w = 0; w < WARPS; ++w) {
             const uint32_t c = whist[w * RADIX + tid];
             whist[w * RADIX + tid] = sum;
@@ -179,7 +208,7 @@ __global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs
         }
         count_full = sum;
         uint32_t count = sum;
-        if (tid == (uint32_t)dmask) count -= (uint32_t)(TILE - tile_n); // pads carry the all-ones digit
+        if (!FULL && tid == (uint32_t)dmask) count -= (uint32_t)(TILE - tile_n); // pads carry the all-ones digit
         uint32_t *st = a.status + (size_t)tile * RADIX + tid;
         st_volatile_u32(st, (tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG) | count);
         incl = warp_inclusive_sum(count_full);
@@ -194,21 +223,37 @@ __global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs
         uint32_t excl = 0;
         if (tile != 0) {
             uint32_t count = count_full;
-            if (tid == (uint32_t)dmask) count -= (uint32_t)(TILE - tile_n);
-            for (int64_t t = (int64_t)tile - 1; t >= 0; --t) {
-                const uint32_t *ps = a.status + (size_t)t * RADIX + tid;
-                uint32_t s = ld_volatile_u32(ps);
-                uint32_t spins = 0;
-                while ((s >> 30) == 0) {
-                    if (++spins > BP_SPIN_LIMIT) {
-                        *a.err = 1;
-                        s = RS_FLAG_INC;
-                        break;
+            if (!FULL && tid == (uint32_t)dmask) count -= (uint32_t)(TILE - tile_n);
+            // walk back over the predecessors LB_BATCH tiles at a time: the status loads of one batch are
+            // independent, so a batch costs one L2 round trip instead of LB_BATCH
+            constexpr int LB_BATCH = 8;
+            int64_t t = (int64_t)tile - 1;
+            bool done = false;
+            while (!done && t >= 0) {
+                uint32_t sv[LB_BATCH];
+#pragma unroll
+                for (int b = 0; b < LB_BATCH; ++b)
+                    sv[b] = (t - b >= 0) ? ld_volatile_u32(a.status + (size_t)(t - b) * RADIX + tid) : RS_FLAG_INC;
+#pragma unroll
+                for (int b = 0; b < LB_BATCH; ++b) {
+                    if (done) break;
+                    uint32_t sb = sv[b];
+                    if ((sb >> 30) == 0) { // not published yet: poll this one
+                        const uint32_t *ps = a.status + (size_t)(t - b) * RADIX + tid;
+                        uint32_t spins = 0;
+                        do {
+                            if (++spins > BP_SPIN_LIMIT) {
+                                *a.err = 1;
+                                sb = RS_FLAG_INC;
+                                break;
+                            }
+                            sb = ld_volatile_u32(ps);
+                        } while ((sb >> 30) == 0);
                     }
-                    s = ld_volatile_u32(ps);
+                    excl += sb & RS_VALUE_MASK;
+                    if ((sb >> 30) == 2) done = true;
                 }
-                excl += s & RS_VALUE_MASK;
-                if ((s >> 30) == 2) break;
+                t -= LB_BATCH;
             }
             st_volatile_u32(a.status + (size_t)tile * RADIX + tid, RS_FLAG_INC | ((excl + count) & RS_VALUE_MASK));
         }
@@ -230,7 +275,7 @@ __global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t i = k * THREADS + tid;
-        if (i < tile_n) {
+        if (FULL || i < tile_n) {
             const K kk = skeys[i];
             const uint32_t d = (uint32_t)((kk >> shift) & dmask);
             dst[k] = gbase[d] + i;
@@ -243,15 +288,38 @@ __global__ void __launch_bounds__(THREADS) radix_pass_kernel(const RadixPassArgs
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
             const uint32_t i = base_i + k * 32;
-            if (i < tile_n) svals[rd[k]] = val[k];
+            if (FULL || i < tile_n) svals[rd[k]] = val[k];
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
             const uint32_t i = k * THREADS + tid;
-            if (i < tile_n) a.vout[dst[k]] = svals[i];
+            if (FULL || i < tile_n) a.vout[dst[k]] = svals[i];
         }
     }
+}
+
+template <class K, class V, int THREADS, int ITEMS, int MINB = 1>
+__global__ void __launch_bounds__(THREADS, MINB) radix_pass_kernel(const RadixPassArgs<K, V> a) {
+    typedef RadixPassCfg<K, V, THREADS, ITEMS> Cfg;
+    constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *whist = (uint32_t *)(smem_raw + Cfg::STAGE_BYTES);
+    uint32_t *misc = whist + WARPS * RADIX + 2 * RADIX;
+
+    const unsigned tid = threadIdx.x;
+    if (tid == 0) misc[0] = atomicAdd(a.tile_counter, 1u);
+    for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
+    __syncthreads();
+    const uint32_t tile = misc[0];
+    const uint32_t n = a.n_dev ? *a.n_dev : a.n_host;
+    const uint64_t tile_begin = (uint64_t)tile * TILE;
+    if (tile_begin >= n) return;
+    const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, (uint64_t)n - tile_begin);
+    if (tile_n == (uint32_t)TILE)
+        radix_pass_tile<K, V, THREADS, ITEMS, true>(a, smem_raw, tile, tile_n);
+    else
+        radix_pass_tile<K, V, THREADS, ITEMS, false>(a, smem_raw, tile, tile_n);
 }
 
 } // namespace bp

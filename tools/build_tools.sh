@@ -1,0 +1,5 @@
+#!/bin/sh
+# builds the standalone tuning harnesses (not part of the product library)
+set -e
+cd "$(dirname "$0")"
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -ccbin /usr/bin/g++ sort_bench.cu -o sort_bench
