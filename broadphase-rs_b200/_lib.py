@@ -56,9 +56,16 @@ SYMBOLS = {
     "bp_layer_records": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
     "bp_layer_records_device": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
     "bp_layer_set_records": (_i, [_vp, _vp, _vp, _sz, _i, _i]),
+    "bp_dist_partition_records": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
+    "bp_dist_partition_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
+    "bp_dist_lookup_ranges": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
+    "bp_layer_set_halo": (_i, [_vp, _sz]),
+    "bp_layer_scan_raw_device": (_i, [_vp, _P(Filter), _P(_vp), _P(_sz)]),
+    "bp_layer_unique_pairs_device": (_i, [_vp, _vp, _sz, _u64, _P(_vp), _P(_sz)]),
     "bp_layer_len": (_i, [_vp, _P(_sz)]),
     "bp_layer_is_sorted": (_i, [_vp, _P(_i)]),
     "bp_layer_min_depth": (_i, [_vp, _P(_u32)]),
+    "bp_layer_masks": (_i, [_vp, _P(_u64), _P(_u64), _P(_u64), _P(_u64)]),
     "bp_layer_set_profiling": (_i, [_vp, _i]),
     "bp_layer_reset_stats": (_i, [_vp]),
     "bp_layer_stats": (_i, [_vp, _P(Stats)]),

@@ -69,6 +69,7 @@ struct bp_layer {
     int last_slot = 0;
     uint64_t key_or = 0, key_and = ~0ull, id_or = 0, id_and = ~0ull;
     uint64_t n_invalid = 0;
+    uint64_t n_halo = 0; // records [0, n_halo) only act as ancestors in scan (multi-GPU halos)
 
     // pending extend result
     bool pending = false;
@@ -295,8 +296,8 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
         a.ghist_excl = hist + (size_t)p * RADIX;
         a.status = status + (size_t)p * tiles * RADIX;
         a.tile_counter = counters + p;
-        a.shift = plan.shift[p];
-        a.bits = plan.bits[p];
+        a.op.shift = plan.shift[p];
+        a.op.mask = (1u << plan.bits[p]) - 1u;
         a.err = L->d_err;
         {
             LaunchScope ls(L, cls_pass, 2.0 * (double)n * (double)elem_bytes);
@@ -525,7 +526,9 @@ template <int KIND, class IdT> struct Impl {
         return BP_OK;
     }
 
-    static int scan(bp_layer *L, const bp_filter *f) {
+    // Everything up to the raw (unsorted, duplicate-carrying) pairs, left in praw[0] (+ praw_b[0]).
+    static int scan_raw(bp_layer *L, const bp_filter *f, uint64_t *out_raw) {
+        *out_raw = 0;
         TRY(sort(L));
         L->n_pairs = 0;
         L->stats.n_work_items = L->stats.n_raw_pairs = L->stats.n_pairs = 0;
@@ -605,6 +608,7 @@ template <int KIND, class IdT> struct Impl {
         ea.chunk_src = (const uint32_t *)L->chunk_src.p;
         ea.n_work = W;
         ea.n_sources = (uint32_t)C;
+        ea.first_owned = (uint32_t)std::min<uint64_t>(L->n_halo, R);
         ea.inactive = nullptr;
         ea.out_packed = wide ? nullptr : (uint64_t *)L->praw[0].p;
         ea.out_a = wide ? (uint64_t *)L->praw[0].p : nullptr;
@@ -636,9 +640,21 @@ template <int KIND, class IdT> struct Impl {
             TRY(emit(L, ea, fk, chunks, emit_bytes));
             TRY(fetch_totals(L));
         }
-        const uint64_t P_raw = L->h_tot->n_raw_pairs;
-        L->stats.n_raw_pairs = P_raw;
+        L->stats.n_raw_pairs = L->h_tot->n_raw_pairs;
+        *out_raw = L->h_tot->n_raw_pairs;
+        return BP_OK;
+    }
+
+    // Sorts the P_raw raw pairs in praw[0] (+ praw_b[0]) and removes duplicates into pout.
+    static int finish_pairs(bp_layer *L, uint64_t P_raw) {
+        const bool wide = sizeof(IdT) == 8;
+        L->n_pairs = 0;
+        L->stats.n_pairs = 0;
+        L->stats.pair_sort_passes = 0;
         if (P_raw == 0) return BP_OK;
+        TRY(ensure(L, L->pout, P_raw * 2 * sizeof(IdT)));
+        TRY(ensure(L, L->praw[1], P_raw * sizeof(uint64_t)));
+        if (wide) TRY(ensure(L, L->praw_b[1], P_raw * sizeof(uint64_t)));
 
         // ---- sort the raw pairs (src/layer.rs:473, :516) ----
         const uint64_t imask = L->id_or & ~L->id_and;
@@ -702,6 +718,100 @@ template <int KIND, class IdT> struct Impl {
         return BP_OK;
     }
 
+    static int scan(bp_layer *L, const bp_filter *f) {
+        uint64_t P_raw = 0;
+        TRY(scan_raw(L, f, &P_raw));
+        return finish_pairs(L, P_raw);
+    }
+
+    // ---- multi-GPU building blocks ---------------------------------------------------------------------
+    // Stable range partition of (key, payload) by `n_spl` splitters on (key >> shift): the same onesweep
+    // pass as the sort, with a splitter-search digit.  counts_out[b] = elements in bucket b.
+    template <class PK, class PV>
+    static int partition(bp_layer *L, const PK *kin, const PV *vin, uint32_t n, const uint64_t *spl, int n_spl, uint32_t shift,
+                         PK *kout, PV *vout, uint64_t *counts_out) {
+        typedef PassTune<PK, PV> Tune;
+        typedef RadixPassCfg<PK, PV, Tune::THREADS, Tune::ITEMS> Cfg;
+        for (int b = 0; b <= n_spl; ++b) counts_out[b] = 0;
+        if (n == 0) return BP_OK;
+        SplitterDigit<PK> op;
+        for (int i = 0; i < MAX_SPLITTERS; ++i) op.spl[i] = i < n_spl ? spl[i] : ~0ull;
+        op.n = (uint32_t)n_spl;
+        op.shift = shift;
+        const uint32_t tiles = (n + Cfg::TILE - 1) / Cfg::TILE;
+        const size_t total = (size_t)(RADIX + 64 + (size_t)tiles * RADIX) * sizeof(uint32_t);
+        TRY(ensure(L, L->scratch, total));
+        uint32_t *hist = (uint32_t *)L->scratch.p, *counters = hist + RADIX, *status = counters + 64;
+        CU(L, cudaMemsetAsync(L->scratch.p, 0, total, L->stream));
+        {
+            LaunchScope ls(L, BP_K_MISC, (double)n * sizeof(PK));
+            const int blocks = (int)std::min<size_t>((n + 4095) / 4096, 148 * 8);
+            partition_hist_kernel<PK><<<std::max(blocks, 1), 512, 0, L->stream>>>(kin, n, op, hist);
+        }
+        TRY(check_launch(L, "partition_hist_kernel"));
+        // bucket counts back to the host (they are the all-to-all split sizes) before the scan overwrites them
+        uint32_t h_counts[RADIX];
+        CU(L, cudaMemcpyAsync(h_counts, hist, (n_spl + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, L->stream));
+        {
+            LaunchScope ls(L, BP_K_MISC, 0);
+            radix_scan_hist_kernel<<<1, RADIX, 0, L->stream>>>(hist);
+        }
+        TRY(check_launch(L, "radix_scan_hist_kernel"));
+        auto kern = radix_pass_kernel<PK, PV, Tune::THREADS, Tune::ITEMS, Tune::MINB, SplitterDigit<PK>>;
+        CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+        RadixPassArgs<PK, PV, SplitterDigit<PK>> a;
+        a.kin = kin;
+        a.kout = kout;
+        a.vin = vin;
+        a.vout = vout;
+        a.n_host = n;
+        a.n_dev = nullptr;
+        a.ghist_excl = hist;
+        a.status = status;
+        a.tile_counter = counters;
+        a.op = op;
+        a.err = L->d_err;
+        {
+            const double eb = std::is_same<PV, NoVal>::value ? sizeof(PK) : sizeof(PK) + sizeof(PV);
+            LaunchScope ls(L, BP_K_MISC, 2.0 * (double)n * eb);
+            kern<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
+        }
+        TRY(check_launch(L, "radix_pass_kernel<splitters>"));
+        CU(L, cudaStreamSynchronize(L->stream));
+        for (int b = 0; b <= n_spl; ++b) counts_out[b] = h_counts[b];
+        return BP_OK;
+    }
+
+    static int partition_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl,
+                                 void *kout, void *vout, uint64_t *counts) {
+        return partition<K, IdT>(L, (const K *)kin, (const IdT *)vin, (uint32_t)n, spl, n_spl, 0, (K *)kout, (IdT *)vout, counts);
+    }
+
+    static int lookup_ranges(bp_layer *L, const void *sorted_keys, size_t n, const uint64_t *queries, int nq, uint64_t *lo,
+                             uint64_t *hi) {
+        if (nq <= 0) return BP_OK;
+        const size_t bytes = (size_t)nq * (sizeof(K) + 2 * sizeof(uint32_t));
+        TRY(ensure(L, L->scratch, bytes));
+        std::vector<K> hq(nq);
+        for (int i = 0; i < nq; ++i) hq[i] = (K)queries[i];
+        K *dq = (K *)L->scratch.p;
+        uint32_t *dlo = (uint32_t *)(dq + nq), *dhi = dlo + nq;
+        CU(L, cudaMemcpyAsync(dq, hq.data(), nq * sizeof(K), cudaMemcpyHostToDevice, L->stream));
+        {
+            LaunchScope ls(L, BP_K_MISC, 0);
+            lookup_ranges_kernel<K><<<(nq + 127) / 128, 128, 0, L->stream>>>((const K *)sorted_keys, (uint32_t)n, dq, (uint32_t)nq, dlo, dhi);
+        }
+        TRY(check_launch(L, "lookup_ranges_kernel"));
+        std::vector<uint32_t> h(2 * nq);
+        CU(L, cudaMemcpyAsync(h.data(), dlo, 2 * nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaStreamSynchronize(L->stream));
+        for (int i = 0; i < nq; ++i) {
+            lo[i] = h[i];
+            hi[i] = h[nq + i];
+        }
+        return BP_OK;
+    }
+
     static int masks_from_records(bp_layer *L, uint64_t n) {
         ExtendResult init;
         memset(&init, 0, sizeof init);
@@ -745,6 +855,19 @@ int do_extend_device(bp_layer *L, const float *sysb, const float *b, const void 
 }
 int do_sort(bp_layer *L) { DISPATCH(L, sort(L)); }
 int do_scan(bp_layer *L, const bp_filter *f) { DISPATCH(L, scan(L, f)); }
+int do_scan_raw(bp_layer *L, const bp_filter *f, uint64_t *out_raw) { DISPATCH(L, scan_raw(L, f, out_raw)); }
+int do_finish_pairs(bp_layer *L, uint64_t n) { DISPATCH(L, finish_pairs(L, n)); }
+int do_partition_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl, void *kout,
+                         void *vout, uint64_t *counts) {
+    DISPATCH(L, partition_records(L, kin, vin, n, spl, n_spl, kout, vout, counts));
+}
+int do_partition_pairs(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *kout, uint64_t *counts) {
+    return Impl<BP_INDEX64_3D, uint32_t>::partition<uint64_t, NoVal>(L, kin, (const NoVal *)nullptr, (uint32_t)n, spl, n_spl, 32, kout,
+                                                                     (NoVal *)nullptr, counts);
+}
+int do_lookup_ranges(bp_layer *L, const void *keys, size_t n, const uint64_t *q, int nq, uint64_t *lo, uint64_t *hi) {
+    DISPATCH(L, lookup_ranges(L, keys, n, q, nq, lo, hi));
+}
 int do_masks(bp_layer *L, uint64_t n) { DISPATCH(L, masks_from_records(L, n)); }
 
 // Folds the result of the last (still asynchronous) extend into the host-side state.
@@ -964,6 +1087,7 @@ int bp_layer_clear(bp_layer *L) {
         L->n_invalid += L->h_res->n_invalid;
     }
     L->n_records = 0;
+    L->n_halo = 0;
     L->dirty = false;
     L->prefix = 0;
     L->tail_sorted = false;
@@ -1077,6 +1201,79 @@ int bp_layer_scan(bp_layer *L, const bp_filter *f, const void **out_pairs, size_
     return BP_OK;
 }
 
+int bp_layer_set_halo(bp_layer *L, size_t n_halo) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    L->n_halo = n_halo;
+    return BP_OK;
+}
+
+int bp_layer_scan_raw_device(bp_layer *L, const bp_filter *f, const void **out_raw, size_t *out_count) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    if (L->id_bytes != 4) return fail(L, BP_ERR_INVALID_ARG, "raw pairs are exposed for 32-bit IDs only");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    uint64_t n = 0;
+    TRY(do_scan_raw(L, f, &n));
+    if (out_raw) *out_raw = n ? L->praw[0].p : nullptr;
+    if (out_count) *out_count = (size_t)n;
+    return BP_OK;
+}
+
+int bp_layer_unique_pairs_device(bp_layer *L, const void *d_raw, size_t n, uint64_t id_mask, const void **out_pairs, size_t *out_count) {
+    if (!L || (n && !d_raw)) return BP_ERR_INVALID_ARG;
+    if (L->id_bytes != 4) return fail(L, BP_ERR_INVALID_ARG, "raw pairs are exposed for 32-bit IDs only");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 pairs");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    if (n) {
+        TRY(ensure(L, L->praw[0], n * sizeof(uint64_t)));
+        if (d_raw != L->praw[0].p)
+            CU(L, cudaMemcpyAsync(L->praw[0].p, d_raw, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, L->stream));
+    }
+    // the digit plan comes from the ID bits that can differ: the caller passes the mask for foreign pairs
+    const uint64_t keep_or = L->id_or, keep_and = L->id_and;
+    if (id_mask) {
+        L->id_or = id_mask;
+        L->id_and = 0;
+    }
+    CU(L, cudaMemsetAsync(L->d_tot, 0, sizeof(ScanTotals), L->stream));
+    const int st = do_finish_pairs(L, n);
+    L->id_or = keep_or;
+    L->id_and = keep_and;
+    TRY(st);
+    if (out_pairs) *out_pairs = L->n_pairs ? L->pout.p : nullptr;
+    if (out_count) *out_count = (size_t)L->n_pairs;
+    return BP_OK;
+}
+
+int bp_dist_partition_records(bp_layer *L, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
+                              int n_splitters, void *d_out_keys, void *d_out_ids, uint64_t *out_counts) {
+    if (!L || !out_counts || n_splitters < 0 || n_splitters > MAX_SPLITTERS || (n_splitters && !splitters))
+        return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_partition_records");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_partition_records(L, d_keys, d_ids, n, splitters, n_splitters, d_out_keys, d_out_ids, out_counts);
+}
+
+int bp_dist_partition_pairs(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
+                            void *d_out_pairs, uint64_t *out_counts) {
+    if (!L || !out_counts || n_splitters < 0 || n_splitters > MAX_SPLITTERS || (n_splitters && !splitters))
+        return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_partition_pairs");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 pairs");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_partition_pairs(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, (uint64_t *)d_out_pairs, out_counts);
+}
+
+int bp_dist_lookup_ranges(bp_layer *L, const void *d_sorted_keys, size_t n, const uint64_t *queries, int n_queries,
+                          uint64_t *out_lo, uint64_t *out_hi) {
+    if (!L || n_queries < 0 || (n_queries && (!queries || !out_lo || !out_hi))) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_lookup_ranges(L, d_sorted_keys, n, queries, n_queries, out_lo, out_hi);
+}
+
 int bp_layer_records_device(bp_layer *L, const void **out_keys, const void **out_ids, size_t *out_n, int *out_sorted) {
     if (!L) return BP_ERR_INVALID_ARG;
     DeviceGuard g(L->device);
@@ -1156,6 +1353,17 @@ int bp_layer_is_sorted(bp_layer *L, int *out_sorted) {
 int bp_layer_min_depth(const bp_layer *L, uint32_t *out) {
     if (!L || !out) return BP_ERR_INVALID_ARG;
     *out = L->min_depth;
+    return BP_OK;
+}
+
+int bp_layer_masks(bp_layer *L, uint64_t *key_or, uint64_t *key_and, uint64_t *id_or, uint64_t *id_and) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    if (key_or) *key_or = L->key_or;
+    if (key_and) *key_and = L->key_and;
+    if (id_or) *id_or = L->id_or;
+    if (id_and) *id_and = L->id_and;
     return BP_OK;
 }
 

@@ -72,8 +72,29 @@ __global__ void __launch_bounds__(RADIX) radix_scan_hist_kernel(uint32_t *__rest
     h[threadIdx.x] = ex;
 }
 
+// ---- digit functors -----------------------------------------------------------------------------------
+// The pass kernel is generic over how a key maps to a bin.  Pads (all-ones keys) must map to max().
+template <class K> struct ShiftMaskDigit { // LSD radix digit: (key >> shift) & mask
+    uint32_t shift, mask;
+    __device__ __forceinline__ uint32_t operator()(K k) const { return (uint32_t)(k >> shift) & mask; }
+    __device__ __forceinline__ uint32_t max() const { return mask; }
+};
+constexpr int MAX_SPLITTERS = 15; // up to 16 shards
+template <class K> struct SplitterDigit { // range partition: number of splitters <= (key >> shift)
+    uint64_t spl[MAX_SPLITTERS];
+    uint32_t n, shift;
+    __device__ __forceinline__ uint32_t operator()(K k) const {
+        const uint64_t v = (uint64_t)k >> shift;
+        uint32_t d = 0;
+#pragma unroll
+        for (int i = 0; i < MAX_SPLITTERS; ++i) d += (i < (int)n && spl[i] <= v) ? 1u : 0u;
+        return d;
+    }
+    __device__ __forceinline__ uint32_t max() const { return n; }
+};
+
 // ---- one onesweep pass --------------------------------------------------------------------------------
-template <class K, class V> struct RadixPassArgs {
+template <class K, class V, class Op = ShiftMaskDigit<K>> struct RadixPassArgs {
     const K *kin;
     K *kout;
     const V *vin;
@@ -83,7 +104,7 @@ template <class K, class V> struct RadixPassArgs {
     const uint32_t *ghist_excl; // [RADIX] exclusive digit offsets of this pass
     uint32_t *status;           // [tiles][RADIX], zeroed; bits 31..30 flag, 29..0 count
     uint32_t *tile_counter;     // zeroed
-    uint32_t shift, bits;
+    Op op;
     int *err;
 };
 
@@ -125,8 +146,8 @@ template <class K, class V, int THREADS, int ITEMS> struct RadixPassCfg {
 };
 
 // The body of one tile.  FULL = the tile has exactly TILE elements: every bounds check disappears.
-template <class K, class V, int THREADS, int ITEMS, bool FULL>
-__device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V> &a, unsigned char *smem_raw, const uint32_t tile,
+template <class K, class V, class Op, int THREADS, int ITEMS, bool FULL>
+__device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a, unsigned char *smem_raw, const uint32_t tile,
                                                 const uint32_t tile_n) {
     typedef RadixPassCfg<K, V, THREADS, ITEMS> Cfg;
     constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS;
@@ -159,15 +180,15 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V> &a, un
     // votes, (2) one shared-memory atomic per group leader (same-address atomics of a warp retire in
     // program order, so earlier items get the lower ranks: the sort stays stable), (3) the leaders'
     // old counter values are broadcast with shuffles.
-    const K dmask = (K)((1u << a.bits) - 1u);
-    const uint32_t shift = a.shift;
+    const Op op = a.op;
+    const uint32_t dmax = op.max();
     uint32_t *wrow = whist + warp * RADIX;
     const unsigned lt = lanemask_lt();
     unsigned mm[ITEMS];
     uint32_t rd[ITEMS]; // low 16 bits: rank, high 16 bits: digit
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        const uint32_t d = (uint32_t)((key[k] >> shift) & dmask);
+        const uint32_t d = op(key[k]);
         mm[k] = match_digit(d);
         rd[k] = d;
     }
@@ -208,7 +229,7 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V> &a, un
         }
         count_full = sum;
         uint32_t count = sum;
-        if (!FULL && tid == (uint32_t)dmask) count -= (uint32_t)(TILE - tile_n); // pads carry the all-ones digit
+        if (!FULL && tid == dmax) count -= (uint32_t)(TILE - tile_n); // pads carry the largest digit
         uint32_t *st = a.status + (size_t)tile * RADIX + tid;
         st_volatile_u32(st, (tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG) | count);
         incl = warp_inclusive_sum(count_full);
@@ -223,7 +244,7 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V> &a, un
         uint32_t excl = 0;
         if (tile != 0) {
             uint32_t count = count_full;
-            if (!FULL && tid == (uint32_t)dmask) count -= (uint32_t)(TILE - tile_n);
+            if (!FULL && tid == dmax) count -= (uint32_t)(TILE - tile_n);
             // walk back over the predecessors LB_BATCH tiles at a time: the status loads of one batch are
             // independent, so a batch costs one L2 round trip instead of LB_BATCH
             constexpr int LB_BATCH = 8;
@@ -277,7 +298,7 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V> &a, un
         const uint32_t i = k * THREADS + tid;
         if (FULL || i < tile_n) {
             const K kk = skeys[i];
-            const uint32_t d = (uint32_t)((kk >> shift) & dmask);
+            const uint32_t d = op(kk);
             dst[k] = gbase[d] + i;
             a.kout[dst[k]] = kk;
         }
@@ -299,8 +320,8 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V> &a, un
     }
 }
 
-template <class K, class V, int THREADS, int ITEMS, int MINB = 1>
-__global__ void __launch_bounds__(THREADS, MINB) radix_pass_kernel(const RadixPassArgs<K, V> a) {
+template <class K, class V, int THREADS, int ITEMS, int MINB = 1, class Op = ShiftMaskDigit<K>>
+__global__ void __launch_bounds__(THREADS, MINB) radix_pass_kernel(const RadixPassArgs<K, V, Op> a) {
     typedef RadixPassCfg<K, V, THREADS, ITEMS> Cfg;
     constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -317,9 +338,61 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_pass_kernel(const RadixPa
     if (tile_begin >= n) return;
     const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, (uint64_t)n - tile_begin);
     if (tile_n == (uint32_t)TILE)
-        radix_pass_tile<K, V, THREADS, ITEMS, true>(a, smem_raw, tile, tile_n);
+        radix_pass_tile<K, V, Op, THREADS, ITEMS, true>(a, smem_raw, tile, tile_n);
     else
-        radix_pass_tile<K, V, THREADS, ITEMS, false>(a, smem_raw, tile, tile_n);
+        radix_pass_tile<K, V, Op, THREADS, ITEMS, false>(a, smem_raw, tile, tile_n);
+}
+
+// ---- bucket counts for a splitter partition (one read of the keys) --------------------------------------
+template <class K>
+__global__ void __launch_bounds__(512) partition_hist_kernel(const K *__restrict__ keys, uint32_t n, SplitterDigit<K> op,
+                                                              uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t sh[MAX_SPLITTERS + 1];
+    if (threadIdx.x <= MAX_SPLITTERS) sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t local[MAX_SPLITTERS + 1];
+#pragma unroll
+    for (int i = 0; i <= MAX_SPLITTERS; ++i) local[i] = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t d = op(ld_stream(keys + i));
+#pragma unroll
+        for (int b = 0; b <= MAX_SPLITTERS; ++b) local[b] += (d == (uint32_t)b) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int b = 0; b <= MAX_SPLITTERS; ++b) {
+        const uint32_t c = warp_sum(local[b]);
+        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh[b], c);
+    }
+    __syncthreads();
+    if (threadIdx.x <= MAX_SPLITTERS && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
+}
+
+// equal ranges of query keys in a sorted key array (halo look-ups); one thread per query
+template <class K>
+__global__ void lookup_ranges_kernel(const K *__restrict__ keys, uint32_t n, const K *__restrict__ queries, uint32_t nq,
+                                     uint32_t *__restrict__ lo_out, uint32_t *__restrict__ hi_out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const K key = queries[q];
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { // lower bound
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (keys[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    const uint32_t first = lo;
+    hi = n;
+    while (lo < hi) { // upper bound
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (keys[mid] <= key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    lo_out[q] = first;
+    hi_out[q] = lo;
 }
 
 } // namespace bp

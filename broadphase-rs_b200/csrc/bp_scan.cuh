@@ -210,6 +210,7 @@ template <class IdT> struct EmitArgs {
     const uint32_t *chunk_src;
     uint64_t n_work;
     uint32_t n_sources;
+    uint32_t first_owned;   // records below this index only act as ancestors (multi-GPU halo): never the later record
     int mode;               // FIRST: emit assuming no inactive records, report same-ID items;
                             // FLAG: only mark inactive[j]; ACTIVE: emit, skipping inactive records
     unsigned char *inactive; // [n records] (FLAG / ACTIVE)
@@ -283,12 +284,12 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
             if (a.mode == EMIT_MODE_FIRST) {
                 const bool same = id_i == id_j;
                 same_seen |= same;
-                emit = !same && FilterFn<FK>::pass(a.filter, id_j, id_i);
+                emit = !same && j >= a.first_owned && FilterFn<FK>::pass(a.filter, id_j, id_i);
             } else if (a.mode == EMIT_MODE_FLAG) {
                 if (id_i == id_j) a.inactive[j] = 1;
                 emit = false;
             } else {
-                emit = !a.inactive[i] && !a.inactive[j] && FilterFn<FK>::pass(a.filter, id_j, id_i);
+                emit = j >= a.first_owned && !a.inactive[i] && !a.inactive[j] && FilterFn<FK>::pass(a.filter, id_j, id_i);
             }
             if (emit) {
                 pa[npass] = (uint64_t)id_j; // (later, earlier) -- src/layer.rs:567

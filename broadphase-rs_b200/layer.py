@@ -171,6 +171,45 @@ class Layer:
             i = np.ascontiguousarray(ids, dtype=self.id_dtype)
             self._ck(lib().bp_layer_set_records(self._h, k.ctypes.data, i.ctypes.data, k.shape[0], int(sorted_), 0))
 
+    # ---- multi-GPU building blocks (include/bp.h) ------------------------------------------------
+    def set_halo(self, n_halo):
+        self._ck(lib().bp_layer_set_halo(self._h, n_halo))
+
+    def scan_raw_device(self, flt=None):
+        """Raw (filtered, unsorted, duplicate-carrying) packed pairs: (device pointer, count)."""
+        f = None if flt is None else flt._c()
+        out, cnt = ctypes.c_void_p(), ctypes.c_size_t()
+        self._ck(lib().bp_layer_scan_raw_device(self._h, None if f is None else ctypes.byref(f), ctypes.byref(out),
+                                                ctypes.byref(cnt)))
+        return out.value, cnt.value
+
+    def unique_pairs_device(self, d_raw, n, id_mask=0):
+        out, cnt = ctypes.c_void_p(), ctypes.c_size_t()
+        self._ck(lib().bp_layer_unique_pairs_device(self._h, _dev_ptr(d_raw), n, id_mask, ctypes.byref(out), ctypes.byref(cnt)))
+        return out.value, cnt.value
+
+    def partition_records(self, d_keys, d_ids, n, splitters, d_out_keys, d_out_ids):
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        counts = np.zeros(spl.shape[0] + 1, dtype=np.uint64)
+        self._ck(lib().bp_dist_partition_records(self._h, _dev_ptr(d_keys), _dev_ptr(d_ids), n, spl.ctypes.data, spl.shape[0],
+                                                 _dev_ptr(d_out_keys), _dev_ptr(d_out_ids), counts.ctypes.data))
+        return counts
+
+    def partition_pairs(self, d_pairs, n, splitters, d_out_pairs):
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        counts = np.zeros(spl.shape[0] + 1, dtype=np.uint64)
+        self._ck(lib().bp_dist_partition_pairs(self._h, _dev_ptr(d_pairs), n, spl.ctypes.data, spl.shape[0],
+                                               _dev_ptr(d_out_pairs), counts.ctypes.data))
+        return counts
+
+    def lookup_ranges(self, d_sorted_keys, n, queries):
+        q = np.ascontiguousarray(queries, dtype=np.uint64)
+        lo = np.zeros(q.shape[0], dtype=np.uint64)
+        hi = np.zeros(q.shape[0], dtype=np.uint64)
+        self._ck(lib().bp_dist_lookup_ranges(self._h, _dev_ptr(d_sorted_keys), n, q.ctypes.data, q.shape[0], lo.ctypes.data,
+                                             hi.ctypes.data))
+        return lo, hi
+
     def __len__(self):
         n = ctypes.c_size_t()
         self._ck(lib().bp_layer_len(self._h, ctypes.byref(n)))
@@ -187,6 +226,12 @@ class Layer:
         d = ctypes.c_uint32()
         self._ck(lib().bp_layer_min_depth(self._h, ctypes.byref(d)))
         return d.value
+
+    def masks(self):
+        """(key_or, key_and, id_or, id_and) over the tree."""
+        v = [ctypes.c_uint64() for _ in range(4)]
+        self._ck(lib().bp_layer_masks(self._h, *[ctypes.byref(x) for x in v]))
+        return tuple(x.value for x in v)
 
     # ---- instrumentation ------------------------------------------------------------------------
     def set_profiling(self, enabled):

@@ -161,6 +161,35 @@ int bp_layer_set_records(bp_layer *layer, const void *keys, const void *ids, siz
 int bp_layer_len(bp_layer *layer, size_t *out_n);
 int bp_layer_is_sorted(bp_layer *layer, int *out_sorted);
 int bp_layer_min_depth(const bp_layer *layer, uint32_t *out_min_depth);
+/* OR and AND over all keys / IDs of the tree (what the sort planner uses; a superset after clear-less reuse). */
+int bp_layer_masks(bp_layer *layer, uint64_t *key_or, uint64_t *key_and, uint64_t *id_or, uint64_t *id_and);
+
+/* ---- multi-GPU building blocks ------------------------------------------------------------------
+ * The reference is single-process (no counterpart in the crate); these are the device operations the
+ * Morton-prefix range sharding of SURVEY.md section 8e is assembled from (broadphase-rs_b200/dist.py):
+ * sample sort of the records, ancestor halos, shard-local scan, range partition of the raw pairs for
+ * the global dedup.  All pointers prefixed d_ are device pointers on the layer's device; the layer is
+ * used as the execution context (stream + scratch).  32-bit IDs only for the pair functions. */
+
+/* Stable partition of n records by `n_splitters` (<= 15) ascending key splitters: bucket b receives
+ * the records with exactly b splitters <= key.  out_counts[0..n_splitters] are the bucket sizes. */
+int bp_dist_partition_records(bp_layer *ctx, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
+                              int n_splitters, void *d_out_keys, void *d_out_ids, uint64_t *out_counts);
+/* The same for packed raw pairs ((later << 32) | earlier), partitioned on `later`. */
+int bp_dist_partition_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
+                            void *d_out_pairs, uint64_t *out_counts);
+/* Equal range [lo, hi) of every query key in a sorted device key array (halo look-ups). */
+int bp_dist_lookup_ranges(bp_layer *ctx, const void *d_sorted_keys, size_t n, const uint64_t *queries, int n_queries,
+                          uint64_t *out_lo, uint64_t *out_hi);
+/* Records [0, n_halo) of the tree are halo: they are ancestors only, never the later record of an
+ * emitted pair.  Reset to 0 by bp_layer_clear / bp_layer_set_records. */
+int bp_layer_set_halo(bp_layer *layer, size_t n_halo);
+/* scan up to the raw pairs (filtered, not yet sorted / deduplicated), packed (later << 32) | earlier. */
+int bp_layer_scan_raw_device(bp_layer *layer, const bp_filter *filter, const void **out_d_raw, size_t *out_count);
+/* Sorts + deduplicates n packed raw pairs (possibly received from other shards) into the final
+ * (later, earlier) layout.  id_mask: OR of all bits in which two IDs may differ (0: use the layer's own). */
+int bp_layer_unique_pairs_device(bp_layer *layer, const void *d_raw, size_t n, uint64_t id_mask, const void **out_d_pairs,
+                                 size_t *out_count);
 
 /* ---- instrumentation -------------------------------------------------------------------------- */
 int bp_layer_set_profiling(bp_layer *layer, int enabled); /* CUDA-event timing of every kernel launch */

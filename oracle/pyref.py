@@ -201,19 +201,22 @@ def _filter(kind, arg, table, a, b):
     raise ValueError(kind)
 
 
-def scan(kind, keys, ids, filter_kind=FILTER_NONE, filter_arg=0, table=None):
-    """Layer::scan_filtered -- src/layer.rs:456-477 -- in closed form.
+def scan_raw(kind, keys, ids, filter_kind=FILTER_NONE, filter_arg=0, table=None, first_owned=0):
+    """The raw (later, earlier) pairs of Layer::scan_filtered -- src/layer.rs:456-477 -- in closed
+    form, before the sort + dedup, as two uint64 arrays.
 
     keys/ids must already be sorted.  For record j the stack of src/layer.rs:550-573 holds exactly
     the pushed earlier records whose cell contains cell(j); those are, for every depth
     d <= depth(j), the run of records with key == (key_j & level_mask(d)) | d that lie before j.
-    Returns (pairs (P, 2) uint64 sorted + unique, raw pair count)."""
+    first_owned > 0: records below that index are halo records of a multi-GPU shard -- they act as
+    ancestors but never as the later record of a pair."""
     _, dim, depth_bits, axis_bits = KINDS[kind]
     keys = np.asarray(keys, dtype=np.uint64)
     ids64 = np.asarray(ids).astype(np.uint64)
     n = keys.shape[0]
+    empty = np.zeros(0, dtype=np.uint64)
     if n == 0:
-        return np.zeros((0, 2), dtype=np.uint64), 0
+        return empty, empty
     depth = (keys & np.uint64((1 << depth_bits) - 1)).astype(np.int64)
     j_all = np.arange(n)
     src_i, src_j = [], []
@@ -234,16 +237,21 @@ def scan(kind, keys, ids, filter_kind=FILTER_NONE, filter_arg=0, table=None):
         src_i.append(ii)
         src_j.append(jj)
     if not src_i:
-        return np.zeros((0, 2), dtype=np.uint64), 0
+        return empty, empty
     ii = np.concatenate(src_i)
     jj = np.concatenate(src_j)
     inactive = np.zeros(n, dtype=bool)
     inactive[jj[ids64[ii] == ids64[jj]]] = True
-    keep = ~inactive[ii] & ~inactive[jj]
+    keep = ~inactive[ii] & ~inactive[jj] & (jj >= first_owned)
     ii, jj = ii[keep], jj[keep]
     a, b = ids64[jj], ids64[ii]
     f = _filter(filter_kind, filter_arg, table, a, b)
-    a, b = a[f], b[f]
+    return a[f], b[f]
+
+
+def scan(kind, keys, ids, filter_kind=FILTER_NONE, filter_arg=0, table=None):
+    """Layer::scan_filtered: (pairs (P, 2) uint64 sorted + unique, raw pair count)."""
+    a, b = scan_raw(kind, keys, ids, filter_kind, filter_arg, table)
     raw = int(a.shape[0])
     pairs = np.stack([a, b], axis=1)
     if raw:

@@ -1,0 +1,157 @@
+"""CPU test double of dist.CudaOps (numpy + the CPU oracle) and the gloo worker that drives
+dist.DistLayer with it.  TEST INFRASTRUCTURE ONLY: lets world_size > 1 tests check the splitter /
+halo / ownership / global-dedup choreography of the multi-GPU path on a CPU-only box.  The product
+path (dist.CudaOps) never touches any of this."""
+import os
+import sys
+import traceback
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import cpu_oracle as co  # noqa: E402
+from oracle import pyref  # noqa: E402
+
+
+def _i64(u):
+    return torch.from_numpy(np.ascontiguousarray(u, dtype=np.uint64).view(np.int64).copy())
+
+
+def _i32(u):
+    return torch.from_numpy(np.ascontiguousarray(u, dtype=np.uint32).view(np.int32).copy())
+
+
+def _u64(t):
+    return t.numpy().view(np.uint64)
+
+
+def _u32(t):
+    return t.numpy().view(np.uint32)
+
+
+class CpuOps:
+    device = torch.device("cpu")
+
+    def __init__(self, kind, min_depth):
+        self.kind, self.min_depth = kind, min_depth
+
+    def encode(self, sys_bounds, bounds, ids, n):
+        L = co.OracleLayer(self.kind, 4, self.min_depth)
+        L.extend(sys_bounds, bounds[:n], ids[:n])
+        k, i = L.records()
+        id_or = int(np.bitwise_or.reduce(i)) if i.size else 0
+        return _i64(k), _i32(i.astype(np.uint32)), id_or
+
+    def partition_records(self, keys, ids, splitters):
+        k, i = _u64(keys), _u32(ids)
+        bucket = np.searchsorted(np.asarray(splitters, dtype=np.uint64), k, side="right")
+        order = np.argsort(bucket, kind="stable")
+        counts = np.bincount(bucket, minlength=len(splitters) + 1)
+        return _i64(k[order]), _i32(i[order]), [int(c) for c in counts]
+
+    def sort_records(self, keys, ids):
+        k, i = pyref.sort_records(_u64(keys), _u32(ids))
+        return _i64(k), _i32(i)
+
+    def lookup_ranges(self, sorted_keys, queries):
+        k = _u64(sorted_keys)
+        q = np.asarray(queries, dtype=np.uint64)
+        return np.searchsorted(k, q, side="left"), np.searchsorted(k, q, side="right")
+
+    def scan_raw(self, keys, ids, n_halo, flt):
+        fk, arg = flt if flt else (0, 0)
+        a, b = pyref.scan_raw(self.kind, _u64(keys), _u32(ids), fk, arg, None, first_owned=n_halo)
+        return _i64((a << np.uint64(32)) | b)
+
+    def partition_pairs(self, raw, splitters):
+        r = _u64(raw)
+        bucket = np.searchsorted(np.asarray(splitters, dtype=np.uint64), r >> np.uint64(32), side="right")
+        order = np.argsort(bucket, kind="stable")
+        counts = np.bincount(bucket, minlength=len(splitters) + 1)
+        return _i64(r[order]), [int(c) for c in counts]
+
+    def unique_pairs(self, raw, id_mask):
+        r = np.unique(_u64(raw))
+        assert ((r >> np.uint64(32)) <= np.uint64(id_mask)).all() and ((r & np.uint64(0xFFFFFFFF)) <= np.uint64(id_mask)).all()
+        out = np.stack([(r >> np.uint64(32)).astype(np.uint32), (r & np.uint64(0xFFFFFFFF)).astype(np.uint32)], axis=1)
+        return torch.from_numpy(out.view(np.int32).copy())
+
+
+def make_case(name):
+    """Deterministic scenes that stress the distributed logic.  Returns (kind, min_depth, sys, bounds, ids, filter)."""
+    rng = np.random.Generator(np.random.Philox(abs(hash(name)) % (1 << 31) if False else sum(map(ord, name))))
+    if name == "uniform3d":
+        n, kind, dim = 6000, 2, 3
+        size = (0.03 * rng.random((n, dim))).astype(np.float32)
+    elif name == "big_objects3d":  # scene-sized boxes: halos at depth 0..2 reach every shard
+        n, kind, dim = 4000, 2, 3
+        size = (0.02 * rng.random((n, dim))).astype(np.float32)
+        size[::50] = (0.3 + 0.6 * rng.random((len(size[::50]), dim))).astype(np.float32)
+    elif name == "multibounds2d":  # several (nested) bounds per ID: inactive records across shard borders
+        n, kind, dim = 5000, 1, 2
+        size = (0.2 * rng.random((n, dim)) ** 3).astype(np.float32)
+    elif name == "skewed3d":  # almost everything in one corner: very uneven key distribution
+        n, kind, dim = 5000, 2, 3
+        size = (0.01 * rng.random((n, dim))).astype(np.float32)
+    else:
+        raise ValueError(name)
+    sysb = np.concatenate([np.zeros(dim), np.ones(dim)]).astype(np.float32)
+    mn = (rng.random((n, dim)) * (1.0 - size)).astype(np.float32)
+    if name == "skewed3d":
+        mn = (mn ** 4).astype(np.float32)
+    bounds = np.concatenate([mn, np.minimum(mn + size, 1.0)], axis=1).astype(np.float32)
+    if name == "multibounds2d":
+        ids = np.sort(rng.integers(0, n // 4, size=n)).astype(np.uint32)
+    else:
+        ids = np.arange(n, dtype=np.uint32)
+    flt = (1, 0) if name == "uniform3d" else None  # ID-parity filter on one case
+    return kind, 0, sysb, bounds, ids, flt
+
+
+def reference_pairs(case):
+    kind, md, sysb, bounds, ids, flt = make_case(case)
+    L = co.OracleLayer(kind, 4, md)
+    L.extend(sysb, bounds, ids)
+    fk, arg = flt if flt else (0, 0)
+    return L.scan(fk, arg).astype(np.uint32)
+
+
+def worker(rank, world, port, cases, empty_rank, out_dir):
+    try:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import _loadpkg
+        bp = _loadpkg.load()
+        from broadphase_rs_b200 import dist as bpd
+        for case in cases:
+            kind, md, sysb, bounds, ids, flt = make_case(case)
+            n = bounds.shape[0]
+            # block distribution by object order; optionally one rank gets nothing
+            holders = [r for r in range(world) if r != empty_rank]
+            cuts = np.linspace(0, n, len(holders) + 1).astype(int)
+            if rank in holders:
+                h = holders.index(rank)
+                lo, hi = cuts[h], cuts[h + 1]
+            else:
+                lo, hi = 0, 0
+            dl = bpd.DistLayer(CpuOps(kind, md), kind)
+            pairs = dl.frame(sysb, bounds[lo:hi], ids[lo:hi], hi - lo, flt)
+            allp = dl.gather_pairs(pairs)
+            if rank == 0:
+                np.save(os.path.join(out_dir, "%s.npy" % case), allp)
+                np.save(os.path.join(out_dir, "%s.halo.npy" % case), np.array([dl.last["halo"]]))
+            halos = [None] * world
+            dist.all_gather_object(halos, dl.last["halo"])
+            if rank == 0:
+                np.save(os.path.join(out_dir, "%s.halos.npy" % case), np.array(halos))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        traceback.print_exc()
+        raise

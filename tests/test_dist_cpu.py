@@ -1,0 +1,47 @@
+"""world_size > 1 tests of the multi-GPU choreography (dist.DistLayer) on CPU: gloo backend, the
+numpy/oracle test double for the shard-local operations.  The concatenation of the ranks' results
+must equal the single-process oracle scan bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from tests import dist_cpu_ops as dco
+
+CASES = ["uniform3d", "big_objects3d", "multibounds2d", "skewed3d"]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,empty_rank", [(2, -1), (3, -1), (2, 1)])
+def test_distributed_frame_equals_single_process_oracle(tmp_path, world, empty_rank):
+    mp.spawn(dco.worker, args=(world, _free_port(), CASES, empty_rank, str(tmp_path)), nprocs=world, join=True)
+    for case in CASES:
+        got = np.load(os.path.join(str(tmp_path), "%s.npy" % case))
+        want = dco.reference_pairs(case)
+        assert got.shape == want.shape, (case, got.shape, want.shape)
+        assert (got == want).all(), case
+    halos = np.load(os.path.join(str(tmp_path), "big_objects3d.halos.npy"))
+    if empty_rank < 0:
+        assert halos[0] == 0 and halos[1:].sum() > 0  # scene-sized objects must have produced halo records
+
+
+def test_ancestor_keys_and_splitters(bp):
+    from broadphase_rs_b200 import dist as bpd
+    from oracle import cpu_oracle as co
+    key = co.make_index(2, 5, [0x12345678 & 0xF8000000, 0x9abcdef0 & 0xF8000000, 0x0fedcba9 & 0xF8000000])  # origin truncated to depth 5
+    anc = bpd.ancestor_keys(2, key)
+    assert len(anc) == 6 and anc[0] == 0 and anc[-1] == key and anc == sorted(anc)
+    for d, a in enumerate(anc):
+        assert a & 31 == d and co.overlaps(2, a, key)
+    s = bpd.choose_splitters(np.arange(1000, dtype=np.uint64), 4)
+    assert list(s) == [250, 500, 750]
+    assert bpd.choose_splitters(np.zeros(0, dtype=np.uint64), 4).shape[0] == 0
