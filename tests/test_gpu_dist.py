@@ -1,0 +1,158 @@
+"""GPU tests of the multi-GPU building blocks (one GPU) and of the NCCL path (>= 2 GPUs, skipped
+otherwise): every rank's slice, concatenated in rank order, must equal the single-process oracle."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from oracle import cpu_oracle as co
+from oracle import pyref
+
+pytestmark = pytest.mark.gpu
+
+
+def _records(bp, n=200_000, seed=3):
+    sc = bp.scenes.lognormal_cubes(n, seed)
+    o = co.OracleLayer(sc["kind"], 4, 0)
+    o.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    k, i = o.records()
+    return sc, k, i.astype(np.uint32)
+
+
+def test_partition_records_is_a_stable_range_partition(bp):
+    import torch
+    sc, k, i = _records(bp)
+    dk = torch.from_numpy(k.view(np.int64)).cuda()
+    di = torch.from_numpy(i.view(np.int32)).cuda()
+    L = bp.Layer(2, "u32")
+    for nspl in (1, 3, 7, 15):
+        spl = np.sort(np.random.Generator(np.random.Philox(nspl)).choice(k, nspl, replace=False)).astype(np.uint64)
+        ok, oi = torch.empty_like(dk), torch.empty_like(di)
+        counts = L.partition_records(dk, di, k.shape[0], spl, ok, oi)
+        bucket = np.searchsorted(spl, k, side="right")
+        order = np.argsort(bucket, kind="stable")
+        assert (counts == np.bincount(bucket, minlength=nspl + 1)).all()
+        assert (ok.cpu().numpy().view(np.uint64) == k[order]).all()
+        assert (oi.cpu().numpy().view(np.uint32) == i[order]).all()
+    # empty input and all-in-one-bucket
+    counts = L.partition_records(dk, di, 0, np.array([5], dtype=np.uint64), ok, oi)
+    assert counts.sum() == 0
+
+
+def test_partition_pairs_and_unique(bp):
+    import torch
+    rng = np.random.Generator(np.random.Philox(9))
+    a = rng.integers(0, 50_000, size=300_000).astype(np.uint64)
+    b = rng.integers(0, 50_000, size=300_000).astype(np.uint64)
+    raw = (a << np.uint64(32)) | b
+    d = torch.from_numpy(raw.view(np.int64)).cuda()
+    out = torch.empty_like(d)
+    L = bp.Layer(2, "u32")
+    spl = np.array([10_000, 20_000, 40_000], dtype=np.uint64)
+    counts = L.partition_pairs(d, raw.shape[0], spl, out)
+    bucket = np.searchsorted(spl, a, side="right")
+    assert (counts == np.bincount(bucket, minlength=4)).all()
+    assert (out.cpu().numpy().view(np.uint64) == raw[np.argsort(bucket, kind="stable")]).all()
+    ptr, n = L.unique_pairs_device(d, raw.shape[0], (1 << 16) - 1)
+    from broadphase_rs_b200.dist import _view
+    got = _view(ptr, 2 * n, torch.int32, torch.device("cuda")).cpu().numpy().view(np.uint32).reshape(n, 2)
+    want = np.unique(raw)
+    assert n == want.shape[0]
+    assert (got[:, 0].astype(np.uint64) == want >> np.uint64(32)).all() and (got[:, 1].astype(np.uint64) == (want & np.uint64(0xFFFFFFFF))).all()
+
+
+def test_lookup_ranges_and_halo_scan(bp):
+    import torch
+    sc, k, i = _records(bp, 100_000, 5)
+    sk, si = pyref.sort_records(k, i)
+    dk = torch.from_numpy(sk.view(np.int64)).cuda()
+    L = bp.Layer(2, "u32")
+    q = np.concatenate([sk[::997], np.array([0, 1, 2**62 - 1], dtype=np.uint64)])
+    lo, hi = L.lookup_ranges(dk, sk.shape[0], q)
+    assert (lo == np.searchsorted(sk, q, side="left")).all() and (hi == np.searchsorted(sk, q, side="right")).all()
+    # treat the first third of the sorted tree as halo: only pairs whose later record is owned remain
+    n_halo = sk.shape[0] // 3
+    L.set_records(sk, si, sorted_=True)
+    L.set_halo(n_halo)
+    ptr, n = L.scan_raw_device(bp.ScanFilter.id_parity())
+    from broadphase_rs_b200.dist import _view
+    raw = np.sort(_view(ptr, n, torch.int64, torch.device("cuda")).cpu().numpy().view(np.uint64))
+    a, b = pyref.scan_raw(2, sk, si, pyref.FILTER_ID_PARITY, 0, None, first_owned=n_halo)
+    want = np.sort((a << np.uint64(32)) | b)
+    assert raw.shape == want.shape and (raw == want).all()
+    L.set_halo(0)
+    assert (L.scan_filtered(bp.ScanFilter.id_parity()).astype(np.uint64) == pyref.scan(2, sk, si, pyref.FILTER_ID_PARITY)[0]).all()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import _loadpkg
+    bp = _loadpkg.load()
+    from broadphase_rs_b200 import dist as bpd
+    from tests import dist_cpu_ops as dco
+    for case in ("uniform3d", "big_objects3d", "skewed3d"):
+        kind, md, sysb, bounds, ids, flt = dco.make_case(case)
+        n = bounds.shape[0]
+        cuts = np.linspace(0, n, world + 1).astype(int)
+        lo, hi = cuts[rank], cuts[rank + 1]
+        ops = bpd.CudaOps(bp, kind, md, rank)
+        dl = bpd.DistLayer(ops, kind)
+        db = torch.from_numpy(bounds[lo:hi].copy()).cuda()
+        di = torch.from_numpy(ids[lo:hi].copy().view(np.int32)).cuda()
+        gflt = bp.ScanFilter.id_parity() if flt else None
+        for _ in range(2):  # twice: buffers are reused across frames
+            pairs = dl.frame(sysb, db, di, hi - lo, gflt)
+        allp = dl.gather_pairs(pairs)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "%s.npy" % case), allp)
+    # the BASELINE config-2 recipe, 2^18 objects per rank
+    import importlib
+    dbm = importlib.import_module("broadphase_rs_b200.dist_bench")
+    sc = dbm._scene_slice(bp, 1 << 18, world, rank, 6)
+    ops = bpd.CudaOps(bp, 2, 0, rank)
+    dl = bpd.DistLayer(ops, 2)
+    db = torch.from_numpy(sc["bounds"]).cuda()
+    di = torch.from_numpy(sc["ids"].view(np.int32)).cuda()
+    pairs = dl.frame(sc["sys_bounds"], db, di, 1 << 18, None)
+    allp = dl.gather_pairs(pairs)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "cfg2slice.npy"), allp)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nccl_frame_equals_oracle(bp, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from tests import dist_cpu_ops as dco
+    for case in ("uniform3d", "big_objects3d", "skewed3d"):
+        got = np.load(os.path.join(str(tmp_path), "%s.npy" % case))
+        want = dco.reference_pairs(case)
+        assert got.shape == want.shape and (got == want).all(), case
+    import importlib
+    dbm = importlib.import_module("broadphase_rs_b200.dist_bench")
+    o = co.OracleLayer(2, 4, 0)
+    for r in range(world):
+        sc = dbm._scene_slice(bp, 1 << 18, world, r, 6)
+        o.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    want = o.par_scan().astype(np.uint32)
+    got = np.load(os.path.join(str(tmp_path), "cfg2slice.npy"))
+    assert got.shape == want.shape and (got == want).all()
