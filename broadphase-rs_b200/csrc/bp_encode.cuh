@@ -30,7 +30,8 @@ constexpr uint32_t ENCODE_MAX_CELLS = 1u << 20;
 constexpr int ENCODE_THREADS = 256;
 constexpr int ENCODE_OPT = 4; // objects per thread
 constexpr int ENCODE_TILE = ENCODE_THREADS * ENCODE_OPT;
-constexpr int ENCODE_WINDOW = 4096; // records staged per write-out round
+constexpr int ENCODE_ROUND = 8192; // records generated per round (= ENCODE_TILE * 2^3: one round at natural depth)
+constexpr int ENCODE_LUT_BITS = 10;
 
 template <class T, class IdT> struct EncodeArgs {
     const float *bounds; // n x 2*DIM
@@ -50,11 +51,18 @@ template <class T, class IdT> struct EncodeArgs {
     int *err;
 };
 
+// Shared-memory layout.  The staged AABBs are dead once every thread has quantised its objects, so the
+// per-round owner table reuses their space.
 template <class T, class IdT> struct EncodeSmem {
     static constexpr size_t BOUNDS_BYTES = (size_t)ENCODE_TILE * 2 * T::DIM * sizeof(float);
-    static constexpr size_t STAGE_BYTES = (size_t)ENCODE_WINDOW * (sizeof(typename T::key_t) + sizeof(IdT));
-    static constexpr size_t UNION_BYTES = BOUNDS_BYTES > STAGE_BYTES ? BOUNDS_BYTES : STAGE_BYTES;
-    static constexpr size_t BYTES = UNION_BYTES + (size_t)ENCODE_TILE * sizeof(uint32_t) + 64 * sizeof(uint64_t);
+    static constexpr size_t OWNER_BYTES = (size_t)ENCODE_ROUND * sizeof(uint16_t);
+    static constexpr size_t UNION_BYTES = BOUNDS_BYTES > OWNER_BYTES ? BOUNDS_BYTES : OWNER_BYTES;
+    static constexpr size_t DESC_OFF = UNION_BYTES;                                         // uint4 per object
+    static constexpr size_t ID_OFF = DESC_OFF + (size_t)ENCODE_TILE * sizeof(uint4);        // IdT per object
+    static constexpr size_t CNT_OFF = ID_OFF + (size_t)ENCODE_TILE * sizeof(IdT);           // u32 per object (+1)
+    static constexpr size_t LUT_OFF = CNT_OFF + (size_t)(ENCODE_TILE + 4) * sizeof(uint32_t); // u32 x 2^LUT_BITS
+    static constexpr size_t RED_OFF = LUT_OFF + ((size_t)4 << ENCODE_LUT_BITS);
+    static constexpr size_t BYTES = RED_OFF + 64 * sizeof(uint64_t);
 };
 
 // SystemBounds::to_local for one scalar (src/geom.rs:148-156): ((g - min) / size * RANGE + 0) as u32
@@ -68,6 +76,15 @@ __device__ __forceinline__ uint32_t quantise(float g, float mn, float size) {
     return __float2uint_rz(r);
 }
 
+// Morton spread of a cell coordinate through a 2^10-entry shared table (bit i -> bit DIM*i): two
+// (3D, <= 19 bits) or three (2D, <= 29 bits) look-ups instead of a 5-step 64-bit mask cascade.
+template <int DIM> __device__ __forceinline__ uint64_t spread_lut(const uint32_t *lut, uint32_t c) {
+    constexpr uint32_t M = (1u << ENCODE_LUT_BITS) - 1u;
+    uint64_t r = (uint64_t)lut[c & M] | ((uint64_t)lut[(c >> ENCODE_LUT_BITS) & M] << (DIM * ENCODE_LUT_BITS));
+    if (DIM == 2) r |= (uint64_t)lut[(c >> (2 * ENCODE_LUT_BITS)) & M] << (2 * DIM * ENCODE_LUT_BITS);
+    return r;
+}
+
 template <class T, class IdT>
 __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs<T, IdT> a) {
     typedef typename T::key_t K;
@@ -77,14 +94,18 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sbounds = (float *)smem_raw;
-    K *skeys = (K *)smem_raw;
-    IdT *sids = (IdT *)(smem_raw + (size_t)ENCODE_WINDOW * sizeof(K));
-    uint32_t *scnt = (uint32_t *)(smem_raw + S::UNION_BYTES);                                   // [ENCODE_TILE]
-    uint64_t *sred = (uint64_t *)(smem_raw + S::UNION_BYTES + ENCODE_TILE * sizeof(uint32_t)); // scratch
+    uint16_t *sowner = (uint16_t *)smem_raw;               // [ENCODE_ROUND] object of every record of the round
+    uint4 *sdesc = (uint4 *)(smem_raw + S::DESC_OFF);      // {cx0, cy0, cz0, depth | nx << 8 | ny << 16 (or general marker)}
+    IdT *sid = (IdT *)(smem_raw + S::ID_OFF);
+    uint32_t *scnt = (uint32_t *)(smem_raw + S::CNT_OFF);  // [ENCODE_TILE + 1] exclusive record offsets
+    uint32_t *slut = (uint32_t *)(smem_raw + S::LUT_OFF);
+    uint64_t *sred = (uint64_t *)(smem_raw + S::RED_OFF);  // scratch
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) *(uint32_t *)sred = atomicAdd(a.tile_counter, 1u);
+    // the spread table: entry v = bits of v moved to positions DIM * i
+    for (uint32_t v = tid; v < (1u << ENCODE_LUT_BITS); v += ENCODE_THREADS) slut[v] = (uint32_t)(DIM == 2 ? spread2(v) : spread3(v));
     __syncthreads();
     const uint32_t tile = *(uint32_t *)sred;
     __syncthreads();
@@ -109,30 +130,23 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
     __syncthreads();
 
     // ---- per object: contains, quantise, depth, cell grid ----------------------------------------
-    uint32_t depth[ENCODE_OPT], tmin[ENCODE_OPT][3], ncell[ENCODE_OPT][3], count[ENCODE_OPT];
-    IdT id[ENCODE_OPT];
+    uint32_t count[ENCODE_OPT];
     uint32_t n_invalid = 0, nonmono = 0, too_many = 0;
     unsigned long long id_or = 0, id_and = ~0ull;
 #pragma unroll
     for (int k = 0; k < ENCODE_OPT; ++k) {
         const uint32_t o = k * ENCODE_THREADS + tid; // striped: conflict-light shared reads, coalesced ID loads
         count[k] = 0;
-        depth[k] = 0;
-        id[k] = 0;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            tmin[k][i] = 0;
-            ncell[k][i] = 1;
-        }
         if (o >= tile_objs) continue;
         const uint32_t g = obj0 + o;
-        id[k] = a.ids[g];
+        const IdT id = a.ids[g];
+        sid[o] = id;
         // IDs ascending in object order => records enter the sort in ascending ID order, so a stable
         // sort on the key alone yields the (Index, ID) order of src/layer.rs:146-165.
         if (g > 0) {
-            if (a.ids[g - 1] > id[k]) nonmono = 1;
+            if (a.ids[g - 1] > id) nonmono = 1;
         } else if (a.prev_last_id) {
-            if (*a.prev_last_id > id[k]) nonmono = 1;
+            if (*a.prev_last_id > id) nonmono = 1;
         }
         const float *b = sbounds + o * FPO;
         bool valid = true;
@@ -149,8 +163,8 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
             ++n_invalid;
             continue;
         }
-        id_or |= (unsigned long long)id[k];
-        id_and &= (unsigned long long)id[k];
+        id_or |= (unsigned long long)id;
+        id_and &= (unsigned long long)id;
         // indices(): depth = leading_zeros(max_axis(sizei) - 1), raised to min_depth, clamped
         uint32_t max_axis = 0;
 #pragma unroll
@@ -158,16 +172,16 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
         uint32_t d = (uint32_t)__clz((int)(max_axis - 1u));
         d = max(d, a.min_depth);
         d = min(d, (uint32_t)T::AXIS_BITS);
-        depth[k] = d;
+        uint32_t c0[3] = {0, 0, 0}, nc[3] = {1, 1, 1};
         uint64_t cells = 1;
-        if (d != 0) { // indices_at_depth(): truncate to the depth grid, count cells per axis
+        if (d != 0) { // indices_at_depth(): cell coordinates at depth d = the top d bits of the local coordinate
             const uint32_t sh = 32u - d;
 #pragma unroll
             for (int i = 0; i < DIM; ++i) {
-                const uint32_t lo = (lmin[i] >> sh) << sh, hi = (lmax[i] >> sh) << sh;
-                tmin[k][i] = lo;
-                ncell[k][i] = hi > lo ? ((hi - lo) >> sh) + 1u : 1u;
-                cells *= ncell[k][i];
+                const uint32_t lo = lmin[i] >> sh, hi = lmax[i] >> sh;
+                c0[i] = lo;
+                nc[i] = hi > lo ? hi - lo + 1u : 1u;
+                cells *= nc[i];
             }
         }
         if (cells > ENCODE_MAX_CELLS) {
@@ -175,8 +189,20 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
             cells = 0;
         }
         count[k] = (uint32_t)cells;
+        // nx, ny <= 255 fit the packed descriptor; larger grids (min_depth far below the natural depth) carry
+        // nx in .w's upper bits and recompute ny from the count -- kept simple: nx in bits 8..19, ny in 20..31
+        uint4 dsc;
+        dsc.x = c0[0];
+        dsc.y = c0[1];
+        dsc.z = c0[2];
+        dsc.w = d | (min(nc[0], 0xfffu) << 8) | (min(nc[1], 0xfffu) << 20);
+        if (nc[0] > 0xfffu || nc[1] > 0xfffu) { // cannot be described: refuse like an oversized object
+            too_many = 1;
+            count[k] = 0;
+        }
+        sdesc[o] = dsc;
     }
-    __syncthreads(); // sbounds is dead from here on (its space becomes the staging window)
+    __syncthreads(); // sbounds is dead from here on (its space becomes the owner table)
 
     // ---- exclusive scan of the counts in object order ---------------------------------------------
 #pragma unroll
@@ -195,6 +221,7 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
         scnt[tid * ENCODE_OPT + k] = ex;
         ex += c4[k];
     }
+    if (tid == 0) scnt[ENCODE_TILE] = tile_total;
     __syncthreads();
 
     // ---- tile offset: decoupled look-back -----------------------------------------------------------
@@ -202,49 +229,61 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
         const uint64_t excl = lookback_exclusive(a.status, tile, (uint64_t)tile_total, a.err);
         if (lane == 0) sred[32] = excl;
     }
-    __syncthreads();
-    const uint64_t tile_base = sred[32];
-    const uint64_t gout = a.out_base + tile_base;
 
-    // ---- generate the records through a shared-memory window, write them coalesced --------------
+    // ---- generate: one record per thread and step ---------------------------------------------------
+    // Every object first stamps its index on the records it owns (a loop of its cell count, one 2-byte
+    // store each); then the threads walk the records in order: record p looks up its owner, turns its
+    // cell number into (ix, iy, iz), spreads the three cell coordinates through the table and stores the
+    // key and the ID straight to their final place -- consecutive threads, consecutive records.
     unsigned long long key_or = 0, key_and = ~0ull;
     uint32_t off[ENCODE_OPT];
 #pragma unroll
     for (int k = 0; k < ENCODE_OPT; ++k) off[k] = scnt[k * ENCODE_THREADS + tid];
-    for (uint32_t w0 = 0; w0 < tile_total; w0 += ENCODE_WINDOW) {
-        const uint32_t w1 = min(tile_total, w0 + (uint32_t)ENCODE_WINDOW);
+    uint64_t gout = 0;
+    for (uint32_t w0 = 0; w0 < tile_total; w0 += ENCODE_ROUND) {
+        const uint32_t w1 = min(tile_total, w0 + (uint32_t)ENCODE_ROUND);
 #pragma unroll
         for (int k = 0; k < ENCODE_OPT; ++k) {
-            if (count[k] == 0) continue;
-            const uint32_t lo = off[k] > w0 ? off[k] : w0;
-            const uint32_t hi = min(off[k] + count[k], w1);
-            if (lo >= hi) continue;
-            const uint32_t d = depth[k];
-            const uint32_t step = d ? (1u << (32u - d)) : 0u;
-            const uint32_t nx = ncell[k][0], nxy = ncell[k][0] * ncell[k][1];
-            for (uint32_t p = lo; p < hi; ++p) {
-                const uint32_t c = p - off[k];
-                const uint32_t iz = c / nxy, r = c - iz * nxy;
-                const uint32_t iy = r / nx, ix = r - iy * nx;
-                uint64_t origin = encode_axis<T>(tmin[k][0] + ix * step) | (encode_axis<T>(tmin[k][1] + iy * step) << 1);
-                if (DIM == 3) origin |= encode_axis<T>(tmin[k][2] + iz * step) << 2;
-                const K key = d ? make_key<T>(d, origin) : (K)0; // depth 0 -> Index::default()
-                key_or |= (unsigned long long)key;
-                key_and &= (unsigned long long)key;
-                skeys[p - w0] = key;
-                sids[p - w0] = id[k];
-            }
+            const uint32_t lo = max(off[k], w0), hi = min(off[k] + count[k], w1);
+            for (uint32_t p = lo; p < hi; ++p) sowner[p - w0] = (uint16_t)(k * ENCODE_THREADS + tid);
         }
-        __syncthreads();
-        for (uint32_t i = tid; i < w1 - w0; i += ENCODE_THREADS) {
-            const uint64_t gi = gout + w0 + i;
+        __syncthreads(); // also publishes sred[32] in the first round
+        if (w0 == 0) gout = a.out_base + sred[32];
+        for (uint32_t p = w0 + tid; p < w1; p += ENCODE_THREADS) {
+            const uint32_t o = sowner[p - w0];
+            const uint4 dsc = sdesc[o];
+            const uint32_t d = dsc.w & 0xffu, nx = (dsc.w >> 8) & 0xfffu, ny = dsc.w >> 20;
+            uint32_t c = p - scnt[o];
+            uint32_t ix, iy, iz;
+            if (nx <= 2 && ny <= 2) { // the natural-depth case: at most two cells per axis
+                ix = c & (nx - 1u);
+                c >>= (nx - 1u);
+                iy = c & (ny - 1u);
+                iz = c >> (ny - 1u);
+            } else {
+                const uint32_t nxy = nx * ny;
+                iz = c / nxy;
+                c -= iz * nxy;
+                iy = c / nx;
+                ix = c - iy * nx;
+            }
+            uint64_t origin = spread_lut<DIM>(slut, dsc.x + ix) | (spread_lut<DIM>(slut, dsc.y + iy) << 1);
+            if (DIM == 3) origin |= spread_lut<DIM>(slut, dsc.z + iz) << 2;
+            // the spread of a coordinate shifted to the top of its AXIS_BITS field is the spread of the cell
+            // coordinate shifted by DIM * (AXIS_BITS - d)
+            const K key = d ? make_key<T>(d, origin << (DIM * (T::AXIS_BITS - (int)d))) : (K)0; // depth 0 -> Index::default()
+            key_or |= (unsigned long long)key;
+            key_and &= (unsigned long long)key;
+            const uint64_t gi = gout + p;
             if (gi < a.capacity) {
-                a.keys_out[gi] = skeys[i];
-                a.ids_out[gi] = sids[i];
+                a.keys_out[gi] = key;
+                a.ids_out[gi] = sid[o];
             }
         }
         __syncthreads();
     }
+    if (tile_total == 0) __syncthreads(); // no round ran: still wait for the look-back result
+    const uint64_t tile_base = sred[32];
 
     // ---- block-level reductions for the sort planner ------------------------------------------------
     key_or = warp_or(key_or);

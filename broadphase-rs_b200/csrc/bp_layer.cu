@@ -224,20 +224,48 @@ void collect_profile(bp_layer *L) {
 template <class T> inline T *ptr(DevBuf &b, size_t off = 0) { return (T *)b.p + off; }
 
 // ---- radix planning --------------------------------------------------------------------------------------
+// Digits for an LSD sort over the bits set in `mask` (bits that differ between keys).  Each pass
+// takes whichever covers more of the remaining bits: one 8-bit window starting at the lowest
+// remaining bit, or two runs of consecutive set bits (the lowest run, then the next one after a
+// gap) of 8 bits in total.
 int plan_passes(uint64_t mask, RadixPlan &plan, int first = 0) {
     int np = first;
+    auto run_len = [](uint64_t m, int from, int cap) {
+        int n = 0;
+        while (n < cap && from + n < 64 && ((m >> (from + n)) & 1ull)) ++n;
+        return n;
+    };
     while (mask && np < RADIX_MAX_PASSES) {
-        const int shift = __builtin_ctzll(mask);
-        uint64_t window = shift + 8 >= 64 ? (mask >> shift) : ((mask >> shift) & 0xffull);
-        window &= 0xffull;
-        const int bits = 64 - __builtin_clzll(window);
-        plan.shift[np] = (unsigned char)shift;
-        plan.bits[np] = (unsigned char)bits;
+        const int s0 = __builtin_ctzll(mask);
+        // option A: one window
+        const uint64_t window = (mask >> s0) & 0xffull;
+        const int bitsA = 64 - __builtin_clzll(window);
+        const int coverA = __builtin_popcountll(window);
+        // option B: two runs
+        const int len0 = run_len(mask, s0, 8);
+        int s1 = 0, len1 = 0;
+        if (len0 < 8) {
+            const uint64_t rest = (s0 + len0 >= 64) ? 0 : (mask >> (s0 + len0)) << (s0 + len0);
+            if (rest) {
+                s1 = __builtin_ctzll(rest);
+                len1 = run_len(mask, s1, 8 - len0);
+            }
+        }
+        if (len0 + len1 > coverA) {
+            plan.shift[np] = (unsigned char)s0;
+            plan.bits[np] = (unsigned char)len0;
+            plan.shift2[np] = (unsigned char)s1;
+            plan.bits2[np] = (unsigned char)len1;
+            for (int i = 0; i < len0; ++i) mask &= ~(1ull << (s0 + i));
+            for (int i = 0; i < len1; ++i) mask &= ~(1ull << (s1 + i));
+        } else {
+            plan.shift[np] = (unsigned char)s0;
+            plan.bits[np] = (unsigned char)bitsA;
+            plan.shift2[np] = 0;
+            plan.bits2[np] = 0;
+            mask &= ~(0xffull << s0);
+        }
         ++np;
-        if (shift + 8 >= 64)
-            mask = 0;
-        else
-            mask &= ~(0xffull << shift);
     }
     plan.npasses = np;
     return np;
@@ -281,29 +309,50 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
         radix_scan_hist_kernel<<<np, RADIX, 0, L->stream>>>(hist);
     }
     TRY(check_launch(L, "radix_scan_hist_kernel"));
-    auto kern = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS, Tune::MINB>;
-    CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    auto kern1 = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS, Tune::MINB, OneFieldDigit<K>>;
+    auto kern2 = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS, Tune::MINB, ShiftMaskDigit<K>>;
+    CU(L, cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+    CU(L, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     K *kin = k0, *kout = k1;
     V *vin = v0, *vout = v1;
     for (int p = 0; p < np; ++p) {
-        RadixPassArgs<K, V> a;
-        a.kin = kin;
-        a.kout = kout;
-        a.vin = vin;
-        a.vout = vout;
-        a.n_host = n;
-        a.n_dev = n_dev;
-        a.ghist_excl = hist + (size_t)p * RADIX;
-        a.status = status + (size_t)p * tiles * RADIX;
-        a.tile_counter = counters + p;
-        a.op.shift = plan.shift[p];
-        a.op.mask = (1u << plan.bits[p]) - 1u;
-        a.err = L->d_err;
-        {
-            LaunchScope ls(L, cls_pass, 2.0 * (double)n * (double)elem_bytes);
-            kern<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
+        LaunchScope ls(L, cls_pass, 2.0 * (double)n * (double)elem_bytes);
+        if (plan.bits2[p] == 0) {
+            RadixPassArgs<K, V, OneFieldDigit<K>> a;
+            a.kin = kin;
+            a.kout = kout;
+            a.vin = vin;
+            a.vout = vout;
+            a.n_host = n;
+            a.n_dev = n_dev;
+            a.ghist_excl = hist + (size_t)p * RADIX;
+            a.status = status + (size_t)p * tiles * RADIX;
+            a.tile_counter = counters + p;
+            a.op.shift = plan.shift[p];
+            a.op.mask = (1u << plan.bits[p]) - 1u;
+            a.err = L->d_err;
+            kern1<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
+        } else {
+            RadixPassArgs<K, V, ShiftMaskDigit<K>> a;
+            a.kin = kin;
+            a.kout = kout;
+            a.vin = vin;
+            a.vout = vout;
+            a.n_host = n;
+            a.n_dev = n_dev;
+            a.ghist_excl = hist + (size_t)p * RADIX;
+            a.status = status + (size_t)p * tiles * RADIX;
+            a.tile_counter = counters + p;
+            a.op.shift = plan.shift[p];
+            a.op.mask = (1u << plan.bits[p]) - 1u;
+            a.op.shift2 = plan.shift2[p];
+            a.op.mask2 = (1u << plan.bits2[p]) - 1u;
+            a.op.bits = plan.bits[p];
+            a.err = L->d_err;
+            kern2<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
         }
-        TRY(check_launch(L, "radix_pass_kernel"));
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(L, BP_ERR_CUDA, "launch of radix_pass_kernel failed: %s", cudaGetErrorString(e));
         std::swap(kin, kout);
         std::swap(vin, vout);
     }
@@ -500,16 +549,18 @@ template <int KIND, class IdT> struct Impl {
 
     // ---- scan ---------------------------------------------------------------------------------------------------
     template <int FK> static int launch_emit(bp_layer *L, EmitArgs<IdT> &a, uint32_t chunks, double bytes) {
+        auto kern = scan_emit_kernel<IdT, FK>;
+        CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EmitSmem<IdT>::BYTES));
         LaunchScope ls(L, BP_K_SCAN_EMIT, bytes);
-        scan_emit_kernel<IdT, FK><<<chunks, EMIT_THREADS, 0, L->stream>>>(a);
+        kern<<<chunks, EMIT_THREADS, EmitSmem<IdT>::BYTES, L->stream>>>(a);
         return BP_OK;
     }
     static int emit(bp_layer *L, EmitArgs<IdT> &a, int fk, uint32_t chunks, double bytes) {
         switch (fk) {
-        case BP_FILTER_NONE: launch_emit<BP_FILTER_NONE>(L, a, chunks, bytes); break;
-        case BP_FILTER_ID_PARITY: launch_emit<BP_FILTER_ID_PARITY>(L, a, chunks, bytes); break;
-        case BP_FILTER_XOR_MASK: launch_emit<BP_FILTER_XOR_MASK>(L, a, chunks, bytes); break;
-        case BP_FILTER_CATEGORY: launch_emit<BP_FILTER_CATEGORY>(L, a, chunks, bytes); break;
+        case BP_FILTER_NONE: TRY(launch_emit<BP_FILTER_NONE>(L, a, chunks, bytes)); break;
+        case BP_FILTER_ID_PARITY: TRY(launch_emit<BP_FILTER_ID_PARITY>(L, a, chunks, bytes)); break;
+        case BP_FILTER_XOR_MASK: TRY(launch_emit<BP_FILTER_XOR_MASK>(L, a, chunks, bytes)); break;
+        case BP_FILTER_CATEGORY: TRY(launch_emit<BP_FILTER_CATEGORY>(L, a, chunks, bytes)); break;
         default: return fail(L, BP_ERR_INVALID_ARG, "unknown filter kind %d", fk);
         }
         return check_launch(L, "scan_emit_kernel");
@@ -958,9 +1009,9 @@ int bp_plan_radix_passes(uint64_t varying_mask, uint32_t *out_shift, uint32_t *o
     RadixPlan plan;
     memset(&plan, 0, sizeof plan);
     const int np = plan_passes(varying_mask, plan);
-    for (int i = 0; i < np && i < max_passes; ++i) {
-        if (out_shift) out_shift[i] = plan.shift[i];
-        if (out_bits) out_bits[i] = plan.bits[i];
+    for (int i = 0; i < np && i < max_passes; ++i) { // second field in the high half-words
+        if (out_shift) out_shift[i] = plan.shift[i] | ((uint32_t)plan.shift2[i] << 16);
+        if (out_bits) out_bits[i] = plan.bits[i] | ((uint32_t)plan.bits2[i] << 16);
     }
     return np;
 }

@@ -22,11 +22,22 @@ struct NoVal {};
 constexpr int RADIX_MAX_PASSES = 16;
 constexpr int RADIX = 256;
 
+// One digit = up to two bit-fields of the key: (key >> shift) & ((1 << bits) - 1), with the second field
+// (shift2, bits2; bits2 may be 0) stacked above the first.  Two fields let the planner skip a gap of
+// constant bits (e.g. between the depth tag and the significant Morton bits) inside one pass.
 struct RadixPlan {
     int npasses;
     unsigned char shift[RADIX_MAX_PASSES];
     unsigned char bits[RADIX_MAX_PASSES];
+    unsigned char shift2[RADIX_MAX_PASSES];
+    unsigned char bits2[RADIX_MAX_PASSES];
 };
+
+template <class K> __host__ __device__ __forceinline__ uint32_t plan_digit(const RadixPlan &pl, int p, K k) {
+    uint32_t d = (uint32_t)(k >> pl.shift[p]) & ((1u << pl.bits[p]) - 1u);
+    if (pl.bits2[p]) d |= ((uint32_t)(k >> pl.shift2[p]) & ((1u << pl.bits2[p]) - 1u)) << pl.bits[p];
+    return d;
+}
 
 // ---- histograms for every planned digit in one read of the keys ---------------------------------
 template <class K>
@@ -34,12 +45,24 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ k
                                                           const uint32_t *__restrict__ n_dev, RadixPlan plan,
                                                           uint32_t *__restrict__ ghist) {
     __shared__ uint32_t sh[RADIX_MAX_PASSES * RADIX];
+    __shared__ uint32_t sdesc[RADIX_MAX_PASSES][5]; // shift, mask, shift2, mask2, bits
     const int np = plan.npasses;
     for (int i = threadIdx.x; i < np * RADIX; i += blockDim.x) sh[i] = 0;
+    if ((int)threadIdx.x < np) {
+        const int p = threadIdx.x;
+        sdesc[p][0] = plan.shift[p];
+        sdesc[p][1] = (1u << plan.bits[p]) - 1u;
+        sdesc[p][2] = plan.shift2[p];
+        sdesc[p][3] = (1u << plan.bits2[p]) - 1u;
+        sdesc[p][4] = plan.bits[p];
+    }
     __syncthreads();
     const uint32_t n = n_dev ? *n_dev : n_host;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     constexpr int UNROLL = 4;
+    auto digit = [&](int p, K k) -> uint32_t {
+        return ((uint32_t)(k >> sdesc[p][0]) & sdesc[p][1]) | (((uint32_t)(k >> sdesc[p][2]) & sdesc[p][3]) << sdesc[p][4]);
+    };
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + (UNROLL - 1) * stride < n; i += UNROLL * stride) {
         K k[UNROLL];
@@ -47,13 +70,11 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ k
         for (int u = 0; u < UNROLL; ++u) k[u] = ld_stream(keys + i + u * stride);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-            for (int p = 0; p < np; ++p)
-                atomicAdd(&sh[p * RADIX + (uint32_t)((k[u] >> plan.shift[p]) & (K)((1u << plan.bits[p]) - 1))], 1u);
+            for (int p = 0; p < np; ++p) atomicAdd(&sh[p * RADIX + digit(p, k[u])], 1u);
     }
     for (; i < n; i += stride) {
         const K k = ld_stream(keys + i);
-        for (int p = 0; p < np; ++p)
-            atomicAdd(&sh[p * RADIX + (uint32_t)((k >> plan.shift[p]) & (K)((1u << plan.bits[p]) - 1))], 1u);
+        for (int p = 0; p < np; ++p) atomicAdd(&sh[p * RADIX + digit(p, k)], 1u);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < np * RADIX; j += blockDim.x) {
@@ -74,7 +95,14 @@ __global__ void __launch_bounds__(RADIX) radix_scan_hist_kernel(uint32_t *__rest
 
 // ---- digit functors -----------------------------------------------------------------------------------
 // The pass kernel is generic over how a key maps to a bin.  Pads (all-ones keys) must map to max().
-template <class K> struct ShiftMaskDigit { // LSD radix digit: (key >> shift) & mask
+template <class K> struct ShiftMaskDigit { // LSD radix digit: one or two bit-fields (see RadixPlan)
+    uint32_t shift, mask, shift2, mask2, bits;
+    __device__ __forceinline__ uint32_t operator()(K k) const {
+        return ((uint32_t)(k >> shift) & mask) | (((uint32_t)(k >> shift2) & mask2) << bits);
+    }
+    __device__ __forceinline__ uint32_t max() const { return mask | (mask2 << bits); }
+};
+template <class K> struct OneFieldDigit { // the common case: one bit-field, (key >> shift) & mask
     uint32_t shift, mask;
     __device__ __forceinline__ uint32_t operator()(K k) const { return (uint32_t)(k >> shift) & mask; }
     __device__ __forceinline__ uint32_t max() const { return mask; }

@@ -70,10 +70,13 @@ template <> struct FilterFn<BP_FILTER_CATEGORY> {
 // ---------------------------------------------------------------------------------------------
 // scan_runs_kernel
 // ---------------------------------------------------------------------------------------------
-constexpr int RUNS_THREADS = 256;
-constexpr int RUNS_IPT = 4;
+// Tiles are 4096 elements: with smaller tiles the decoupled look-back is the bottleneck -- so many tiles
+// are in flight that the nearest inclusive prefix is hundreds of tiles back (profiles/r1_scan_before.txt:
+// 41 % / 31 % of the stall samples of the two kernels were the barrier behind the look-back).
+constexpr int RUNS_THREADS = 512;
+constexpr int RUNS_IPT = 8;
 constexpr int RUNS_TILE = RUNS_THREADS * RUNS_IPT;
-constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_THREADS = 512;
 constexpr int EMIT_IPT = 8;
 constexpr int EMIT_CHUNK = EMIT_THREADS * EMIT_IPT;
 
@@ -225,26 +228,35 @@ template <class IdT> struct EmitArgs {
     int *err;
 };
 
+template <class IdT> struct EmitSmem {
+    static constexpr bool WIDE = sizeof(IdT) == 8;
+    static constexpr size_t OFF_WORDS = EMIT_CHUNK + 2;                               // u64: run offsets, later the staged output
+    static constexpr size_t IDX_WORDS = WIDE ? EMIT_CHUNK : (EMIT_CHUNK + 2) / 2;     // u64: run record indices (u32), later `earlier`
+    static constexpr size_t BYTES = (OFF_WORDS + IDX_WORDS + EMIT_THREADS / 32 + 4) * sizeof(uint64_t);
+};
+
 template <class IdT, int FK>
 __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<IdT> a) {
     constexpr bool WIDE = sizeof(IdT) == 8;
-    __shared__ uint64_t soff[EMIT_CHUNK + 2];
+    typedef EmitSmem<IdT> S;
+    extern __shared__ __align__(16) unsigned char emit_smem[];
+    uint64_t *soff = (uint64_t *)emit_smem;
     // sidx holds the source record indices during the walk; for u64 IDs it is sized so that it can
     // stage the `earlier` half of the output afterwards
-    __shared__ uint64_t sidx_raw[WIDE ? EMIT_CHUNK : (EMIT_CHUNK + 2) / 2];
-    __shared__ uint64_t sscratch[EMIT_THREADS / 32 + 2];
-    __shared__ uint64_t sbase;
-    __shared__ uint32_t stile;
+    uint64_t *sidx_raw = soff + S::OFF_WORDS;
+    uint64_t *sscratch = sidx_raw + S::IDX_WORDS;
+    uint64_t *sbase_p = sscratch + EMIT_THREADS / 32 + 2;
+    uint32_t *stile_p = (uint32_t *)(sbase_p + 1);
     uint32_t *sidx = (uint32_t *)sidx_raw;
-    // the staged output reuses soff / sidx: every thread has finished its walk before the first
-    // barrier inside block_exclusive_sum, and staging starts after it
+    // the staged output reuses soff / sidx: every thread has finished its walk before the barrier that
+    // precedes the staging
     uint64_t *spa = soff;     // packed pair, or `later`
     uint64_t *spb = sidx_raw; // `earlier` (u64 IDs only)
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) stile = atomicAdd(a.tile_counter, 1u);
+    if (tid == 0) *stile_p = atomicAdd(a.tile_counter, 1u);
     __syncthreads();
-    const uint32_t chunk = stile;
+    const uint32_t chunk = *stile_p;
     const uint64_t w0 = (uint64_t)chunk * EMIT_CHUNK;
     if (w0 >= a.n_work) return;
     const uint32_t chunk_n = (uint32_t)min((uint64_t)EMIT_CHUNK, a.n_work - w0);
@@ -255,6 +267,11 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
     for (uint32_t i = tid; i < nsrc + 1; i += EMIT_THREADS) soff[i] = a.src_off[c0 + i]; // src_off[n_sources] = n_work
     for (uint32_t i = tid; i < nsrc; i += EMIT_THREADS) sidx[i] = a.src_idx[c0 + i];
     __syncthreads();
+
+    // Without a filter and while no same-ID item has been seen, every work item yields exactly one pair:
+    // the output position is the work-item index and no compaction (block scan + look-back) is needed.
+    // If a same-ID item does turn up, the host discards this emission and re-emits in ACTIVE mode.
+    const bool identity = FK == BP_FILTER_NONE && a.mode == EMIT_MODE_FIRST && a.first_owned == 0;
 
     // each thread owns EMIT_IPT consecutive work items: one bisection, then a linear walk
     const uint32_t first = tid * EMIT_IPT;
@@ -284,7 +301,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
             if (a.mode == EMIT_MODE_FIRST) {
                 const bool same = id_i == id_j;
                 same_seen |= same;
-                emit = !same && j >= a.first_owned && FilterFn<FK>::pass(a.filter, id_j, id_i);
+                emit = identity || (!same && j >= a.first_owned && FilterFn<FK>::pass(a.filter, id_j, id_i));
             } else if (a.mode == EMIT_MODE_FLAG) {
                 if (id_i == id_j) a.inactive[j] = 1;
                 emit = false;
@@ -301,11 +318,17 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
     }
     if (a.mode == EMIT_MODE_FLAG) return;
 
-    uint32_t chunk_pass;
-    const uint32_t ex = block_exclusive_sum<EMIT_THREADS, uint32_t>(npass, (uint32_t *)sscratch, &chunk_pass);
-    if (warp == 0) {
-        const uint64_t e = lookback_exclusive(a.status, chunk, (uint64_t)chunk_pass, a.err);
-        if (lane == 0) sbase = e;
+    uint32_t chunk_pass, ex;
+    if (identity) {
+        chunk_pass = chunk_n;
+        ex = first;
+        __syncthreads(); // all walks done before soff / sidx are overwritten
+    } else {
+        ex = block_exclusive_sum<EMIT_THREADS, uint32_t>(npass, (uint32_t *)sscratch, &chunk_pass);
+        if (warp == 0) {
+            const uint64_t e = lookback_exclusive(a.status, chunk, (uint64_t)chunk_pass, a.err);
+            if (lane == 0) *sbase_p = e;
+        }
     }
     // stage, then write coalesced
 #pragma unroll
@@ -320,7 +343,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
         }
     }
     __syncthreads();
-    const uint64_t base = sbase;
+    const uint64_t base = identity ? w0 : *sbase_p;
     for (uint32_t i = tid; i < chunk_pass; i += EMIT_THREADS) {
         const uint64_t g = base + i;
         if (g < a.capacity) {

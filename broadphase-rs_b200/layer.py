@@ -294,7 +294,13 @@ def plan_radix_passes(mask):
     sh = (ctypes.c_uint32 * 16)()
     bt = (ctypes.c_uint32 * 16)()
     n = lib().bp_plan_radix_passes(mask, sh, bt, 16)
-    return [(sh[i], bt[i]) for i in range(n)]
+    out = []
+    for i in range(n):  # (shift, bits) or, with a second bit-field, (shift, bits, shift2, bits2)
+        f = (sh[i] & 0xFFFF, bt[i] & 0xFFFF)
+        if bt[i] >> 16:
+            f += (sh[i] >> 16, bt[i] >> 16)
+        out.append(f)
+    return out
 
 
 def device_count():

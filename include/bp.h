@@ -201,7 +201,9 @@ int bp_version(void);
 int bp_device_count(int *out_count);
 
 /* Host-side radix planning, exposed for tests: given the mask of key bits that differ between
- * any two records, writes up to 16 (shift, bits) digit descriptors and returns how many. */
+ * any two records, writes up to 16 digit descriptors and returns how many.  A digit is one or two
+ * bit-fields: the low half-words of out_shift[i] / out_bits[i] describe the first field, the high
+ * half-words the second (bits == 0: absent), stacked above the first. */
 int bp_plan_radix_passes(uint64_t varying_mask, uint32_t *out_shift, uint32_t *out_bits, int max_passes);
 
 #ifdef __cplusplus

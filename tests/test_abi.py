@@ -54,6 +54,15 @@ def test_invalid_arguments(bp):
     assert L.bp_layer_destroy(None) == 0
 
 
+def _covered(plan):
+    c = 0
+    for f in plan:
+        c |= ((1 << f[1]) - 1) << f[0]
+        if len(f) == 4:
+            c |= ((1 << f[3]) - 1) << f[2]
+    return c
+
+
 def test_radix_planner(bp):
     plan = bp.plan_radix_passes
     assert plan(0) == []
@@ -62,21 +71,35 @@ def test_radix_planner(bp):
     # Index64_3D, every record at depth 7: only the top 21 origin bits vary -> 3 passes, not 8
     mask = ((1 << 21) - 1) << (5 + 57 - 21)
     p = plan(mask)
-    assert len(p) == 3 and p[0][0] == 41 and sum(b for _, b in p) == 21
-    # multi-depth keys: depth bits + top origin bits, with a gap in between
+    assert len(p) == 3 and p[0][0] == 41 and _covered(p) & mask == mask
+    # multi-depth keys: 4 depth bits + 39 origin bits with a gap in between: 43 bits -> 6 passes, the
+    # first digit made of two bit-fields (depth bits + the lowest origin bits)
     mask = 0xF | (((1 << 39) - 1) << 23)
     p = plan(mask)
-    assert p[0] == (0, 4) and len(p) == 6
-    covered = 0
-    for s, b in p:
-        assert 1 <= b <= 8
-        covered |= ((1 << b) - 1) << s
-    assert covered & mask == mask
-    # full 62-bit key: 8 passes
+    assert len(p) == 6 and p[0] == (0, 4, 23, 4)
+    assert _covered(p) & mask == mask
+    # packed ID pairs with 20-bit IDs: 40 bits in two fields -> 5 passes
+    mask = 0xFFFFF | (0xFFFFF << 32)
+    p = plan(mask)
+    assert len(p) == 5 and _covered(p) & mask == mask
+    # scattered bits: the single 8-bit window wins over two 1-bit runs
+    p = plan(0b10101010)
+    assert p == [(1, 7)]
+    # digits never overlap, are processed from the least significant bit up, and hold <= 8 bits
+    for mask in (0xDEADBEEFCAFEF00D, (1 << 62) - 1, (1 << 64) - 1, 0x8000000000000001):
+        p = plan(mask)
+        assert _covered(p) & mask == mask
+        seen, last_top = 0, -1
+        for f in p:
+            fields = [(f[0], f[1])] + ([(f[2], f[3])] if len(f) == 4 else [])
+            assert sum(b for _, b in fields) <= 8
+            for sft, b in fields:
+                m = ((1 << b) - 1) << sft
+                assert m & seen == 0 and sft + b <= 64 and sft > last_top
+                seen |= m
+                last_top = sft + b - 1
     assert len(plan((1 << 62) - 1)) == 8
     assert len(plan((1 << 64) - 1)) == 8
-    for s, b in plan((1 << 64) - 1):
-        assert s + b <= 64
 
 
 def test_scene_recipes_are_deterministic(bp):

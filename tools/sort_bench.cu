@@ -56,6 +56,8 @@ void run(const char *name, K *k0, V *v0, K *k1, V *v1, uint32_t n, uint64_t mask
         uint64_t w = (m >> sh) & 0xff;
         plan.shift[np] = sh;
         plan.bits[np] = 64 - __builtin_clzll(w);
+        plan.shift2[np] = 0;
+        plan.bits2[np] = 0;
         np++;
         if (sh + 8 >= 64) break;
         m &= ~(0xffull << sh);
@@ -68,7 +70,7 @@ void run(const char *name, K *k0, V *v0, K *k1, V *v1, uint32_t n, uint64_t mask
         printf("%s: scratch too small\n", name);
         return;
     }
-    auto kern = radix_pass_kernel<K, V, THREADS, ITEMS, MINB>;
+    auto kern = radix_pass_kernel<K, V, THREADS, ITEMS, MINB, OneFieldDigit<K>>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, Cfg::SMEM_BYTES));
@@ -91,7 +93,7 @@ void run(const char *name, K *k0, V *v0, K *k1, V *v1, uint32_t n, uint64_t mask
         V *vin = v0, *vout = v1;
         cudaEventRecord(e0);
         for (int p = 0; p < np; ++p) {
-            RadixPassArgs<K, V> a;
+            RadixPassArgs<K, V, OneFieldDigit<K>> a;
             a.kin = kin; a.kout = kout; a.vin = vin; a.vout = vout;
             a.n_host = n; a.n_dev = nullptr;
             a.ghist_excl = hist + p * RADIX;
