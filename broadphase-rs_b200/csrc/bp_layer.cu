@@ -607,7 +607,7 @@ template <int KIND, class IdT> struct Impl {
 
         // ---- runs ----
         const uint32_t rtiles = (uint32_t)((R + RUNS_TILE - 1) / RUNS_TILE);
-        const size_t sbytes = 64 + 2 * (size_t)rtiles * sizeof(uint64_t);
+        const size_t sbytes = 64;
         TRY(ensure(L, L->scratch, sbytes));
         TRY(ensure(L, L->src_idx, R * sizeof(uint32_t)));
         TRY(ensure(L, L->src_off, (R + 1) * sizeof(uint64_t)));
@@ -619,8 +619,7 @@ template <int KIND, class IdT> struct Impl {
         ra.src_idx = (uint32_t *)L->src_idx.p;
         ra.src_off = (uint64_t *)L->src_off.p;
         ra.tile_counter = (uint32_t *)L->scratch.p;
-        ra.status_cnt = (uint64_t *)((char *)L->scratch.p + 64);
-        ra.status_work = ra.status_cnt + rtiles;
+        ra.packed_counter = (unsigned long long *)((char *)L->scratch.p + 8);
         ra.totals = L->d_tot;
         ra.err = L->d_err;
         {
@@ -629,6 +628,7 @@ template <int KIND, class IdT> struct Impl {
         }
         TRY(check_launch(L, "scan_runs_kernel"));
         TRY(fetch_totals(L));
+        if (L->h_tot->pad) return fail(L, BP_ERR_TOO_LARGE, "scan would visit more than 2^33 record pairs");
         const uint64_t C = L->h_tot->n_sources, W = L->h_tot->n_work;
         L->stats.n_work_items = W;
         L->stats.algo_bytes[BP_K_SCAN_RUNS] += (double)C * 12.0;
@@ -650,7 +650,7 @@ template <int KIND, class IdT> struct Impl {
                                                                                   (uint32_t *)L->chunk_src.p);
         }
         TRY(check_launch(L, "scan_chunks_kernel"));
-        const size_t ebytes = 64 + (size_t)chunks * sizeof(uint64_t);
+        const size_t ebytes = 64;
         TRY(ensure(L, L->scratch, ebytes));
         EmitArgs<IdT> ea;
         ea.ids = ids(L, L->cur);
@@ -665,8 +665,7 @@ template <int KIND, class IdT> struct Impl {
         ea.out_a = wide ? (uint64_t *)L->praw[0].p : nullptr;
         ea.out_b = wide ? (uint64_t *)L->praw_b[0].p : nullptr;
         ea.capacity = W;
-        ea.tile_counter = (uint32_t *)L->scratch.p;
-        ea.status = (uint64_t *)((char *)L->scratch.p + 64);
+        ea.pair_counter = (unsigned long long *)L->scratch.p;
         ea.totals = L->d_tot;
         ea.filter = fa;
         ea.err = L->d_err;
@@ -675,6 +674,7 @@ template <int KIND, class IdT> struct Impl {
         CU(L, cudaMemsetAsync(L->scratch.p, 0, ebytes, L->stream));
         ea.mode = EMIT_MODE_FIRST;
         TRY(emit(L, ea, fk, chunks, emit_bytes));
+        CU(L, cudaMemcpyAsync(&L->d_tot->n_raw_pairs, L->scratch.p, 8, cudaMemcpyDeviceToDevice, L->stream));
         TRY(fetch_totals(L));
         if (L->h_tot->any_same_id) {
             // some ID owns nested bounds: the reference skips such records entirely (src/layer.rs:562-564),
@@ -689,6 +689,7 @@ template <int KIND, class IdT> struct Impl {
             CU(L, cudaMemsetAsync(L->scratch.p, 0, ebytes, L->stream));
             ea.mode = EMIT_MODE_ACTIVE;
             TRY(emit(L, ea, fk, chunks, emit_bytes));
+            CU(L, cudaMemcpyAsync(&L->d_tot->n_raw_pairs, L->scratch.p, 8, cudaMemcpyDeviceToDevice, L->stream));
             TRY(fetch_totals(L));
         }
         L->stats.n_raw_pairs = L->h_tot->n_raw_pairs;

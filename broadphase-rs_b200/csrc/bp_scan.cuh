@@ -94,96 +94,163 @@ template <class T> struct RunsArgs {
     uint32_t n;
     uint32_t *src_idx;   // [n]   compacted: record index of each non-empty run
     uint64_t *src_off;   // [n+1] compacted: exclusive prefix of run lengths (+ total at [n_sources])
-    uint64_t *status_cnt; // look-back chains, one status word per tile each, zeroed
-    uint64_t *status_work;
-    uint32_t *tile_counter; // zeroed
+    unsigned long long *packed_counter; // zeroed: (sources << RUNS_WORK_BITS) | work, bumped once per tile
+    uint32_t *tile_counter; // zeroed; counts finished tiles
     ScanTotals *totals;
     int *err;
 };
 
+constexpr int RUNS_WORK_BITS = 34; // 30 bits of source count above 34 bits of work items
+
+// Sources (records with a non-empty descendant run) may be listed in any order as long as src_off is
+// the running sum of their lengths in that order: the pairs are sorted afterwards anyway.  So a tile does
+// not need the prefix over all EARLIER tiles (a chained scan, whose look-back made every tile wait for
+// its slowest predecessor) -- it only needs a private range, which one 64-bit atomicAdd hands out.
 template <class T>
 __global__ void __launch_bounds__(RUNS_THREADS) scan_runs_kernel(const RunsArgs<T> a) {
     typedef typename T::key_t K;
+    constexpr int WARPS = RUNS_THREADS / 32;
+    constexpr int WSPAN = 32 * RUNS_IPT; // records per warp
     __shared__ K skeys[RUNS_TILE + 1];
-    __shared__ uint64_t sscratch[RUNS_THREADS / 32 + 2];
-    __shared__ uint64_t sbase[2];
-    __shared__ uint32_t stile;
+    __shared__ uint32_t swc[WARPS];
+    __shared__ unsigned long long sww[WARPS];
+    __shared__ unsigned long long sbase;
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) stile = atomicAdd(a.tile_counter, 1u);
-    __syncthreads();
-    const uint32_t tile = stile;
+    const unsigned lt = lanemask_lt();
+    const uint32_t tile = blockIdx.x;
     const uint32_t r0 = tile * RUNS_TILE;
     if (r0 >= a.n) return;
     const uint32_t tile_n = min((uint32_t)RUNS_TILE, a.n - r0);
+    const bool has_next = r0 + tile_n < a.n; // skeys[tile_n] = first key of the next tile
 
-    // keys of the tile plus the first key of the next one, coalesced
     for (uint32_t i = tid; i < tile_n + 1; i += RUNS_THREADS)
-        if (r0 + i < a.n) skeys[i] = a.keys[r0 + i];
+        if (r0 + i < a.n) skeys[i] = ld_stream(a.keys + r0 + i);
     __syncthreads();
+    const K tile_last = skeys[tile_n - 1];
 
+    // warp-striped: item q of lane l of warp w is tile record w*WSPAN + q*32 + l (conflict-free shared reads)
     uint32_t len[RUNS_IPT];
-    uint32_t nz = 0;
-    uint64_t work = 0;
+    uint32_t far_mask[RUNS_IPT]; // per item: lanes whose run leaves the tile (resolved cooperatively below)
 #pragma unroll
     for (int q = 0; q < RUNS_IPT; ++q) {
-        const uint32_t li = tid * RUNS_IPT + q; // blocked: a thread owns consecutive records
+        const uint32_t li = warp * WSPAN + q * 32 + lane;
         len[q] = 0;
-        if (li >= tile_n) continue;
-        const uint32_t i = r0 + li;
-        if (i + 1 >= a.n) continue;
-        const K hi = run_upper_key<T>(skeys[li]);
-        if (skeys[li + 1] > hi) continue; // the common case: no later record inside this cell
-        // gallop, then bisect, for the first index whose key exceeds hi
-        uint32_t lo = i + 1, step = 1;
-        while (lo + step < a.n && a.keys[lo + step] <= hi) {
-            lo += step;
-            step <<= 1;
+        bool far = false;
+        if (li < tile_n && r0 + li + 1 < a.n) {
+            const K hi = run_upper_key<T>(skeys[li]);
+            if (li + 1 < tile_n || has_next) {
+                if (!(skeys[li + 1] > hi)) {        // not the common case "no later record inside this cell"
+                    if (tile_last > hi) {           // the run ends inside the tile: bisect in shared memory
+                        uint32_t lo = li + 1, end = tile_n - 1; // keys[lo] <= hi < keys[end]
+                        while (lo + 1 < end) {
+                            const uint32_t mid = (lo + end) >> 1;
+                            if (skeys[mid] <= hi)
+                                lo = mid;
+                            else
+                                end = mid;
+                        }
+                        len[q] = lo - li;
+                    } else {
+                        far = true; // every remaining record of the tile is inside; the end is further on
+                    }
+                }
+            }
         }
-        uint32_t end = min(lo + step, a.n); // keys[lo] <= hi, (end == n or keys[end] > hi)
-        while (lo + 1 < end) {
-            const uint32_t mid = lo + ((end - lo) >> 1);
-            if (a.keys[mid] <= hi)
-                lo = mid;
-            else
-                end = mid;
+        far_mask[q] = __ballot_sync(BP_FULL_MASK, far);
+    }
+    // runs that leave the tile: the whole warp searches [tile end, n) 32 probes at a time
+#pragma unroll
+    for (int q = 0; q < RUNS_IPT; ++q) {
+        uint32_t m = far_mask[q];
+        while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t li = warp * WSPAN + q * 32 + src;
+            const K hi = run_upper_key<T>(skeys[li]);
+            // invariant: keys[lo] <= hi, (end == n or keys[end] > hi)
+            uint32_t lo = r0 + tile_n - 1, end = a.n;
+            while (end - lo > 1) {
+                const uint32_t span = end - lo - 1;              // unknown positions lo+1 .. end-1
+                const uint32_t step = (span + 31) / 32;           // >= 1
+                const uint64_t pos64 = (uint64_t)lo + (uint64_t)(lane + 1) * step;
+                const bool in = pos64 < end;
+                const bool gt = in ? (a.keys[(uint32_t)pos64] > hi) : true;
+                const uint32_t b = __ballot_sync(BP_FULL_MASK, gt);
+                const int f = b ? __ffs(b) - 1 : 32;              // first probe beyond the run (32: all probes are inside)
+                // probes of lanes < f are inside the run, the probe of lane f (if any) is beyond it or out of range
+                if (f < 32) {
+                    const uint64_t new_end = (uint64_t)lo + (uint64_t)(f + 1) * step;
+                    end = (uint32_t)(new_end < end ? new_end : end);
+                }
+                if (f > 0) lo += (uint32_t)f * step;
+            }
+            if ((int)lane == src) len[q] = lo - (r0 + li);
         }
-        len[q] = lo - i;
-        ++nz;
-        work += len[q];
     }
 
-    // block scans of (non-empty count, work)
-    uint32_t nz_total;
-    uint64_t work_total;
-    const uint32_t nz_ex = block_exclusive_sum<RUNS_THREADS, uint32_t>(nz, (uint32_t *)sscratch, &nz_total);
-    __syncthreads();
-    const uint64_t work_ex = block_exclusive_sum<RUNS_THREADS, uint64_t>(work, sscratch, &work_total);
-    __syncthreads();
-    // two look-back chains, walked by two different warps at the same time
-    if (warp == 0) {
-        const uint64_t e = lookback_exclusive(a.status_cnt, tile, (uint64_t)nz_total, a.err);
-        if (lane == 0) sbase[0] = e;
-    } else if (warp == 1) {
-        const uint64_t e = lookback_exclusive(a.status_work, tile, work_total, a.err);
-        if (lane == 0) sbase[1] = e;
-    }
-    __syncthreads();
-    uint32_t c = (uint32_t)sbase[0] + nz_ex;
-    uint64_t w = sbase[1] + work_ex;
+    // ranks inside the warp in record order (q, lane), then across the warps, then one atomic for the tile
+    uint32_t cpos[RUNS_IPT];
+    unsigned long long wpos[RUNS_IPT];
+    uint32_t wc = 0;
+    unsigned long long ww = 0;
 #pragma unroll
     for (int q = 0; q < RUNS_IPT; ++q) {
-        if (len[q] == 0) continue;
-        a.src_idx[c] = r0 + tid * RUNS_IPT + q;
-        a.src_off[c] = w;
-        ++c;
-        w += len[q];
+        const uint32_t nzm = __ballot_sync(BP_FULL_MASK, len[q] != 0);
+        const unsigned long long incl = warp_inclusive_sum((unsigned long long)len[q]);
+        cpos[q] = wc + __popc(nzm & lt);
+        wpos[q] = ww + incl - len[q];
+        wc += __popc(nzm);
+        ww += __shfl_sync(BP_FULL_MASK, incl, 31);
     }
-    if (r0 + tile_n == a.n && tid == 0) { // last tile: totals and the sentinel offset
-        const uint64_t ns = sbase[0] + nz_total, nw = sbase[1] + work_total;
-        a.totals->n_sources = ns;
-        a.totals->n_work = nw;
-        a.src_off[ns] = nw;
+    if (lane == 0) {
+        swc[warp] = wc;
+        sww[warp] = ww;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t c = lane < WARPS ? swc[lane] : 0;
+        unsigned long long w = lane < WARPS ? sww[lane] : 0;
+        const uint32_t ci = warp_inclusive_sum(c);
+        const unsigned long long wi = warp_inclusive_sum(w);
+        if (lane < WARPS) {
+            swc[lane] = ci - c;
+            sww[lane] = wi - w;
+        }
+        if (lane == 31) {
+            unsigned long long add = ((unsigned long long)ci << RUNS_WORK_BITS) + wi;
+            if (wi >= (1ull << (RUNS_WORK_BITS - 1))) { // cannot be packed: the host reports BP_ERR_TOO_LARGE
+                a.totals->pad = 1u;
+                add = 0;
+            }
+            const unsigned long long old = atomicAdd(a.packed_counter, add);
+            // a carry out of the work field would corrupt the source count: exactly one tile sees it happen
+            if ((old & ((1ull << RUNS_WORK_BITS) - 1)) + wi >= (1ull << RUNS_WORK_BITS)) a.totals->pad = 1u;
+            sbase = old;
+        }
+    }
+    __syncthreads();
+    const uint32_t cbase = (uint32_t)(sbase >> RUNS_WORK_BITS) + swc[warp];
+    const unsigned long long wbase = (sbase & ((1ull << RUNS_WORK_BITS) - 1)) + sww[warp];
+#pragma unroll
+    for (int q = 0; q < RUNS_IPT; ++q) {
+        if (len[q] != 0) {
+            a.src_idx[cbase + cpos[q]] = r0 + warp * WSPAN + q * 32 + lane;
+            a.src_off[cbase + cpos[q]] = wbase + wpos[q];
+        }
+    }
+    // the last tile to finish publishes the totals and the sentinel offset
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t done = atomicAdd(a.tile_counter, 1u);
+        if (done == gridDim.x - 1) {
+            const unsigned long long tot = atomicAdd(a.packed_counter, 0ull);
+            const unsigned long long ns = tot >> RUNS_WORK_BITS, nw = tot & ((1ull << RUNS_WORK_BITS) - 1);
+            a.totals->n_sources = ns;
+            a.totals->n_work = nw;
+            a.src_off[ns] = nw;
+        }
     }
 }
 
@@ -221,8 +288,8 @@ template <class IdT> struct EmitArgs {
     uint64_t *out_a;        // u64 IDs: later
     uint64_t *out_b;        //          earlier
     uint64_t capacity;      // pairs the output arrays can hold
-    uint64_t *status;       // look-back, one per chunk, zeroed
-    uint32_t *tile_counter; // zeroed
+    unsigned long long *pair_counter; // zeroed: running count of emitted pairs (output slots are handed out by
+                                      // atomicAdd: the order of the raw pairs is irrelevant, they are sorted next)
     ScanTotals *totals;
     FilterArgs filter;
     int *err;
@@ -246,17 +313,14 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
     uint64_t *sidx_raw = soff + S::OFF_WORDS;
     uint64_t *sscratch = sidx_raw + S::IDX_WORDS;
     uint64_t *sbase_p = sscratch + EMIT_THREADS / 32 + 2;
-    uint32_t *stile_p = (uint32_t *)(sbase_p + 1);
     uint32_t *sidx = (uint32_t *)sidx_raw;
     // the staged output reuses soff / sidx: every thread has finished its walk before the barrier that
     // precedes the staging
     uint64_t *spa = soff;     // packed pair, or `later`
     uint64_t *spb = sidx_raw; // `earlier` (u64 IDs only)
 
-    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) *stile_p = atomicAdd(a.tile_counter, 1u);
-    __syncthreads();
-    const uint32_t chunk = *stile_p;
+    const unsigned tid = threadIdx.x;
+    const uint32_t chunk = blockIdx.x;
     const uint64_t w0 = (uint64_t)chunk * EMIT_CHUNK;
     if (w0 >= a.n_work) return;
     const uint32_t chunk_n = (uint32_t)min((uint64_t)EMIT_CHUNK, a.n_work - w0);
@@ -325,10 +389,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
         __syncthreads(); // all walks done before soff / sidx are overwritten
     } else {
         ex = block_exclusive_sum<EMIT_THREADS, uint32_t>(npass, (uint32_t *)sscratch, &chunk_pass);
-        if (warp == 0) {
-            const uint64_t e = lookback_exclusive(a.status, chunk, (uint64_t)chunk_pass, a.err);
-            if (lane == 0) *sbase_p = e;
-        }
+        if (tid == 0) *sbase_p = atomicAdd(a.pair_counter, (unsigned long long)chunk_pass);
     }
     // stage, then write coalesced
 #pragma unroll
@@ -355,7 +416,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
             }
         }
     }
-    if (w0 + chunk_n == a.n_work && tid == 0) a.totals->n_raw_pairs = base + chunk_pass;
+    if (identity && w0 + chunk_n == a.n_work && tid == 0) *a.pair_counter = a.n_work; // identity: one pair per work item
 }
 
 // ---------------------------------------------------------------------------------------------
