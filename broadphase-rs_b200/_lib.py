@@ -59,6 +59,10 @@ SYMBOLS = {
     "bp_dist_partition_records": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
     "bp_dist_partition_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "bp_dist_lookup_ranges": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
+    "bp_dist_count_records": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
+    "bp_dist_scatter_records": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _vp]),
+    "bp_dist_count_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp]),
+    "bp_dist_scatter_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp]),
     "bp_layer_set_halo": (_i, [_vp, _sz]),
     "bp_layer_scan_raw_device": (_i, [_vp, _P(Filter), _P(_vp), _P(_sz)]),
     "bp_layer_unique_pairs_device": (_i, [_vp, _vp, _sz, _u64, _P(_vp), _P(_sz)]),

@@ -798,7 +798,7 @@ template <int KIND, class IdT> struct Impl {
         {
             LaunchScope ls(L, BP_K_MISC, (double)n * sizeof(PK));
             const int blocks = (int)std::min<size_t>((n + 4095) / 4096, 148 * 8);
-            partition_hist_kernel<PK><<<std::max(blocks, 1), 512, 0, L->stream>>>(kin, n, op, hist);
+            partition_hist_kernel<PK, T, false><<<std::max(blocks, 1), 512, 0, L->stream>>>(kin, n, op, hist, nullptr);
         }
         TRY(check_launch(L, "partition_hist_kernel"));
         // bucket counts back to the host (they are the all-to-all split sizes) before the scan overwrites them
@@ -832,6 +832,106 @@ template <int KIND, class IdT> struct Impl {
         CU(L, cudaStreamSynchronize(L->stream));
         for (int b = 0; b <= n_spl; ++b) counts_out[b] = h_counts[b];
         return BP_OK;
+    }
+
+    // Bucket sizes of a splitter partition (and, for records, the halo copies every bucket will receive).
+    template <class PK, bool HALO>
+    static int partition_count(bp_layer *L, const PK *kin, uint32_t n, const uint64_t *spl, int n_spl, uint32_t shift,
+                               uint64_t *counts_out, uint64_t *halo_out) {
+        for (int b = 0; b <= n_spl; ++b) {
+            counts_out[b] = 0;
+            if (halo_out) halo_out[b] = 0;
+        }
+        if (n == 0) return BP_OK;
+        SplitterDigit<PK> op;
+        for (int i = 0; i < MAX_SPLITTERS; ++i) op.spl[i] = i < n_spl ? spl[i] : ~0ull;
+        op.n = (uint32_t)n_spl;
+        op.shift = shift;
+        TRY(ensure(L, L->scratch, 256));
+        uint32_t *hist = (uint32_t *)L->scratch.p, *halo = hist + 32;
+        CU(L, cudaMemsetAsync(L->scratch.p, 0, 256, L->stream));
+        {
+            LaunchScope ls(L, BP_K_MISC, (double)n * sizeof(PK));
+            const int blocks = (int)std::min<size_t>((n + 4095) / 4096, 148 * 8);
+            partition_hist_kernel<PK, T, HALO><<<std::max(blocks, 1), 512, 0, L->stream>>>(kin, n, op, hist, halo);
+        }
+        TRY(check_launch(L, "partition_hist_kernel"));
+        uint32_t h[64];
+        CU(L, cudaMemcpyAsync(h, hist, 64 * sizeof(uint32_t), cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaStreamSynchronize(L->stream));
+        for (int b = 0; b <= n_spl; ++b) {
+            counts_out[b] = h[b];
+            if (halo_out) halo_out[b] = h[32 + b];
+        }
+        return BP_OK;
+    }
+
+    // The partition pass with one destination array per bucket (device addresses; peers' symmetric
+    // memory in the multi-GPU path), plus the halo copies.  Nothing is returned: the sizes are known
+    // from partition_count, which is also how the caller computed the destinations.
+    template <class PK, class PV>
+    static int partition_scatter(bp_layer *L, const PK *kin, const PV *vin, uint32_t n, const uint64_t *spl, int n_spl,
+                                 uint32_t shift, const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst,
+                                 const uint64_t *hvdst) {
+        typedef PassTune<PK, PV> Tune;
+        typedef RadixPassCfg<PK, PV, Tune::THREADS, Tune::ITEMS> Cfg;
+        if (n == 0) return BP_OK;
+        SplitterScatterDigit<PK> op;
+        for (int i = 0; i < MAX_SPLITTERS; ++i) op.spl[i] = i < n_spl ? spl[i] : ~0ull;
+        op.n = (uint32_t)n_spl;
+        op.shift = shift;
+        for (int b = 0; b <= MAX_SPLITTERS; ++b) {
+            op.kdst[b] = b <= n_spl ? kdst[b] : 0;
+            op.vdst[b] = (b <= n_spl && vdst) ? vdst[b] : 0;
+        }
+        const uint32_t tiles = (n + Cfg::TILE - 1) / Cfg::TILE;
+        const size_t total = (size_t)(RADIX + 64 + (size_t)tiles * RADIX) * sizeof(uint32_t);
+        TRY(ensure(L, L->scratch, total));
+        uint32_t *zero_hist = (uint32_t *)L->scratch.p, *counters = zero_hist + RADIX, *status = counters + 64;
+        CU(L, cudaMemsetAsync(L->scratch.p, 0, total, L->stream));
+        auto kern = radix_pass_kernel<PK, PV, Tune::THREADS, Tune::ITEMS, Tune::MINB, SplitterScatterDigit<PK>>;
+        CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+        RadixPassArgs<PK, PV, SplitterScatterDigit<PK>> a;
+        a.kin = kin;
+        a.kout = nullptr;
+        a.vin = vin;
+        a.vout = nullptr;
+        a.n_host = n;
+        a.n_dev = nullptr;
+        a.ghist_excl = zero_hist; // every bucket starts at offset 0 of its own destination
+        a.status = status;
+        a.tile_counter = counters;
+        a.op = op;
+        a.err = L->d_err;
+        {
+            const double eb = std::is_same<PV, NoVal>::value ? sizeof(PK) : sizeof(PK) + sizeof(PV);
+            LaunchScope ls(L, BP_K_MISC, 2.0 * (double)n * eb);
+            kern<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
+        }
+        TRY(check_launch(L, "radix_pass_kernel<scatter>"));
+        if constexpr (!std::is_same<PV, NoVal>::value) {
+            if (hkdst && hvdst) {
+                SplitterScatterDigit<PK> hop = op;
+                for (int b = 0; b <= MAX_SPLITTERS; ++b) {
+                    hop.kdst[b] = b <= n_spl ? hkdst[b] : 0;
+                    hop.vdst[b] = b <= n_spl ? hvdst[b] : 0;
+                }
+                uint32_t *cursor = counters + 32; // zeroed above
+                LaunchScope ls(L, BP_K_MISC, (double)n * sizeof(PK));
+                const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
+                halo_scatter_kernel<PK, PV, T><<<std::max(blocks, 1), 256, 0, L->stream>>>(kin, vin, n, hop, cursor);
+                TRY(check_launch(L, "halo_scatter_kernel"));
+            }
+        }
+        return BP_OK;
+    }
+
+    static int count_records(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *counts, uint64_t *halo) {
+        return partition_count<K, true>(L, (const K *)kin, (uint32_t)n, spl, n_spl, 0, counts, halo);
+    }
+    static int scatter_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl,
+                               const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst) {
+        return partition_scatter<K, IdT>(L, (const K *)kin, (const IdT *)vin, (uint32_t)n, spl, n_spl, 0, kdst, vdst, hkdst, hvdst);
     }
 
     static int partition_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl,
@@ -916,6 +1016,20 @@ int do_partition_records(bp_layer *L, const void *kin, const void *vin, size_t n
 int do_partition_pairs(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *kout, uint64_t *counts) {
     return Impl<BP_INDEX64_3D, uint32_t>::partition<uint64_t, NoVal>(L, kin, (const NoVal *)nullptr, (uint32_t)n, spl, n_spl, 32, kout,
                                                                      (NoVal *)nullptr, counts);
+}
+int do_count_records(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *counts, uint64_t *halo) {
+    DISPATCH(L, count_records(L, kin, n, spl, n_spl, counts, halo));
+}
+int do_scatter_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl, const uint64_t *kdst,
+                       const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst) {
+    DISPATCH(L, scatter_records(L, kin, vin, n, spl, n_spl, kdst, vdst, hkdst, hvdst));
+}
+int do_count_pairs(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *counts) {
+    return Impl<BP_INDEX64_3D, uint32_t>::partition_count<uint64_t, false>(L, kin, (uint32_t)n, spl, n_spl, 32, counts, nullptr);
+}
+int do_scatter_pairs(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, const uint64_t *kdst) {
+    return Impl<BP_INDEX64_3D, uint32_t>::partition_scatter<uint64_t, NoVal>(L, kin, (const NoVal *)nullptr, (uint32_t)n, spl, n_spl, 32,
+                                                                             kdst, nullptr, nullptr, nullptr);
 }
 int do_lookup_ranges(bp_layer *L, const void *keys, size_t n, const uint64_t *q, int nq, uint64_t *lo, uint64_t *hi) {
     DISPATCH(L, lookup_ranges(L, keys, n, q, nq, lo, hi));
@@ -1316,6 +1430,45 @@ int bp_dist_partition_pairs(bp_layer *L, const void *d_pairs, size_t n, const ui
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
     return do_partition_pairs(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, (uint64_t *)d_out_pairs, out_counts);
+}
+
+static bool bad_splitters(const uint64_t *splitters, int n) { return n < 0 || n > MAX_SPLITTERS || (n && !splitters); }
+
+int bp_dist_count_records(bp_layer *L, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
+                          uint64_t *out_counts, uint64_t *out_halo_counts) {
+    if (!L || !out_counts || bad_splitters(splitters, n_splitters)) return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_records");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_count_records(L, d_keys, n, splitters, n_splitters, out_counts, out_halo_counts);
+}
+
+int bp_dist_scatter_records(bp_layer *L, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
+                            int n_splitters, const uint64_t *dst_keys, const uint64_t *dst_ids, const uint64_t *halo_dst_keys,
+                            const uint64_t *halo_dst_ids) {
+    if (!L || !dst_keys || !dst_ids || bad_splitters(splitters, n_splitters))
+        return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_scatter_records");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_scatter_records(L, d_keys, d_ids, n, splitters, n_splitters, dst_keys, dst_ids, halo_dst_keys, halo_dst_ids);
+}
+
+int bp_dist_count_pairs(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t *out_counts) {
+    if (!L || !out_counts || bad_splitters(splitters, n_splitters)) return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_pairs");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 pairs");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_count_pairs(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, out_counts);
+}
+
+int bp_dist_scatter_pairs(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
+                          const uint64_t *dst_pairs) {
+    if (!L || !dst_pairs || bad_splitters(splitters, n_splitters)) return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_scatter_pairs");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 pairs");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_scatter_pairs(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, dst_pairs);
 }
 
 int bp_dist_lookup_ranges(bp_layer *L, const void *d_sorted_keys, size_t n, const uint64_t *queries, int n_queries,

@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(RADIX) radix_scan_hist_kernel(uint32_t *__rest
 // ---- digit functors -----------------------------------------------------------------------------------
 // The pass kernel is generic over how a key maps to a bin.  Pads (all-ones keys) must map to max().
 template <class K> struct ShiftMaskDigit { // LSD radix digit: one or two bit-fields (see RadixPlan)
+    static constexpr bool SCATTER = false;
     uint32_t shift, mask, shift2, mask2, bits;
     __device__ __forceinline__ uint32_t operator()(K k) const {
         return ((uint32_t)(k >> shift) & mask) | (((uint32_t)(k >> shift2) & mask2) << bits);
@@ -103,22 +104,30 @@ template <class K> struct ShiftMaskDigit { // LSD radix digit: one or two bit-fi
     __device__ __forceinline__ uint32_t max() const { return mask | (mask2 << bits); }
 };
 template <class K> struct OneFieldDigit { // the common case: one bit-field, (key >> shift) & mask
+    static constexpr bool SCATTER = false;
     uint32_t shift, mask;
     __device__ __forceinline__ uint32_t operator()(K k) const { return (uint32_t)(k >> shift) & mask; }
     __device__ __forceinline__ uint32_t max() const { return mask; }
 };
 constexpr int MAX_SPLITTERS = 15; // up to 16 shards
 template <class K> struct SplitterDigit { // range partition: number of splitters <= (key >> shift)
+    static constexpr bool SCATTER = false;
     uint64_t spl[MAX_SPLITTERS];
     uint32_t n, shift;
     __device__ __forceinline__ uint32_t operator()(K k) const {
         const uint64_t v = (uint64_t)k >> shift;
         uint32_t d = 0;
-#pragma unroll
-        for (int i = 0; i < MAX_SPLITTERS; ++i) d += (i < (int)n && spl[i] <= v) ? 1u : 0u;
+        for (uint32_t i = 0; i < n; ++i) d += (spl[i] <= v) ? 1u : 0u; // n is warp-uniform and small
         return d;
     }
     __device__ __forceinline__ uint32_t max() const { return n; }
+};
+// The same partition, but every bucket has its own destination array -- e.g. the receive buffer of
+// another GPU mapped over NVLink (symmetric memory): the partition pass IS the all-to-all.
+template <class K> struct SplitterScatterDigit : SplitterDigit<K> {
+    static constexpr bool SCATTER = true;
+    uint64_t kdst[MAX_SPLITTERS + 1]; // device addresses of the key destination of every bucket
+    uint64_t vdst[MAX_SPLITTERS + 1]; // ... and of the payload
 };
 
 // ---- one onesweep pass --------------------------------------------------------------------------------
@@ -321,6 +330,7 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
     }
     __syncthreads();
     uint32_t dst[ITEMS];
+    uint32_t dig[Op::SCATTER ? ITEMS : 1];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t i = k * THREADS + tid;
@@ -328,7 +338,12 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
             const K kk = skeys[i];
             const uint32_t d = op(kk);
             dst[k] = gbase[d] + i;
-            a.kout[dst[k]] = kk;
+            if constexpr (Op::SCATTER) {
+                dig[k] = d;
+                ((K *)a.op.kdst[d])[dst[k]] = kk; // possibly a store into a peer GPU's memory
+            } else {
+                a.kout[dst[k]] = kk;
+            }
         }
     }
     if constexpr (HAS_V) {
@@ -343,7 +358,12 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
 #pragma unroll
         for (int k = 0; k < ITEMS; ++k) {
             const uint32_t i = k * THREADS + tid;
-            if (FULL || i < tile_n) a.vout[dst[k]] = svals[i];
+            if (FULL || i < tile_n) {
+                if constexpr (Op::SCATTER)
+                    ((V *)a.op.vdst[dig[k]])[dst[k]] = svals[i];
+                else
+                    a.vout[dst[k]] = svals[i];
+            }
         }
     }
 }
@@ -372,27 +392,67 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_pass_kernel(const RadixPa
 }
 
 // ---- bucket counts for a splitter partition (one read of the keys) --------------------------------------
-template <class K>
+// With HALO (records of a multi-GPU shard exchange): a record whose cell reaches past later splitters is an
+// ancestor of records other shards will own, so it is also counted as a halo copy for each of those
+// shards: home = #splitters <= key, last = #splitters <= run_upper_key(key), halo copies for home+1..last.
+template <class K, class T, bool HALO>
 __global__ void __launch_bounds__(512) partition_hist_kernel(const K *__restrict__ keys, uint32_t n, SplitterDigit<K> op,
-                                                              uint32_t *__restrict__ ghist) {
-    __shared__ uint32_t sh[MAX_SPLITTERS + 1];
-    if (threadIdx.x <= MAX_SPLITTERS) sh[threadIdx.x] = 0;
+                                                              uint32_t *__restrict__ ghist, uint32_t *__restrict__ ghalo) {
+    __shared__ uint32_t sh[2 * (MAX_SPLITTERS + 1)];
+    if (threadIdx.x < 2 * (MAX_SPLITTERS + 1)) sh[threadIdx.x] = 0;
     __syncthreads();
-    uint32_t local[MAX_SPLITTERS + 1];
-#pragma unroll
-    for (int i = 0; i <= MAX_SPLITTERS; ++i) local[i] = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t d = op(ld_stream(keys + i));
-#pragma unroll
-        for (int b = 0; b <= MAX_SPLITTERS; ++b) local[b] += (d == (uint32_t)b) ? 1u : 0u;
+    const uint32_t nb = op.n + 1; // buckets in use
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t mine = 0; // lane b of every warp accumulates bucket b
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t nround = ((size_t)n + stride - 1) / stride * stride; // whole warps stay in the loop together
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        const bool live = i < n;
+        const K k = live ? ld_stream(keys + i) : (K)0;
+        const uint32_t d = live ? op(k) : 0xffffffffu;
+        for (uint32_t b = 0; b < nb; ++b) { // one ballot per bucket in use (2..16), warp-uniform trip count
+            const uint32_t c = __popc(__ballot_sync(BP_FULL_MASK, d == b));
+            if (lane == b) mine += c;
+        }
+        if constexpr (HALO) {
+            // common case: the cell ends before the next splitter -- one comparison
+            if (live && d < op.n) {
+                const K hi = run_upper_key<T>(k);
+                if (((uint64_t)hi >> op.shift) >= op.spl[d]) {
+                    const uint32_t last = op(hi);
+                    for (uint32_t s = d + 1; s <= last; ++s) atomicAdd(&sh[MAX_SPLITTERS + 1 + s], 1u); // rare
+                }
+            }
+        }
     }
-#pragma unroll
-    for (int b = 0; b <= MAX_SPLITTERS; ++b) {
-        const uint32_t c = warp_sum(local[b]);
-        if ((threadIdx.x & 31) == 0 && c) atomicAdd(&sh[b], c);
-    }
+    if (lane < nb && mine) atomicAdd(&sh[lane], mine);
     __syncthreads();
     if (threadIdx.x <= MAX_SPLITTERS && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], sh[threadIdx.x]);
+    if (HALO && threadIdx.x <= MAX_SPLITTERS && sh[MAX_SPLITTERS + 1 + threadIdx.x])
+        atomicAdd(&ghalo[threadIdx.x], sh[MAX_SPLITTERS + 1 + threadIdx.x]);
+}
+
+// Writes the halo copies counted above into their destinations (slots handed out by atomics: the
+// receiver sorts its records anyway).
+template <class K, class V, class T>
+__global__ void __launch_bounds__(256) halo_scatter_kernel(const K *__restrict__ keys, const V *__restrict__ vals, uint32_t n,
+                                                            SplitterScatterDigit<K> op, uint32_t *__restrict__ cursor) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const K k = ld_stream(keys + i);
+        const uint32_t d = op(k);
+        if (d >= op.n) continue; // already in the last shard
+        const K hi = run_upper_key<T>(k);
+        if (((uint64_t)hi >> op.shift) < op.spl[d]) continue; // the cell ends before the next splitter
+        const uint32_t last = op(hi);
+        if (last > d) {
+            const V v = vals[i];
+            for (uint32_t s = d + 1; s <= last; ++s) {
+                const uint32_t slot = atomicAdd(&cursor[s], 1u);
+                ((K *)op.kdst[s])[slot] = k;
+                ((V *)op.vdst[s])[slot] = v;
+            }
+        }
+    }
 }
 
 // equal ranges of query keys in a sorted key array (halo look-ups); one thread per query

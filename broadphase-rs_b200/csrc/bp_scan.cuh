@@ -141,8 +141,15 @@ __global__ void __launch_bounds__(RUNS_THREADS) scan_runs_kernel(const RunsArgs<
             const K hi = run_upper_key<T>(skeys[li]);
             if (li + 1 < tile_n || has_next) {
                 if (!(skeys[li + 1] > hi)) {        // not the common case "no later record inside this cell"
-                    if (tile_last > hi) {           // the run ends inside the tile: bisect in shared memory
-                        uint32_t lo = li + 1, end = tile_n - 1; // keys[lo] <= hi < keys[end]
+                    if (tile_last > hi) {           // the run ends inside the tile: gallop, then bisect, in shared memory
+                        // most runs are a handful of records long: doubling steps find the end in 1-3 probes
+                        const uint32_t last = tile_n - 1; // keys[last] > hi
+                        uint32_t lo = li + 1, step = 1;   // keys[lo] <= hi
+                        while (lo + step < last && skeys[lo + step] <= hi) {
+                            lo += step;
+                            step <<= 1;
+                        }
+                        uint32_t end = min(lo + step, last); // keys[end] > hi
                         while (lo + 1 < end) {
                             const uint32_t mid = (lo + end) >> 1;
                             if (skeys[mid] <= hi)
@@ -240,9 +247,9 @@ __global__ void __launch_bounds__(RUNS_THREADS) scan_runs_kernel(const RunsArgs<
         }
     }
     // the last tile to finish publishes the totals and the sentinel offset
-    __threadfence();
     __syncthreads();
     if (tid == 0) {
+        __threadfence(); // the tile's stores (made visible to this thread by the barrier) before the ticket
         const uint32_t done = atomicAdd(a.tile_counter, 1u);
         if (done == gridDim.x - 1) {
             const unsigned long long tot = atomicAdd(a.packed_counter, 0ull);

@@ -3,29 +3,33 @@
 The reference is single-process (Rayon on one host); this is the B200-native way to scale its hot
 path over NVLink.  One frame, on every rank r of g:
 
-  1. encode     the rank's own objects -> unsorted (Index, ID) records          [K1, local]
-  2. splitters  a regular sample of the local keys is all-gathered; every rank derives the same
-                g-1 key splitters (sample sort)                                  [all_gather, tiny]
-  3. exchange   records are range-partitioned by splitter (the onesweep pass with a splitter-search
-                digit; stable) and exchanged with ONE all-to-all over NVLink     [all_to_all]
-  4. sort       the received records (IDs still ascend in record order when every rank's IDs ascend
-                and ranks hold ascending ID blocks, so the key-only sort applies) [K2, local]
-  5. halo       by the contiguity lemma the only records of earlier shards that can be
-                ancestors of anything in shard s are those whose cell contains the cell of s's FIRST
-                record: for every depth d <= depth(first) the equal-key run of
-                (key_first & level_mask(d)) | d.  Earlier shards look these runs up and send them
-                (usually nothing; a few records for scene-sized objects)          [all_gather + all_to_all, tiny]
-  6. scan       over [halo | owned]; only pairs whose LATER record is owned are emitted, so every raw
-                pair is produced exactly once globally                            [K3, local]
-  7. dedup      the same ID pair can be produced in several shards, and the reference returns one
-                globally sorted vector: raw pairs are range-partitioned on the later ID and
-                exchanged, then sorted + deduplicated per rank.  Concatenating the ranks' results in
-                rank order is exactly the reference's scan() output.              [all_to_all, K4]
+  1. encode     the rank's own objects -> unsorted (Index, ID) records                       [K1, local]
+  2. splitters  g-1 key splitters from an all-gathered regular sample of the local keys (sample sort).
+                They are kept across frames while the shards stay balanced (objects move little from
+                frame to frame) and recomputed when the imbalance exceeds 15 %.            [all_gather, tiny]
+  3. exchange   every rank counts its records per destination shard (+ halo copies, below) and the count
+                matrix is all-gathered, so every rank knows where its records go inside every receive
+                buffer; then ONE partition pass (the onesweep radix pass with a splitter-search digit)
+                writes each record straight into the destination GPU's receive buffer through NVLink
+                peer pointers (torch symmetric memory): the pack kernel IS the all-to-all.     [fused, NVLink]
+     halos      by the contiguity lemma a record of an earlier shard can only be an ancestor
+                of something in shard s if its cell reaches past s's lower splitter S_s, i.e. if
+                run_upper_key(key) >= S_s.  Such records (scene-sized objects; usually none) are sent to
+                s as well, by the same pass.  All of them sort before S_s, so after the local sort they are
+                exactly the first n_halo records of the shard.
+  4. sort       the received records                                                         [K2, local]
+  5. scan       over [halo | owned]; only pairs whose LATER record is owned are emitted, so every raw
+                pair is produced exactly once globally                                       [K3, local]
+  6. dedup      the same ID pair can be produced in several shards, and the reference returns one
+                globally sorted vector: raw pairs are range-partitioned on the later ID (splitters from a
+                sample of the raw pairs) and scattered to their owners the same way, then sorted +
+                deduplicated per rank.  Concatenating the ranks' results in rank order is exactly the
+                reference's scan() output.                                                   [fused, NVLink; K4]
 
 The choreography below is independent of where the local operations run: `ops` is CudaOps (the
-product: every operation is a C-ABI call into libbroadphase_b200.so on device tensors, collectives
-over NCCL) or, in the CPU tests only, a numpy test double with gloo -- which lets world_size-2 tests
-check the splitter / halo / ownership logic without GPUs.  32-bit IDs only.
+product: every operation is a C-ABI call into libbroadphase_b200.so on device tensors) or, in the CPU
+tests only, a numpy test double with gloo -- which lets world_size-2 tests check the splitter / halo /
+ownership logic without GPUs.  32-bit IDs only.
 """
 import numpy as np
 import torch
@@ -35,6 +39,7 @@ import torch.distributed as dist
 KIND_PARAMS = {0: (32, 2, 4, 14), 1: (64, 2, 5, 29), 2: (64, 3, 5, 19)}
 SAMPLES_PER_RANK = 2048
 U64_MAX = np.uint64(0xFFFFFFFFFFFFFFFF)
+REBALANCE_AT = 1.15  # recompute cached splitters when the fullest shard exceeds the mean by this factor
 
 
 def level_mask(kind, depth):
@@ -42,6 +47,14 @@ def level_mask(kind, depth):
     if depth <= 0:
         return 0
     return ((1 << (dim * depth)) - 1) << (dim * axis_bits + depth_bits - dim * depth)
+
+
+def run_upper_key(kind, key):
+    """Largest key a record inside cell(key) can have (csrc/bp_common.cuh run_upper_key)."""
+    _, dim, depth_bits, axis_bits = KIND_PARAMS[kind]
+    used = (1 << (dim * axis_bits + depth_bits)) - 1
+    depth = key & ((1 << depth_bits) - 1)
+    return key | (~level_mask(kind, depth) & used)
 
 
 def ancestor_keys(kind, key):
@@ -56,9 +69,19 @@ def choose_splitters(sample, parts):
     rank because the gathered sample is."""
     s = np.sort(np.asarray(sample, dtype=np.uint64))
     if s.shape[0] == 0:
-        return np.zeros(0, dtype=np.uint64)
+        return np.full(parts - 1, U64_MAX, dtype=np.uint64)
     q = [s[min(s.shape[0] - 1, (i * s.shape[0]) // parts)] for i in range(1, parts)]
     return np.asarray(q, dtype=np.uint64)
+
+
+def chunk_offsets(m_own, m_halo, me):
+    """Where this rank's chunks start inside every destination's receive buffer.  The buffer of
+    destination d is laid out source by source: [owned from 0 | halo from 0 | owned from 1 | ...]."""
+    g = m_own.shape[0]
+    both = m_own + m_halo
+    own_off = [int(both[:me, d].sum()) for d in range(g)]
+    halo_off = [own_off[d] + int(m_own[me, d]) for d in range(g)]
+    return own_off, halo_off
 
 
 class _CudaView:
@@ -75,21 +98,40 @@ def _view(ptr, n, dtype, device):
     return torch.as_tensor(_CudaView(ptr, n, typestr), device=device)
 
 
-class CudaOps:
-    """The shard-local operations on one B200, every one a call through the C ABI."""
+class _SymmBuffer:
+    """A receive buffer every rank can store into over NVLink (torch symmetric memory)."""
 
-    def __init__(self, bp, kind, min_depth, device):
+    def __init__(self, nbytes, device, group):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.nbytes = nbytes
+        self.t = symm_mem.empty(nbytes, dtype=torch.uint8, device=device)
+        self.hdl = symm_mem.rendezvous(self.t, group.group_name)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+
+    def barrier(self):
+        self.hdl.barrier()
+
+
+class CudaOps:
+    """The shard-local operations on one B200, every one a call through the C ABI; the exchanges are
+    partition passes that store directly into the peers' symmetric receive buffers."""
+
+    def __init__(self, bp, kind, min_depth, device, group=None):
         if kind == 0:
             raise NotImplementedError("the distributed path handles the 64-bit index types")
         self.bp, self.kind, self.device = bp, kind, torch.device("cuda", device)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         mk = lambda: bp.LayerBuilder().with_min_depth(min_depth).with_device(device).build(kind, "u32")
-        self.enc, self.shard, self.scanl = mk(), mk(), mk()
+        self.enc, self.shard = mk(), mk()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        for l in (self.enc, self.shard, self.scanl):
+        for l in self.layers():
             l.set_stream(stream)
+        self.rec_cap = self.pair_cap = 0
+        self.rk = self.ri = self.rp = None
 
     def layers(self):
-        return (self.enc, self.shard, self.scanl)
+        return (self.enc, self.shard)
 
     def encode(self, sys_bounds, bounds, ids, n):
         self.enc.clear()
@@ -98,11 +140,26 @@ class CudaOps:
         id_or = self.enc.masks()[2]
         return _view(kp, r, torch.int64, self.device), _view(ip, r, torch.int32, self.device), id_or
 
-    def partition_records(self, keys, ids, splitters):
-        n = keys.shape[0]
-        ok, oi = torch.empty_like(keys), torch.empty_like(ids)
-        counts = self.enc.partition_records(keys, ids, n, splitters, ok, oi)
-        return ok, oi, [int(c) for c in counts]
+    def count_records(self, keys, splitters):
+        c, h = self.enc.count_records(keys, keys.shape[0], splitters)
+        return [int(x) for x in c], [int(x) for x in h]
+
+    def exchange_records(self, keys, ids, splitters, m_own, m_halo):
+        me, g = self.rank, self.world
+        need = int((m_own + m_halo).sum(axis=0).max())
+        if need > self.rec_cap:  # the matrices are global, so every rank grows (collectively) at the same time
+            self.rec_cap = int(need * 1.25) + 1024
+            self.rk = _SymmBuffer(self.rec_cap * 8, self.device, self.group)
+            self.ri = _SymmBuffer(self.rec_cap * 4, self.device, self.group)
+        own_off, halo_off = chunk_offsets(m_own, m_halo, me)
+        dk = [self.rk.ptrs[d] + 8 * own_off[d] for d in range(g)]
+        di = [self.ri.ptrs[d] + 4 * own_off[d] for d in range(g)]
+        hk = [self.rk.ptrs[d] + 8 * halo_off[d] for d in range(g)]
+        hi = [self.ri.ptrs[d] + 4 * halo_off[d] for d in range(g)]
+        self.enc.scatter_records(keys, ids, keys.shape[0], splitters, dk, di, hk, hi)
+        self.rk.barrier()  # every rank's stores have landed before anybody reads its receive buffer
+        n_recv = int((m_own + m_halo)[:, me].sum())
+        return self.rk.t.view(torch.int64)[:n_recv], self.ri.t.view(torch.int32)[:n_recv]
 
     def sort_records(self, keys, ids):
         self.shard.set_records(keys, ids, sorted_=False, on_device=True, n=keys.shape[0])
@@ -110,146 +167,147 @@ class CudaOps:
         kp, ip, r, _ = self.shard.records_device()
         return _view(kp, r, torch.int64, self.device), _view(ip, r, torch.int32, self.device)
 
-    def lookup_ranges(self, sorted_keys, queries):
-        return self.shard.lookup_ranges(sorted_keys, sorted_keys.shape[0], queries)
-
     def scan_raw(self, keys, ids, n_halo, flt):
-        """keys/ids: the shard's sorted records with n_halo halo records in front."""
-        if n_halo == 0:
-            layer = self.shard  # the sorted records already live in this layer
-        else:
-            layer = self.scanl
-            layer.set_records(keys, ids, sorted_=True, on_device=True, n=keys.shape[0])
-        layer.set_halo(n_halo)
-        ptr, n = layer.scan_raw_device(flt)
-        layer.set_halo(0)
+        """The sorted records live in self.shard; its first n_halo records are halo."""
+        self.shard.set_halo(n_halo)
+        ptr, n = self.shard.scan_raw_device(flt)
+        self.shard.set_halo(0)
         return _view(ptr, n, torch.int64, self.device)
 
-    def partition_pairs(self, raw, splitters):
-        out = torch.empty_like(raw)
-        counts = self.scanl.partition_pairs(raw, raw.shape[0], splitters, out)
-        return out, [int(c) for c in counts]
+    def count_pairs(self, raw, splitters):
+        return [int(x) for x in self.shard.count_pairs(raw, raw.shape[0], splitters)]
+
+    def exchange_pairs(self, raw, splitters, m):
+        me, g = self.rank, self.world
+        need = int(m.sum(axis=0).max())
+        if need > self.pair_cap:
+            self.pair_cap = int(need * 1.25) + 1024
+            self.rp = _SymmBuffer(self.pair_cap * 8, self.device, self.group)
+        dst = [self.rp.ptrs[d] + 8 * int(m[:me, d].sum()) for d in range(g)]
+        self.shard.scatter_pairs(raw, raw.shape[0], splitters, dst)
+        self.rp.barrier()
+        return self.rp.t.view(torch.int64)[:int(m[:, me].sum())]
 
     def unique_pairs(self, raw, id_mask):
-        ptr, n = self.scanl.unique_pairs_device(raw, raw.shape[0], id_mask)
+        ptr, n = self.shard.unique_pairs_device(raw, raw.shape[0], id_mask)
         return _view(ptr, 2 * n, torch.int32, self.device).view(-1, 2)
 
 
 class DistLayer:
     """The distributed counterpart of clear -> extend -> par_sort -> par_scan(_filtered) for one frame."""
 
-    def __init__(self, ops, kind, group=None):
+    def __init__(self, ops, kind, group=None, trace=False, reuse_splitters=True):
         self.ops, self.kind, self.group = ops, kind, group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.trace = trace  # per-phase wall times (device-synchronised) in self.last["phases_ms"]; for tuning only
+        self.reuse_splitters = reuse_splitters
+        self._splitters = self._a_splitters = None
+        self._id_mask = 0
         self.last = {}
 
-    # -- collectives (device tensors over NCCL in production, CPU tensors over gloo in the tests) --
+    # -- small collectives (device tensors over NCCL in production, CPU tensors over gloo in the tests) --
     def _all_gather(self, t):
         out = [torch.empty_like(t) for _ in range(self.world)]
         dist.all_gather(out, t, group=self.group)
         return torch.stack(out)
 
-    def _all_to_all(self, send, send_counts, recv_counts):
-        recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
-        dist.all_to_all_single(recv, send, [int(c) for c in recv_counts], [int(c) for c in send_counts], group=self.group)
-        return recv
+    def _gather_rows(self, row, device):
+        t = torch.tensor([int(c) for c in row], dtype=torch.int64, device=device)
+        return self._all_gather(t).cpu().numpy()  # [source, ...]
 
-    def _count_matrix(self, my_counts, device):
-        row = torch.tensor([int(c) for c in my_counts], dtype=torch.int64, device=device)
-        return self._all_gather(row).cpu().numpy()  # [source, destination]
+    @staticmethod
+    def _imbalance(col_sums):
+        mean = float(np.mean(col_sums))
+        return float(np.max(col_sums)) / mean if mean > 0 else 1.0
 
     def frame(self, sys_bounds, bounds, ids, n, flt=None):
         """Runs one frame on this rank's objects.  Returns the rank's slice of the globally sorted,
         deduplicated pair list as an (P_r, 2) int32 tensor (bit patterns of the u32 IDs)."""
         ops, g, me = self.ops, self.world, self.rank
         dev = ops.device
+        phases = []
 
+        def mark(name):
+            if self.trace:
+                import time
+                if dev.type == "cuda":
+                    torch.cuda.synchronize(dev)
+                phases.append((name, time.perf_counter()))
+
+        mark("start")
         # 1. encode
         keys, rids, id_or = ops.encode(sys_bounds, bounds, ids, n)
         r_loc = keys.shape[0]
+        mark("encode")
 
-        # 2. splitters from an all-gathered sample (+ the ID bits and a sample of IDs, piggybacked)
+        # 2. key splitters (+ the ID bits, piggybacked) from an all-gathered sample
         m = SAMPLES_PER_RANK
-        meta = torch.full((2 * m + 2,), -1, dtype=torch.int64, device=dev)
-        if r_loc:
-            step = max(1, r_loc // m)
-            ks = keys[::step][:m]
-            meta[:ks.shape[0]] = ks
-            meta[m:m + ks.shape[0]] = rids[::step][:m].to(torch.int64) & 0xFFFFFFFF
-        meta[2 * m] = id_or
-        meta[2 * m + 1] = r_loc
-        gathered = self._all_gather(meta).cpu().numpy()
-        key_sample = gathered[:, :m].reshape(-1)
-        key_sample = key_sample[key_sample >= 0].view(np.uint64) if key_sample.size else key_sample.view(np.uint64)
-        id_sample = gathered[:, m:2 * m].reshape(-1)
-        id_sample = id_sample[id_sample >= 0].astype(np.uint64)
+        if self._splitters is None or not self.reuse_splitters:
+            meta = torch.full((m + 1,), -1, dtype=torch.int64, device=dev)
+            if r_loc:
+                ks = keys[::max(1, r_loc // m)][:m]
+                meta[:ks.shape[0]] = ks
+            meta[m] = id_or
+            gathered = self._all_gather(meta).cpu().numpy()
+            sample = gathered[:, :m].reshape(-1)
+            self._splitters = choose_splitters(sample[sample >= 0].view(np.uint64), g)
+            id_bits = 0
+            for v in gathered[:, m]:
+                id_bits |= int(v)
+            self._id_mask = (1 << max(1, id_bits.bit_length())) - 1
+        splitters = self._splitters
+        mark("splitters")
+
+        # 3. count, all-gather the count matrix, scatter straight into the owners' receive buffers
+        counts, halo = ops.count_records(keys, splitters)
+        mat = self._gather_rows(counts + halo + [id_or], dev)
+        m_own, m_halo = mat[:, :g], mat[:, g:2 * g]
         id_bits = 0
-        for v in gathered[:, 2 * m]:
+        for v in mat[:, 2 * g]:
             id_bits |= int(v)
-        id_mask = (1 << max(1, id_bits.bit_length())) - 1
-        splitters = choose_splitters(key_sample, g)
-        if splitters.shape[0] < g - 1:  # no records anywhere
-            splitters = np.full(g - 1, U64_MAX, dtype=np.uint64)
+        self._id_mask |= (1 << max(1, id_bits.bit_length())) - 1  # IDs seen since the splitters were cached
+        mark("counts")
+        rk, ri = ops.exchange_records(keys, rids, splitters, m_own, m_halo)
+        n_halo = int(m_halo[:, me].sum())
+        mark("exchange")
 
-        # 3. partition + one all-to-all of the records
-        pk, pi, send_counts = ops.partition_records(keys, rids, splitters)
-        cm = self._count_matrix(send_counts, dev)
-        recv_counts = cm[:, me]
-        rk = self._all_to_all(pk, send_counts, recv_counts)
-        ri = self._all_to_all(pi, send_counts, recv_counts)
-
-        # 4. local sort
+        # 4. local sort: the halo records (all < my lower splitter) end up in front
         sk, si = ops.sort_records(rk, ri)
-        r_own = sk.shape[0]
+        mark("sort")
 
-        # 5. halos: earlier shards send the records whose cell contains the cell of my first record
-        first = torch.full((2,), -1, dtype=torch.int64, device=dev)
-        if r_own:
-            first[0] = sk[0]
-            first[1] = 1
-        firsts = self._all_gather(first).cpu().numpy()
-        queries, owner = [], []
-        for s in range(me + 1, g):
-            if firsts[s, 1] == 1:
-                for q in ancestor_keys(self.kind, int(np.uint64(firsts[s, 0]))):
-                    queries.append(q)
-                    owner.append(s)
-        halo_send = [0] * g
-        ranges = []
-        if queries and r_own:
-            lo, hi = ops.lookup_ranges(sk, np.asarray(queries, dtype=np.uint64))
-            for s, a, b in zip(owner, lo, hi):
-                if b > a:
-                    halo_send[s] += int(b - a)
-                    ranges.append((s, int(a), int(b)))
-        hm = self._count_matrix(halo_send, dev)
-        n_halo = int(hm[:, me].sum())
-        if hm.sum() > 0:  # the matrix is identical everywhere, so every rank takes the same branch
-            if ranges:  # ranges are grouped by destination and ascend within it
-                idx = torch.cat([torch.arange(a, b, device=dev) for _, a, b in ranges])
-                hk_send, hi_send = sk[idx], si[idx]
-            else:
-                hk_send, hi_send = sk[:0], si[:0]
-            hk = self._all_to_all(hk_send.contiguous(), halo_send, hm[:, me])
-            hi_ = self._all_to_all(hi_send.contiguous(), halo_send, hm[:, me])
-            if n_halo:
-                sk = torch.cat([hk, sk])
-                si = torch.cat([hi_, si])
-
-        # 6. shard-local scan; pairs whose later record is a halo record belong to an earlier shard
+        # 5. shard-local scan; pairs whose later record is a halo record belong to an earlier shard
         raw = ops.scan_raw(sk, si, n_halo, flt)
+        p_raw = raw.shape[0]
+        mark("scan")
 
-        # 7. global dedup: range-partition the raw pairs on the later ID, exchange, sort + unique
-        a_splitters = choose_splitters(id_sample, g)
-        if a_splitters.shape[0] < g - 1:
-            a_splitters = np.full(g - 1, U64_MAX, dtype=np.uint64)
-        pp, psend = ops.partition_pairs(raw, a_splitters)
-        pm = self._count_matrix(psend, dev)
-        rp = self._all_to_all(pp, psend, pm[:, me])
-        pairs = ops.unique_pairs(rp, id_mask)
-        self.last = dict(records_local=r_loc, records_owned=r_own, halo=n_halo, raw_pairs=int(raw.shape[0]),
-                         pairs=int(pairs.shape[0]), record_matrix=cm, pair_matrix=pm)
+        # 6. global dedup: range-partition the raw pairs on the later ID, scatter, sort + unique
+        if self._a_splitters is None or not self.reuse_splitters:
+            ps = torch.full((m,), -1, dtype=torch.int64, device=dev)
+            if p_raw:
+                a = (raw[::max(1, p_raw // m)][:m] >> 32) & 0xFFFFFFFF
+                ps[:a.shape[0]] = a
+            gathered = self._all_gather(ps).cpu().numpy().reshape(-1)
+            self._a_splitters = choose_splitters(gathered[gathered >= 0].astype(np.uint64), g)
+        a_splitters = self._a_splitters
+        pc = ops.count_pairs(raw, a_splitters)
+        pm = self._gather_rows(pc, dev)
+        mark("pair_counts")
+        rp = ops.exchange_pairs(raw, a_splitters, pm)
+        mark("pair_exchange")
+        pairs = ops.unique_pairs(rp, self._id_mask)
+        mark("unique")
+
+        # cached splitters are recomputed next frame when a shard has drifted too far from the mean
+        if self.reuse_splitters:
+            if self._imbalance((m_own + m_halo).sum(axis=0)) > REBALANCE_AT:
+                self._splitters = None
+            if self._imbalance(pm.sum(axis=0)) > REBALANCE_AT:
+                self._a_splitters = None
+        phases_ms = {b[0]: (b[1] - a_[1]) * 1e3 for a_, b in zip(phases[:-1], phases[1:])}
+        self.last = dict(phases_ms=phases_ms, records_local=r_loc, records_owned=int(m_own[:, me].sum()), halo=n_halo,
+                         raw_pairs=int(p_raw), pairs=int(pairs.shape[0]), record_matrix=m_own, halo_matrix=m_halo,
+                         pair_matrix=pm)
         return pairs
 
     def gather_pairs(self, pairs):

@@ -202,6 +202,36 @@ class Layer:
                                                _dev_ptr(d_out_pairs), counts.ctypes.data))
         return counts
 
+    def count_records(self, d_keys, n, splitters):
+        """(bucket sizes, halo copies per bucket) of a splitter partition of n records."""
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        counts = np.zeros(spl.shape[0] + 1, dtype=np.uint64)
+        halo = np.zeros(spl.shape[0] + 1, dtype=np.uint64)
+        self._ck(lib().bp_dist_count_records(self._h, _dev_ptr(d_keys), n, spl.ctypes.data, spl.shape[0], counts.ctypes.data,
+                                             halo.ctypes.data))
+        return counts, halo
+
+    def scatter_records(self, d_keys, d_ids, n, splitters, dst_keys, dst_ids, halo_dst_keys=None, halo_dst_ids=None):
+        """Partition pass writing bucket b to the device addresses dst_keys[b] / dst_ids[b]."""
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        arrs = [np.ascontiguousarray(x, dtype=np.uint64) for x in (dst_keys, dst_ids)]
+        h = [None if x is None else np.ascontiguousarray(x, dtype=np.uint64) for x in (halo_dst_keys, halo_dst_ids)]
+        self._ck(lib().bp_dist_scatter_records(self._h, _dev_ptr(d_keys), _dev_ptr(d_ids), n, spl.ctypes.data, spl.shape[0],
+                                               arrs[0].ctypes.data, arrs[1].ctypes.data,
+                                               None if h[0] is None else h[0].ctypes.data,
+                                               None if h[1] is None else h[1].ctypes.data))
+
+    def count_pairs(self, d_pairs, n, splitters):
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        counts = np.zeros(spl.shape[0] + 1, dtype=np.uint64)
+        self._ck(lib().bp_dist_count_pairs(self._h, _dev_ptr(d_pairs), n, spl.ctypes.data, spl.shape[0], counts.ctypes.data))
+        return counts
+
+    def scatter_pairs(self, d_pairs, n, splitters, dst_pairs):
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        dst = np.ascontiguousarray(dst_pairs, dtype=np.uint64)
+        self._ck(lib().bp_dist_scatter_pairs(self._h, _dev_ptr(d_pairs), n, spl.ctypes.data, spl.shape[0], dst.ctypes.data))
+
     def lookup_ranges(self, d_sorted_keys, n, queries):
         q = np.ascontiguousarray(queries, dtype=np.uint64)
         lo = np.zeros(q.shape[0], dtype=np.uint64)

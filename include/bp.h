@@ -178,6 +178,21 @@ int bp_dist_partition_records(bp_layer *ctx, const void *d_keys, const void *d_i
 /* The same for packed raw pairs ((later << 32) | earlier), partitioned on `later`. */
 int bp_dist_partition_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
                             void *d_out_pairs, uint64_t *out_counts);
+/* The fused form used over NVLink: bucket sizes first (out_counts), then a partition pass that writes
+ * every bucket straight to its own destination array -- dst_keys[b] / dst_ids[b] are device ADDRESSES,
+ * typically inside the receive buffers of peer GPUs (symmetric memory), so the pass is the all-to-all.
+ * Halos: a record whose cell reaches past later splitters is an ancestor of records those shards will
+ * own; out_halo_counts[b] counts the copies bucket b receives and bp_dist_scatter_records writes them
+ * (unordered) to halo_dst_keys[b] / halo_dst_ids[b] (NULL: no halo copies). */
+int bp_dist_count_records(bp_layer *ctx, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
+                          uint64_t *out_counts, uint64_t *out_halo_counts);
+int bp_dist_scatter_records(bp_layer *ctx, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
+                            int n_splitters, const uint64_t *dst_keys, const uint64_t *dst_ids, const uint64_t *halo_dst_keys,
+                            const uint64_t *halo_dst_ids);
+int bp_dist_count_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
+                        uint64_t *out_counts);
+int bp_dist_scatter_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
+                          const uint64_t *dst_pairs);
 /* Equal range [lo, hi) of every query key in a sorted device key array (halo look-ups). */
 int bp_dist_lookup_ranges(bp_layer *ctx, const void *d_sorted_keys, size_t n, const uint64_t *queries, int n_queries,
                           uint64_t *out_lo, uint64_t *out_hi);

@@ -47,33 +47,73 @@ class CpuOps:
         id_or = int(np.bitwise_or.reduce(i)) if i.size else 0
         return _i64(k), _i32(i.astype(np.uint32)), id_or
 
-    def partition_records(self, keys, ids, splitters):
+    # -- helpers ---------------------------------------------------------------------------------
+    def _hi(self, k):
+        """run_upper_key for an array of keys (numpy)."""
+        _, dim, depth_bits, axis_bits = pyref.KINDS[self.kind]
+        used = (1 << (dim * axis_bits + depth_bits)) - 1
+        low = np.array([(~pyref.level_mask(self.kind, d)) & used for d in range(axis_bits + 1)], dtype=np.uint64)
+        depth = (k & np.uint64((1 << depth_bits) - 1)).astype(np.int64)
+        return k | low[depth]
+
+    def _homes(self, k, splitters):
+        spl = np.asarray(splitters, dtype=np.uint64)
+        return np.searchsorted(spl, k, side="right"), np.searchsorted(spl, self._hi(k), side="right")
+
+    def count_records(self, keys, splitters):
+        k = _u64(keys)
+        g = len(splitters) + 1
+        home, last = self._homes(k, splitters)
+        counts = np.bincount(home, minlength=g)
+        halo = np.zeros(g, dtype=np.int64)
+        for s in range(1, g):
+            halo[s] = int(((home < s) & (last >= s)).sum())
+        return [int(c) for c in counts], [int(h) for h in halo]
+
+    def _a2a(self, send, send_counts, recv_counts):
+        recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype)
+        dist.all_to_all_single(recv, send, [int(c) for c in recv_counts], [int(c) for c in send_counts])
+        return recv
+
+    def exchange_records(self, keys, ids, splitters, m_own, m_halo):
+        """Test-double transport: per-destination chunks [owned | halo copies] through a gloo all-to-all
+        (the product scatters the same chunks into the peers' symmetric memory instead)."""
+        me = dist.get_rank()
         k, i = _u64(keys), _u32(ids)
-        bucket = np.searchsorted(np.asarray(splitters, dtype=np.uint64), k, side="right")
-        order = np.argsort(bucket, kind="stable")
-        counts = np.bincount(bucket, minlength=len(splitters) + 1)
-        return _i64(k[order]), _i32(i[order]), [int(c) for c in counts]
+        g = len(splitters) + 1
+        home, last = self._homes(k, splitters)
+        ck, ci = [], []
+        for d in range(g):
+            own = home == d
+            hal = (home < d) & (last >= d)
+            assert int(own.sum()) == int(m_own[me, d]) and int(hal.sum()) == int(m_halo[me, d])
+            ck += [k[own], k[hal]]
+            ci += [i[own], i[hal]]
+        both = m_own + m_halo
+        rk = self._a2a(_i64(np.concatenate(ck)), both[me, :], both[:, me])
+        ri = self._a2a(_i32(np.concatenate(ci)), both[me, :], both[:, me])
+        return rk, ri
 
     def sort_records(self, keys, ids):
         k, i = pyref.sort_records(_u64(keys), _u32(ids))
         return _i64(k), _i32(i)
-
-    def lookup_ranges(self, sorted_keys, queries):
-        k = _u64(sorted_keys)
-        q = np.asarray(queries, dtype=np.uint64)
-        return np.searchsorted(k, q, side="left"), np.searchsorted(k, q, side="right")
 
     def scan_raw(self, keys, ids, n_halo, flt):
         fk, arg = flt if flt else (0, 0)
         a, b = pyref.scan_raw(self.kind, _u64(keys), _u32(ids), fk, arg, None, first_owned=n_halo)
         return _i64((a << np.uint64(32)) | b)
 
-    def partition_pairs(self, raw, splitters):
+    def count_pairs(self, raw, splitters):
+        r = _u64(raw)
+        bucket = np.searchsorted(np.asarray(splitters, dtype=np.uint64), r >> np.uint64(32), side="right")
+        return [int(c) for c in np.bincount(bucket, minlength=len(splitters) + 1)]
+
+    def exchange_pairs(self, raw, splitters, m):
+        me = dist.get_rank()
         r = _u64(raw)
         bucket = np.searchsorted(np.asarray(splitters, dtype=np.uint64), r >> np.uint64(32), side="right")
         order = np.argsort(bucket, kind="stable")
-        counts = np.bincount(bucket, minlength=len(splitters) + 1)
-        return _i64(r[order]), [int(c) for c in counts]
+        return self._a2a(_i64(r[order]), m[me, :], m[:, me])
 
     def unique_pairs(self, raw, id_mask):
         r = np.unique(_u64(raw))
@@ -141,7 +181,8 @@ def worker(rank, world, port, cases, empty_rank, out_dir):
             else:
                 lo, hi = 0, 0
             dl = bpd.DistLayer(CpuOps(kind, md), kind)
-            pairs = dl.frame(sysb, bounds[lo:hi], ids[lo:hi], hi - lo, flt)
+            dl.frame(sysb, bounds[lo:hi], ids[lo:hi], hi - lo, flt)  # first frame computes the splitters
+            pairs = dl.frame(sysb, bounds[lo:hi], ids[lo:hi], hi - lo, flt)  # second frame reuses them
             allp = dl.gather_pairs(pairs)
             if rank == 0:
                 np.save(os.path.join(out_dir, "%s.npy" % case), allp)

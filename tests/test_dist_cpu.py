@@ -44,4 +44,10 @@ def test_ancestor_keys_and_splitters(bp):
         assert a & 31 == d and co.overlaps(2, a, key)
     s = bpd.choose_splitters(np.arange(1000, dtype=np.uint64), 4)
     assert list(s) == [250, 500, 750]
-    assert bpd.choose_splitters(np.zeros(0, dtype=np.uint64), 4).shape[0] == 0
+    assert list(bpd.choose_splitters(np.zeros(0, dtype=np.uint64), 4)) == [2**64 - 1] * 3
+    # run_upper_key: the cell of `key` at depth 5 spans the low 3*(19-5) origin bits + the depth field
+    assert bpd.run_upper_key(2, key) == key | ((1 << (5 + 3 * 14)) - 1)
+    m_own = np.array([[5, 1], [2, 7]])
+    m_halo = np.array([[0, 3], [0, 0]])
+    assert bpd.chunk_offsets(m_own, m_halo, 0) == ([0, 0], [5, 1])
+    assert bpd.chunk_offsets(m_own, m_halo, 1) == ([5, 4], [7, 11])

@@ -85,6 +85,70 @@ def test_lookup_ranges_and_halo_scan(bp):
     assert (L.scan_filtered(bp.ScanFilter.id_parity()).astype(np.uint64) == pyref.scan(2, sk, si, pyref.FILTER_ID_PARITY)[0]).all()
 
 
+def test_count_and_scatter_records_with_halo_copies(bp):
+    """The fused exchange on one GPU: every bucket gets its own destination array (here slices of one
+    local tensor; peers' symmetric buffers in the real path) and records whose cell reaches past later
+    splitters are copied to those buckets as halo."""
+    import torch
+    from tests.dist_cpu_ops import CpuOps
+    sc, k, i = _records(bp, 150_000, 11)
+    # a few scene-sized objects so that halo copies exist
+    big = bp.scenes.uniform_cubes(64, 5, id_base=1_000_000, edge_factor=0.4 * 64 ** (1.0 / 3.0) * 0.9)
+    o = co.OracleLayer(2, 4, 0)
+    o.extend(big["sys_bounds"], big["bounds"], big["ids"])
+    kb, ib = o.records()
+    k = np.concatenate([k, kb]); i = np.concatenate([i, ib.astype(np.uint32)])
+    n = k.shape[0]
+    dk = torch.from_numpy(k.view(np.int64)).cuda()
+    di = torch.from_numpy(i.view(np.int32)).cuda()
+    L = bp.Layer(2, "u32")
+    ref = CpuOps(2, 0)
+    for nspl in (1, 3, 7):
+        spl = np.sort(np.random.Generator(np.random.Philox(nspl)).choice(k, nspl, replace=False)).astype(np.uint64)
+        counts, halo = L.count_records(dk, n, spl)
+        want_c, want_h = ref.count_records(torch.from_numpy(k.view(np.int64)), spl)
+        assert [int(c) for c in counts] == want_c and [int(h) for h in halo] == want_h
+        assert sum(want_h) > 0
+        g = nspl + 1
+        tot = counts + halo
+        off = np.concatenate([[0], np.cumsum(tot)]).astype(np.int64)
+        ok = torch.zeros(int(off[-1]), dtype=torch.int64, device="cuda")
+        oi = torch.zeros(int(off[-1]), dtype=torch.int32, device="cuda")
+        dst_k = [ok.data_ptr() + 8 * int(off[b]) for b in range(g)]
+        dst_i = [oi.data_ptr() + 4 * int(off[b]) for b in range(g)]
+        hk = [ok.data_ptr() + 8 * int(off[b] + counts[b]) for b in range(g)]
+        hi = [oi.data_ptr() + 4 * int(off[b] + counts[b]) for b in range(g)]
+        L.scatter_records(dk, di, n, spl, dst_k, dst_i, hk, hi)
+        torch.cuda.synchronize()
+        gk, gi = ok.cpu().numpy().view(np.uint64), oi.cpu().numpy().view(np.uint32)
+        home, last = ref._homes(k, spl)
+        for b in range(g):
+            own = slice(int(off[b]), int(off[b] + counts[b]))
+            assert (gk[own] == k[home == b]).all() and (gi[own] == i[home == b]).all()       # stable partition
+            hs = slice(int(off[b] + counts[b]), int(off[b + 1]))
+            sel = (home < b) & (last >= b)
+            got = sorted(zip(gk[hs].tolist(), gi[hs].tolist()))
+            assert got == sorted(zip(k[sel].tolist(), i[sel].tolist()))                        # halo copies, any order
+
+
+def test_count_and_scatter_pairs(bp):
+    import torch
+    rng = np.random.Generator(np.random.Philox(19))
+    a = rng.integers(0, 70_000, size=200_000).astype(np.uint64)
+    raw = (a << np.uint64(32)) | rng.integers(0, 70_000, size=200_000).astype(np.uint64)
+    d = torch.from_numpy(raw.view(np.int64)).cuda()
+    L = bp.Layer(2, "u32")
+    spl = np.array([5_000, 30_000, 30_001, 65_000], dtype=np.uint64)
+    counts = L.count_pairs(d, raw.shape[0], spl)
+    bucket = np.searchsorted(spl, a, side="right")
+    assert (counts == np.bincount(bucket, minlength=5)).all()
+    out = torch.zeros_like(d)
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    L.scatter_pairs(d, raw.shape[0], spl, [out.data_ptr() + 8 * int(off[b]) for b in range(5)])
+    torch.cuda.synchronize()
+    assert (out.cpu().numpy().view(np.uint64) == raw[np.argsort(bucket, kind="stable")]).all()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
