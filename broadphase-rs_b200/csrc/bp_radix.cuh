@@ -45,36 +45,31 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ k
                                                           const uint32_t *__restrict__ n_dev, RadixPlan plan,
                                                           uint32_t *__restrict__ ghist) {
     __shared__ uint32_t sh[RADIX_MAX_PASSES * RADIX];
-    __shared__ uint32_t sdesc[RADIX_MAX_PASSES][5]; // shift, mask, shift2, mask2, bits
     const int np = plan.npasses;
     for (int i = threadIdx.x; i < np * RADIX; i += blockDim.x) sh[i] = 0;
-    if ((int)threadIdx.x < np) {
-        const int p = threadIdx.x;
-        sdesc[p][0] = plan.shift[p];
-        sdesc[p][1] = (1u << plan.bits[p]) - 1u;
-        sdesc[p][2] = plan.shift2[p];
-        sdesc[p][3] = (1u << plan.bits2[p]) - 1u;
-        sdesc[p][4] = plan.bits[p];
-    }
     __syncthreads();
     const uint32_t n = n_dev ? *n_dev : n_host;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    constexpr int UNROLL = 4;
-    auto digit = [&](int p, K k) -> uint32_t {
-        return ((uint32_t)(k >> sdesc[p][0]) & sdesc[p][1]) | (((uint32_t)(k >> sdesc[p][2]) & sdesc[p][3]) << sdesc[p][4]);
-    };
+    constexpr int UNROLL = 8;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // keys in registers, passes in the outer loop: the digit descriptor of a pass is fetched once per
+    // UNROLL keys (warp-uniform constant-bank loads)
     for (; i + (UNROLL - 1) * stride < n; i += UNROLL * stride) {
         K k[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) k[u] = ld_stream(keys + i + u * stride);
+        for (int p = 0; p < np; ++p) {
+            const uint32_t s0 = plan.shift[p], m0 = (1u << plan.bits[p]) - 1u, b0 = plan.bits[p];
+            const uint32_t s1 = plan.shift2[p], m1 = (1u << plan.bits2[p]) - 1u;
+            uint32_t *h = sh + p * RADIX;
 #pragma unroll
-        for (int u = 0; u < UNROLL; ++u)
-            for (int p = 0; p < np; ++p) atomicAdd(&sh[p * RADIX + digit(p, k[u])], 1u);
+            for (int u = 0; u < UNROLL; ++u)
+                atomicAdd(&h[((uint32_t)(k[u] >> s0) & m0) | (((uint32_t)(k[u] >> s1) & m1) << b0)], 1u);
+        }
     }
     for (; i < n; i += stride) {
         const K k = ld_stream(keys + i);
-        for (int p = 0; p < np; ++p) atomicAdd(&sh[p * RADIX + digit(p, k)], 1u);
+        for (int p = 0; p < np; ++p) atomicAdd(&sh[p * RADIX + plan_digit<K>(plan, p, k)], 1u);
     }
     __syncthreads();
     for (int j = threadIdx.x; j < np * RADIX; j += blockDim.x) {
@@ -242,19 +237,9 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
         rd[k] = (old + __popc(mm[k] & lt)) | (d << 16);
     }
 
-    // payload loads are issued now so that their latency overlaps the look-back
-    V val[HAS_V ? ITEMS : 1];
-    if constexpr (HAS_V) {
-        const V *vin = a.vin + tile_begin;
-#pragma unroll
-        for (int k = 0; k < ITEMS; ++k) {
-            const uint32_t i = base_i + k * 32;
-            if (FULL || i < tile_n) val[k] = ld_stream(vin + i);
-        }
-    }
     __syncthreads();
 
-    // ---- per digit: exclusive scan over the warps, publish the tile count, look back -------------
+    // ---- per digit: exclusive scan over the warps, publish the tile count ----------------------------
     uint32_t count_full = 0, incl = 0;
     if (tid < RADIX) {
         uint32_t sum = 0;
@@ -276,15 +261,41 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
     if (tid < RADIX) {
         uint32_t off = 0;
         for (unsigned w = 0; w < warp; ++w) off += misc[1 + w];
-        const uint32_t ds = off + incl - count_full;
-        dstart[tid] = ds;
+        dstart[tid] = off + incl - count_full;
+    }
+    __syncthreads();
+
+    // ---- stage the keys in digit order (their registers die here, before the look-back needs its own) ----
+    K *skeys = (K *)stage;
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t d = rd[k] >> 16;
+        const uint32_t r = (rd[k] & 0xffffu) + whist[warp * RADIX + d] + dstart[d];
+        rd[k] = r;
+        skeys[r] = key[k];
+    }
+    // payload loads are issued now so that their latency overlaps the look-back
+    V val[HAS_V ? ITEMS : 1];
+    if constexpr (HAS_V) {
+        const V *vin = a.vin + tile_begin;
+#pragma unroll
+        for (int k = 0; k < ITEMS; ++k) {
+            const uint32_t i = base_i + k * 32;
+            if (FULL || i < tile_n) val[k] = ld_stream(vin + i);
+        }
+    }
+
+    // ---- look back: global offset of every digit run of this tile ------------------------------------
+    if (tid < RADIX) {
         uint32_t excl = 0;
         if (tile != 0) {
             uint32_t count = count_full;
             if (!FULL && tid == dmax) count -= (uint32_t)(TILE - tile_n);
-            // walk back over the predecessors LB_BATCH tiles at a time: the status loads of one batch are
-            // independent, so a batch costs one L2 round trip instead of LB_BATCH
-            constexpr int LB_BATCH = 8;
+            // Walk back over the predecessors LB_BATCH tiles at a time: the status loads of one batch are
+            // independent, so a batch costs one L2 round trip.  The batch size sets how fast the first
+            // wave of tiles (none of which has an inclusive prefix to offer yet) resolves: about
+            // tile / (2 * LB_BATCH) round trips for tile number `tile`.
+            constexpr int LB_BATCH = 16;
             int64_t t = (int64_t)tile - 1;
             bool done = false;
             while (!done && t >= 0) {
@@ -315,18 +326,7 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
             }
             st_volatile_u32(a.status + (size_t)tile * RADIX + tid, RS_FLAG_INC | ((excl + count) & RS_VALUE_MASK));
         }
-        gbase[tid] = a.ghist_excl[tid] + excl - ds;
-    }
-    __syncthreads();
-
-    // ---- stage the keys in digit order, then write each digit run with coalesced stores ----------
-    K *skeys = (K *)stage;
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const uint32_t d = rd[k] >> 16;
-        const uint32_t r = (rd[k] & 0xffffu) + whist[warp * RADIX + d] + dstart[d];
-        rd[k] = r;
-        skeys[r] = key[k];
+        gbase[tid] = a.ghist_excl[tid] + excl - dstart[tid];
     }
     __syncthreads();
     uint32_t dst[ITEMS];
