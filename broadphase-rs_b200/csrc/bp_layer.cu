@@ -709,61 +709,98 @@ template <int KIND, class IdT> struct Impl {
         if (wide) TRY(ensure(L, L->praw_b[1], P_raw * sizeof(uint64_t)));
 
         // ---- sort the raw pairs (src/layer.rs:473, :516) ----
+        // Fast path: radix passes over the LATER ID's bits only, then pair_finish_kernel orders and
+        // deduplicates the (tiny) groups of equal later IDs.  Fallback (a group larger than the finish
+        // kernel's window): the remaining passes over all bits, then pair_unique_kernel.
         const uint64_t imask = L->id_or & ~L->id_and;
-        uint64_t *sorted_a = nullptr, *sorted_b = nullptr;
+        uint64_t *a0 = (uint64_t *)L->praw[0].p, *a1 = (uint64_t *)L->praw[1].p;
+        uint64_t *b0 = wide ? (uint64_t *)L->praw_b[0].p : nullptr, *b1 = wide ? (uint64_t *)L->praw_b[1].p : nullptr;
         int passes = 0, total_passes = 0;
         bool in_alt = false;
         if (!wide) {
-            const uint64_t pmask = (imask << 32) | (imask & 0xffffffffull);
-            TRY((radix_sort<uint64_t, NoVal>(L, (uint64_t *)L->praw[0].p, (NoVal *)nullptr, (uint64_t *)L->praw[1].p,
-                                             (NoVal *)nullptr, (uint32_t)P_raw, nullptr, pmask, BP_K_PAIR_HIST, BP_K_PAIR_PASS,
-                                             &passes, &in_alt, 8)));
-            total_passes = passes;
-            sorted_a = (uint64_t *)L->praw[in_alt ? 1 : 0].p;
+            TRY((radix_sort<uint64_t, NoVal>(L, a0, (NoVal *)nullptr, a1, (NoVal *)nullptr, (uint32_t)P_raw, nullptr, imask << 32,
+                                             BP_K_PAIR_HIST, BP_K_PAIR_PASS, &passes, &in_alt, 8)));
         } else {
-            uint64_t *a0 = (uint64_t *)L->praw[0].p, *a1 = (uint64_t *)L->praw[1].p;
-            uint64_t *b0 = (uint64_t *)L->praw_b[0].p, *b1 = (uint64_t *)L->praw_b[1].p;
-            TRY((radix_sort<uint64_t, uint64_t>(L, b0, a0, b1, a1, (uint32_t)P_raw, nullptr, imask, BP_K_PAIR_HIST,
-                                                BP_K_PAIR_PASS, &passes, &in_alt, 16)));
-            total_passes = passes;
-            if (in_alt) {
-                std::swap(a0, a1);
-                std::swap(b0, b1);
+            TRY((radix_sort<uint64_t, uint64_t>(L, a0, b0, a1, b1, (uint32_t)P_raw, nullptr, imask, BP_K_PAIR_HIST, BP_K_PAIR_PASS,
+                                                &passes, &in_alt, 16)));
+        }
+        total_passes = passes;
+        if (in_alt) {
+            std::swap(a0, a1);
+            std::swap(b0, b1);
+        }
+        {
+            const uint32_t ftiles = (uint32_t)((P_raw + FinCfg<IdT>::TILE - 1) / FinCfg<IdT>::TILE);
+            const size_t fbytes = 64 + (size_t)ftiles * sizeof(uint64_t);
+            TRY(ensure(L, L->scratch, fbytes));
+            CU(L, cudaMemsetAsync(L->scratch.p, 0, fbytes, L->stream));
+            CU(L, cudaMemsetAsync(&L->d_tot->pad, 0, sizeof(unsigned int), L->stream));
+            FinishArgs<IdT> fa;
+            fa.in_packed = wide ? nullptr : a0;
+            fa.in_a = wide ? a0 : nullptr;
+            fa.in_b = b0;
+            fa.n = (uint32_t)P_raw;
+            fa.out = (IdT *)L->pout.p;
+            fa.tile_counter = (uint32_t *)L->scratch.p;
+            fa.status = (uint64_t *)((char *)L->scratch.p + 64);
+            fa.totals = L->d_tot;
+            fa.err = L->d_err;
+            {
+                LaunchScope ls(L, BP_K_PAIR_UNIQUE, (double)P_raw * 2.0 * sizeof(IdT));
+                pair_finish_kernel<IdT><<<ftiles, FIN_THREADS, 0, L->stream>>>(fa);
             }
-            TRY((radix_sort<uint64_t, uint64_t>(L, a0, b0, a1, b1, (uint32_t)P_raw, nullptr, imask, BP_K_PAIR_HIST,
-                                                BP_K_PAIR_PASS, &passes, &in_alt, 16)));
-            total_passes += passes;
-            if (in_alt) {
-                std::swap(a0, a1);
-                std::swap(b0, b1);
+            TRY(check_launch(L, "pair_finish_kernel"));
+            TRY(fetch_totals(L));
+        }
+        if (L->h_tot->pad) { // some later ID has more partners than the finish window: full-width sort instead
+            uint64_t *sorted_a = nullptr, *sorted_b = nullptr;
+            if (!wide) {
+                const uint64_t pmask = (imask << 32) | (imask & 0xffffffffull);
+                TRY((radix_sort<uint64_t, NoVal>(L, a0, (NoVal *)nullptr, a1, (NoVal *)nullptr, (uint32_t)P_raw, nullptr, pmask,
+                                                 BP_K_PAIR_HIST, BP_K_PAIR_PASS, &passes, &in_alt, 8)));
+                total_passes += passes;
+                sorted_a = in_alt ? a1 : a0;
+            } else {
+                TRY((radix_sort<uint64_t, uint64_t>(L, b0, a0, b1, a1, (uint32_t)P_raw, nullptr, imask, BP_K_PAIR_HIST,
+                                                    BP_K_PAIR_PASS, &passes, &in_alt, 16)));
+                total_passes += passes;
+                if (in_alt) {
+                    std::swap(a0, a1);
+                    std::swap(b0, b1);
+                }
+                TRY((radix_sort<uint64_t, uint64_t>(L, a0, b0, a1, b1, (uint32_t)P_raw, nullptr, imask, BP_K_PAIR_HIST,
+                                                    BP_K_PAIR_PASS, &passes, &in_alt, 16)));
+                total_passes += passes;
+                if (in_alt) {
+                    std::swap(a0, a1);
+                    std::swap(b0, b1);
+                }
+                sorted_a = a0;
+                sorted_b = b0;
             }
-            sorted_a = a0;
-            sorted_b = b0;
+            const uint32_t utiles = (uint32_t)((P_raw + UNIQ_TILE - 1) / UNIQ_TILE);
+            const size_t ubytes = 64 + (size_t)utiles * sizeof(uint64_t);
+            TRY(ensure(L, L->scratch, ubytes));
+            CU(L, cudaMemsetAsync(L->scratch.p, 0, ubytes, L->stream));
+            UniqueArgs<IdT> ua;
+            ua.in_packed = wide ? nullptr : sorted_a;
+            ua.in_a = wide ? sorted_a : nullptr;
+            ua.in_b = sorted_b;
+            ua.n_host = (uint32_t)P_raw;
+            ua.n_dev = nullptr;
+            ua.out = (IdT *)L->pout.p;
+            ua.tile_counter = (uint32_t *)L->scratch.p;
+            ua.status = (uint64_t *)((char *)L->scratch.p + 64);
+            ua.totals = L->d_tot;
+            ua.err = L->d_err;
+            {
+                LaunchScope ls(L, BP_K_PAIR_UNIQUE, (double)P_raw * 2.0 * sizeof(IdT));
+                pair_unique_kernel<IdT><<<utiles, UNIQ_THREADS, 0, L->stream>>>(ua);
+            }
+            TRY(check_launch(L, "pair_unique_kernel"));
+            TRY(fetch_totals(L));
         }
         L->stats.pair_sort_passes = (uint32_t)total_passes;
-
-        // ---- dedup (src/layer.rs:474, :517) ----
-        const uint32_t utiles = (uint32_t)((P_raw + UNIQ_TILE - 1) / UNIQ_TILE);
-        const size_t ubytes = 64 + (size_t)utiles * sizeof(uint64_t);
-        TRY(ensure(L, L->scratch, ubytes));
-        CU(L, cudaMemsetAsync(L->scratch.p, 0, ubytes, L->stream));
-        UniqueArgs<IdT> ua;
-        ua.in_packed = wide ? nullptr : sorted_a;
-        ua.in_a = wide ? sorted_a : nullptr;
-        ua.in_b = sorted_b;
-        ua.n_host = (uint32_t)P_raw;
-        ua.n_dev = nullptr;
-        ua.out = (IdT *)L->pout.p;
-        ua.tile_counter = (uint32_t *)L->scratch.p;
-        ua.status = (uint64_t *)((char *)L->scratch.p + 64);
-        ua.totals = L->d_tot;
-        ua.err = L->d_err;
-        {
-            LaunchScope ls(L, BP_K_PAIR_UNIQUE, (double)P_raw * 2.0 * sizeof(IdT));
-            pair_unique_kernel<IdT><<<utiles, UNIQ_THREADS, 0, L->stream>>>(ua);
-        }
-        TRY(check_launch(L, "pair_unique_kernel"));
-        TRY(fetch_totals(L));
         L->n_pairs = L->h_tot->n_pairs;
         L->stats.n_pairs = L->n_pairs;
         L->stats.algo_bytes[BP_K_PAIR_UNIQUE] += (double)L->n_pairs * 2.0 * sizeof(IdT);

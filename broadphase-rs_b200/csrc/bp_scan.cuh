@@ -536,4 +536,162 @@ __global__ void __launch_bounds__(UNIQ_THREADS) pair_unique_kernel(const UniqueA
     if (t0 + tile_n == n && tid == 0) a.totals->n_pairs = sbase + swtot[WARPS];
 }
 
+// ---------------------------------------------------------------------------------------------
+// pair_finish_kernel -- the second half of `collisions.sort_unstable(); collisions.dedup()`
+// (src/layer.rs:473-474, 516-517) when the radix passes only ordered the pairs by their LATER ID.
+//
+// A later ID has a handful of partners (config 2: 3 raw pairs per object on average), so after a
+// stable radix sort on the later ID alone every group of equal later IDs is tiny.  Ordering the
+// earlier IDs inside such a group and dropping duplicates is quadratic work on 3-element groups --
+// far cheaper than the three more full radix passes over the earlier ID's bits it replaces.
+//   keep(e)  <=>  no element before e in its group has the same earlier ID
+//   rank(e)   =   number of kept elements of the group with a smaller earlier ID
+// A tile owns the groups that START in it; its window extends FIN_HALO elements past the tile so those
+// groups are complete.  A group that does not fit sets `overflow` and the host falls back to the
+// full-width sort + pair_unique_kernel (no result is lost: the input is only read).
+// ---------------------------------------------------------------------------------------------
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_HALO = 512;
+template <class IdT> struct FinCfg { // u64 IDs stage two arrays twice: a smaller tile keeps the kernel under 48 KB of shared memory
+    static constexpr int TILE = sizeof(IdT) == 8 ? 512 : 2048;
+    static constexpr int WIN = TILE + FIN_HALO;
+    static constexpr int IPT = WIN / FIN_THREADS;
+};
+
+template <class IdT> struct FinishArgs {
+    const uint64_t *in_packed; // u32 IDs: packed pairs sorted by the later ID (the high half)
+    const uint64_t *in_a;      // u64 IDs: later IDs (sorted) ...
+    const uint64_t *in_b;      //          ... and their partners
+    uint32_t n;
+    IdT *out;               // [2 * n] (later, earlier) interleaved
+    uint64_t *status;       // look-back, one per tile, zeroed
+    uint32_t *tile_counter; // zeroed
+    ScanTotals *totals;     // n_pairs; pad = 1 on overflow
+    int *err;
+};
+
+// Per element: one walk over its group gives its stable position inside the group ordered by the
+// earlier ID (#smaller + #equal-before); the group is rewritten in that order in a second shared buffer,
+// where duplicates are adjacent, so dedup + ordered compaction + coalesced stores are the usual
+// adjacent-difference / scan / look-back.
+template <class IdT>
+__global__ void __launch_bounds__(FIN_THREADS) pair_finish_kernel(const FinishArgs<IdT> a) {
+    constexpr bool WIDE = sizeof(IdT) == 8;
+    constexpr int FIN_TILE = FinCfg<IdT>::TILE, FIN_WIN = FinCfg<IdT>::WIN, FIN_IPT = FinCfg<IdT>::IPT;
+    constexpr uint64_t HOLE = ~0ull; // marks window slots this tile does not own
+    __shared__ uint64_t sa[FIN_WIN + 1];            // packed pair, or later ID (+1: the element after the window, for the overflow test)
+    __shared__ uint64_t sb[WIDE ? FIN_WIN + 1 : 1]; // earlier ID (u64 IDs only)
+    __shared__ uint64_t ta[FIN_WIN];                // the owned groups, each ordered by the earlier ID
+    __shared__ uint64_t tb[WIDE ? FIN_WIN : 1];
+    __shared__ uint32_t sscratch[FIN_THREADS / 32 + 2];
+    __shared__ uint64_t sbase;
+    __shared__ uint32_t stile;
+
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) stile = atomicAdd(a.tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = stile;
+    const uint64_t t0 = (uint64_t)tile * FIN_TILE;
+    if (t0 >= a.n) return;
+    const uint32_t tile_n = (uint32_t)min((uint64_t)FIN_TILE, (uint64_t)a.n - t0);
+    const uint32_t win_n = (uint32_t)min((uint64_t)FIN_WIN, (uint64_t)a.n - t0);
+    const bool more = t0 + win_n < a.n; // an element exists right after the window
+
+    for (uint32_t i = tid; i < win_n + (more ? 1u : 0u); i += FIN_THREADS) {
+        sa[i] = WIDE ? a.in_a[t0 + i] : a.in_packed[t0 + i];
+        if (WIDE) sb[i] = a.in_b[t0 + i];
+    }
+    for (uint32_t i = tid; i < (uint32_t)FIN_WIN; i += FIN_THREADS) {
+        ta[i] = HOLE;
+        if (WIDE) tb[i] = HOLE; // (max, max) is not a pair, so both halves equal to HOLE can only be a hole
+    }
+    // does the first group of the window continue a group of the previous tile?
+    const uint64_t prev = t0 > 0 ? (WIDE ? a.in_a[t0 - 1] : (a.in_packed[t0 - 1] >> 32)) : 0;
+    __syncthreads();
+    const bool cont0 = t0 > 0 && prev == (WIDE ? sa[0] : (sa[0] >> 32));
+
+    // ---- one walk per element: head of its group, stable position inside the group ------------------
+#pragma unroll 1
+    for (uint32_t i = tid; i < win_n; i += FIN_THREADS) {
+        const uint64_t x = sa[i];
+        const uint64_t la = WIDE ? x : (x >> 32);
+        const uint64_t eb = WIDE ? sb[i] : (x & 0xffffffffull);
+        uint32_t h = i, pos = 0;
+        while (h > 0) { // elements before i in the group: smaller or equal earlier IDs come first (stable)
+            const uint64_t y = sa[h - 1];
+            if ((WIDE ? y : (y >> 32)) != la) break;
+            --h;
+            pos += ((WIDE ? sb[h] : (y & 0xffffffffull)) <= eb) ? 1u : 0u;
+        }
+        if (h >= tile_n || (h == 0 && cont0)) continue; // the group belongs to a neighbouring tile
+        uint32_t e = i + 1;
+        while (e < win_n) { // elements after i: only strictly smaller ones come first
+            const uint64_t y = sa[e];
+            if ((WIDE ? y : (y >> 32)) != la) break;
+            pos += ((WIDE ? sb[e] : (y & 0xffffffffull)) < eb) ? 1u : 0u;
+            ++e;
+        }
+        // an owned group that runs past the window cannot be finished here
+        if (e == win_n && more && (WIDE ? sa[win_n] : (sa[win_n] >> 32)) == la) a.totals->pad = 1u;
+        ta[h + pos] = x;
+        if (WIDE) tb[h + pos] = eb;
+    }
+    __syncthreads();
+
+    // ---- duplicates are adjacent now: keep the first of each run, compact in order ---------------------
+    uint32_t keepbits = 0, mine = 0;
+#pragma unroll
+    for (int q = 0; q < FIN_IPT; ++q) { // blocked: thread t owns window slots [t*IPT, t*IPT + IPT)
+        const uint32_t i = tid * FIN_IPT + q;
+        bool keep = false;
+        if (i < win_n && (ta[i] != HOLE || (WIDE && tb[i] != HOLE))) {
+            keep = i == 0 || ta[i - 1] != ta[i] || (WIDE && tb[i - 1] != tb[i]);
+        }
+        if (keep) {
+            keepbits |= 1u << q;
+            ++mine;
+        }
+    }
+    uint32_t tile_keep;
+    uint32_t ex = block_exclusive_sum<FIN_THREADS, uint32_t>(mine, sscratch, &tile_keep);
+    if (warp == 0) {
+        const uint64_t e = lookback_exclusive(a.status, tile, (uint64_t)tile_keep, a.err);
+        if (lane == 0) sbase = e;
+    }
+    // kept elements move to the front of the (now dead) input buffers, in order
+    uint64_t ka[FIN_IPT], kb[WIDE ? FIN_IPT : 1];
+#pragma unroll
+    for (int q = 0; q < FIN_IPT; ++q) {
+        const uint32_t i = tid * FIN_IPT + q;
+        if (keepbits & (1u << q)) {
+            ka[q] = ta[i];
+            if (WIDE) kb[q] = tb[i];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < FIN_IPT; ++q) {
+        if (keepbits & (1u << q)) {
+            sa[ex] = ka[q];
+            if (WIDE) sb[ex] = kb[q];
+            ++ex;
+        }
+    }
+    __syncthreads();
+    const uint64_t base = sbase;
+    for (uint32_t i = tid; i < tile_keep; i += FIN_THREADS) {
+        if (WIDE) {
+            ulonglong2 p;
+            p.x = sa[i]; // later
+            p.y = sb[i]; // earlier
+            ((ulonglong2 *)a.out)[base + i] = p;
+        } else {
+            uint2 p;
+            p.x = (uint32_t)(sa[i] >> 32); // later
+            p.y = (uint32_t)sa[i];         // earlier
+            ((uint2 *)a.out)[base + i] = p;
+        }
+    }
+    if (t0 + tile_n == a.n && tid == 0) a.totals->n_pairs = base + tile_keep;
+}
+
 } // namespace bp

@@ -242,6 +242,34 @@ def test_set_records_roundtrip_and_scan(bp):
     _assert_records_equal(g, o)
 
 
+@pytest.mark.parametrize("id_bytes", [4, 8])
+def test_crowded_cell_takes_the_full_width_pair_sort(bp, id_bytes):
+    """Hundreds of objects in one cell: the later ID with the most partners has more of them than
+    pair_finish_kernel's window, so the scan must fall back to the full-width pair sort."""
+    sc = bp.scenes.uniform_cubes(20_000, 12)
+    crowd = 900
+    sc["bounds"][:crowd] = np.array([0.4001, 0.4001, 0.4001, 0.4019, 0.4019, 0.4019], dtype=np.float32)
+    # a second, smaller crowd that still fits the window (up to 8 raw copies of each of its ~40 pairs per ID)
+    sc["bounds"][crowd:crowd + 40] = np.array([0.7001, 0.2001, 0.6001, 0.7012, 0.2012, 0.6012], dtype=np.float32)
+    ids = sc["ids"].astype(np.uint64 if id_bytes == 8 else np.uint32)
+    g = bp.Layer(2, "u32" if id_bytes == 4 else "u64")
+    o = co.OracleLayer(2, id_bytes, 0)
+    g.extend(sc["sys_bounds"], sc["bounds"], ids)
+    o.extend(sc["sys_bounds"], sc["bounds"], ids)
+    gp = g.par_scan()
+    op = o.par_scan()
+    _assert_pairs_equal(gp, op)
+    assert gp.shape[0] > crowd * (crowd - 1) // 2
+    assert g.stats()["pair_sort_passes"] >= 5  # later-ID passes + the full-width fallback
+    # without the big crowd the finish kernel handles everything (fewer passes)
+    g2 = bp.Layer(2, "u32" if id_bytes == 4 else "u64")
+    o2 = co.OracleLayer(2, id_bytes, 0)
+    g2.extend(sc["sys_bounds"], sc["bounds"][crowd:], ids[crowd:])
+    o2.extend(sc["sys_bounds"], sc["bounds"][crowd:], ids[crowd:])
+    _assert_pairs_equal(g2.par_scan(), o2.par_scan())
+    assert g2.stats()["pair_sort_passes"] <= 3
+
+
 # ---- BASELINE.json configs at sizes the oracle finishes in seconds --------------------------------------
 
 def _run_scene(bp, sc, id_type="u32", flt=None, oflt=(0, 0, None), check_unsorted=True):
