@@ -123,7 +123,7 @@ class CudaOps:
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         mk = lambda: bp.LayerBuilder().with_min_depth(min_depth).with_device(device).build(kind, "u32")
-        self.enc, self.shard = mk(), mk()
+        self.enc, self.shard, self.static = mk(), mk(), mk()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         for l in self.layers():
             l.set_stream(stream)
@@ -131,7 +131,7 @@ class CudaOps:
         self.rk = self.ri = self.rp = None
 
     def layers(self):
-        return (self.enc, self.shard)
+        return (self.enc, self.shard, self.static)
 
     def encode(self, sys_bounds, bounds, ids, n):
         self.enc.clear()
@@ -166,6 +166,19 @@ class CudaOps:
         self.shard.sort()
         kp, ip, r, _ = self.shard.records_device()
         return _view(kp, r, torch.int64, self.device), _view(ip, r, torch.int32, self.device)
+
+    def keep_static(self, keys, ids):
+        """Sorts the received static records once and keeps them resident (Layer::merge's "static scene
+        layer", reference README: sorted once, merged into every frame's dynamic layer)."""
+        self.static.set_records(keys, ids, sorted_=False, on_device=True, n=keys.shape[0])
+        self.static.sort()
+        return len(self.static)
+
+    def merge_static(self):
+        """Layer::merge of the resident static shard into this frame's sorted dynamic shard; the scan's
+        implicit sort is then one merge-path merge."""
+        self.shard.merge(self.static)
+        return len(self.shard)
 
     def scan_raw(self, keys, ids, n_halo, flt):
         """The sorted records live in self.shard; its first n_halo records are halo."""
@@ -204,6 +217,8 @@ class DistLayer:
         self.reuse_splitters = reuse_splitters
         self._splitters = self._a_splitters = None
         self._id_mask = 0
+        self._static_halo = None  # halo records at the front of the resident static shard (None: no static layer)
+        self._static_id_bits = 0
         self.last = {}
 
     # -- small collectives (device tensors over NCCL in production, CPU tensors over gloo in the tests) --
@@ -220,6 +235,34 @@ class DistLayer:
     def _imbalance(col_sums):
         mean = float(np.mean(col_sums))
         return float(np.max(col_sums)) / mean if mean > 0 else 1.0
+
+    def set_static(self, sys_bounds, bounds, ids, n):
+        """Shards a static scene once (config 4 at N > 1): its records are range-partitioned with splitters
+        sampled from the static keys -- which stay FIXED from then on, so every frame's dynamic records are
+        routed to the same owners -- sorted, and kept resident.  frame() then merges them in
+        (Layer::merge, src/layer.rs:127-138) before the scan.  Halo copies of static records sit at the
+        front of the static shard, exactly like those of the dynamic records."""
+        ops, g, me = self.ops, self.world, self.rank
+        dev = ops.device
+        keys, rids, id_or = ops.encode(sys_bounds, bounds, ids, n)
+        m = SAMPLES_PER_RANK
+        meta = torch.full((m + 1,), -1, dtype=torch.int64, device=dev)
+        if keys.shape[0]:
+            ks = keys[::max(1, keys.shape[0] // m)][:m]
+            meta[:ks.shape[0]] = ks
+        meta[m] = id_or
+        gathered = self._all_gather(meta).cpu().numpy()
+        sample = gathered[:, :m].reshape(-1)
+        self._splitters = choose_splitters(sample[sample >= 0].view(np.uint64), g)
+        for v in gathered[:, m]:
+            self._static_id_bits |= int(v)
+        counts, halo = ops.count_records(keys, self._splitters)
+        mat = self._gather_rows(counts + halo, dev)
+        m_own, m_halo = mat[:, :g], mat[:, g:2 * g]
+        rk, ri = ops.exchange_records(keys, rids, self._splitters, m_own, m_halo)
+        self._static_halo = int(m_halo[:, me].sum())
+        n_static = ops.keep_static(rk, ri)
+        return n_static
 
     def frame(self, sys_bounds, bounds, ids, n, flt=None):
         """Runs one frame on this rank's objects.  Returns the rank's slice of the globally sorted,
@@ -243,7 +286,7 @@ class DistLayer:
 
         # 2. key splitters (+ the ID bits, piggybacked) from an all-gathered sample
         m = SAMPLES_PER_RANK
-        if self._splitters is None or not self.reuse_splitters:
+        if self._splitters is None or (not self.reuse_splitters and self._static_halo is None):
             meta = torch.full((m + 1,), -1, dtype=torch.int64, device=dev)
             if r_loc:
                 ks = keys[::max(1, r_loc // m)][:m]
@@ -266,6 +309,7 @@ class DistLayer:
         id_bits = 0
         for v in mat[:, 2 * g]:
             id_bits |= int(v)
+        id_bits |= self._static_id_bits
         self._id_mask |= (1 << max(1, id_bits.bit_length())) - 1  # IDs seen since the splitters were cached
         mark("counts")
         rk, ri = ops.exchange_records(keys, rids, splitters, m_own, m_halo)
@@ -274,6 +318,9 @@ class DistLayer:
 
         # 4. local sort: the halo records (all < my lower splitter) end up in front
         sk, si = ops.sort_records(rk, ri)
+        if self._static_halo is not None:  # Layer::merge of the resident static shard (sorted runs: merge path)
+            ops.merge_static()
+            n_halo += self._static_halo
         mark("sort")
 
         # 5. shard-local scan; pairs whose later record is a halo record belong to an earlier shard
@@ -300,8 +347,8 @@ class DistLayer:
 
         # cached splitters are recomputed next frame when a shard has drifted too far from the mean
         if self.reuse_splitters:
-            if self._imbalance((m_own + m_halo).sum(axis=0)) > REBALANCE_AT:
-                self._splitters = None
+            if self._static_halo is None and self._imbalance((m_own + m_halo).sum(axis=0)) > REBALANCE_AT:
+                self._splitters = None  # (with a static layer the record splitters are fixed)
             if self._imbalance(pm.sum(axis=0)) > REBALANCE_AT:
                 self._a_splitters = None
         phases_ms = {b[0]: (b[1] - a_[1]) * 1e3 for a_, b in zip(phases[:-1], phases[1:])}

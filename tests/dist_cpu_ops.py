@@ -98,8 +98,22 @@ class CpuOps:
         k, i = pyref.sort_records(_u64(keys), _u32(ids))
         return _i64(k), _i32(i)
 
+    def keep_static(self, keys, ids):
+        self._static = pyref.sort_records(_u64(keys), _u32(ids))
+        return self._static[0].shape[0]
+
+    def merge_static(self):
+        self._merge = True
+        return 0
+
     def scan_raw(self, keys, ids, n_halo, flt):
         fk, arg = flt if flt else (0, 0)
+        if getattr(self, "_merge", False):  # the double simply re-sorts the concatenation, like the reference does
+            k = np.concatenate([_u64(keys), self._static[0]])
+            i = np.concatenate([_u32(ids), self._static[1]])
+            k, i = pyref.sort_records(k, i)
+            keys, ids = _i64(k), _i32(i)
+            self._merge = False
         a, b = pyref.scan_raw(self.kind, _u64(keys), _u32(ids), fk, arg, None, first_owned=n_halo)
         return _i64((a << np.uint64(32)) | b)
 
@@ -161,6 +175,21 @@ def reference_pairs(case):
     return L.scan(fk, arg).astype(np.uint32)
 
 
+def reference_static_dynamic(frame):
+    kind, md, sysb, sb, sids, _ = make_case("big_objects3d")
+    _, _, _, db, dids, _ = make_case("uniform3d")
+    dids = (dids + np.uint32(100_000)).astype(np.uint32)
+    moved = np.clip(db + np.float32(0.001 * frame), 0.0, 1.0).astype(np.float32)
+    S = co.OracleLayer(kind, 4, md)
+    S.extend(sysb, sb, sids)
+    S.sort()
+    D = co.OracleLayer(kind, 4, md)
+    D.extend(sysb, moved, dids)
+    D.sort()
+    D.merge(S)
+    return D.scan().astype(np.uint32)
+
+
 def worker(rank, world, port, cases, empty_rank, out_dir):
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -191,6 +220,21 @@ def worker(rank, world, port, cases, empty_rank, out_dir):
             dist.all_gather_object(halos, dl.last["halo"])
             if rank == 0:
                 np.save(os.path.join(out_dir, "%s.halos.npy" % case), np.array(halos))
+        # config-4 shape: a static scene sharded once, a fresh dynamic layer merged in every frame
+        kind, md, sysb, sb, sids, _ = make_case("big_objects3d")
+        _, _, _, db, dids, _ = make_case("uniform3d")
+        dids = (dids + np.uint32(100_000)).astype(np.uint32)
+        cs = np.linspace(0, sb.shape[0], world + 1).astype(int)
+        cd = np.linspace(0, db.shape[0], world + 1).astype(int)
+        dl = bpd.DistLayer(CpuOps(kind, md), kind)
+        dl.set_static(sysb, sb[cs[rank]:cs[rank + 1]], sids[cs[rank]:cs[rank + 1]], cs[rank + 1] - cs[rank])
+        for frame in range(2):
+            shift = np.float32(0.001 * frame)
+            moved = np.clip(db + shift, 0.0, 1.0).astype(np.float32)
+            pairs = dl.frame(sysb, moved[cd[rank]:cd[rank + 1]], dids[cd[rank]:cd[rank + 1]], cd[rank + 1] - cd[rank], None)
+            allp = dl.gather_pairs(pairs)
+            if rank == 0:
+                np.save(os.path.join(out_dir, "static_dynamic_%d.npy" % frame), allp)
         dist.barrier()
         dist.destroy_process_group()
     except Exception:

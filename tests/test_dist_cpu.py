@@ -29,6 +29,10 @@ def test_distributed_frame_equals_single_process_oracle(tmp_path, world, empty_r
         want = dco.reference_pairs(case)
         assert got.shape == want.shape, (case, got.shape, want.shape)
         assert (got == want).all(), case
+    for frame in range(2):  # static layer sharded once + dynamic layer merged per frame (config 4 at N > 1)
+        got = np.load(os.path.join(str(tmp_path), "static_dynamic_%d.npy" % frame))
+        want = dco.reference_static_dynamic(frame)
+        assert got.shape == want.shape and (got == want).all(), ("static+dynamic", frame)
     halos = np.load(os.path.join(str(tmp_path), "big_objects3d.halos.npy"))
     if empty_rank < 0:
         assert halos[0] == 0 and halos[1:].sum() > 0  # scene-sized objects must have produced halo records

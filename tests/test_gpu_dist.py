@@ -183,6 +183,24 @@ def _nccl_worker(rank, world, port, out_dir):
         allp = dl.gather_pairs(pairs)
         if rank == 0:
             np.save(os.path.join(out_dir, "%s.npy" % case), allp)
+    # config-4 shape: static scene sharded once, dynamic layer merged in per frame (Layer::merge)
+    kind, md, sysb, sb, sids, _ = dco.make_case("big_objects3d")
+    _, _, _, dbn, dids, _ = dco.make_case("uniform3d")
+    dids = (dids + np.uint32(100_000)).astype(np.uint32)
+    cs = np.linspace(0, sb.shape[0], world + 1).astype(int)
+    cd = np.linspace(0, dbn.shape[0], world + 1).astype(int)
+    ops = bpd.CudaOps(bp, kind, md, rank)
+    dl = bpd.DistLayer(ops, kind)
+    dl.set_static(sysb, torch.from_numpy(sb[cs[rank]:cs[rank + 1]].copy()).cuda(),
+                  torch.from_numpy(sids[cs[rank]:cs[rank + 1]].copy().view(np.int32)).cuda(), cs[rank + 1] - cs[rank])
+    for frame in range(2):
+        moved = np.clip(dbn + np.float32(0.001 * frame), 0.0, 1.0).astype(np.float32)
+        pairs = dl.frame(sysb, torch.from_numpy(moved[cd[rank]:cd[rank + 1]].copy()).cuda(),
+                         torch.from_numpy(dids[cd[rank]:cd[rank + 1]].copy().view(np.int32)).cuda(), cd[rank + 1] - cd[rank], None)
+        allp = dl.gather_pairs(pairs)
+        if rank == 0:
+            np.save(os.path.join(out_dir, "static_dynamic_%d.npy" % frame), allp)
+    assert ops.shard.stats()["merged"] == 1
     # the BASELINE config-2 recipe, 2^18 objects per rank
     import importlib
     dbm = importlib.import_module("broadphase_rs_b200.dist_bench")
@@ -211,6 +229,10 @@ def test_nccl_frame_equals_oracle(bp, tmp_path):
         got = np.load(os.path.join(str(tmp_path), "%s.npy" % case))
         want = dco.reference_pairs(case)
         assert got.shape == want.shape and (got == want).all(), case
+    for frame in range(2):
+        got = np.load(os.path.join(str(tmp_path), "static_dynamic_%d.npy" % frame))
+        want = dco.reference_static_dynamic(frame)
+        assert got.shape == want.shape and (got == want).all(), ("static+dynamic", frame)
     import importlib
     dbm = importlib.import_module("broadphase_rs_b200.dist_bench")
     o = co.OracleLayer(2, 4, 0)
