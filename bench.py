@@ -165,7 +165,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": "objects/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "objects/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
@@ -317,14 +317,30 @@ def run_ours(args):
     }
     if extra:
         line["other_workloads"] = extra
-    print(json.dumps(line))
+    emit_line(line)
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(line):
+    """The one JSON line goes to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
-    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout must carry exactly one JSON line, but libraries print there too (NCCL's version banner,
+    # for one): point fd 1 at stderr for the whole run and keep the original for the JSON line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -140,7 +140,7 @@ def run(args, bp):
         }
         if extra:
             line["other_workloads"] = extra
-        print(json.dumps(line))
+        bench.emit_line(line)
     dist.barrier()
     dist.destroy_process_group()
     return 0
