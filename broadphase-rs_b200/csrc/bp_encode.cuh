@@ -41,6 +41,7 @@ template <class T, class IdT> struct EncodeArgs {
     uint32_t min_depth;
     typename T::key_t *keys_out; // tree arrays
     IdT *ids_out;
+    uint8_t *cell_flags_out; // per record: bit a set = the object also covers the previous cell along axis a (or null)
     uint64_t out_base;     // records already in the tree
     uint64_t capacity;     // records the tree arrays can hold
     uint64_t *status;      // look-back status, one per tile, zeroed
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
             if (gi < a.capacity) {
                 a.keys_out[gi] = key;
                 a.ids_out[gi] = sid[o];
+                if (a.cell_flags_out) a.cell_flags_out[gi] = (uint8_t)((ix ? 1u : 0u) | (iy ? 2u : 0u) | (iz ? 4u : 0u));
             }
         }
         __syncthreads();
@@ -306,6 +308,18 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
         a.result->total_records = tile_base + tile_total;
         if (a.next_last_id) *a.next_last_id = a.ids[a.n - 1];
     }
+}
+
+// The cell flags ride through the sort in the unused top 3 bits of the ID payload (the host checks that
+// the IDs leave them free) and are removed again before the IDs are shown to anybody.
+template <class IdT> __global__ void __launch_bounds__(256) flags_merge_kernel(IdT *__restrict__ ids, const uint8_t *__restrict__ flags, uint32_t n) {
+    constexpr int SH = 8 * sizeof(IdT) - 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        ids[i] |= (IdT)flags[i] << SH;
+}
+template <class IdT> __global__ void __launch_bounds__(256) flags_strip_kernel(IdT *__restrict__ ids, uint32_t n) {
+    constexpr IdT MASK = (IdT)(((IdT)1 << (8 * sizeof(IdT) - 3)) - 1);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) ids[i] &= MASK;
 }
 
 // OR / AND of keys and IDs + "IDs ascending" for a tree that did not come from encode_kernel

@@ -70,6 +70,12 @@ struct bp_layer {
     uint64_t key_or = 0, key_and = ~0ull, id_or = 0, id_and = ~0ull;
     uint64_t n_invalid = 0;
     uint64_t n_halo = 0; // records [0, n_halo) only act as ancestors in scan (multi-GPU halos)
+    // dedup at the source: encode writes 3 cell flags per record (cell_flags); a full sort of a tree that
+    // only holds encoded records moves them into the top 3 bits of the IDs (ids_flagged) so that they
+    // travel with the records; any other mutation strips them again
+    DevBuf cell_flags;
+    bool flags_valid = true; // every record of the tree has its flags in cell_flags
+    bool ids_flagged = false;
 
     // pending extend result
     bool pending = false;
@@ -379,7 +385,22 @@ template <int KIND, class IdT> struct Impl {
         TRY(ensure(L, L->ids[L->cur], want * sizeof(IdT), true, live * sizeof(IdT)));
         TRY(ensure(L, L->keys[L->cur ^ 1], want * sizeof(K)));
         TRY(ensure(L, L->ids[L->cur ^ 1], want * sizeof(IdT)));
+        TRY(ensure(L, L->cell_flags, want, true, live));
         L->cap_records = want;
+        return BP_OK;
+    }
+
+    // Removes the cell flags from the IDs (before anything but the scan looks at them).
+    static int strip_flags(bp_layer *L) {
+        if (!L->ids_flagged) return BP_OK;
+        if (L->n_records) {
+            LaunchScope ls(L, BP_K_MISC, 2.0 * (double)L->n_records * sizeof(IdT));
+            const int blocks = (int)std::min<uint64_t>((L->n_records + 1023) / 1024, 148 * 8);
+            flags_strip_kernel<IdT><<<blocks, 256, 0, L->stream>>>(ids(L, L->cur), (uint32_t)L->n_records);
+        }
+        TRY(check_launch(L, "flags_strip_kernel"));
+        L->ids_flagged = false;
+        L->flags_valid = false;
         return BP_OK;
     }
 
@@ -399,6 +420,7 @@ template <int KIND, class IdT> struct Impl {
         a.min_depth = L->min_depth;
         a.keys_out = keys(L, L->cur);
         a.ids_out = ids(L, L->cur);
+        a.cell_flags_out = L->flags_valid ? (uint8_t *)L->cell_flags.p : nullptr;
         a.out_base = L->n_records;
         a.capacity = L->cap_records;
         const uint32_t tiles = (n + ENCODE_TILE - 1) / ENCODE_TILE;
@@ -437,6 +459,7 @@ template <int KIND, class IdT> struct Impl {
 
     static int extend_device(bp_layer *L, const float *sysb, const float *d_bounds, const void *d_ids, size_t n) {
         if (n == 0) return BP_OK;
+        TRY(strip_flags(L));
         if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "too many objects in one extend");
         const uint64_t per_obj = 1ull << T::DIM;
         TRY(ensure_tree(L, std::min<uint64_t>(L->n_records + n * per_obj, MAX_RECORDS)));
@@ -529,7 +552,18 @@ template <int KIND, class IdT> struct Impl {
         const uint64_t tail = R - prefix;
         if (R >= 2 && tail > 0) {
             if (prefix == 0) {
-                if (!L->tail_sorted) TRY(sort_range(L, 0, R, L->tail_nonmono));
+                if (!L->tail_sorted) {
+                    // the whole tree came from extend(): let the cell flags ride in the IDs' spare top bits
+                    const int id_bits = 64 - (L->id_or ? __builtin_clzll(L->id_or) : 64);
+                    if (L->flags_valid && !L->ids_flagged && id_bits <= (int)(8 * sizeof(IdT)) - 3) {
+                        LaunchScope ls(L, BP_K_MISC, (double)R * (2.0 * sizeof(IdT) + 1.0));
+                        const int blocks = (int)std::min<uint64_t>((R + 1023) / 1024, 148 * 8);
+                        flags_merge_kernel<IdT><<<blocks, 256, 0, L->stream>>>(ids(L, L->cur), (const uint8_t *)L->cell_flags.p, (uint32_t)R);
+                        L->ids_flagged = true;
+                    }
+                    TRY(check_launch(L, "flags_merge_kernel"));
+                    TRY(sort_range(L, 0, R, L->tail_nonmono));
+                }
             } else if (L->tail_sorted || prefix * 8 >= R) {
                 // two sorted runs: one linear merge.  An unsorted tail is radix-sorted on its own first,
                 // unless the sorted prefix is so short that re-sorting everything is cheaper.
@@ -548,22 +582,25 @@ template <int KIND, class IdT> struct Impl {
     }
 
     // ---- scan ---------------------------------------------------------------------------------------------------
-    template <int FK> static int launch_emit(bp_layer *L, EmitArgs<IdT> &a, uint32_t chunks, double bytes) {
-        auto kern = scan_emit_kernel<IdT, FK>;
+    template <int FK, bool DEDUP> static int launch_emit(bp_layer *L, EmitArgs<IdT> &a, uint32_t chunks, double bytes) {
+        auto kern = scan_emit_kernel<IdT, FK, T, DEDUP>;
         CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EmitSmem<IdT>::BYTES));
         LaunchScope ls(L, BP_K_SCAN_EMIT, bytes);
         kern<<<chunks, EMIT_THREADS, EmitSmem<IdT>::BYTES, L->stream>>>(a);
         return BP_OK;
     }
-    static int emit(bp_layer *L, EmitArgs<IdT> &a, int fk, uint32_t chunks, double bytes) {
+    template <bool DEDUP> static int emit_fk(bp_layer *L, EmitArgs<IdT> &a, int fk, uint32_t chunks, double bytes) {
         switch (fk) {
-        case BP_FILTER_NONE: TRY(launch_emit<BP_FILTER_NONE>(L, a, chunks, bytes)); break;
-        case BP_FILTER_ID_PARITY: TRY(launch_emit<BP_FILTER_ID_PARITY>(L, a, chunks, bytes)); break;
-        case BP_FILTER_XOR_MASK: TRY(launch_emit<BP_FILTER_XOR_MASK>(L, a, chunks, bytes)); break;
-        case BP_FILTER_CATEGORY: TRY(launch_emit<BP_FILTER_CATEGORY>(L, a, chunks, bytes)); break;
+        case BP_FILTER_NONE: TRY((launch_emit<BP_FILTER_NONE, DEDUP>(L, a, chunks, bytes))); break;
+        case BP_FILTER_ID_PARITY: TRY((launch_emit<BP_FILTER_ID_PARITY, DEDUP>(L, a, chunks, bytes))); break;
+        case BP_FILTER_XOR_MASK: TRY((launch_emit<BP_FILTER_XOR_MASK, DEDUP>(L, a, chunks, bytes))); break;
+        case BP_FILTER_CATEGORY: TRY((launch_emit<BP_FILTER_CATEGORY, DEDUP>(L, a, chunks, bytes))); break;
         default: return fail(L, BP_ERR_INVALID_ARG, "unknown filter kind %d", fk);
         }
         return check_launch(L, "scan_emit_kernel");
+    }
+    static int emit(bp_layer *L, EmitArgs<IdT> &a, int fk, uint32_t chunks, double bytes, bool dedup) {
+        return dedup ? emit_fk<true>(L, a, fk, chunks, bytes) : emit_fk<false>(L, a, fk, chunks, bytes);
     }
 
     static int fetch_totals(bp_layer *L) {
@@ -654,6 +691,9 @@ template <int KIND, class IdT> struct Impl {
         TRY(ensure(L, L->scratch, ebytes));
         EmitArgs<IdT> ea;
         ea.ids = ids(L, L->cur);
+        ea.keys = keys(L, L->cur);
+        ea.id_mask = L->ids_flagged ? (IdT)((((IdT)1) << (8 * sizeof(IdT) - 3)) - 1) : (IdT) ~(IdT)0;
+        const bool dedup = L->ids_flagged && L->n_halo == 0;
         ea.src_idx = (const uint32_t *)L->src_idx.p;
         ea.src_off = (const uint64_t *)L->src_off.p;
         ea.chunk_src = (const uint32_t *)L->chunk_src.p;
@@ -673,7 +713,7 @@ template <int KIND, class IdT> struct Impl {
         const double emit_bytes = (double)W * (2.0 * sizeof(IdT) + 2.0 * sizeof(IdT)) + (double)C * 12.0;
         CU(L, cudaMemsetAsync(L->scratch.p, 0, ebytes, L->stream));
         ea.mode = EMIT_MODE_FIRST;
-        TRY(emit(L, ea, fk, chunks, emit_bytes));
+        TRY(emit(L, ea, fk, chunks, emit_bytes + (dedup ? (double)W * 2.0 * sizeof(K) : 0.0), dedup));
         CU(L, cudaMemcpyAsync(&L->d_tot->n_raw_pairs, L->scratch.p, 8, cudaMemcpyDeviceToDevice, L->stream));
         TRY(fetch_totals(L));
         if (L->h_tot->any_same_id) {
@@ -685,10 +725,10 @@ template <int KIND, class IdT> struct Impl {
             ea.inactive = (unsigned char *)L->inactive.p;
             CU(L, cudaMemsetAsync(L->scratch.p, 0, ebytes, L->stream));
             ea.mode = EMIT_MODE_FLAG;
-            TRY(emit(L, ea, fk, chunks, (double)W * 2.0 * sizeof(IdT)));
+            TRY(emit(L, ea, fk, chunks, (double)W * 2.0 * sizeof(IdT), false));
             CU(L, cudaMemsetAsync(L->scratch.p, 0, ebytes, L->stream));
             ea.mode = EMIT_MODE_ACTIVE;
-            TRY(emit(L, ea, fk, chunks, emit_bytes));
+            TRY(emit(L, ea, fk, chunks, emit_bytes, false));
             CU(L, cudaMemcpyAsync(&L->d_tot->n_raw_pairs, L->scratch.p, 8, cudaMemcpyDeviceToDevice, L->stream));
             TRY(fetch_totals(L));
         }
@@ -1072,6 +1112,7 @@ int do_lookup_ranges(bp_layer *L, const void *keys, size_t n, const uint64_t *q,
     DISPATCH(L, lookup_ranges(L, keys, n, q, nq, lo, hi));
 }
 int do_masks(bp_layer *L, uint64_t n) { DISPATCH(L, masks_from_records(L, n)); }
+int do_strip_flags(bp_layer *L) { DISPATCH(L, strip_flags(L)); }
 
 // Folds the result of the last (still asynchronous) extend into the host-side state.
 int resolve_pending(bp_layer *L) {
@@ -1237,6 +1278,7 @@ int bp_layer_destroy(bp_layer *L) {
         release(L->praw_b[i]);
     }
     release(L->scratch);
+    release(L->cell_flags);
     release(L->stage_bounds);
     release(L->stage_ids);
     release(L->src_idx);
@@ -1291,6 +1333,8 @@ int bp_layer_clear(bp_layer *L) {
     }
     L->n_records = 0;
     L->n_halo = 0;
+    L->flags_valid = true;
+    L->ids_flagged = false;
     L->dirty = false;
     L->prefix = 0;
     L->tail_sorted = false;
@@ -1333,6 +1377,9 @@ int bp_layer_merge(bp_layer *L, const bp_layer *O_) {
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
     TRY(resolve_pending(O));
+    TRY(do_strip_flags(L));
+    TRY(do_strip_flags(O));
+    L->flags_valid = false; // the appended records carry no cell flags
     if (O->min_depth < L->min_depth) L->min_depth = O->min_depth; // src/layer.rs:131-134
     const uint64_t base = L->n_records, add = O->n_records;
     if (add) {
@@ -1520,6 +1567,7 @@ int bp_layer_records_device(bp_layer *L, const void **out_keys, const void **out
     if (!L) return BP_ERR_INVALID_ARG;
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
+    TRY(do_strip_flags(L));
     if (out_keys) *out_keys = L->keys[L->cur].p;
     if (out_ids) *out_ids = L->ids[L->cur].p;
     if (out_n) *out_n = (size_t)L->n_records;
@@ -1531,6 +1579,7 @@ int bp_layer_records(bp_layer *L, const void **out_keys, const void **out_ids, s
     if (!L) return BP_ERR_INVALID_ARG;
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
+    TRY(do_strip_flags(L));
     const size_t n = (size_t)L->n_records;
     if (n) {
         TRY(pinned_ensure(L, &L->h_keys, &L->h_keys_cap, n * L->key_bytes));
@@ -1563,6 +1612,7 @@ int bp_layer_set_records(bp_layer *L, const void *keys, const void *ids, size_t 
         CU(L, cudaMemcpyAsync(L->ids[L->cur].p, ids, n * L->id_bytes, kind, L->stream));
     }
     L->n_records = n;
+    L->flags_valid = false; // foreign records: no cell flags
     TRY(do_masks(L, n));
     L->key_or = L->h_res->key_or;
     L->key_and = L->h_res->key_and;

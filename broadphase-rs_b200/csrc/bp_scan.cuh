@@ -281,7 +281,9 @@ __global__ void __launch_bounds__(256) scan_chunks_kernel(const uint64_t *__rest
 enum { EMIT_MODE_FIRST = 0, EMIT_MODE_FLAG = 1, EMIT_MODE_ACTIVE = 2 };
 
 template <class IdT> struct EmitArgs {
-    const IdT *ids; // sorted tree IDs
+    const IdT *ids; // sorted tree IDs (with the cell flags in their top 3 bits when id_mask != ~0)
+    const void *keys; // sorted tree keys (dedup-at-source only)
+    IdT id_mask;      // removes the cell flags from a loaded ID
     const uint32_t *src_idx;
     const uint64_t *src_off;
     const uint32_t *chunk_src;
@@ -309,9 +311,39 @@ template <class IdT> struct EmitSmem {
     static constexpr size_t BYTES = (OFF_WORDS + IDX_WORDS + EMIT_THREADS / 32 + 4) * sizeof(uint64_t);
 };
 
-template <class IdT, int FK>
+// Dedup at the source.  Two objects that share several cells meet once per shared cell, so the raw pairs
+// carry every ID pair up to 2^DIM times (config 3: 3.4x).  The shared cells of a pair form a box; the pair
+// is emitted only from the box's minimum corner.  With fX = "object X also covers the previous cell along
+// this axis" (3 bits per record, written by encode_kernel) and s = depth(later) - depth(earlier), the
+// later record's cell c is the corner along an axis iff
+//      !fLater  ||  (!fEarlier && the s low bits of c's coordinate are zero)
+// (c-1 is either not the later object's, or it falls into the previous cell of the earlier object's depth
+// which that object does not cover).  Only used while no same-ID (inactive) record has been seen; the
+// pair sort + dedup that follows stays in place (IDs owning several bounds still produce duplicates).
+template <class T> __device__ __forceinline__ bool canonical_cell(typename T::key_t key_i, typename T::key_t key_j, uint32_t fi, uint32_t fj) {
+    typedef typename T::key_t K;
+    if (fj == 0) return true;
+    const uint32_t da = key_depth<T>(key_i), db = key_depth<T>(key_j);
+    const K between = (K)(level_mask<T>(db) ^ level_mask<T>(da)); // Morton bits of the levels da+1 .. db
+    // bit pattern of one axis inside the origin field: every DIM-th bit
+    constexpr uint64_t ONE_AXIS = T::DIM == 2 ? 0x5555555555555555ull : 0x9249249249249249ull;
+    constexpr int ORIGIN_BITS = T::DIM * T::AXIS_BITS;
+    // axis `ax` of coordinate bit t sits at origin bit DIM*t + ax; align the pattern so that bit 0 of the origin field is axis 0
+    const uint64_t field = (((uint64_t)1 << ORIGIN_BITS) - 1) << T::DEPTH_BITS;
+#pragma unroll
+    for (int ax = 0; ax < T::DIM; ++ax) {
+        if (!((fj >> ax) & 1u)) continue;
+        if ((fi >> ax) & 1u) return false;
+        const uint64_t axis_mask = ((ONE_AXIS << ax) << T::DEPTH_BITS) & field;
+        if (((uint64_t)key_j & (uint64_t)between & axis_mask) != 0) return false;
+    }
+    return true;
+}
+
+template <class IdT, int FK, class T = IndexTraits<BP_INDEX64_3D>, bool DEDUP = false>
 __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<IdT> a) {
     constexpr bool WIDE = sizeof(IdT) == 8;
+    constexpr int FLAG_SHIFT = 8 * sizeof(IdT) - 3;
     typedef EmitSmem<IdT> S;
     extern __shared__ __align__(16) unsigned char emit_smem[];
     uint64_t *soff = (uint64_t *)emit_smem;
@@ -342,7 +374,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
     // Without a filter and while no same-ID item has been seen, every work item yields exactly one pair:
     // the output position is the work-item index and no compaction (block scan + look-back) is needed.
     // If a same-ID item does turn up, the host discards this emission and re-emits in ACTIVE mode.
-    const bool identity = FK == BP_FILTER_NONE && a.mode == EMIT_MODE_FIRST && a.first_owned == 0;
+    const bool identity = !DEDUP && FK == BP_FILTER_NONE && a.mode == EMIT_MODE_FIRST && a.first_owned == 0;
 
     // each thread owns EMIT_IPT consecutive work items: one bisection, then a linear walk
     const uint32_t first = tid * EMIT_IPT;
@@ -367,12 +399,19 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
             while (wq >= soff[s + 1]) ++s;
             const uint32_t i = sidx[s];
             const uint32_t j = i + 1u + (uint32_t)(wq - soff[s]);
-            const IdT id_i = a.ids[i], id_j = a.ids[j];
+            const IdT raw_i = a.ids[i], raw_j = a.ids[j];
+            const IdT id_i = raw_i & a.id_mask, id_j = raw_j & a.id_mask;
             bool emit;
             if (a.mode == EMIT_MODE_FIRST) {
                 const bool same = id_i == id_j;
                 same_seen |= same;
                 emit = identity || (!same && j >= a.first_owned && FilterFn<FK>::pass(a.filter, id_j, id_i));
+                if constexpr (DEDUP) {
+                    if (emit) {
+                        const typename T::key_t *keys = (const typename T::key_t *)a.keys;
+                        emit = canonical_cell<T>(keys[i], keys[j], (uint32_t)(raw_i >> FLAG_SHIFT), (uint32_t)(raw_j >> FLAG_SHIFT));
+                    }
+                }
             } else if (a.mode == EMIT_MODE_FLAG) {
                 if (id_i == id_j) a.inactive[j] = 1;
                 emit = false;

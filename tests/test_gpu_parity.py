@@ -242,6 +242,47 @@ def test_set_records_roundtrip_and_scan(bp):
     _assert_records_equal(g, o)
 
 
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("id_bytes", [4, 8])
+@pytest.mark.parametrize("min_depth", [0, 4])
+def test_dedup_at_source_path(bp, kind, id_bytes, min_depth):
+    """clear -> extend -> scan without looking at the records in between: the sort moves the cell flags
+    into the IDs and the scan emits every ID pair from one canonical shared cell only.  The result must
+    still be the oracle's, and fewer raw pairs must have been produced than the reference's sweep makes."""
+    sysb, bounds, ids = _random_scene(kind, 20000, 300 + kind + min_depth, span=0.03, shuffle_ids=False)
+    if id_bytes == 8:
+        ids = ids.astype(np.uint64) + np.uint64(1 << 40)
+    g, o = _pair(bp, kind, id_bytes, min_depth)
+    table = np.random.Generator(np.random.Philox(3)).integers(0, 16, size=(15000, 2)).astype(np.uint32)
+    cases = [(None, (co.FILTER_NONE, 0, None)), (bp.ScanFilter.id_parity(), (co.FILTER_ID_PARITY, 0, None)),
+             (bp.ScanFilter.xor_mask(5), (co.FILTER_XOR_MASK, 5, None))]
+    if id_bytes == 4:
+        cases.append((bp.ScanFilter.category(table), (co.FILTER_CATEGORY, 0, table)))
+    for flt, oflt in cases:
+        g.clear(); o.clear()
+        g.extend(sysb, bounds[:12000], ids[:12000]); o.extend(sysb, bounds[:12000], ids[:12000])
+        g.extend(sysb, bounds[12000:], ids[12000:]); o.extend(sysb, bounds[12000:], ids[12000:])
+        gp = g.scan_filtered(flt)
+        op = o.scan(*oflt)
+        _assert_pairs_equal(gp, op)
+        st = g.stats()
+        assert st["n_pairs"] <= st["n_raw_pairs"] < o.num_raw_collisions
+        assert st["rescans"] == 0
+    _assert_records_equal(g, o)   # the flags are gone again once the records are looked at
+    _assert_pairs_equal(g.scan(), o.scan())
+
+
+def test_dedup_at_source_large_ids_are_left_alone(bp):
+    """IDs that use the top 3 bits of their type leave no room for the cell flags: plain emission."""
+    sysb, bounds, ids = _random_scene(2, 5000, 41, span=0.05, shuffle_ids=False)
+    big = (ids.astype(np.uint64) + np.uint64(0xE0000000)).astype(np.uint32)
+    g, o = _pair(bp, 2, 4, 0)
+    g.extend(sysb, bounds, big); o.extend(sysb, bounds, big)
+    _assert_pairs_equal(g.scan(), o.scan())
+    assert g.stats()["n_raw_pairs"] == o.num_raw_collisions
+    _assert_records_equal(g, o)
+
+
 @pytest.mark.parametrize("id_bytes", [4, 8])
 def test_crowded_cell_takes_the_full_width_pair_sort(bp, id_bytes):
     """Hundreds of objects in one cell: the later ID with the most partners has more of them than
