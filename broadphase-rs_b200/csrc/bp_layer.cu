@@ -285,7 +285,7 @@ struct RadixScratch {
 
 template <class K, class V>
 int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32_t *n_dev, uint64_t mask, int cls_hist,
-               int cls_pass, int *out_passes, bool *out_in_alt, size_t elem_bytes) {
+               int cls_pass, int *out_passes, bool *out_in_alt, size_t elem_bytes, const uint8_t *first_pass_vflags = nullptr) {
     typedef PassTune<K, V> Tune;
     typedef RadixPassCfg<K, V, Tune::THREADS, Tune::ITEMS> Cfg;
     *out_in_alt = false;
@@ -336,6 +336,7 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
             a.tile_counter = counters + p;
             a.op.shift = plan.shift[p];
             a.op.mask = (1u << plan.bits[p]) - 1u;
+            a.vflags = p == 0 ? first_pass_vflags : nullptr;
             a.err = L->d_err;
             kern1<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
         } else {
@@ -354,6 +355,7 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
             a.op.shift2 = plan.shift2[p];
             a.op.mask2 = (1u << plan.bits2[p]) - 1u;
             a.op.bits = plan.bits[p];
+            a.vflags = p == 0 ? first_pass_vflags : nullptr;
             a.err = L->d_err;
             kern2<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
         }
@@ -480,7 +482,8 @@ template <int KIND, class IdT> struct Impl {
     // ---- sort --------------------------------------------------------------------------------------------------
     // Sorts records [off, off + cnt) of the current buffer by (key, id); the result is left in the
     // current buffer.
-    static int sort_range(bp_layer *L, uint64_t off, uint64_t cnt, bool need_id_passes) {
+    static int sort_range(bp_layer *L, uint64_t off, uint64_t cnt, bool need_id_passes, const uint8_t *fold_flags = nullptr,
+                          bool *flags_folded = nullptr) {
         const int c = L->cur, o = c ^ 1;
         K *k0 = keys(L, c) + off, *k1 = keys(L, o) + off;
         IdT *v0 = ids(L, c) + off, *v1 = ids(L, o) + off;
@@ -497,8 +500,11 @@ template <int KIND, class IdT> struct Impl {
             }
         }
         bool in_alt2 = false;
+        // (the flags can only ride along when the key passes are the first thing that touches the records)
+        const uint8_t *vf = (fold_flags && !(need_id_passes && imask)) ? fold_flags + off : nullptr;
         TRY((radix_sort<K, IdT>(L, k0, v0, k1, v1, (uint32_t)cnt, nullptr, kmask, BP_K_SORT_HIST, BP_K_SORT_PASS, &passes,
-                                &in_alt2, sizeof(K) + sizeof(IdT))));
+                                &in_alt2, sizeof(K) + sizeof(IdT), vf)));
+        if (flags_folded) *flags_folded = vf != nullptr && passes > 0;
         total_passes += passes;
         const bool final_in_alt = in_alt != in_alt2;
         L->stats.sort_passes = (uint32_t)total_passes;
@@ -553,16 +559,29 @@ template <int KIND, class IdT> struct Impl {
         if (R >= 2 && tail > 0) {
             if (prefix == 0) {
                 if (!L->tail_sorted) {
-                    // the whole tree came from extend(): let the cell flags ride in the IDs' spare top bits
+                    // the whole tree came from extend(): let the cell flags ride in the IDs' spare top bits.
+                    // Normally the first radix pass folds them in while it loads the IDs; if that pass does not
+                    // exist (all keys equal) or the ID digits come first, a small kernel does it instead.
                     const int id_bits = 64 - (L->id_or ? __builtin_clzll(L->id_or) : 64);
-                    if (L->flags_valid && !L->ids_flagged && id_bits <= (int)(8 * sizeof(IdT)) - 3) {
+                    const bool want_flags = L->flags_valid && !L->ids_flagged && id_bits <= (int)(8 * sizeof(IdT)) - 3;
+                    const bool id_passes_first = L->tail_nonmono && (L->id_or & ~L->id_and) != 0;
+                    auto fold_in_place = [&]() {
                         LaunchScope ls(L, BP_K_MISC, (double)R * (2.0 * sizeof(IdT) + 1.0));
                         const int blocks = (int)std::min<uint64_t>((R + 1023) / 1024, 148 * 8);
                         flags_merge_kernel<IdT><<<blocks, 256, 0, L->stream>>>(ids(L, L->cur), (const uint8_t *)L->cell_flags.p, (uint32_t)R);
                         L->ids_flagged = true;
+                    };
+                    if (want_flags && id_passes_first) fold_in_place(); // before the ID-digit passes move the records
+                    bool folded = false;
+                    TRY(sort_range(L, 0, R, L->tail_nonmono,
+                                   (want_flags && !id_passes_first) ? (const uint8_t *)L->cell_flags.p : nullptr, &folded));
+                    if (want_flags && !id_passes_first) {
+                        if (folded)
+                            L->ids_flagged = true;
+                        else
+                            fold_in_place(); // no key pass ran: the records did not move
                     }
                     TRY(check_launch(L, "flags_merge_kernel"));
-                    TRY(sort_range(L, 0, R, L->tail_nonmono));
                 }
             } else if (L->tail_sorted || prefix * 8 >= R) {
                 // two sorted runs: one linear merge.  An unsorted tail is radix-sorted on its own first,
@@ -898,6 +917,7 @@ template <int KIND, class IdT> struct Impl {
         a.ghist_excl = hist;
         a.status = status;
         a.tile_counter = counters;
+        a.vflags = nullptr;
         a.op = op;
         a.err = L->d_err;
         {
@@ -978,6 +998,7 @@ template <int KIND, class IdT> struct Impl {
         a.ghist_excl = zero_hist; // every bucket starts at offset 0 of its own destination
         a.status = status;
         a.tile_counter = counters;
+        a.vflags = nullptr;
         a.op = op;
         a.err = L->d_err;
         {

@@ -136,6 +136,7 @@ template <class K, class V, class Op = ShiftMaskDigit<K>> struct RadixPassArgs {
     const uint32_t *ghist_excl; // [RADIX] exclusive digit offsets of this pass
     uint32_t *status;           // [tiles][RADIX], zeroed; bits 31..30 flag, 29..0 count
     uint32_t *tile_counter;     // zeroed
+    const uint8_t *vflags;      // optional: 3 flag bits per input element, OR-ed into the top bits of the payload as it is loaded
     Op op;
     int *err;
 };
@@ -282,6 +283,14 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
         for (int k = 0; k < ITEMS; ++k) {
             const uint32_t i = base_i + k * 32;
             if (FULL || i < tile_n) val[k] = ld_stream(vin + i);
+        }
+        if (a.vflags) { // the first pass of a record sort folds the cell flags into the IDs' spare top bits
+            const uint8_t *fl = a.vflags + tile_begin;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const uint32_t i = base_i + k * 32;
+                if (FULL || i < tile_n) val[k] |= (V)fl[i] << (8 * sizeof(V) - 3);
+            }
         }
     }
 

@@ -100,6 +100,7 @@ void run(const char *name, K *k0, V *v0, K *k1, V *v1, uint32_t n, uint64_t mask
             a.status = status + (size_t)p * tiles * RADIX;
             a.tile_counter = counters + p;
             a.op.shift = plan.shift[p]; a.op.mask = (1u << plan.bits[p]) - 1u;
+            a.vflags = nullptr;
             a.err = d_err;
             kern<<<tiles, THREADS, Cfg::SMEM_BYTES>>>(a);
             std::swap(kin, kout);
