@@ -276,11 +276,14 @@ def run_ours(args):
     cores = co.lib().bpo_max_threads()
     sample_n = min(n, 1 << 20)
     sc_cpu = sc if sample_n == n else make_scene(bp, wl, sample_n)
-    cpu_times, cpu_pairs = cpu_frames(co, sc_cpu, wl == "cfg3", 3, 1)
+    # bounded sample: about 10-15 s of CPU work (one frame first, to size the loop)
+    probe, _ = cpu_frames(co, sc_cpu, wl == "cfg3", 1, 1)
+    cpu_steps = int(max(3, min(200, 12.0 / max(probe[0], 1e-3))))
+    cpu_times, cpu_pairs = cpu_frames(co, sc_cpu, wl == "cfg3", cpu_steps, 0)
     cpu_ms = 1e3 * sum(cpu_times) / len(cpu_times)
     cpu_baseline = {"value": sample_n / (cpu_ms * 1e-3), "unit": "objects/s", "cores": cores, "kind": "port",
-                    "sample": "%d-object frames (clear+extend+par_sort+par_scan), 3 timed after 1 warm-up; C++ restatement "
-                              "of the reference (no Rust toolchain)" % sample_n,
+                    "sample": "%d-object frames (clear+extend+par_sort+par_scan), %d timed after 2 warm-ups; C++ restatement "
+                              "of the reference (no Rust toolchain)" % (sample_n, cpu_steps),
                     "ms_per_step": cpu_ms}
 
     extra = {}
@@ -295,6 +298,9 @@ def run_ours(args):
                 "per_class_ms_per_step": {c: p3["kernel_ms"][c] / max(3, min(args.steps, 5)) for c in p3["kernel_ms"]},
                 "sort_pass_gbs": (p3["algo_bytes"]["sort_pass"] / (p3["kernel_ms"]["sort_pass"] * 1e-3) / 1e9)
                 if p3["kernel_ms"]["sort_pass"] > 0 else None,
+                "sort_pass_frac_of_peak": (p3["algo_bytes"]["sort_pass"] / (p3["kernel_ms"]["sort_pass"] * 1e-3) / 1e9 / peak)
+                if p3["kernel_ms"]["sort_pass"] > 0 else None,
+                "peak_gbs": peak, "peak_source": peak_src,
             }
         except Exception as e:  # never lose the headline line to the extra measurement
             extra["cfg3_error"] = repr(e)

@@ -191,5 +191,15 @@ int main(int argc, char **argv) {
     RUN(384, 8, 4);
     RUN(320, 12, 3);
     RUN(288, 14, 3);
+    RUN(448, 10, 3);
+    RUN(416, 11, 3);
+    RUN(512, 9, 2);
+    RUN(352, 13, 3);
+    RUN(352, 12, 3);
+    RUN(384, 11, 3);
+    RUN(384, 10, 3);
+    RUN(384, 13, 3);
+    RUN(480, 9, 2);
+    RUN(256, 14, 4);
     return 0;
 }
