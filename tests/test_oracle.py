@@ -239,3 +239,34 @@ def test_scene_recipes_have_expected_shape():
     L = co.OracleLayer(sc["kind"], 4, sc["min_depth"])
     L.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
     assert len(L) >= 2000 and L.scan().shape[0] > 0
+
+
+# ---- the candidate set is a correct broadphase: every truly overlapping pair of boxes is in it -----------
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("min_depth", [0, 3])
+def test_candidate_pairs_cover_all_overlapping_boxes(kind, min_depth):
+    """Independent of any restatement detail: two objects whose quantised boxes overlap share at least
+    one cell chain, so the scan must report them (in one orientation or the other).  Brute force O(n^2)."""
+    dim = co.DIM[kind]
+    sysb, bounds, ids = _random_scene(kind, 1500, 77 + kind, False, span=0.12)
+    ok = pyref.contains(sysb, bounds, dim)
+    loc = pyref.to_local(sysb, bounds, dim).astype(np.int64)
+    lo, hi = loc[:, :dim], loc[:, dim:]
+    L = co.OracleLayer(kind, 4, min_depth)
+    L.extend(sysb, bounds, ids)
+    pairs = L.scan()
+    got = set((int(a), int(b)) for a, b in pairs) | set((int(b), int(a)) for a, b in pairs)
+    idx = np.flatnonzero(ok & (hi >= lo).all(axis=1))  # valid, non-inverted boxes
+    missing = 0
+    overlapping = 0
+    for x in range(idx.shape[0]):
+        i = idx[x]
+        others = idx[x + 1:]
+        ov = ((lo[others] <= hi[i]) & (hi[others] >= lo[i])).all(axis=1)
+        for j in others[ov]:
+            overlapping += 1
+            if (int(ids[i]), int(ids[j])) not in got:
+                missing += 1
+    assert overlapping > 50
+    assert missing == 0
