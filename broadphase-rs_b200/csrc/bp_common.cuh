@@ -201,6 +201,36 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *status, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA bulk copies (1-D cp.async.bulk, global -> shared, completion on an mbarrier): a whole tile arrives
+// without passing through registers, one thread issues it.  Addresses and size must be multiples of 16.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile("{\n\t"
+                 ".reg .pred p;\n\t"
+                 "BP_MBAR_WAIT:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra BP_MBAR_DONE;\n\t"
+                 "bra BP_MBAR_WAIT;\n\t"
+                 "BP_MBAR_DONE:\n\t"
+                 "}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // streaming loads: data that is read exactly once should not displace the look-back state in L1
 // ---------------------------------------------------------------------------------------------
 template <class T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }

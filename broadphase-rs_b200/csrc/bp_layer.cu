@@ -94,6 +94,9 @@ struct bp_layer {
     DevBuf src_idx, src_off, chunk_src, inactive;
     DevBuf praw[2], praw_b[2];     // raw pairs, ping-pong (u32 IDs: packed; u64 IDs: later / earlier)
     DevBuf pout;                   // final pairs
+    DevBuf pair_cnt;               // pairs per later ID (counting sort of the pairs; dense 32-bit IDs only)
+    bool want_pair_counts = false; // the caller of scan_raw will finish the pairs itself (scan), not hand them out raw
+    uint64_t pair_cnt_n = 0;       // > 0: the last emission counted its pairs per later ID into pair_cnt[0, pair_cnt_n)
     DevBuf filter_table;
     void *h_pairs = nullptr;
     size_t h_pairs_cap = 0;
@@ -636,6 +639,7 @@ template <int KIND, class IdT> struct Impl {
     // Everything up to the raw (unsorted, duplicate-carrying) pairs, left in praw[0] (+ praw_b[0]).
     static int scan_raw(bp_layer *L, const bp_filter *f, uint64_t *out_raw) {
         *out_raw = 0;
+        L->pair_cnt_n = 0;
         TRY(sort(L));
         L->n_pairs = 0;
         L->stats.n_work_items = L->stats.n_raw_pairs = L->stats.n_pairs = 0;
@@ -679,8 +683,10 @@ template <int KIND, class IdT> struct Impl {
         ra.totals = L->d_tot;
         ra.err = L->d_err;
         {
+            auto kern = scan_runs_kernel<T>;
+            CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RunsSmem<T>::BYTES));
             LaunchScope ls(L, BP_K_SCAN_RUNS, (double)R * sizeof(K));
-            scan_runs_kernel<T><<<rtiles, RUNS_THREADS, 0, L->stream>>>(ra);
+            kern<<<rtiles, RUNS_THREADS, RunsSmem<T>::BYTES, L->stream>>>(ra);
         }
         TRY(check_launch(L, "scan_runs_kernel"));
         TRY(fetch_totals(L));
@@ -725,6 +731,23 @@ template <int KIND, class IdT> struct Impl {
         ea.out_b = wide ? (uint64_t *)L->praw_b[0].p : nullptr;
         ea.capacity = W;
         ea.pair_counter = (unsigned long long *)L->scratch.p;
+        // dense 32-bit IDs: the emission also counts the pairs of every later ID, and finish_pairs replaces the
+        // radix passes over the later ID by one scan over the ID range + one scatter (see pair_scatter_kernel)
+        L->pair_cnt_n = 0;
+        ea.later_count = nullptr;
+        // Only while the pairs and the count array stay resident in the 126 MB L2: the scatter writes 8 bytes at
+        // random places, which costs a DRAM read-modify-write per pair once they do not (measured at config 3,
+        // 13.7M pairs: 0.54 ms against 0.30 ms for the three radix passes; at config 2, 2.1M pairs: 0.03 against 0.08).
+        if (L->want_pair_counts && !wide && L->id_or < (1ull << 22) && W <= (1ull << 22)) {
+            const int id_bits = 64 - (L->id_or ? __builtin_clzll(L->id_or) : 64);
+            const uint64_t M = std::max<uint64_t>(4, 1ull << id_bits);
+            {
+                TRY(ensure(L, L->pair_cnt, M * sizeof(uint32_t)));
+                CU(L, cudaMemsetAsync(L->pair_cnt.p, 0, M * sizeof(uint32_t), L->stream));
+                ea.later_count = (uint32_t *)L->pair_cnt.p;
+                L->pair_cnt_n = M;
+            }
+        }
         ea.totals = L->d_tot;
         ea.filter = fa;
         ea.err = L->d_err;
@@ -746,6 +769,7 @@ template <int KIND, class IdT> struct Impl {
             ea.mode = EMIT_MODE_FLAG;
             TRY(emit(L, ea, fk, chunks, (double)W * 2.0 * sizeof(IdT), false));
             CU(L, cudaMemsetAsync(L->scratch.p, 0, ebytes, L->stream));
+            if (ea.later_count) CU(L, cudaMemsetAsync(L->pair_cnt.p, 0, L->pair_cnt_n * sizeof(uint32_t), L->stream));
             ea.mode = EMIT_MODE_ACTIVE;
             TRY(emit(L, ea, fk, chunks, emit_bytes, false));
             CU(L, cudaMemcpyAsync(&L->d_tot->n_raw_pairs, L->scratch.p, 8, cudaMemcpyDeviceToDevice, L->stream));
@@ -776,7 +800,28 @@ template <int KIND, class IdT> struct Impl {
         uint64_t *b0 = wide ? (uint64_t *)L->praw_b[0].p : nullptr, *b1 = wide ? (uint64_t *)L->praw_b[1].p : nullptr;
         int passes = 0, total_passes = 0;
         bool in_alt = false;
-        if (!wide) {
+        if (!wide && L->pair_cnt_n) {
+            // counting sort by the later ID: offsets = exclusive scan of the per-ID counts, then one scatter
+            const uint32_t M = (uint32_t)L->pair_cnt_n;
+            const uint32_t ctiles = (M + CSCAN_TILE - 1) / CSCAN_TILE;
+            const size_t cbytes = 64 + (size_t)ctiles * sizeof(uint64_t);
+            TRY(ensure(L, L->scratch, cbytes));
+            CU(L, cudaMemsetAsync(L->scratch.p, 0, cbytes, L->stream));
+            {
+                LaunchScope ls(L, BP_K_PAIR_HIST, 2.0 * (double)M * sizeof(uint32_t));
+                count_scan_kernel<<<ctiles, CSCAN_THREADS, 0, L->stream>>>((uint32_t *)L->pair_cnt.p, M, (uint64_t *)((char *)L->scratch.p + 64),
+                                                                         (uint32_t *)L->scratch.p, L->d_err);
+            }
+            TRY(check_launch(L, "count_scan_kernel"));
+            {
+                LaunchScope ls(L, BP_K_PAIR_PASS, 2.0 * (double)P_raw * sizeof(uint64_t));
+                const int blocks = (int)std::min<uint64_t>((P_raw + 1023) / 1024, 148 * 8);
+                pair_scatter_kernel<<<blocks, 256, 0, L->stream>>>(a0, (uint32_t)P_raw, (uint32_t *)L->pair_cnt.p, a1);
+            }
+            TRY(check_launch(L, "pair_scatter_kernel"));
+            L->pair_cnt_n = 0; // consumed
+            in_alt = true;
+        } else if (!wide) {
             TRY((radix_sort<uint64_t, NoVal>(L, a0, (NoVal *)nullptr, a1, (NoVal *)nullptr, (uint32_t)P_raw, nullptr, imask << 32,
                                              BP_K_PAIR_HIST, BP_K_PAIR_PASS, &passes, &in_alt, 8)));
         } else {
@@ -868,7 +913,10 @@ template <int KIND, class IdT> struct Impl {
 
     static int scan(bp_layer *L, const bp_filter *f) {
         uint64_t P_raw = 0;
-        TRY(scan_raw(L, f, &P_raw));
+        L->want_pair_counts = true;
+        const int st = scan_raw(L, f, &P_raw);
+        L->want_pair_counts = false;
+        TRY(st);
         return finish_pairs(L, P_raw);
     }
 
@@ -1307,6 +1355,7 @@ int bp_layer_destroy(bp_layer *L) {
     release(L->chunk_src);
     release(L->inactive);
     release(L->pout);
+    release(L->pair_cnt);
     release(L->filter_table);
     if (L->h_pairs) cudaFreeHost(L->h_pairs);
     if (L->h_keys) cudaFreeHost(L->h_keys);

@@ -105,145 +105,224 @@ constexpr int RUNS_WORK_BITS = 34; // 30 bits of source count above 34 bits of w
 // Sources (records with a non-empty descendant run) may be listed in any order as long as src_off is
 // the running sum of their lengths in that order: the pairs are sorted afterwards anyway.  So a tile does
 // not need the prefix over all EARLIER tiles (a chained scan, whose look-back made every tile wait for
-// its slowest predecessor) -- it only needs a private range, which one 64-bit atomicAdd hands out.
-template <class T>
-__global__ void __launch_bounds__(RUNS_THREADS) scan_runs_kernel(const RunsArgs<T> a) {
+// its slowest predecessor) -- it only needs a private range, which one 64-bit atomicAdd hands out -- and
+// inside the tile the sources are listed thread by thread (two warp scans per thread instead of two per item).
+//
+// Where a run ends.  j > i lies in cell(i) iff key_j shares the top DIM * depth_i origin bits with key_i,
+// and in a sorted sequence two keys share a prefix iff every adjacent pair between them does.  With
+// lcp[p] = number of whole levels on which keys p and p + 1 agree, the run of i therefore ends at the first
+// p >= i with lcp[p] < depth_i ("next smaller value").  The tile answers that without searching the keys:
+// one bitmap per depth d (bit p = lcp[p] < d; every lane's column ~0 << (lcp + 1) of 32 records is
+// transposed across the warp so that lane d holds the word of row d), a 1-bit-per-word summary above
+// it, and a find-next-set-bit per record -- instead of a galloping + bisecting search over 64-bit keys
+// (the first version: 224 thread instructions per record, 70 % issue-bound, profiles/r1_scan_runs.txt).
+// The tile's keys arrive by one TMA bulk copy.
+template <class T> struct RunsSmem {
     typedef typename T::key_t K;
+    static constexpr int WORDS = RUNS_TILE / 32;     // bitmap words per depth
+    static constexpr int STRIDE = WORDS + 1;         // row stride in words: lane d stores row d, one bank each
+    static constexpr int SWORDS = (WORDS + 31) / 32; // summary words per depth
+    static constexpr int ROWS = T::AXIS_BITS + 1;    // depths 0 .. AXIS_BITS
+    static constexpr size_t KEYS_BYTES = ((size_t)(RUNS_TILE + 1) * sizeof(K) + 15) & ~(size_t)15;
+    static constexpr size_t BITS_OFF = KEYS_BYTES;
+    static constexpr size_t SUM_OFF = BITS_OFF + (size_t)ROWS * STRIDE * 4;
+    static constexpr size_t MISC_OFF = (SUM_OFF + (size_t)ROWS * SWORDS * 4 + 15) & ~(size_t)15;
+    static constexpr size_t BYTES = MISC_OFF + 16 /*mbarrier, sbase*/ + (RUNS_THREADS / 32) * 12;
+    static_assert(RUNS_IPT == 8 && SWORDS * 4 == RUNS_THREADS / 32, "one summary byte per warp: 8 bitmap words each");
+    static_assert(ROWS <= 32, "lane d holds bitmap row d");
+};
+
+// 32 x 32 bit-matrix transpose across a warp: lane r passes row r (bit c = column c) and gets column r
+// (bit c = row c's bit r).  Five butterfly steps, each one shuffle + three logic ops: in step k the lanes
+// r and r ^ k exchange the off-diagonal k x k blocks (the masked halves contain no bit that a rotation
+// could wrap around, so one funnel shift moves them either way).
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, unsigned lane) {
+#pragma unroll
+    for (int s = 4; s >= 0; --s) {
+        const uint32_t k = 1u << s;
+        const uint32_t lo = s == 4 ? 0x0000ffffu : s == 3 ? 0x00ff00ffu : s == 2 ? 0x0f0f0f0fu : s == 1 ? 0x33333333u : 0x55555555u;
+        const bool upper = (lane & k) != 0;
+        const uint32_t m = upper ? ~lo : lo;           // the half this lane keeps; the partner's same half moves across
+        const uint32_t y = __shfl_xor_sync(BP_FULL_MASK, x, k) & m;
+        x = (x & m) | __funnelshift_l(y, y, upper ? 32u - k : k);
+    }
+    return x;
+}
+
+// End of a run that leaves its tile: the whole warp probes [lo, n) 32 positions per step.
+// Invariant: keys[lo] <= hi, (end == n or keys[end] > hi).  Returns the last index inside the run.
+template <class K> __device__ __noinline__ uint32_t runs_far_search(const K *__restrict__ keys, uint32_t n, uint32_t lo, K hi) {
+    const unsigned lane = lane_id();
+    uint32_t end = n;
+    while (end - lo > 1) {
+        const uint32_t span = end - lo - 1;    // unknown positions lo+1 .. end-1
+        const uint32_t step = (span + 31) / 32; // >= 1
+        const uint64_t pos64 = (uint64_t)lo + (uint64_t)(lane + 1) * step;
+        const bool in = pos64 < end;
+        const bool gt = in ? (keys[(uint32_t)pos64] > hi) : true;
+        const uint32_t b = __ballot_sync(BP_FULL_MASK, gt);
+        const int f = b ? __ffs(b) - 1 : 32; // first probe beyond the run (32: all probes are inside)
+        if (f < 32) {
+            const uint64_t new_end = (uint64_t)lo + (uint64_t)(f + 1) * step;
+            end = (uint32_t)(new_end < end ? new_end : end);
+        }
+        if (f > 0) lo += (uint32_t)f * step;
+    }
+    return lo;
+}
+
+template <class T>
+__global__ void __launch_bounds__(RUNS_THREADS, 3) scan_runs_kernel(const RunsArgs<T> a) {
+    typedef typename T::key_t K;
+    typedef RunsSmem<T> S;
     constexpr int WARPS = RUNS_THREADS / 32;
     constexpr int WSPAN = 32 * RUNS_IPT; // records per warp
-    __shared__ K skeys[RUNS_TILE + 1];
-    __shared__ uint32_t swc[WARPS];
-    __shared__ unsigned long long sww[WARPS];
-    __shared__ unsigned long long sbase;
+    constexpr int STRIDE = S::STRIDE, SWORDS = S::SWORDS, ROWS = S::ROWS;
+    constexpr int TOTAL = T::DIM * T::AXIS_BITS + T::DEPTH_BITS;
+    constexpr K ORIGIN = (K)((((uint64_t)1 << (T::DIM * T::AXIS_BITS)) - 1) << T::DEPTH_BITS);
+    extern __shared__ __align__(16) unsigned char runs_smem[];
+    K *skeys = (K *)runs_smem;                               // [tile_n + 1]
+    uint32_t *sbits = (uint32_t *)(runs_smem + S::BITS_OFF); // [ROWS][STRIDE]
+    uint32_t *ssum = (uint32_t *)(runs_smem + S::SUM_OFF);   // [ROWS][SWORDS]: bit w = bitmap word w is not zero
+    uint64_t *mbar = (uint64_t *)(runs_smem + S::MISC_OFF);
+    unsigned long long *sbase = (unsigned long long *)(mbar + 1);
+    unsigned long long *sww = sbase + 1;
+    uint32_t *swc = (uint32_t *)(sww + WARPS);
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const unsigned lt = lanemask_lt();
     const uint32_t tile = blockIdx.x;
     const uint32_t r0 = tile * RUNS_TILE;
     if (r0 >= a.n) return;
     const uint32_t tile_n = min((uint32_t)RUNS_TILE, a.n - r0);
-    const bool has_next = r0 + tile_n < a.n; // skeys[tile_n] = first key of the next tile
-
-    for (uint32_t i = tid; i < tile_n + 1; i += RUNS_THREADS)
-        if (r0 + i < a.n) skeys[i] = ld_stream(a.keys + r0 + i);
+    const bool bulk = tile_n == (uint32_t)RUNS_TILE && ((uintptr_t)a.keys & 15u) == 0;
+    if (tid == 0) {
+        if (bulk) {
+            mbar_init(mbar, 1);
+            mbar_expect_tx(mbar, (uint32_t)(RUNS_TILE * sizeof(K)));
+            bulk_load(skeys, a.keys + r0, (uint32_t)(RUNS_TILE * sizeof(K)), mbar);
+        }
+        if (r0 + tile_n < a.n) skeys[tile_n] = a.keys[r0 + tile_n]; // first key of the next tile
+    }
+    if (!bulk)
+        for (uint32_t i = tid; i < tile_n; i += RUNS_THREADS) skeys[i] = ld_stream(a.keys + r0 + i);
     __syncthreads();
-    const K tile_last = skeys[tile_n - 1];
+    if (bulk) mbar_wait(mbar, 0);
 
-    // warp-striped: item q of lane l of warp w is tile record w*WSPAN + q*32 + l (conflict-free shared reads)
+    // warp-striped: item q of lane l of warp w is tile record w*WSPAN + q*32 + l, i.e. bit l of bitmap word w*IPT + q.
+    // dl = depth | (lcp + 1) << 8;  lcp = levels shared with the next record, -1: there is no next record
+    // (ends every run), 254: not a record.  The lane's column of the bit matrix "lcp < d" is ~0 << (lcp + 1);
+    // the transpose hands lane d the 32 records' bits of row d.
+    uint32_t dl[RUNS_IPT];
+    uint32_t nz8 = 0; // bit q: this lane's row has a set bit in word q of the warp
+#pragma unroll
+    for (int q = 0; q < RUNS_IPT; ++q) {
+        const uint32_t li = warp * WSPAN + q * 32 + lane;
+        uint32_t d = 0, l1 = 255u;
+        if (li < tile_n) {
+            const K k = skeys[li];
+            d = min(key_depth<T>(k), (uint32_t)T::AXIS_BITS);
+            l1 = 0;
+            if (r0 + li + 1 < a.n) {
+                const K x = (K)((k ^ skeys[li + 1]) & ORIGIN);
+                l1 = 1u + (x ? (uint32_t)(TOTAL - 64 + __clzll((long long)(uint64_t)x)) / (uint32_t)T::DIM : (uint32_t)T::AXIS_BITS);
+            }
+        }
+        dl[q] = d | (l1 << 8);
+        const uint32_t row = warp_transpose32(l1 < 32u ? 0xffffffffu << l1 : 0u, lane);
+        if (lane < (unsigned)ROWS) sbits[lane * STRIDE + warp * RUNS_IPT + q] = row;
+        nz8 |= (row != 0u ? 1u : 0u) << q;
+    }
+    if (lane < (unsigned)ROWS) ((unsigned char *)ssum)[lane * (SWORDS * 4) + warp] = (unsigned char)nz8;
+    __syncthreads();
+
     uint32_t len[RUNS_IPT];
-    uint32_t far_mask[RUNS_IPT]; // per item: lanes whose run leaves the tile (resolved cooperatively below)
+    uint32_t far_bits = 0; // bit q: this thread's item q has a run that leaves the tile
 #pragma unroll
     for (int q = 0; q < RUNS_IPT; ++q) {
         const uint32_t li = warp * WSPAN + q * 32 + lane;
         len[q] = 0;
-        bool far = false;
-        if (li < tile_n && r0 + li + 1 < a.n) {
-            const K hi = run_upper_key<T>(skeys[li]);
-            if (li + 1 < tile_n || has_next) {
-                if (!(skeys[li + 1] > hi)) {        // not the common case "no later record inside this cell"
-                    if (tile_last > hi) {           // the run ends inside the tile: gallop, then bisect, in shared memory
-                        // most runs are a handful of records long: doubling steps find the end in 1-3 probes
-                        const uint32_t last = tile_n - 1; // keys[last] > hi
-                        uint32_t lo = li + 1, step = 1;   // keys[lo] <= hi
-                        while (lo + step < last && skeys[lo + step] <= hi) {
-                            lo += step;
-                            step <<= 1;
-                        }
-                        uint32_t end = min(lo + step, last); // keys[end] > hi
-                        while (lo + 1 < end) {
-                            const uint32_t mid = (lo + end) >> 1;
-                            if (skeys[mid] <= hi)
-                                lo = mid;
-                            else
-                                end = mid;
-                        }
-                        len[q] = lo - li;
-                    } else {
-                        far = true; // every remaining record of the tile is inside; the end is further on
-                    }
+        const uint32_t d = dl[q] & 0xffu, l1 = dl[q] >> 8;
+        if (l1 != 255u && l1 > d) { // lcp >= d: the next record is still inside this record's cell
+            const uint32_t *row = sbits + d * STRIDE;
+            uint32_t w = li >> 5;
+            uint32_t m = row[w] & (0xfffffffeu << (li & 31u));
+            if (m == 0) {
+                const uint32_t *srow = ssum + d * SWORDS;
+                uint32_t sw = w >> 5;
+                uint32_t sm = srow[sw] & ((w & 31u) == 31u ? 0u : (0xfffffffeu << (w & 31u)));
+                while (sm == 0 && ++sw < (uint32_t)SWORDS) sm = srow[sw];
+                if (sm) {
+                    w = (sw << 5) + (uint32_t)__ffs(sm) - 1u;
+                    m = row[w];
                 }
             }
+            if (m)
+                len[q] = (w << 5) + (uint32_t)__ffs(m) - 1u - li;
+            else
+                far_bits |= 1u << q; // every remaining record of the tile is inside; the end is further on
         }
-        far_mask[q] = __ballot_sync(BP_FULL_MASK, far);
     }
-    // runs that leave the tile: the whole warp searches [tile end, n) 32 probes at a time
+    // runs that leave the tile (rare): resolved one at a time by the whole warp
+    if (__any_sync(BP_FULL_MASK, far_bits != 0)) {
 #pragma unroll
-    for (int q = 0; q < RUNS_IPT; ++q) {
-        uint32_t m = far_mask[q];
-        while (m) {
-            const int src = __ffs(m) - 1;
-            m &= m - 1;
-            const uint32_t li = warp * WSPAN + q * 32 + src;
-            const K hi = run_upper_key<T>(skeys[li]);
-            // invariant: keys[lo] <= hi, (end == n or keys[end] > hi)
-            uint32_t lo = r0 + tile_n - 1, end = a.n;
-            while (end - lo > 1) {
-                const uint32_t span = end - lo - 1;              // unknown positions lo+1 .. end-1
-                const uint32_t step = (span + 31) / 32;           // >= 1
-                const uint64_t pos64 = (uint64_t)lo + (uint64_t)(lane + 1) * step;
-                const bool in = pos64 < end;
-                const bool gt = in ? (a.keys[(uint32_t)pos64] > hi) : true;
-                const uint32_t b = __ballot_sync(BP_FULL_MASK, gt);
-                const int f = b ? __ffs(b) - 1 : 32;              // first probe beyond the run (32: all probes are inside)
-                // probes of lanes < f are inside the run, the probe of lane f (if any) is beyond it or out of range
-                if (f < 32) {
-                    const uint64_t new_end = (uint64_t)lo + (uint64_t)(f + 1) * step;
-                    end = (uint32_t)(new_end < end ? new_end : end);
-                }
-                if (f > 0) lo += (uint32_t)f * step;
+        for (int q = 0; q < RUNS_IPT; ++q) {
+            uint32_t m = __ballot_sync(BP_FULL_MASK, (far_bits >> q) & 1u);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint32_t li = warp * WSPAN + q * 32 + src;
+                const uint32_t last = runs_far_search<K>(a.keys, a.n, r0 + tile_n - 1, run_upper_key<T>(skeys[li]));
+                if ((int)lane == src) len[q] = last - (r0 + li);
             }
-            if ((int)lane == src) len[q] = lo - (r0 + li);
         }
     }
 
-    // ranks inside the warp in record order (q, lane), then across the warps, then one atomic for the tile
-    uint32_t cpos[RUNS_IPT];
-    unsigned long long wpos[RUNS_IPT];
-    uint32_t wc = 0;
-    unsigned long long ww = 0;
+    // list positions: thread by thread (the order of the sources is free), then across warps, then one atomic for the tile
+    uint32_t tc = 0;
+    unsigned long long ts = 0;
 #pragma unroll
     for (int q = 0; q < RUNS_IPT; ++q) {
-        const uint32_t nzm = __ballot_sync(BP_FULL_MASK, len[q] != 0);
-        const unsigned long long incl = warp_inclusive_sum((unsigned long long)len[q]);
-        cpos[q] = wc + __popc(nzm & lt);
-        wpos[q] = ww + incl - len[q];
-        wc += __popc(nzm);
-        ww += __shfl_sync(BP_FULL_MASK, incl, 31);
+        tc += len[q] != 0 ? 1u : 0u;
+        ts += len[q];
     }
-    if (lane == 0) {
-        swc[warp] = wc;
-        sww[warp] = ww;
+    const uint32_t ci = warp_inclusive_sum(tc);
+    const unsigned long long wi = warp_inclusive_sum(ts);
+    if (lane == 31) {
+        swc[warp] = ci;
+        sww[warp] = wi;
     }
     __syncthreads();
     if (warp == 0) {
         uint32_t c = lane < WARPS ? swc[lane] : 0;
         unsigned long long w = lane < WARPS ? sww[lane] : 0;
-        const uint32_t ci = warp_inclusive_sum(c);
-        const unsigned long long wi = warp_inclusive_sum(w);
+        const uint32_t cinc = warp_inclusive_sum(c);
+        const unsigned long long winc = warp_inclusive_sum(w);
         if (lane < WARPS) {
-            swc[lane] = ci - c;
-            sww[lane] = wi - w;
+            swc[lane] = cinc - c;
+            sww[lane] = winc - w;
         }
         if (lane == 31) {
-            unsigned long long add = ((unsigned long long)ci << RUNS_WORK_BITS) + wi;
-            if (wi >= (1ull << (RUNS_WORK_BITS - 1))) { // cannot be packed: the host reports BP_ERR_TOO_LARGE
+            unsigned long long add = ((unsigned long long)cinc << RUNS_WORK_BITS) + winc;
+            if (winc >= (1ull << (RUNS_WORK_BITS - 1))) { // cannot be packed: the host reports BP_ERR_TOO_LARGE
                 a.totals->pad = 1u;
                 add = 0;
             }
             const unsigned long long old = atomicAdd(a.packed_counter, add);
             // a carry out of the work field would corrupt the source count: exactly one tile sees it happen
-            if ((old & ((1ull << RUNS_WORK_BITS) - 1)) + wi >= (1ull << RUNS_WORK_BITS)) a.totals->pad = 1u;
-            sbase = old;
+            if ((old & ((1ull << RUNS_WORK_BITS) - 1)) + winc >= (1ull << RUNS_WORK_BITS)) a.totals->pad = 1u;
+            *sbase = old;
         }
     }
     __syncthreads();
-    const uint32_t cbase = (uint32_t)(sbase >> RUNS_WORK_BITS) + swc[warp];
-    const unsigned long long wbase = (sbase & ((1ull << RUNS_WORK_BITS) - 1)) + sww[warp];
+    uint32_t c = (uint32_t)(*sbase >> RUNS_WORK_BITS) + swc[warp] + ci - tc;
+    unsigned long long w = (*sbase & ((1ull << RUNS_WORK_BITS) - 1)) + sww[warp] + wi - ts;
 #pragma unroll
     for (int q = 0; q < RUNS_IPT; ++q) {
         if (len[q] != 0) {
-            a.src_idx[cbase + cpos[q]] = r0 + warp * WSPAN + q * 32 + lane;
-            a.src_off[cbase + cpos[q]] = wbase + wpos[q];
+            a.src_idx[c] = r0 + warp * WSPAN + q * 32 + lane;
+            a.src_off[c] = w;
+            ++c;
+            w += len[q];
         }
     }
     // the last tile to finish publishes the totals and the sentinel offset
@@ -299,6 +378,7 @@ template <class IdT> struct EmitArgs {
     uint64_t capacity;      // pairs the output arrays can hold
     unsigned long long *pair_counter; // zeroed: running count of emitted pairs (output slots are handed out by
                                       // atomicAdd: the order of the raw pairs is irrelevant, they are sorted next)
+    uint32_t *later_count;  // optional, zeroed, [max ID + 1]: pairs emitted per later ID (counting sort of the pairs)
     ScanTotals *totals;
     FilterArgs filter;
     int *err;
@@ -422,6 +502,7 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
                 pa[npass] = (uint64_t)id_j; // (later, earlier) -- src/layer.rs:567
                 pb[npass] = (uint64_t)id_i;
                 ++npass;
+                if (a.later_count) atomicAdd(a.later_count + (size_t)id_j, 1u);
             }
         }
         if (same_seen) a.totals->any_same_id = 1u;
@@ -463,6 +544,70 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
         }
     }
     if (identity && w0 + chunk_n == a.n_work && tid == 0) *a.pair_counter = a.n_work; // identity: one pair per work item
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counting sort of the raw pairs by their later ID -- the first half of `collisions.sort_unstable()`
+// (src/layer.rs:473, :516) when the IDs are dense 32-bit numbers (the usual 0..N): scan_emit_kernel
+// counts the pairs of every later ID as it emits them, one exclusive scan over the ID range turns the
+// counts into group offsets, and one pass drops every pair into its group (slots by atomicAdd: the order
+// inside a group is settled by pair_finish_kernel anyway).  One read + one write of the pairs instead of
+// one histogram read + three radix passes; the two atomics per pair hit an array that lives in L2.
+// ---------------------------------------------------------------------------------------------
+constexpr int CSCAN_THREADS = 256;
+constexpr int CSCAN_IPT = 16;
+constexpr int CSCAN_TILE = CSCAN_THREADS * CSCAN_IPT;
+
+// in-place exclusive prefix sum of counts[0, n) (n a multiple of 4, array 16-byte aligned)
+__global__ void __launch_bounds__(CSCAN_THREADS) count_scan_kernel(uint32_t *__restrict__ counts, uint32_t n, uint64_t *status,
+                                                                    uint32_t *tile_counter, int *err) {
+    __shared__ uint32_t swt[CSCAN_THREADS / 32 + 1];
+    __shared__ uint32_t stile;
+    __shared__ uint32_t sexcl;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) stile = atomicAdd(tile_counter, 1u);
+    __syncthreads();
+    const uint32_t tile = stile;
+    const uint32_t t0 = tile * CSCAN_TILE;
+    if (t0 >= n) return;
+    uint4 v[CSCAN_IPT / 4];
+    uint32_t sum = 0;
+    uint4 *p4 = (uint4 *)(counts + t0) + tid * (CSCAN_IPT / 4); // thread t owns CSCAN_IPT consecutive counts
+#pragma unroll
+    for (int k = 0; k < CSCAN_IPT / 4; ++k) {
+        const uint32_t e = t0 + tid * CSCAN_IPT + k * 4;
+        v[k] = e < n ? p4[k] : make_uint4(0, 0, 0, 0);
+        sum += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+    uint32_t tile_total;
+    uint32_t ex = block_exclusive_sum<CSCAN_THREADS, uint32_t>(sum, swt, &tile_total);
+    if (warp == 0) {
+        const uint64_t e = lookback_exclusive(status, tile, (uint64_t)tile_total, err);
+        if (lane == 0) sexcl = (uint32_t)e;
+    }
+    __syncthreads();
+    ex += sexcl;
+#pragma unroll
+    for (int k = 0; k < CSCAN_IPT / 4; ++k) {
+        const uint32_t e = t0 + tid * CSCAN_IPT + k * 4;
+        uint4 o;
+        o.x = ex;
+        o.y = o.x + v[k].x;
+        o.z = o.y + v[k].y;
+        o.w = o.z + v[k].z;
+        ex = o.w + v[k].w;
+        if (e < n) p4[k] = o;
+    }
+}
+
+// every pair into the group of its later ID; cursor[] holds the group offsets and is consumed
+__global__ void __launch_bounds__(256) pair_scatter_kernel(const uint64_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ cursor,
+                                                            uint64_t *__restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t p = ld_stream(in + i);
+        const uint32_t slot = atomicAdd(cursor + (size_t)(p >> 32), 1u);
+        out[slot] = p;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -301,7 +301,9 @@ def test_crowded_cell_takes_the_full_width_pair_sort(bp, id_bytes):
     op = o.par_scan()
     _assert_pairs_equal(gp, op)
     assert gp.shape[0] > crowd * (crowd - 1) // 2
-    assert g.stats()["pair_sort_passes"] >= 5  # later-ID passes + the full-width fallback
+    # the full-width fallback (>= 4 passes over 2 x 15 ID bits), after the later-ID passes (u64 IDs) or the
+    # counting sort by later ID (dense u32 IDs, no radix pass)
+    assert g.stats()["pair_sort_passes"] >= (4 if id_bytes == 4 else 5)
     # without the big crowd the finish kernel handles everything (fewer passes)
     g2 = bp.Layer(2, "u32" if id_bytes == 4 else "u64")
     o2 = co.OracleLayer(2, id_bytes, 0)
@@ -309,6 +311,30 @@ def test_crowded_cell_takes_the_full_width_pair_sort(bp, id_bytes):
     o2.extend(sc["sys_bounds"], sc["bounds"][crowd:], ids[crowd:])
     _assert_pairs_equal(g2.par_scan(), o2.par_scan())
     assert g2.stats()["pair_sort_passes"] <= 3
+
+
+@pytest.mark.parametrize("id_base", [0, 1 << 23])
+@pytest.mark.parametrize("multi", [False, True])
+def test_pair_sort_counting_and_radix_paths(bp, id_base, multi):
+    """Dense small u32 IDs take the counting sort of the pairs (count per later ID in scan_emit_kernel, scan,
+    scatter); IDs at or above 2^22 take the radix passes over the later ID.  Same pairs either way; IDs that
+    own several bounds add duplicates and (a, b) / (b, a) twins that only the finish kernel removes."""
+    sysb, bounds, ids = _random_scene(2, 30_000, 77, multi_bounds=multi, span=0.08)
+    ids = (ids + np.uint32(id_base)).astype(np.uint32)
+    g, o = _pair(bp, 2, 4, 0)
+    g.extend(sysb, bounds, ids)
+    o.extend(sysb, bounds, ids)
+    gp, op = g.par_scan(), o.par_scan()
+    _assert_pairs_equal(gp, op)
+    assert gp.shape[0] > 1000 and _is_strictly_increasing(gp)
+    passes = g.stats()["pair_sort_passes"]
+    if id_base:
+        assert passes >= 1
+    elif not multi:   # (with several bounds per ID a crowded later ID may still force the full-width fallback)
+        assert passes == 0
+    gf = g.par_scan_filtered(bp.ScanFilter.id_parity())
+    of = o.par_scan(co.FILTER_ID_PARITY)
+    _assert_pairs_equal(gf, of)
 
 
 # ---- BASELINE.json configs at sizes the oracle finishes in seconds --------------------------------------
