@@ -9,9 +9,9 @@ SO_PATH = os.path.join(_HERE, "libbroadphase_b200.so")
 BP_OK = 0
 STATUS = {0: "BP_OK", 1: "BP_ERR_INVALID_ARG", 2: "BP_ERR_CUDA", 3: "BP_ERR_OOM", 4: "BP_ERR_TOO_LARGE",
           5: "BP_ERR_INTERNAL", 6: "BP_ERR_MISMATCH"}
-BP_K_COUNT = 10
+BP_K_COUNT = 11
 KERNEL_CLASSES = ["encode", "sort_hist", "sort_pass", "merge", "scan_runs", "scan_emit", "pair_hist", "pair_pass",
-                  "pair_unique", "misc"]
+                  "pair_unique", "misc", "query"]
 
 
 class BpError(RuntimeError):
@@ -53,6 +53,8 @@ SYMBOLS = {
     "bp_layer_sort": (_i, [_vp]),
     "bp_layer_scan": (_i, [_vp, _P(Filter), _P(_vp), _P(_sz)]),
     "bp_layer_scan_device": (_i, [_vp, _P(Filter), _P(_vp), _P(_sz)]),
+    "bp_layer_test_box_batch": (_i, [_vp, _vp, _vp, _sz, ctypes.c_int32, _i, _P(_vp), _P(_vp), _P(_sz)]),
+    "bp_layer_test_ray_batch": (_i, [_vp, _vp, _vp, _sz, ctypes.c_int32, _i, _P(_vp), _P(_vp), _P(_sz)]),
     "bp_layer_records": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
     "bp_layer_records_device": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
     "bp_layer_set_records": (_i, [_vp, _vp, _vp, _sz, _i, _i]),

@@ -18,6 +18,7 @@
 #include "bp_common.cuh"
 #include "bp_encode.cuh"
 #include "bp_merge.cuh"
+#include "bp_query.cuh"
 #include "bp_radix.cuh"
 #include "bp_scan.cuh"
 
@@ -94,6 +95,10 @@ struct bp_layer {
     DevBuf src_idx, src_off, chunk_src, inactive;
     DevBuf praw[2], praw_b[2];     // raw pairs, ping-pong (u32 IDs: packed; u64 IDs: later / earlier)
     DevBuf pout;                   // final pairs
+    DevBuf query_params, query_counts, query_offsets; // batched queries: geometry parameters, per-query counts, CSR offsets
+    void *h_offsets = nullptr;     // pinned mirror of query_offsets
+    size_t h_offsets_cap = 0;
+    bool pairs_grouped = false;    // finish_pairs: the raw pairs are already grouped by their first ID, in order
     DevBuf pair_cnt;               // pairs per later ID (counting sort of the pairs; dense 32-bit IDs only)
     bool want_pair_counts = false; // the caller of scan_raw will finish the pairs itself (scan), not hand them out raw
     uint64_t pair_cnt_n = 0;       // > 0: the last emission counted its pairs per later ID into pair_cnt[0, pair_cnt_n)
@@ -800,7 +805,9 @@ template <int KIND, class IdT> struct Impl {
         uint64_t *b0 = wide ? (uint64_t *)L->praw_b[0].p : nullptr, *b1 = wide ? (uint64_t *)L->praw_b[1].p : nullptr;
         int passes = 0, total_passes = 0;
         bool in_alt = false;
-        if (!wide && L->pair_cnt_n) {
+        if (L->pairs_grouped) {
+            // (query, ID) pairs of a batched query: written query by query, only the order inside a group is open
+        } else if (!wide && L->pair_cnt_n) {
             // counting sort by the later ID: offsets = exclusive scan of the per-ID counts, then one scatter
             const uint32_t M = (uint32_t)L->pair_cnt_n;
             const uint32_t ctiles = (M + CSCAN_TILE - 1) / CSCAN_TILE;
@@ -918,6 +925,90 @@ template <int KIND, class IdT> struct Impl {
         L->want_pair_counts = false;
         TRY(st);
         return finish_pairs(L, P_raw);
+    }
+
+    // ---- batched queries (Layer::test_box / test_ray, src/layer.rs:244-351) --------------------------------
+    // d_params: n_queries x Geom::PARAMS floats on the device.  Leaves the sorted, duplicate-free (query, id)
+    // pairs in pout (n_pairs of them) and the CSR offsets of every query in query_offsets.
+    template <class Geom> static int query(bp_layer *L, const float *sysb, const float *d_params, size_t nq, int max_depth) {
+        TRY(sort(L)); // `self.sort()` -- src/layer.rs:262
+        L->n_pairs = 0;
+        TRY(ensure(L, L->query_offsets, (nq + 1) * sizeof(uint32_t)));
+        CU(L, cudaMemsetAsync(L->query_offsets.p, 0, (nq + 1) * sizeof(uint32_t), L->stream));
+        const uint64_t R = L->n_records;
+        if (nq == 0 || R == 0) return BP_OK;
+        const bool wide = sizeof(IdT) == 8;
+        const size_t ncnt = (nq + 3) & ~(size_t)3; // count_scan_kernel works on whole uint4
+        TRY(ensure(L, L->query_counts, ncnt * sizeof(uint32_t)));
+        CU(L, cudaMemsetAsync(L->query_counts.p, 0, ncnt * sizeof(uint32_t), L->stream));
+        const uint32_t ctiles = (uint32_t)((ncnt + CSCAN_TILE - 1) / CSCAN_TILE);
+        const size_t sbytes = 64 + (size_t)ctiles * sizeof(uint64_t);
+        TRY(ensure(L, L->scratch, sbytes));
+        CU(L, cudaMemsetAsync(L->scratch.p, 0, sbytes, L->stream));
+        QueryArgs<T, IdT> qa;
+        qa.keys = keys(L, L->cur);
+        qa.ids = ids(L, L->cur);
+        qa.id_mask = L->ids_flagged ? (IdT)((((IdT)1) << (8 * sizeof(IdT) - 3)) - 1) : (IdT) ~(IdT)0;
+        qa.n = (uint32_t)R;
+        qa.params = d_params;
+        qa.n_queries = (uint32_t)nq;
+        for (int i = 0; i < 6; ++i) qa.sysb[i] = i < 2 * T::DIM ? sysb[i] : 0.f;
+        qa.max_depth = max_depth;
+        qa.counts = (uint32_t *)L->query_counts.p;
+        qa.out_packed = qa.out_a = qa.out_b = nullptr;
+        qa.total = (unsigned long long *)L->scratch.p;
+        qa.err = L->d_err;
+        const int blocks = (int)std::min<size_t>((nq + QUERY_WARPS - 1) / QUERY_WARPS, 148 * 16);
+        {
+            LaunchScope ls(L, BP_K_QUERY, (double)nq * Geom::PARAMS * 4);
+            query_kernel<T, IdT, Geom, true><<<blocks, QUERY_THREADS, 0, L->stream>>>(qa);
+        }
+        TRY(check_launch(L, "query_kernel<count>"));
+        CU(L, cudaMemcpyAsync(&L->d_tot->n_work, L->scratch.p, 8, cudaMemcpyDeviceToDevice, L->stream));
+        {
+            LaunchScope ls(L, BP_K_MISC, 2.0 * (double)ncnt * sizeof(uint32_t));
+            count_scan_kernel<<<ctiles, CSCAN_THREADS, 0, L->stream>>>((uint32_t *)L->query_counts.p, (uint32_t)ncnt,
+                                                                     (uint64_t *)((char *)L->scratch.p + 64), (uint32_t *)L->scratch.p + 2, L->d_err);
+        }
+        TRY(check_launch(L, "count_scan_kernel"));
+        TRY(fetch_totals(L));
+        const uint64_t P_raw = L->h_tot->n_work;
+        if (P_raw > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "the queries report %llu records (limit 2^30)", (unsigned long long)P_raw);
+        if (P_raw == 0) return BP_OK;
+        TRY(ensure(L, L->praw[0], P_raw * sizeof(uint64_t)));
+        if (wide) TRY(ensure(L, L->praw_b[0], P_raw * sizeof(uint64_t)));
+        qa.out_packed = wide ? nullptr : (uint64_t *)L->praw[0].p;
+        qa.out_a = wide ? (uint64_t *)L->praw[0].p : nullptr;
+        qa.out_b = wide ? (uint64_t *)L->praw_b[0].p : nullptr;
+        {
+            LaunchScope ls(L, BP_K_QUERY, (double)P_raw * (sizeof(IdT) + 2.0 * sizeof(IdT)));
+            query_kernel<T, IdT, Geom, false><<<blocks, QUERY_THREADS, 0, L->stream>>>(qa);
+        }
+        TRY(check_launch(L, "query_kernel<write>"));
+        // `results.sort(); results.dedup()` (src/layer.rs:276-277) for every query: the pairs are grouped by query
+        // already; the digit plan of the (rare) full-width fallback has to cover the query numbers as well
+        const uint64_t keep_or = L->id_or, keep_and = L->id_and;
+        uint64_t qbits = 0;
+        while ((qbits + 1) < nq) qbits = (qbits << 1) | 1;
+        L->id_or |= qbits;
+        L->id_and = 0;
+        L->pairs_grouped = true;
+        CU(L, cudaMemsetAsync(L->d_tot, 0, sizeof(ScanTotals), L->stream));
+        const int st = finish_pairs(L, P_raw);
+        L->pairs_grouped = false;
+        L->id_or = keep_or;
+        L->id_and = keep_and;
+        TRY(st);
+        {
+            LaunchScope ls(L, BP_K_MISC, (double)L->n_pairs * sizeof(IdT) + (double)nq * sizeof(uint32_t));
+            const uint32_t np = (uint32_t)L->n_pairs;
+            query_offsets_kernel<IdT><<<(np + 1 + 255) / 256, 256, 0, L->stream>>>((const IdT *)L->pout.p, np, (uint32_t)nq,
+                                                                                 (uint32_t *)L->query_offsets.p);
+        }
+        return check_launch(L, "query_offsets_kernel");
+    }
+    static int query_kind(bp_layer *L, int ray, const float *sysb, const float *d_params, size_t nq, int max_depth) {
+        return ray ? query<RayTestGeom<T::DIM>>(L, sysb, d_params, nq, max_depth) : query<BoxTestGeom<T::DIM>>(L, sysb, d_params, nq, max_depth);
     }
 
     // ---- multi-GPU building blocks ---------------------------------------------------------------------
@@ -1155,6 +1246,9 @@ int do_sort(bp_layer *L) { DISPATCH(L, sort(L)); }
 int do_scan(bp_layer *L, const bp_filter *f) { DISPATCH(L, scan(L, f)); }
 int do_scan_raw(bp_layer *L, const bp_filter *f, uint64_t *out_raw) { DISPATCH(L, scan_raw(L, f, out_raw)); }
 int do_finish_pairs(bp_layer *L, uint64_t n) { DISPATCH(L, finish_pairs(L, n)); }
+int do_query(bp_layer *L, int ray, const float *sysb, const float *d_params, size_t nq, int max_depth) {
+    DISPATCH(L, query_kind(L, ray, sysb, d_params, nq, max_depth));
+}
 int do_partition_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl, void *kout,
                          void *vout, uint64_t *counts) {
     DISPATCH(L, partition_records(L, kin, vin, n, spl, n_spl, kout, vout, counts));
@@ -1356,8 +1450,12 @@ int bp_layer_destroy(bp_layer *L) {
     release(L->inactive);
     release(L->pout);
     release(L->pair_cnt);
+    release(L->query_params);
+    release(L->query_counts);
+    release(L->query_offsets);
     release(L->filter_table);
     if (L->h_pairs) cudaFreeHost(L->h_pairs);
+    if (L->h_offsets) cudaFreeHost(L->h_offsets);
     if (L->h_keys) cudaFreeHost(L->h_keys);
     if (L->h_ids) cudaFreeHost(L->h_ids);
     if (L->h_res) cudaFreeHost(L->h_res);
@@ -1519,6 +1617,50 @@ int bp_layer_scan(bp_layer *L, const bp_filter *f, const void **out_pairs, size_
     if (out_pairs) *out_pairs = bytes ? L->h_pairs : nullptr;
     if (out_count) *out_count = (size_t)L->n_pairs;
     return BP_OK;
+}
+
+static int query_batch(bp_layer *L, int ray, const float *sysb, const float *params, size_t nq, int32_t max_depth, int on_device,
+                       const void **out_pairs, const uint32_t **out_offsets, size_t *out_count) {
+    if (!L || !sysb || (nq && !params)) return fail(L, BP_ERR_INVALID_ARG, "bad arguments to a batched query");
+    if (nq >= (1ull << 30)) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 queries in one batch");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    const size_t per = (size_t)(ray ? 2 * L->dim + 2 : 2 * L->dim) * sizeof(float);
+    const float *d_params = params;
+    if (!on_device && nq) {
+        TRY(ensure(L, L->query_params, nq * per));
+        CU(L, cudaMemcpyAsync(L->query_params.p, params, nq * per, cudaMemcpyHostToDevice, L->stream));
+        d_params = (const float *)L->query_params.p;
+    }
+    TRY(do_query(L, ray, sysb, d_params, nq, max_depth));
+    const void *pairs = L->n_pairs ? L->pout.p : nullptr;
+    const uint32_t *offsets = (const uint32_t *)L->query_offsets.p;
+    if (!on_device) {
+        const size_t pbytes = (size_t)L->n_pairs * 2 * L->id_bytes, obytes = (nq + 1) * sizeof(uint32_t);
+        TRY(pinned_ensure(L, &L->h_offsets, &L->h_offsets_cap, obytes));
+        CU(L, cudaMemcpyAsync(L->h_offsets, L->query_offsets.p, obytes, cudaMemcpyDeviceToHost, L->stream));
+        if (pbytes) {
+            TRY(pinned_ensure(L, &L->h_pairs, &L->h_pairs_cap, pbytes));
+            CU(L, cudaMemcpyAsync(L->h_pairs, L->pout.p, pbytes, cudaMemcpyDeviceToHost, L->stream));
+        }
+        CU(L, cudaStreamSynchronize(L->stream));
+        pairs = pbytes ? L->h_pairs : nullptr;
+        offsets = (const uint32_t *)L->h_offsets;
+    }
+    if (out_pairs) *out_pairs = pairs;
+    if (out_offsets) *out_offsets = offsets;
+    if (out_count) *out_count = (size_t)L->n_pairs;
+    return BP_OK;
+}
+
+int bp_layer_test_box_batch(bp_layer *L, const float *sysb, const float *boxes, size_t nq, int32_t max_depth, int on_device,
+                            const void **out_pairs, const uint32_t **out_offsets, size_t *out_count) {
+    return query_batch(L, 0, sysb, boxes, nq, max_depth, on_device, out_pairs, out_offsets, out_count);
+}
+
+int bp_layer_test_ray_batch(bp_layer *L, const float *sysb, const float *rays, size_t nq, int32_t max_depth, int on_device,
+                            const void **out_pairs, const uint32_t **out_offsets, size_t *out_count) {
+    return query_batch(L, 1, sysb, rays, nq, max_depth, on_device, out_pairs, out_offsets, out_count);
 }
 
 int bp_layer_set_halo(bp_layer *L, size_t n_halo) {

@@ -123,7 +123,8 @@ template <class T> struct RunsSmem {
     static constexpr int STRIDE = WORDS + 1;         // row stride in words: lane d stores row d, one bank each
     static constexpr int SWORDS = (WORDS + 31) / 32; // summary words per depth
     static constexpr int ROWS = T::AXIS_BITS + 1;    // depths 0 .. AXIS_BITS
-    static constexpr size_t KEYS_BYTES = ((size_t)(RUNS_TILE + 1) * sizeof(K) + 15) & ~(size_t)15;
+    static constexpr int HALO = 32;                  // keys after the tile that are staged with it
+    static constexpr size_t KEYS_BYTES = ((size_t)(RUNS_TILE + HALO) * sizeof(K) + 15) & ~(size_t)15;
     static constexpr size_t BITS_OFF = KEYS_BYTES;
     static constexpr size_t SUM_OFF = BITS_OFF + (size_t)ROWS * STRIDE * 4;
     static constexpr size_t MISC_OFF = (SUM_OFF + (size_t)ROWS * SWORDS * 4 + 15) & ~(size_t)15;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(RUNS_THREADS, 3) scan_runs_kernel(const RunsAr
     constexpr int TOTAL = T::DIM * T::AXIS_BITS + T::DEPTH_BITS;
     constexpr K ORIGIN = (K)((((uint64_t)1 << (T::DIM * T::AXIS_BITS)) - 1) << T::DEPTH_BITS);
     extern __shared__ __align__(16) unsigned char runs_smem[];
-    K *skeys = (K *)runs_smem;                               // [tile_n + 1]
+    K *skeys = (K *)runs_smem;                               // [tile_n + halo_n]
     uint32_t *sbits = (uint32_t *)(runs_smem + S::BITS_OFF); // [ROWS][STRIDE]
     uint32_t *ssum = (uint32_t *)(runs_smem + S::SUM_OFF);   // [ROWS][SWORDS]: bit w = bitmap word w is not zero
     uint64_t *mbar = (uint64_t *)(runs_smem + S::MISC_OFF);
@@ -201,8 +202,10 @@ __global__ void __launch_bounds__(RUNS_THREADS, 3) scan_runs_kernel(const RunsAr
             mbar_expect_tx(mbar, (uint32_t)(RUNS_TILE * sizeof(K)));
             bulk_load(skeys, a.keys + r0, (uint32_t)(RUNS_TILE * sizeof(K)), mbar);
         }
-        if (r0 + tile_n < a.n) skeys[tile_n] = a.keys[r0 + tile_n]; // first key of the next tile
     }
+    // the first keys after the tile: the successor of the last record, and where most runs that leave the tile end
+    const uint32_t halo_n = min((uint32_t)S::HALO, a.n - (r0 + tile_n));
+    if (tid < halo_n) skeys[tile_n + tid] = a.keys[r0 + tile_n + tid];
     if (!bulk)
         for (uint32_t i = tid; i < tile_n; i += RUNS_THREADS) skeys[i] = ld_stream(a.keys + r0 + i);
     __syncthreads();
@@ -262,7 +265,9 @@ __global__ void __launch_bounds__(RUNS_THREADS, 3) scan_runs_kernel(const RunsAr
                 far_bits |= 1u << q; // every remaining record of the tile is inside; the end is further on
         }
     }
-    // runs that leave the tile (rare): resolved one at a time by the whole warp
+    // Runs that leave the tile (a few per tile: the cells that straddle its end), one at a time by the whole warp.
+    // Most of them end within the next few records -- the staged halo answers those without a global load;
+    // only cells holding more than HALO records past the tile end take the search over the rest of the tree.
     if (__any_sync(BP_FULL_MASK, far_bits != 0)) {
 #pragma unroll
         for (int q = 0; q < RUNS_IPT; ++q) {
@@ -271,7 +276,14 @@ __global__ void __launch_bounds__(RUNS_THREADS, 3) scan_runs_kernel(const RunsAr
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
                 const uint32_t li = warp * WSPAN + q * 32 + src;
-                const uint32_t last = runs_far_search<K>(a.keys, a.n, r0 + tile_n - 1, run_upper_key<T>(skeys[li]));
+                const K hi = run_upper_key<T>(skeys[li]);
+                // lane h looks at the h-th record after the tile; past the end of the tree counts as "beyond the run"
+                const uint32_t beyond = __ballot_sync(BP_FULL_MASK, lane < halo_n ? skeys[tile_n + lane] > hi : true);
+                uint32_t last; // last record inside the run
+                if (beyond)
+                    last = r0 + tile_n + (uint32_t)__ffs(beyond) - 2u;
+                else
+                    last = runs_far_search<K>(a.keys, a.n, r0 + tile_n + (uint32_t)S::HALO - 1u, hi);
                 if ((int)lane == src) len[q] = last - (r0 + li);
             }
         }

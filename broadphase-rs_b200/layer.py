@@ -146,6 +146,41 @@ class Layer:
         """Like scan_filtered but leaves the pairs on the device: returns (device pointer, count)."""
         return self._scan(flt, device=True)
 
+    # ---- queries (Layer::test_box / test_ray, src/layer.rs:278-351), batched ----------------------
+    def _query_batch(self, fn, system_bounds, params, width, max_depth):
+        sysb = np.ascontiguousarray(system_bounds, dtype=np.float32).reshape(2 * self.dim)
+        q = np.ascontiguousarray(params, dtype=np.float32).reshape(-1, width)
+        pairs, offs, cnt = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t()
+        md = -1 if max_depth is None else int(max_depth)
+        self._ck(fn(self._h, sysb.ctypes.data, q.ctypes.data, q.shape[0], md, 0, ctypes.byref(pairs), ctypes.byref(offs),
+                    ctypes.byref(cnt)))
+        nq, n = q.shape[0], cnt.value
+        ob = (ctypes.c_char * (4 * (nq + 1))).from_address(offs.value)
+        offsets = np.frombuffer(ob, dtype=np.uint32).copy()
+        if n == 0:
+            return offsets, np.zeros(0, dtype=self.id_dtype)
+        pb = (ctypes.c_char * (n * 2 * self.id_bytes)).from_address(pairs.value)
+        return offsets, np.frombuffer(pb, dtype=self.id_dtype).reshape(n, 2)[:, 1].copy()
+
+    def test_box_batch(self, system_bounds, boxes, max_depth=None):
+        """Layer::test_box for every row of `boxes` ((n, 2*D): min.., max..) in one call.  Returns (offsets, ids):
+        ids[offsets[q]:offsets[q + 1]] is the sorted, duplicate-free ID list the reference returns for box q."""
+        return self._query_batch(lib().bp_layer_test_box_batch, system_bounds, boxes, 2 * self.dim, max_depth)
+
+    def test_ray_batch(self, system_bounds, rays, max_depth=None):
+        """Layer::test_ray for every row of `rays` ((n, 2*D + 2): origin.., direction.., range_min, range_max)."""
+        return self._query_batch(lib().bp_layer_test_ray_batch, system_bounds, rays, 2 * self.dim + 2, max_depth)
+
+    def test_box(self, system_bounds, test_bounds, max_depth=None):
+        """Layer::test_box -- src/layer.rs:278-299: the IDs whose cells overlap test_bounds, sorted, unique."""
+        return self.test_box_batch(system_bounds, np.asarray(test_bounds, dtype=np.float32).reshape(1, -1), max_depth)[1]
+
+    def test_ray(self, system_bounds, origin, direction, range_min, range_max, max_depth=None):
+        """Layer::test_ray -- src/layer.rs:313-351."""
+        ray = np.concatenate([np.asarray(origin, dtype=np.float32).reshape(-1), np.asarray(direction, dtype=np.float32).reshape(-1),
+                              np.asarray([range_min, range_max], dtype=np.float32)])
+        return self.test_ray_batch(system_bounds, ray.reshape(1, -1), max_depth)[1]
+
     def iter(self):
         """Layer::iter: (keys, ids) numpy copies of the tree in its current order."""
         k, i, n, s = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int()

@@ -76,7 +76,7 @@ typedef struct bp_layer_config {
     int32_t device;            /* CUDA device ordinal; -1 = current device */
     size_t index_capacity;     /* with_index_capacity    src/layer.rs:652-655 (records) */
     size_t collision_capacity; /* with_collision_capacity src/layer.rs:658-661 (pairs) */
-    size_t test_capacity;      /* with_test_capacity     src/layer.rs:664-667 (accepted, unused: queries are out of scope) */
+    size_t test_capacity;      /* with_test_capacity     src/layer.rs:664-667 (accepted; query buffers grow on demand) */
 } bp_layer_config;
 
 typedef struct bp_layer bp_layer;
@@ -93,7 +93,8 @@ enum {
     BP_K_PAIR_PASS = 7, /* pair sort: one onesweep pass */
     BP_K_PAIR_UNIQUE = 8, /* dedup + final pair layout */
     BP_K_MISC = 9,      /* small helpers (histogram scans, masks, gathers) */
-    BP_K_COUNT = 10
+    BP_K_QUERY = 10,    /* batched box / ray queries: hierarchy descent (count pass + write pass) */
+    BP_K_COUNT = 11
 };
 
 typedef struct bp_stats {
@@ -149,6 +150,24 @@ int bp_layer_sort(bp_layer *layer);
  * bp_layer_scan copies the pairs to pinned host memory; _device leaves them on the device. */
 int bp_layer_scan(bp_layer *layer, const bp_filter *filter, const void **out_pairs, size_t *out_count);
 int bp_layer_scan_device(bp_layer *layer, const bp_filter *filter, const void **out_d_pairs, size_t *out_count);
+
+/* Layer::test_box -- src/layer.rs:278-299 (BoxTestGeometry, src/geom.rs:353-460) and Layer::test_ray --
+ * src/layer.rs:313-351 (RayTestGeometry, src/geom.rs:462-615), both through Layer::test / test_impl
+ * (src/layer.rs:167-277), for a BATCH of test geometries in one call.  Sorts if needed, like the reference.
+ *   boxes: n_queries x 2*D floats (test_bounds min.., max..)
+ *   rays:  n_queries x (2*D + 2) floats (origin.., direction.., range_min, range_max; the ranges may be
+ *          -inf / +inf and are clamped to the system bounds like RayTestGeometry::with_system_bounds)
+ *   max_depth: Option<u32> of the reference; < 0 = None
+ *   on_device: 0 = `boxes` / `rays` are host pointers and the results are copied to pinned host memory,
+ *              1 = device pointers in, device pointers out
+ * Result: out_pairs = out_count x {query number, object ID} (two consecutive IDs of id_bytes each), sorted
+ * by (query, ID) without duplicates; out_offsets[q] .. out_offsets[q + 1] delimit query q (n_queries + 1
+ * entries) -- slice q is exactly the `&Vec<ID>` the reference returns for that geometry.  `pick` / `pick_ray`
+ * (src/layer.rs:364-446) take a user closure and are not offered. */
+int bp_layer_test_box_batch(bp_layer *layer, const float *system_bounds, const float *boxes, size_t n_queries, int32_t max_depth,
+                            int on_device, const void **out_pairs, const uint32_t **out_offsets, size_t *out_count);
+int bp_layer_test_ray_batch(bp_layer *layer, const float *system_bounds, const float *rays, size_t n_queries, int32_t max_depth,
+                            int on_device, const void **out_pairs, const uint32_t **out_offsets, size_t *out_count);
 
 /* Layer::iter -- src/layer.rs:79-81, and the state PartialEq compares (src/layer.rs:582-585):
  * keys (4 or 8 bytes each) and ids as separate arrays + the sorted flag. */

@@ -220,6 +220,138 @@ struct Filter {
 };
 
 // ---------------------------------------------------------------------------------------------
+// Test geometries -- src/geom.rs:322-615.  QUERIES ARE "PARITY UNPINNED": the reference holds no test
+// or fixture for test_box / test_ray, and Bounds::center (src/geom.rs:130-132) calls cgmath ^0.17's
+// EuclideanSpace::midpoint (un-vendored dependency, version range from Cargo.toml:21), restated here from
+// its published source as `self + (other - self) / 2`.
+// ---------------------------------------------------------------------------------------------
+inline float midpoint_f32(float a, float b) {
+    const float d = b - a;
+    const float h = d / 2.0f;
+    return a + h;
+}
+inline bool is_finite_f32(float x) { return x - x == 0.0f; } // false for NaN and +-inf
+inline float f32_max(float a, float b) { return a != a ? b : (b != b ? a : (a > b ? a : b)); } // Rust f32::max: NaN loses
+inline float f32_min(float a, float b) { return a != a ? b : (b != b ? a : (a < b ? a : b)); }
+
+// BoxTestGeometry -- src/geom.rs:353-460
+template <int DIM> struct BoxGeom {
+    float cmin[DIM], cmax[DIM]; // cell_bounds
+    float tmin[DIM], tmax[DIM]; // test_bounds
+    // with_system_bounds -- src/geom.rs:367-378; params = test_bounds (min.., max..)
+    static BoxGeom make(const float *sys, const float *params) {
+        BoxGeom g;
+        for (int i = 0; i < DIM; ++i) {
+            g.cmin[i] = sys[i];
+            g.cmax[i] = sys[DIM + i];
+            g.tmin[i] = params[i];
+            g.tmax[i] = params[DIM + i];
+        }
+        return g;
+    }
+    // subdivide -- src/geom.rs:386-407 (2D), :425-448 (3D): child `cell`, bit `axis` set = upper half
+    void subdivide(BoxGeom *out) const {
+        float center[DIM];
+        for (int i = 0; i < DIM; ++i) center[i] = midpoint_f32(cmin[i], cmax[i]);
+        for (int cell = 0; cell < (1 << DIM); ++cell) {
+            out[cell] = *this;
+            for (int axis = 0; axis < DIM; ++axis) {
+                if (cell & (1 << axis)) out[cell].cmin[axis] = center[axis];
+                else out[cell].cmax[axis] = center[axis];
+            }
+        }
+    }
+    // test_order -- src/geom.rs:409-411: identity
+    void test_order(int *order) const { for (int i = 0; i < (1 << DIM); ++i) order[i] = i; }
+    // should_test -- src/geom.rs:413-416: cell_bounds.overlaps(test_bounds) (src/geom.rs:104-111)
+    bool should_test(float) const {
+        for (int i = 0; i < DIM; ++i)
+            if (cmin[i] > tmax[i] || cmax[i] < tmin[i]) return false;
+        return true;
+    }
+};
+
+// RayTestGeometry -- src/geom.rs:462-615
+template <int DIM> struct RayGeom {
+    float cmin[DIM], cmax[DIM], origin[DIM], direction[DIM], range_min, range_max;
+    // with_system_bounds -- src/geom.rs:512-535; params = origin.., direction.., range_min, range_max
+    static RayGeom make(const float *sys, const float *params) {
+        RayGeom g;
+        g.range_min = params[2 * DIM];
+        g.range_max = params[2 * DIM + 1];
+        for (int i = 0; i < DIM; ++i) {
+            g.cmin[i] = sys[i];
+            g.cmax[i] = sys[DIM + i];
+            g.origin[i] = params[i];
+            g.direction[i] = params[DIM + i];
+        }
+        for (int axis = 0; axis < DIM; ++axis) {
+            const float n0 = g.cmin[axis] - g.origin[axis];
+            const float distance_0 = n0 / g.direction[axis];
+            const float n1 = g.cmax[axis] - g.origin[axis];
+            const float distance_1 = n1 / g.direction[axis];
+            const bool is_forward = g.direction[axis] > 0.0f;
+            const float d0 = is_forward ? distance_0 : distance_1;
+            const float d1 = is_forward ? distance_1 : distance_0;
+            if (is_finite_f32(d0)) g.range_min = f32_max(g.range_min, d0);
+            if (is_finite_f32(d1)) g.range_max = f32_min(g.range_max, d1);
+        }
+        return g;
+    }
+    // subdivide -- src/geom.rs:537-577 (2D and 3D are the same loop over their axes)
+    void subdivide(RayGeom *out) const {
+        float center[DIM], distance[DIM];
+        for (int i = 0; i < DIM; ++i) {
+            center[i] = midpoint_f32(cmin[i], cmax[i]);
+            const float n = center[i] - origin[i];
+            distance[i] = n / direction[i];
+        }
+        for (int cell = 0; cell < (1 << DIM); ++cell) {
+            out[cell] = *this;
+            for (int axis = 0; axis < DIM; ++axis) {
+                const bool side = (cell & (1 << axis)) != 0;
+                if (is_finite_f32(distance[axis])) {
+                    const bool is_towards = (direction[axis] > 0.0f) != side;
+                    if (is_towards) out[cell].range_max = f32_min(out[cell].range_max, distance[axis]);
+                    else out[cell].range_min = f32_max(out[cell].range_min, distance[axis]);
+                } else if ((origin[axis] > center[axis]) != side) {
+                    out[cell].range_min = __builtin_inff();
+                    out[cell].range_max = -__builtin_inff();
+                }
+            }
+            for (int axis = 0; axis < DIM; ++axis) {
+                if (cell & (1 << axis)) out[cell].cmin[axis] = center[axis];
+                else out[cell].cmax[axis] = center[axis];
+            }
+        }
+    }
+    // test_order -- src/geom.rs:579-610: cells nearest along the ray first (only matters for `pick`)
+    void test_order(int *order) const {
+        float ab[DIM];
+        for (int i = 0; i < DIM; ++i) ab[i] = direction[i] < 0 ? -direction[i] : direction[i];
+        int axes[3] = {0, 1, 2};
+        if (DIM == 2) {
+            if (!(ab[0] <= ab[1])) { axes[0] = 1; axes[1] = 0; }
+        } else {
+            const float x = ab[0], y = ab[1], z = ab[DIM - 1];
+            if (x <= y && x <= z) { axes[0] = 0; if (y <= z) { axes[1] = 1; axes[2] = 2; } else { axes[1] = 2; axes[2] = 1; } }
+            else if (y <= z) { axes[0] = 1; if (x <= z) { axes[1] = 0; axes[2] = 2; } else { axes[1] = 2; axes[2] = 0; } }
+            else { axes[0] = 2; if (x <= y) { axes[1] = 0; axes[2] = 1; } else { axes[1] = 1; axes[2] = 0; } }
+        }
+        for (int src = 0; src < (1 << DIM); ++src) {
+            int dst = 0;
+            for (int k = 0; k < DIM; ++k) {
+                const bool ik = ((src >> k) & 1) == (direction[axes[k]] >= 0.0f ? 1 : 0);
+                dst |= (ik ? 1 : 0) << axes[k];
+            }
+            order[src] = dst;
+        }
+    }
+    // should_test -- src/geom.rs:612-614
+    bool should_test(float nearest) const { return range_min < range_max && range_min < nearest; }
+};
+
+// ---------------------------------------------------------------------------------------------
 // Layer -- src/layer.rs:40-165, 448-573
 // ---------------------------------------------------------------------------------------------
 struct LayerBase {
@@ -234,6 +366,8 @@ struct LayerBase {
     virtual void records(uint64_t *keys, uint64_t *ids) const = 0;
     virtual void collisions_out(uint64_t *a, uint64_t *b) const = 0;
     virtual void set_records(const uint64_t *keys, const uint64_t *ids, size_t n, bool sorted) = 0;
+    virtual size_t test(int ray, const float *sys, const float *params, int max_depth) = 0;
+    virtual void test_results_out(uint64_t *ids) const = 0;
     int kind = 0, id_bytes = 0;
     uint32_t min_depth = 0;
     bool sorted = true; // LayerBuilder::build starts with sorted = true -- src/layer.rs:681
@@ -361,6 +495,77 @@ template <class Ix, class ID> struct LayerT : LayerBase {
         }
         collisions.erase(std::unique(collisions.begin(), collisions.end()), collisions.end()); // dedup()
         return collisions.size();
+    }
+
+    // Layer::test_impl -- src/layer.rs:167-242, restated literally (recursion, binary searches, fold order)
+    std::vector<ID> test_results;
+    template <class Geom>
+    static float test_impl(const Rec *tree, size_t n, K cell, const Geom &geom, float nearest, int max_depth, std::vector<ID> &results) {
+        const int NC = 1 << Ix::DIM;
+        if (n == 0 || !geom.should_test(nearest)) return nearest;                         // :180-182
+        const uint32_t depth = Ix::depth(cell);
+        if (max_depth >= 0 && depth >= (uint32_t)max_depth) {                              // :189-197
+            for (size_t i = 0; i < n; ++i) results.push_back(tree[i].second);              // callback pushes, returns nearest
+            return nearest;
+        }
+        if (depth < (uint32_t)Ix::AXIS_BITS) {                                             // cell.subdivide() -- src/index.rs:251-290
+            K sub_cells[8];
+            const int shift = Ix::ORIGIN_BITS + Ix::ORIGIN_SHIFT - Ix::DIM * ((int)depth + 1);
+            for (int c = 0; c < NC; ++c) {
+                K k = (K)(cell | ((K)c << shift));
+                k = (K)((k & ~Ix::depth_mask()) | (K)Ix::clamp_depth(depth + 1));         // set_depth -- src/index.rs:106-112
+                sub_cells[c] = k;
+            }
+            // :199-212 -- split the slice at every child key; the head before the first child = records at this cell
+            const Rec *heads[9];
+            size_t lens[9];
+            const Rec *rest = tree;
+            size_t nrest = n;
+            for (int c = 0; c < NC; ++c) {
+                size_t lo = 0, hi = nrest; // partition point of `index < cell`
+                while (lo < hi) {
+                    const size_t mid = lo + (hi - lo) / 2;
+                    if (rest[mid].first < sub_cells[c]) lo = mid + 1; else hi = mid;
+                }
+                heads[c] = rest;
+                lens[c] = lo;
+                rest += lo;
+                nrest -= lo;
+            }
+            heads[NC] = rest;
+            lens[NC] = nrest;
+            for (size_t i = 0; i < lens[0]; ++i) results.push_back(heads[0][i].second);    // :213-217
+            Geom sub_tests[8];
+            geom.subdivide(sub_tests);
+            int order[8];
+            geom.test_order(order);
+            for (int k = 0; k < NC; ++k) {                                                 // :222-230
+                const int i = order[k];
+                nearest = test_impl(heads[i + 1], lens[i + 1], sub_cells[i], sub_tests[i], nearest, max_depth, results);
+            }
+            return nearest;
+        }
+        for (size_t i = 0; i < n; ++i) results.push_back(tree[i].second);                  // :236-240
+        return nearest;
+    }
+
+    // Layer::test -- src/layer.rs:254-280; test_box -- :293-311; test_ray -- :326-351
+    size_t test(int ray, const float *sys, const float *params, int max_depth) override {
+        sort(false);
+        test_results.clear();
+        if (ray) {
+            const RayGeom<Ix::DIM> g = RayGeom<Ix::DIM>::make(sys, params);
+            test_impl(tree.data(), tree.size(), (K)0, g, __builtin_inff(), max_depth, test_results);
+        } else {
+            const BoxGeom<Ix::DIM> g = BoxGeom<Ix::DIM>::make(sys, params);
+            test_impl(tree.data(), tree.size(), (K)0, g, __builtin_inff(), max_depth, test_results);
+        }
+        std::sort(test_results.begin(), test_results.end());
+        test_results.erase(std::unique(test_results.begin(), test_results.end()), test_results.end());
+        return test_results.size();
+    }
+    void test_results_out(uint64_t *ids) const override {
+        for (size_t i = 0; i < test_results.size(); ++i) ids[i] = (uint64_t)test_results[i];
     }
 
     size_t len() const override { return tree.size(); }
@@ -495,6 +700,10 @@ void bpo_to_global(int dim, const float *sys, const uint32_t *local, float *out)
         out[dim + i] = to_global_scalar(local[dim + i], sys[i], s);
     }
 }
+
+size_t bpo_layer_test_box(bpo_layer *l, const float *sys, const float *box, int max_depth) { return l->impl->test(0, sys, box, max_depth); }
+size_t bpo_layer_test_ray(bpo_layer *l, const float *sys, const float *ray, int max_depth) { return l->impl->test(1, sys, ray, max_depth); }
+void bpo_layer_test_results(const bpo_layer *l, uint64_t *ids) { l->impl->test_results_out(ids); }
 
 int bpo_max_threads(void) { return omp_get_max_threads(); }
 void bpo_set_threads(int n) { omp_set_num_threads(n); }

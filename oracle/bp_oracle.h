@@ -58,6 +58,14 @@ void bpo_layer_collisions(const bpo_layer *, uint64_t *a, uint64_t *b);
 /* loads records directly (keys/ids widened to u64) -- used to test sort/scan on arbitrary trees */
 void bpo_layer_set_records(bpo_layer *, const uint64_t *keys, const uint64_t *ids, size_t n, int sorted);
 
+/* Layer::test_box / test_ray (src/layer.rs:244-351) for one geometry; max_depth < 0 = None.  box: 2*D floats
+ * (min.., max..); ray: 2*D + 2 floats (origin.., direction.., range_min, range_max).  Returns the number of
+ * IDs; bpo_layer_test_results copies them (sorted, unique, widened to u64).  PARITY UNPINNED: the reference has
+ * no test for its queries, and the cell centres come from cgmath's midpoint (restated, see bp_oracle.cpp). */
+size_t bpo_layer_test_box(bpo_layer *, const float *sys_bounds, const float *box, int max_depth);
+size_t bpo_layer_test_ray(bpo_layer *, const float *sys_bounds, const float *ray, int max_depth);
+void bpo_layer_test_results(const bpo_layer *, uint64_t *ids);
+
 /* codec + quantiser, exposed for the known-answer tests */
 uint64_t bpo_encode_axis(int kind, uint32_t v);
 uint32_t bpo_decode_axis(int kind, uint64_t origin_bits);

@@ -53,6 +53,9 @@ def lib():
         "bpo_layer_records": (None, [vp, vp, vp]),
         "bpo_layer_collisions": (None, [vp, vp, vp]),
         "bpo_layer_set_records": (None, [vp, vp, vp, sz, i32]),
+        "bpo_layer_test_box": (sz, [vp, vp, vp, i32]),
+        "bpo_layer_test_ray": (sz, [vp, vp, vp, i32]),
+        "bpo_layer_test_results": (None, [vp, vp]),
         "bpo_encode_axis": (u64, [i32, u32]),
         "bpo_decode_axis": (u32, [i32, u64]),
         "bpo_make_index": (u64, [i32, u32, vp]),
@@ -147,6 +150,25 @@ class OracleLayer:
         k = np.ascontiguousarray(keys, dtype=np.uint64)
         i = np.ascontiguousarray(ids, dtype=np.uint64)
         lib().bpo_layer_set_records(self._h, _ptr(k), _ptr(i), k.shape[0], int(sorted_))
+
+    def _test(self, fn, system_bounds, params, max_depth):
+        sysb = np.ascontiguousarray(system_bounds, dtype=np.float32)
+        q = np.ascontiguousarray(params, dtype=np.float32)
+        n = fn(self._h, _ptr(sysb), _ptr(q), -1 if max_depth is None else int(max_depth))
+        out = np.zeros(n, dtype=np.uint64)
+        if n:
+            lib().bpo_layer_test_results(self._h, _ptr(out))
+        return out
+
+    def test_box(self, system_bounds, test_bounds, max_depth=None):
+        """Layer::test_box (src/layer.rs:293-311): sorted unique IDs, widened to u64."""
+        return self._test(lib().bpo_layer_test_box, system_bounds, test_bounds, max_depth)
+
+    def test_ray(self, system_bounds, origin, direction, range_min, range_max, max_depth=None):
+        """Layer::test_ray (src/layer.rs:326-351)."""
+        ray = np.concatenate([np.asarray(origin, dtype=np.float32).reshape(-1), np.asarray(direction, dtype=np.float32).reshape(-1),
+                              np.asarray([range_min, range_max], dtype=np.float32)])
+        return self._test(lib().bpo_layer_test_ray, system_bounds, ray, max_depth)
 
     def collisions(self):
         n = lib().bpo_layer_num_collisions(self._h)

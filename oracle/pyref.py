@@ -257,3 +257,101 @@ def scan(kind, keys, ids, filter_kind=FILTER_NONE, filter_arg=0, table=None):
     if raw:
         pairs = np.unique(pairs, axis=0)  # lexicographic sort + dedup
     return pairs, raw
+
+
+# ---------------------------------------------------------------------------------------------
+# Queries -- Layer::test_box / test_ray (src/layer.rs:244-351) in closed form.
+#
+# test_impl (src/layer.rs:167-242) reports a record exactly when the test geometry, subdivided along
+# the record's own path of cells, passes should_test at every level from the root down to
+# min(depth, max_depth): the descent reaches the record's cell (or its max_depth ancestor) and
+# reports the slice it sits in.  So instead of walking the hierarchy, every record replays its own
+# path -- vectorised over all records, one numpy step per level.  The f32 arithmetic is the
+# reference's: centre = min + (max - min) / 2 (cgmath 0.17 EuclideanSpace::midpoint behind
+# Bounds::center, src/geom.rs:130-132), ray distances = (centre - origin) / direction.
+# PARITY UNPINNED: the reference has no test for its queries; this is cross-checked against the
+# literal recursion in bp_oracle.cpp only.
+# ---------------------------------------------------------------------------------------------
+def _query(kind, keys, ids, sys_bounds, max_depth, geom):
+    bits, dim, depth_bits, axis_bits = KINDS[kind]
+    keys = np.asarray(keys, dtype=np.uint64)
+    ids = np.asarray(ids, dtype=np.uint64)
+    n = keys.shape[0]
+    if n == 0:
+        return np.zeros(0, dtype=np.uint64)
+    total = dim * axis_bits + depth_bits
+    depth = np.minimum((keys & np.uint64((1 << depth_bits) - 1)).astype(np.int64), axis_bits)
+    eff = depth if max_depth is None else np.minimum(depth, int(max_depth))
+    sysb = np.asarray(sys_bounds, dtype=np.float32)
+    cmin = np.repeat(sysb[None, :dim], n, axis=0).copy()
+    cmax = np.repeat(sysb[None, dim:], n, axis=0).copy()
+    state = geom["init"](n, cmin, cmax)
+    ok = geom["should_test"](cmin, cmax, state)
+    two = np.float32(2.0)
+    with np.errstate(all="ignore"):
+        for level in range(1, int(eff.max()) + 1 if n else 1):
+            active = eff >= level
+            digit = ((keys >> np.uint64(total - dim * level)) & np.uint64((1 << dim) - 1)).astype(np.int64)
+            center = (cmin + (cmax - cmin) / two).astype(np.float32)
+            side = np.stack([((digit >> a) & 1) == 1 for a in range(dim)], axis=1)
+            new_state = geom["child"](center, side, state)
+            new_min = np.where(side, center, cmin)
+            new_max = np.where(side, cmax, center)
+            cmin = np.where(active[:, None], new_min, cmin)
+            cmax = np.where(active[:, None], new_max, cmax)
+            state = [np.where(active, ns, s) for ns, s in zip(new_state, state)]
+            ok &= (~active) | geom["should_test"](cmin, cmax, state)
+    return np.unique(ids[ok])
+
+
+def test_box(kind, keys, ids, sys_bounds, test_bounds, max_depth=None):
+    """Layer::test_box -- src/layer.rs:293-311 with BoxTestGeometry, src/geom.rs:353-460."""
+    dim = KINDS[kind][1]
+    tb = np.asarray(test_bounds, dtype=np.float32)
+    tmin, tmax = tb[:dim], tb[dim:]
+    geom = {
+        "init": lambda n, cmin, cmax: [],
+        "child": lambda center, side, state: [],
+        # cell_bounds.overlaps(test_bounds) -- src/geom.rs:104-111
+        "should_test": lambda cmin, cmax, state: ~((cmin > tmax[None, :]) | (cmax < tmin[None, :])).any(axis=1),
+    }
+    return _query(kind, keys, ids, sys_bounds, max_depth, geom)
+
+
+def test_ray(kind, keys, ids, sys_bounds, origin, direction, range_min, range_max, max_depth=None):
+    """Layer::test_ray -- src/layer.rs:326-351 with RayTestGeometry, src/geom.rs:462-615."""
+    dim = KINDS[kind][1]
+    org = np.asarray(origin, dtype=np.float32)
+    dirn = np.asarray(direction, dtype=np.float32)
+    sysb = np.asarray(sys_bounds, dtype=np.float32)
+    rmin, rmax = np.float32(range_min), np.float32(range_max)
+    with np.errstate(all="ignore"):  # with_system_bounds -- src/geom.rs:512-535
+        for axis in range(dim):
+            d_lo = np.float32(np.float32(sysb[axis] - org[axis]) / dirn[axis])
+            d_hi = np.float32(np.float32(sysb[dim + axis] - org[axis]) / dirn[axis])
+            d0, d1 = (d_lo, d_hi) if dirn[axis] > 0 else (d_hi, d_lo)
+            if np.isfinite(d0):
+                rmin = np.fmax(rmin, d0)
+            if np.isfinite(d1):
+                rmax = np.fmin(rmax, d1)
+
+    def child(center, side, state):  # subdivide -- src/geom.rs:537-577
+        lo, hi = state[0].copy(), state[1].copy()
+        for axis in range(dim):
+            dist = ((center[:, axis] - org[axis]) / dirn[axis]).astype(np.float32)
+            fin = np.isfinite(dist)
+            towards = (dirn[axis] > 0) != side[:, axis]
+            hi = np.where(fin & towards, np.fmin(hi, dist), hi)
+            lo = np.where(fin & ~towards, np.fmax(lo, dist), lo)
+            kill = ~fin & ((org[axis] > center[:, axis]) != side[:, axis])
+            lo = np.where(kill, np.float32(np.inf), lo)
+            hi = np.where(kill, np.float32(-np.inf), hi)
+        return [lo.astype(np.float32), hi.astype(np.float32)]
+
+    geom = {
+        "init": lambda n, cmin, cmax: [np.full(n, rmin, dtype=np.float32), np.full(n, rmax, dtype=np.float32)],
+        "child": child,
+        # should_test(nearest = inf) -- src/geom.rs:612-614
+        "should_test": lambda cmin, cmax, state: (state[0] < state[1]) & (state[0] < np.float32(np.inf)),
+    }
+    return _query(kind, keys, ids, sys_bounds, max_depth, geom)
