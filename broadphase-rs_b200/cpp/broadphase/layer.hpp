@@ -15,6 +15,9 @@
 //   layer.scan() / par_scan()              src/layer.rs:449 layer.scan() / par_scan()   -> const std::vector-like view
 //   layer.scan_filtered(f) / par_..        src/layer.rs:456 layer.scan_filtered(Filter) / par_scan_filtered(Filter)
 //   layer.iter()                           src/layer.rs:79  layer.iter()
+//   layer.test_box(system_bounds, b, d)    src/layer.rs:293 layer.test_box(system_bounds, b, max_depth) -> std::vector<ID>
+//   layer.test_ray(system_bounds, o, v, ..) src/layer.rs:326 layer.test_ray(system_bounds, origin, direction, rmin, rmax, max_depth)
+//   (many geometries in one call)                           layer.test_box_batch(...) / test_ray_batch(...) -> QueryResults<ID>
 //
 // Errors: the reference never returns errors from these methods; allocation failure aborts.  Here a
 // failed C-ABI call throws broadphase::Error (status + message).
@@ -67,6 +70,12 @@ template <class ID> struct PairView {
     size_t size() const { return size_; }
     bool empty() const { return size_ == 0; }
     const std::pair<ID, ID> &operator[](size_t i) const { return data_[i]; }
+};
+
+// results of a batched query: ids[offsets[q] .. offsets[q + 1]) is the sorted, duplicate-free ID list of geometry q
+template <class ID> struct QueryResults {
+    std::vector<uint32_t> offsets;
+    std::vector<ID> ids;
 };
 
 template <class Index, class ID> class Layer {
@@ -127,6 +136,29 @@ public:
     PairView<ID> par_scan() { return scan_filtered(Filter::none()); }                    // src/layer.rs:482-487
     PairView<ID> par_scan_filtered(const Filter &f) { return scan_filtered(f); }         // src/layer.rs:489-520
 
+    // Layer::test_box / test_ray -- src/layer.rs:293-351, batched (max_depth < 0 = None).  boxes: n x Bounds;
+    // rays: n x (origin[DIM], direction[DIM], range_min, range_max) floats.
+    QueryResults<ID> test_box_batch(const Bounds<Index::DIM> &system_bounds, const Bounds<Index::DIM> *boxes, size_t n, int max_depth = -1) {
+        return collect(0, system_bounds, boxes ? boxes[0].min : nullptr, n, max_depth);
+    }
+    QueryResults<ID> test_ray_batch(const Bounds<Index::DIM> &system_bounds, const float *rays, size_t n, int max_depth = -1) {
+        return collect(1, system_bounds, rays, n, max_depth);
+    }
+    std::vector<ID> test_box(const Bounds<Index::DIM> &system_bounds, const Bounds<Index::DIM> &test_bounds, int max_depth = -1) {
+        return test_box_batch(system_bounds, &test_bounds, 1, max_depth).ids;
+    }
+    std::vector<ID> test_ray(const Bounds<Index::DIM> &system_bounds, const float (&origin)[Index::DIM], const float (&direction)[Index::DIM],
+                             float range_min, float range_max, int max_depth = -1) {
+        float ray[2 * Index::DIM + 2];
+        for (int i = 0; i < Index::DIM; ++i) {
+            ray[i] = origin[i];
+            ray[Index::DIM + i] = direction[i];
+        }
+        ray[2 * Index::DIM] = range_min;
+        ray[2 * Index::DIM + 1] = range_max;
+        return test_ray_batch(system_bounds, ray, 1, max_depth).ids;
+    }
+
     // Layer::iter -- src/layer.rs:79-81
     std::vector<std::pair<key_type, ID>> iter() {
         const void *k = nullptr, *i = nullptr;
@@ -141,6 +173,20 @@ public:
     bool is_sorted() { int s = 0; ck(bp_layer_is_sorted(h_, &s)); return s != 0; }
     uint32_t min_depth() const { uint32_t d = 0; bp_layer_min_depth(h_, &d); return d; }
     bp_stats stats() { bp_stats s; ck(bp_layer_stats(h_, &s)); return s; }
+
+private:
+    QueryResults<ID> collect(int ray, const Bounds<Index::DIM> &system_bounds, const float *params, size_t n, int max_depth) {
+        const void *pairs = nullptr;
+        const uint32_t *offsets = nullptr;
+        size_t count = 0;
+        ck(ray ? bp_layer_test_ray_batch(h_, system_bounds.min, params, n, max_depth, 0, &pairs, &offsets, &count)
+               : bp_layer_test_box_batch(h_, system_bounds.min, params, n, max_depth, 0, &pairs, &offsets, &count));
+        QueryResults<ID> r;
+        r.offsets.assign(offsets, offsets + n + 1);
+        r.ids.resize(count);
+        for (size_t i = 0; i < count; ++i) r.ids[i] = static_cast<const ID *>(pairs)[2 * i + 1]; // {query, id}
+        return r;
+    }
 };
 
 // LayerBuilder -- src/layer.rs:620-696

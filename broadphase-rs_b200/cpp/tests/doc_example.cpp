@@ -20,7 +20,15 @@ int main() {
         auto pairs = layer.scan();
         std::printf("records=%zu pairs=%zu\n", layer.len(), pairs.size());
         for (const auto &p : pairs) std::printf("(%llu, %llu)\n", (unsigned long long)p.first, (unsigned long long)p.second);
-        return (pairs.size() == 1 && pairs[0].first == 9 && pairs[0].second == 7) ? 0 : 1;
+        // (the view borrows the layer's result buffer: it is only valid until the next call, like the reference's &Vec)
+        const bool scan_ok = pairs.size() == 1 && pairs[0].first == 9 && pairs[0].second == 7;
+        // a box query around the far object (Layer::test_box, src/layer.rs:293-311)
+        auto hit = layer.test_box(system_bounds, Bounds<3>{{-9.5f, -9.5f, -9.5f}, {-8.5f, -8.5f, -8.5f}});
+        std::printf("test_box=%zu", hit.size());
+        for (auto id : hit) std::printf(" %llu", (unsigned long long)id);
+        std::printf("\n");
+        const bool query_ok = hit.size() == 1 && hit[0] == 11;
+        return (scan_ok && query_ok) ? 0 : 1;
     } catch (const Error &e) {
         std::printf("error: %s\n", e.what());
         return e.status == BP_ERR_CUDA ? 77 : 2; // 77: no GPU here

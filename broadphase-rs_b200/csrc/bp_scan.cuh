@@ -399,8 +399,10 @@ template <class IdT> struct EmitArgs {
 template <class IdT> struct EmitSmem {
     static constexpr bool WIDE = sizeof(IdT) == 8;
     static constexpr size_t OFF_WORDS = EMIT_CHUNK + 2;                               // u64: run offsets, later the staged output
-    static constexpr size_t IDX_WORDS = WIDE ? EMIT_CHUNK : (EMIT_CHUNK + 2) / 2;     // u64: run record indices (u32), later `earlier`
-    static constexpr size_t BYTES = (OFF_WORDS + IDX_WORDS + EMIT_THREADS / 32 + 4) * sizeof(uint64_t);
+    static constexpr size_t IDX_WORDS = WIDE ? EMIT_CHUNK : ((EMIT_CHUNK + 2) / 2 + 1) & ~(size_t)1; // u64: run record indices (u32), later `earlier`; even, so that the owner table stays 16-byte aligned
+    static constexpr size_t OWNER_WORDS = EMIT_CHUNK / 4;                             // u64: source of every work item (u16 each)
+    static constexpr size_t BYTES = (OFF_WORDS + IDX_WORDS + OWNER_WORDS + EMIT_THREADS / 32 + 4) * sizeof(uint64_t);
+    static_assert(EMIT_CHUNK < 65536 && EMIT_IPT == 8, "owner entries are u16; a thread scans 8 of them as one uint4");
 };
 
 // Dedup at the source.  Two objects that share several cells meet once per shared cell, so the raw pairs
@@ -442,7 +444,8 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
     // sidx holds the source record indices during the walk; for u64 IDs it is sized so that it can
     // stage the `earlier` half of the output afterwards
     uint64_t *sidx_raw = soff + S::OFF_WORDS;
-    uint64_t *sscratch = sidx_raw + S::IDX_WORDS;
+    uint16_t *sowner = (uint16_t *)(sidx_raw + S::IDX_WORDS); // [EMIT_CHUNK] run (index into soff / sidx, + 1) of every work item
+    uint64_t *sscratch = sidx_raw + S::IDX_WORDS + S::OWNER_WORDS;
     uint64_t *sbase_p = sscratch + EMIT_THREADS / 32 + 2;
     uint32_t *sidx = (uint32_t *)sidx_raw;
     // the staged output reuses soff / sidx: every thread has finished its walk before the barrier that
@@ -468,29 +471,58 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
     // If a same-ID item does turn up, the host discards this emission and re-emits in ACTIVE mode.
     const bool identity = !DEDUP && FK == BP_FILTER_NONE && a.mode == EMIT_MODE_FIRST && a.first_owned == 0;
 
-    // each thread owns EMIT_IPT consecutive work items: one bisection, then a linear walk
-    const uint32_t first = tid * EMIT_IPT;
-    uint32_t npass = 0;
-    uint64_t pa[EMIT_IPT], pb[EMIT_IPT];
-    if (first < chunk_n) {
-        const uint64_t w = w0 + first;
-        uint32_t lo = 0, hi = nsrc; // largest s with soff[s] <= w
-        while (lo + 1 < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (soff[mid] <= w)
-                lo = mid;
-            else
-                hi = mid;
+    // Which run owns which work item: every run stamps its number on its first work item of the chunk, a
+    // running maximum spreads it over the rest (thread t scans its 8 consecutive entries as one 16-byte
+    // word, then warps, then the block).  After that the work items are handed out STRIPED -- item q of thread
+    // t is w0 + q * THREADS + t -- so that the lanes of a warp read consecutive records: the descendant's ID
+    // and key are coalesced loads, the ancestor's a broadcast.  (With 8 consecutive items per thread every
+    // load instruction touched 32 different sectors; profiles/r1_emit_blocked.txt: 65 % of the LSU wavefront
+    // peak, long-scoreboard stalls on top.)
+    for (uint32_t i = tid; i < EMIT_CHUNK / 8; i += EMIT_THREADS) ((uint4 *)sowner)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    for (uint32_t i = tid; i < nsrc; i += EMIT_THREADS) {
+        const uint64_t o = soff[i];
+        if (o < w0 + chunk_n) sowner[o > w0 ? (uint32_t)(o - w0) : 0u] = (uint16_t)(i + 1); // run starts are distinct
+    }
+    __syncthreads();
+    {
+        uint4 v = ((const uint4 *)sowner)[tid];
+        uint32_t e[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
+#pragma unroll
+        for (int k = 1; k < 8; ++k) e[k] = max(e[k], e[k - 1]);
+        uint32_t incl = e[7];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(BP_FULL_MASK, incl, o);
+            if ((tid & 31u) >= (unsigned)o) incl = max(incl, t);
         }
-        uint32_t s = lo;
+        uint32_t *swmax = (uint32_t *)sscratch;
+        if ((tid & 31u) == 31u) swmax[tid >> 5] = incl;
+        __syncthreads();
+        uint32_t before = __shfl_up_sync(BP_FULL_MASK, incl, 1); // maximum over the earlier threads of this warp ...
+        if ((tid & 31u) == 0u) before = 0;
+        for (unsigned w = 0; w < (tid >> 5); ++w) before = max(before, swmax[w]); // ... and over the earlier warps
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = max(e[k], before);
+        v.x = e[0] | (e[1] << 16);
+        v.y = e[2] | (e[3] << 16);
+        v.z = e[4] | (e[5] << 16);
+        v.w = e[6] | (e[7] << 16);
+        ((uint4 *)sowner)[tid] = v;
+    }
+    __syncthreads();
+
+    uint32_t emit_bits = 0; // bit q: item q of this thread yields a pair (pa[q], pb[q])
+    uint64_t pa[EMIT_IPT], pb[EMIT_IPT];
+    {
         bool same_seen = false;
 #pragma unroll
         for (int q = 0; q < EMIT_IPT; ++q) {
-            if (first + q >= chunk_n) break;
-            const uint64_t wq = w + q;
-            while (wq >= soff[s + 1]) ++s;
+            const uint32_t w = q * EMIT_THREADS + tid;
+            if (w >= chunk_n) break;
+            const uint32_t s = (uint32_t)sowner[w] - 1u;
             const uint32_t i = sidx[s];
-            const uint32_t j = i + 1u + (uint32_t)(wq - soff[s]);
+            const uint32_t j = i + 1u + (uint32_t)(w0 + w - soff[s]);
             const IdT raw_i = a.ids[i], raw_j = a.ids[j];
             const IdT id_i = raw_i & a.id_mask, id_j = raw_j & a.id_mask;
             bool emit;
@@ -510,40 +542,51 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
             } else {
                 emit = j >= a.first_owned && !a.inactive[i] && !a.inactive[j] && FilterFn<FK>::pass(a.filter, id_j, id_i);
             }
-            if (emit) {
-                pa[npass] = (uint64_t)id_j; // (later, earlier) -- src/layer.rs:567
-                pb[npass] = (uint64_t)id_i;
-                ++npass;
+            if (identity) { // one pair per work item, at the work item's own index: written straight out, coalesced
+                const uint64_t g = w0 + w;
+                if (g < a.capacity) {
+                    if (WIDE) {
+                        a.out_a[g] = (uint64_t)id_j;
+                        a.out_b[g] = (uint64_t)id_i;
+                    } else {
+                        a.out_packed[g] = ((uint64_t)id_j << 32) | (uint64_t)id_i;
+                    }
+                }
+                if (a.later_count) atomicAdd(a.later_count + (size_t)id_j, 1u);
+            } else if (emit) {
+                pa[q] = (uint64_t)id_j; // (later, earlier) -- src/layer.rs:567
+                pb[q] = (uint64_t)id_i;
+                emit_bits |= 1u << q;
                 if (a.later_count) atomicAdd(a.later_count + (size_t)id_j, 1u);
             }
         }
         if (same_seen) a.totals->any_same_id = 1u;
     }
+    if (identity) {
+        if (w0 + chunk_n == a.n_work && tid == 0) *a.pair_counter = a.n_work; // identity: one pair per work item
+        return;
+    }
     if (a.mode == EMIT_MODE_FLAG) return;
 
-    uint32_t chunk_pass, ex;
-    if (identity) {
-        chunk_pass = chunk_n;
-        ex = first;
-        __syncthreads(); // all walks done before soff / sidx are overwritten
-    } else {
-        ex = block_exclusive_sum<EMIT_THREADS, uint32_t>(npass, (uint32_t *)sscratch, &chunk_pass);
-        if (tid == 0) *sbase_p = atomicAdd(a.pair_counter, (unsigned long long)chunk_pass);
-    }
+    __syncthreads(); // every thread is done with soff / sidx before the staged output overwrites them
+    uint32_t chunk_pass;
+    const uint32_t ex = block_exclusive_sum<EMIT_THREADS, uint32_t>((uint32_t)__popc(emit_bits), (uint32_t *)sscratch, &chunk_pass);
+    if (tid == 0) *sbase_p = atomicAdd(a.pair_counter, (unsigned long long)chunk_pass);
     // stage, then write coalesced
 #pragma unroll
     for (int q = 0; q < EMIT_IPT; ++q) {
-        if (q < (int)npass) {
+        if (emit_bits & (1u << q)) {
+            const uint32_t slot = ex + (uint32_t)__popc(emit_bits & ((1u << q) - 1u));
             if (WIDE) {
-                spa[ex + q] = pa[q];
-                spb[ex + q] = pb[q];
+                spa[slot] = pa[q];
+                spb[slot] = pb[q];
             } else {
-                spa[ex + q] = (pa[q] << 32) | pb[q];
+                spa[slot] = (pa[q] << 32) | pb[q];
             }
         }
     }
     __syncthreads();
-    const uint64_t base = identity ? w0 : *sbase_p;
+    const uint64_t base = *sbase_p;
     for (uint32_t i = tid; i < chunk_pass; i += EMIT_THREADS) {
         const uint64_t g = base + i;
         if (g < a.capacity) {
@@ -555,7 +598,6 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
             }
         }
     }
-    if (identity && w0 + chunk_n == a.n_work && tid == 0) *a.pair_counter = a.n_work; // identity: one pair per work item
 }
 
 // ---------------------------------------------------------------------------------------------
