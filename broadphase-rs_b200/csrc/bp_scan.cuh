@@ -415,27 +415,22 @@ template <class IdT> struct EmitSmem {
 // which that object does not cover).  Only used while no same-ID (inactive) record has been seen; the
 // pair sort + dedup that follows stays in place (IDs owning several bounds still produce duplicates).
 template <class T> __device__ __forceinline__ bool canonical_cell(typename T::key_t key_i, typename T::key_t key_j, uint32_t fi, uint32_t fj) {
-    typedef typename T::key_t K;
     if (fj == 0) return true;
+    constexpr int TOTAL = T::DIM * T::AXIS_BITS + T::DEPTH_BITS;
+    constexpr uint64_t ONE_AXIS = T::DIM == 2 ? 0x5555555555555555ull : 0x9249249249249249ull; // every DIM-th bit
     const uint32_t da = key_depth<T>(key_i), db = key_depth<T>(key_j);
-    const K between = (K)(level_mask<T>(db) ^ level_mask<T>(da)); // Morton bits of the levels da+1 .. db
-    // bit pattern of one axis inside the origin field: every DIM-th bit
-    constexpr uint64_t ONE_AXIS = T::DIM == 2 ? 0x5555555555555555ull : 0x9249249249249249ull;
-    constexpr int ORIGIN_BITS = T::DIM * T::AXIS_BITS;
-    // axis `ax` of coordinate bit t sits at origin bit DIM*t + ax; align the pattern so that bit 0 of the origin field is axis 0
-    const uint64_t field = (((uint64_t)1 << ORIGIN_BITS) - 1) << T::DEPTH_BITS;
+    // the Morton digits of the levels da+1 .. db of the later record's cell, lowest level at bit 0: bit DIM*t + ax is
+    // bit t of the cell coordinate along ax (below the earlier record's cell size)
+    const uint32_t width = (uint32_t)T::DIM * (db - da);
+    const uint64_t digits = ((uint64_t)key_j >> (TOTAL - (int)(T::DIM * db))) & (((uint64_t)1 << width) - 1u);
+    uint32_t nonzero = 0; // bit ax: the coordinate along ax has a non-zero bit among those levels
 #pragma unroll
-    for (int ax = 0; ax < T::DIM; ++ax) {
-        if (!((fj >> ax) & 1u)) continue;
-        if ((fi >> ax) & 1u) return false;
-        const uint64_t axis_mask = ((ONE_AXIS << ax) << T::DEPTH_BITS) & field;
-        if (((uint64_t)key_j & (uint64_t)between & axis_mask) != 0) return false;
-    }
-    return true;
+    for (int ax = 0; ax < T::DIM; ++ax) nonzero |= ((digits & (ONE_AXIS << ax)) != 0 ? 1u : 0u) << ax;
+    return ((fi | nonzero) & fj) == 0;
 }
 
 template <class IdT, int FK, class T = IndexTraits<BP_INDEX64_3D>, bool DEDUP = false>
-__global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<IdT> a) {
+__global__ void __launch_bounds__(EMIT_THREADS, 2) scan_emit_kernel(const EmitArgs<IdT> a) {
     constexpr bool WIDE = sizeof(IdT) == 8;
     constexpr int FLAG_SHIFT = 8 * sizeof(IdT) - 3;
     typedef EmitSmem<IdT> S;
@@ -515,49 +510,67 @@ __global__ void __launch_bounds__(EMIT_THREADS) scan_emit_kernel(const EmitArgs<
     uint32_t emit_bits = 0; // bit q: item q of this thread yields a pair (pa[q], pb[q])
     uint64_t pa[EMIT_IPT], pb[EMIT_IPT];
     {
+        typedef typename T::key_t K;
+        constexpr int BATCH = 4; // items whose loads are in flight together: one memory round trip per batch, not per item
         bool same_seen = false;
 #pragma unroll
-        for (int q = 0; q < EMIT_IPT; ++q) {
-            const uint32_t w = q * EMIT_THREADS + tid;
-            if (w >= chunk_n) break;
-            const uint32_t s = (uint32_t)sowner[w] - 1u;
-            const uint32_t i = sidx[s];
-            const uint32_t j = i + 1u + (uint32_t)(w0 + w - soff[s]);
-            const IdT raw_i = a.ids[i], raw_j = a.ids[j];
-            const IdT id_i = raw_i & a.id_mask, id_j = raw_j & a.id_mask;
-            bool emit;
-            if (a.mode == EMIT_MODE_FIRST) {
-                const bool same = id_i == id_j;
-                same_seen |= same;
-                emit = identity || (!same && j >= a.first_owned && FilterFn<FK>::pass(a.filter, id_j, id_i));
+        for (int h = 0; h < EMIT_IPT; h += BATCH) {
+            uint32_t ii[BATCH], jj[BATCH];
+            IdT ri[BATCH], rj[BATCH];
+            K ki[BATCH], kj[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const uint32_t w = (h + u) * EMIT_THREADS + tid;
+                const uint32_t wc = w < chunk_n ? w : 0u; // (item 0 exists: the loads below stay in bounds)
+                const uint32_t s = (uint32_t)sowner[wc] - 1u;
+                ii[u] = sidx[s];
+                jj[u] = ii[u] + 1u + (uint32_t)(w0 + wc - soff[s]);
+                ri[u] = a.ids[ii[u]];
+                rj[u] = a.ids[jj[u]];
                 if constexpr (DEDUP) {
-                    if (emit) {
-                        const typename T::key_t *keys = (const typename T::key_t *)a.keys;
-                        emit = canonical_cell<T>(keys[i], keys[j], (uint32_t)(raw_i >> FLAG_SHIFT), (uint32_t)(raw_j >> FLAG_SHIFT));
-                    }
+                    const K *keys = (const K *)a.keys;
+                    ki[u] = keys[ii[u]];
+                    kj[u] = keys[jj[u]];
                 }
-            } else if (a.mode == EMIT_MODE_FLAG) {
-                if (id_i == id_j) a.inactive[j] = 1;
-                emit = false;
-            } else {
-                emit = j >= a.first_owned && !a.inactive[i] && !a.inactive[j] && FilterFn<FK>::pass(a.filter, id_j, id_i);
             }
-            if (identity) { // one pair per work item, at the work item's own index: written straight out, coalesced
-                const uint64_t g = w0 + w;
-                if (g < a.capacity) {
-                    if (WIDE) {
-                        a.out_a[g] = (uint64_t)id_j;
-                        a.out_b[g] = (uint64_t)id_i;
-                    } else {
-                        a.out_packed[g] = ((uint64_t)id_j << 32) | (uint64_t)id_i;
+#pragma unroll
+            for (int u = 0; u < BATCH; ++u) {
+                const int q = h + u;
+                const uint32_t w = q * EMIT_THREADS + tid;
+                if (w >= chunk_n) continue;
+                const uint32_t i = ii[u], j = jj[u];
+                const IdT id_i = ri[u] & a.id_mask, id_j = rj[u] & a.id_mask;
+                bool emit;
+                if (a.mode == EMIT_MODE_FIRST) {
+                    const bool same = id_i == id_j;
+                    same_seen |= same;
+                    emit = identity || (!same && j >= a.first_owned && FilterFn<FK>::pass(a.filter, id_j, id_i));
+                    if constexpr (DEDUP) {
+                        if (emit) emit = canonical_cell<T>(ki[u], kj[u], (uint32_t)(ri[u] >> FLAG_SHIFT), (uint32_t)(rj[u] >> FLAG_SHIFT));
                     }
+                } else if (a.mode == EMIT_MODE_FLAG) {
+                    if (id_i == id_j) a.inactive[j] = 1;
+                    emit = false;
+                } else {
+                    emit = j >= a.first_owned && !a.inactive[i] && !a.inactive[j] && FilterFn<FK>::pass(a.filter, id_j, id_i);
                 }
-                if (a.later_count) atomicAdd(a.later_count + (size_t)id_j, 1u);
-            } else if (emit) {
-                pa[q] = (uint64_t)id_j; // (later, earlier) -- src/layer.rs:567
-                pb[q] = (uint64_t)id_i;
-                emit_bits |= 1u << q;
-                if (a.later_count) atomicAdd(a.later_count + (size_t)id_j, 1u);
+                if (identity) { // one pair per work item, at the work item's own index: written straight out, coalesced
+                    const uint64_t g = w0 + w;
+                    if (g < a.capacity) {
+                        if (WIDE) {
+                            a.out_a[g] = (uint64_t)id_j;
+                            a.out_b[g] = (uint64_t)id_i;
+                        } else {
+                            a.out_packed[g] = ((uint64_t)id_j << 32) | (uint64_t)id_i;
+                        }
+                    }
+                    if (a.later_count) atomicAdd(a.later_count + (size_t)id_j, 1u);
+                } else if (emit) {
+                    pa[q] = (uint64_t)id_j; // (later, earlier) -- src/layer.rs:567
+                    pb[q] = (uint64_t)id_i;
+                    emit_bits |= 1u << q;
+                    if (a.later_count) atomicAdd(a.later_count + (size_t)id_j, 1u);
+                }
             }
         }
         if (same_seen) a.totals->any_same_id = 1u;
