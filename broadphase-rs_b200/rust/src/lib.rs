@@ -41,6 +41,10 @@ extern "C" {
     fn bp_layer_sort(layer: *mut BpLayer) -> c_int;
     fn bp_layer_scan(layer: *mut BpLayer, filter: *const BpFilter, out_pairs: *mut *const c_void, out_count: *mut usize) -> c_int;
     fn bp_layer_records(layer: *mut BpLayer, keys: *mut *const c_void, ids: *mut *const c_void, n: *mut usize, sorted: *mut c_int) -> c_int;
+    fn bp_layer_test_box_batch(layer: *mut BpLayer, system_bounds: *const f32, boxes: *const f32, n_queries: usize, max_depth: i32,
+                               on_device: c_int, out_pairs: *mut *const c_void, out_offsets: *mut *const u32, out_count: *mut usize) -> c_int;
+    fn bp_layer_test_ray_batch(layer: *mut BpLayer, system_bounds: *const f32, rays: *const f32, n_queries: usize, max_depth: i32,
+                               on_device: c_int, out_pairs: *mut *const c_void, out_offsets: *mut *const u32, out_count: *mut usize) -> c_int;
     fn bp_layer_last_error(layer: *const BpLayer) -> *const c_char;
 }
 
@@ -166,6 +170,48 @@ impl<Index: SpatialIndex, ID: ObjectID> Layer<Index, ID> {
     /// src/layer.rs:489-520
     pub fn par_scan_filtered<'a>(&'a mut self, filter: Filter) -> &'a [(ID, ID)] {
         self.scan_filtered(filter)
+    }
+
+    /// src/layer.rs:293-311, for a batch of boxes: `ids[offsets[q]..offsets[q + 1]]` is what the reference's
+    /// `test_box(system_bounds, boxes[q], max_depth)` returns (sorted, duplicate-free).
+    pub fn test_box_batch(&mut self, system_bounds: Bounds<Index::Point>, boxes: &[Bounds<Index::Point>], max_depth: Option<u32>)
+        -> (Vec<u32>, Vec<ID>)
+    {
+        let (mut pairs, mut offsets): (*const c_void, *const u32) = (std::ptr::null(), std::ptr::null());
+        let mut n: usize = 0;
+        let s = unsafe {
+            bp_layer_test_box_batch(self.handle, &system_bounds as *const _ as *const f32, boxes.as_ptr() as *const f32, boxes.len(),
+                                    max_depth.map_or(-1, |d| d as i32), 0, &mut pairs, &mut offsets, &mut n)
+        };
+        self.check(s);
+        let off = unsafe { std::slice::from_raw_parts(offsets, boxes.len() + 1) }.to_vec();
+        let ids = if n == 0 { Vec::new() } else {
+            unsafe { std::slice::from_raw_parts(pairs as *const (ID, ID), n) }.iter().map(|&(_query, id)| id).collect()
+        };
+        (off, ids)
+    }
+
+    /// src/layer.rs:293-311
+    pub fn test_box(&mut self, system_bounds: Bounds<Index::Point>, test_bounds: Bounds<Index::Point>, max_depth: Option<u32>) -> Vec<ID> {
+        self.test_box_batch(system_bounds, &[test_bounds], max_depth).1
+    }
+
+    /// src/layer.rs:326-351, for a batch of rays given as rows of `2 * DIM + 2` floats
+    /// (origin.., direction.., range_min, range_max).
+    pub fn test_ray_batch(&mut self, system_bounds: Bounds<Index::Point>, rays: &[f32], max_depth: Option<u32>) -> (Vec<u32>, Vec<ID>) {
+        let nq = rays.len() / (2 * Index::DIM + 2);
+        let (mut pairs, mut offsets): (*const c_void, *const u32) = (std::ptr::null(), std::ptr::null());
+        let mut n: usize = 0;
+        let s = unsafe {
+            bp_layer_test_ray_batch(self.handle, &system_bounds as *const _ as *const f32, rays.as_ptr(), nq,
+                                    max_depth.map_or(-1, |d| d as i32), 0, &mut pairs, &mut offsets, &mut n)
+        };
+        self.check(s);
+        let off = unsafe { std::slice::from_raw_parts(offsets, nq + 1) }.to_vec();
+        let ids = if n == 0 { Vec::new() } else {
+            unsafe { std::slice::from_raw_parts(pairs as *const (ID, ID), n) }.iter().map(|&(_query, id)| id).collect()
+        };
+        (off, ids)
     }
 
     /// src/layer.rs:79-81 (copies the tree back from the device)
