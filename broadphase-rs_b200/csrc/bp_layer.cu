@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -47,6 +48,27 @@ struct ProfEvent {
     cudaEvent_t start, stop;
     int cls;
 };
+
+// How a count gets back to the host.  A cudaMemcpyAsync + stream/event synchronise costs ~22 us of idle GPU per
+// round trip at config 2 (two copy operations, the wake-up of the waiting thread, then the launch latency of what
+// follows: three such gaps were 14 % of the frame, profiles/r1_timeline_cfg2.txt).  Instead a one-thread kernel
+// stores the few words into pinned, device-mapped host memory, fences, and stores a sequence number; the host
+// spins on that number (checking the stream now and then, so a failed kernel cannot hang it).
+struct Mailbox {
+    unsigned long long words[12];
+    unsigned int err;
+    unsigned int seq;
+};
+
+__global__ void post_kernel(const unsigned long long *__restrict__ src, int nwords, const int *__restrict__ err, Mailbox *mb,
+                            unsigned int seq) { // one warp: the loads of the words overlap
+    const int lane = (int)threadIdx.x;
+    if (lane < nwords) mb->words[lane] = src[lane];
+    if (lane == 31) mb->err = (unsigned int)*err;
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) *(volatile unsigned int *)&mb->seq = seq;
+}
 
 } // namespace
 
@@ -89,6 +111,9 @@ struct bp_layer {
     ScanTotals *d_tot = nullptr;
     int *d_err = nullptr;
     int *h_err = nullptr; // pinned
+    Mailbox *h_mail[2] = {nullptr, nullptr}; // pinned + mapped: [0] extend results, [1] scan / query totals
+    Mailbox *d_mail[2] = {nullptr, nullptr}; // the same memory as the device sees it
+    unsigned int mail_seq = 0, pending_seq = 0;
 
     DevBuf scratch;                // look-back status words, tile counters, histograms
     DevBuf stage_bounds, stage_ids; // extend_host staging
@@ -226,7 +251,58 @@ int check_launch(bp_layer *L, const char *what) {
     return BP_OK;
 }
 
+// Enqueues the post of `nwords` 64-bit words at d_src (+ the error flag) to mailbox `box`; returns the sequence number.
+int post_mail(bp_layer *L, int box, const void *d_src, int nwords, unsigned int *out_seq) {
+    const unsigned int seq = ++L->mail_seq;
+    {
+        LaunchScope ls(L, BP_K_MISC, 0);
+        post_kernel<<<1, 32, 0, L->stream>>>((const unsigned long long *)d_src, nwords, L->d_err, L->d_mail[box], seq);
+    }
+    *out_seq = seq;
+    return check_launch(L, "post_kernel");
+}
+
+// Waits until mailbox `box` carries `seq`, then copies `bytes` of it to `dst`.
+int wait_mail(bp_layer *L, int box, unsigned int seq, void *dst, size_t bytes) {
+    volatile Mailbox *mb = L->h_mail[box];
+    for (unsigned int spins = 1; mb->seq != seq; ++spins) {
+        if ((spins & 0xffffu) == 0) { // the stream must still be busy (or have just finished); anything else is an error
+            const cudaError_t e = cudaStreamQuery(L->stream);
+            if (e == cudaSuccess) {
+                if (mb->seq == seq) break;
+                return fail(L, BP_ERR_INTERNAL, "the stream drained without posting its result");
+            }
+            if (e != cudaErrorNotReady) {
+                cudaGetLastError();
+                return fail(L, BP_ERR_CUDA, "waiting for a device result: %s", cudaGetErrorString(e));
+            }
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    memcpy(dst, (const void *)L->h_mail[box]->words, bytes);
+    if (L->h_mail[box]->err) {
+        cudaMemsetAsync(L->d_err, 0, sizeof(int), L->stream);
+        return fail(L, BP_ERR_INTERNAL, "a kernel reported a look-back time-out");
+    }
+    return BP_OK;
+}
+
 void collect_profile(bp_layer *L) {
+    // BP_TIMELINE=1: print where every launch of the collected interval started and ended (ms after the first one),
+    // i.e. the gaps the stream spent on memsets, small copies and host round trips (a tuning aid)
+    static const bool timeline = getenv("BP_TIMELINE") != nullptr;
+    if (timeline && !L->prof_events.empty()) {
+        static const char *names[BP_K_COUNT] = {"encode", "sort_hist", "sort_pass", "merge", "scan_runs", "scan_emit",
+                                                "pair_hist", "pair_pass", "pair_unique", "misc", "query"};
+        float prev_end = 0.f;
+        for (ProfEvent &pe : L->prof_events) {
+            float t0 = 0.f, t1 = 0.f;
+            cudaEventElapsedTime(&t0, L->prof_events[0].start, pe.start);
+            cudaEventElapsedTime(&t1, L->prof_events[0].start, pe.stop);
+            fprintf(stderr, "[bp timeline] %-11s start %8.4f  dur %7.4f  gap before %7.4f\n", names[pe.cls], t0, t1 - t0, t0 - prev_end);
+            prev_end = t1;
+        }
+    }
     for (ProfEvent &pe : L->prof_events) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, pe.start, pe.stop) == cudaSuccess) L->stats.kernel_ms[pe.cls] += ms;
@@ -460,8 +536,7 @@ template <int KIND, class IdT> struct Impl {
             kern<<<tiles, ENCODE_THREADS, S::BYTES, L->stream>>>(a);
         }
         TRY(check_launch(L, "encode_kernel"));
-        CU(L, cudaMemcpyAsync(L->h_res, L->d_res, sizeof(ExtendResult), cudaMemcpyDeviceToHost, L->stream));
-        CU(L, cudaEventRecord(L->ev_sync, L->stream));
+        TRY(post_mail(L, 0, L->d_res, (int)(sizeof(ExtendResult) / 8), &L->pending_seq));
         L->pending = true;
         L->pending_base = L->n_records;
         return BP_OK;
@@ -478,7 +553,7 @@ template <int KIND, class IdT> struct Impl {
             if (L->min_depth == 0 && L->n_records + n * per_obj <= L->cap_records) return BP_OK; // cannot overflow: stays async
             // min_depth can push objects below their natural depth: the record count is only
             // known after the kernel, so check it now and redo the call once with enough room
-            CU(L, cudaEventSynchronize(L->ev_sync));
+            TRY(wait_mail(L, 0, L->pending_seq, L->h_res, sizeof(ExtendResult)));
             const uint64_t total = L->h_res->total_records;
             if (L->pending_base + total <= L->cap_records) return BP_OK;
             L->pending = false;
@@ -631,14 +706,9 @@ template <int KIND, class IdT> struct Impl {
     }
 
     static int fetch_totals(bp_layer *L) {
-        CU(L, cudaMemcpyAsync(L->h_tot, L->d_tot, sizeof(ScanTotals), cudaMemcpyDeviceToHost, L->stream));
-        CU(L, cudaMemcpyAsync(L->h_err, L->d_err, sizeof(int), cudaMemcpyDeviceToHost, L->stream));
-        CU(L, cudaStreamSynchronize(L->stream));
-        if (*L->h_err) {
-            cudaMemsetAsync(L->d_err, 0, sizeof(int), L->stream);
-            return fail(L, BP_ERR_INTERNAL, "a kernel reported a look-back time-out");
-        }
-        return BP_OK;
+        unsigned int seq = 0;
+        TRY(post_mail(L, 1, L->d_tot, (int)(sizeof(ScanTotals) / 8), &seq));
+        return wait_mail(L, 1, seq, L->h_tot, sizeof(ScanTotals));
     }
 
     // Everything up to the raw (unsorted, duplicate-carrying) pairs, left in praw[0] (+ praw_b[0]).
@@ -1280,7 +1350,7 @@ int do_strip_flags(bp_layer *L) { DISPATCH(L, strip_flags(L)); }
 // Folds the result of the last (still asynchronous) extend into the host-side state.
 int resolve_pending(bp_layer *L) {
     if (!L->pending) return BP_OK;
-    CU(L, cudaEventSynchronize(L->ev_sync));
+    TRY(wait_mail(L, 0, L->pending_seq, L->h_res, sizeof(ExtendResult)));
     L->pending = false;
     const ExtendResult &r = *L->h_res;
     L->n_invalid += r.n_invalid;
@@ -1409,6 +1479,11 @@ int bp_layer_create(const bp_layer_config *cfg, bp_layer **out) {
     if (cudaMallocHost((void **)&L->h_res, sizeof(ExtendResult)) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMallocHost((void **)&L->h_tot, sizeof(ScanTotals)) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMallocHost((void **)&L->h_err, sizeof(int)) != cudaSuccess) return bail(BP_ERR_OOM);
+    for (int i = 0; i < 2; ++i) {
+        if (cudaHostAlloc((void **)&L->h_mail[i], sizeof(Mailbox), cudaHostAllocMapped) != cudaSuccess) return bail(BP_ERR_OOM);
+        memset(L->h_mail[i], 0, sizeof(Mailbox));
+        if (cudaHostGetDevicePointer((void **)&L->d_mail[i], L->h_mail[i], 0) != cudaSuccess) return bail(BP_ERR_CUDA);
+    }
     if (cudaMalloc((void **)&L->d_res, sizeof(ExtendResult)) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMalloc((void **)&L->d_tot, sizeof(ScanTotals)) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMalloc((void **)&L->d_err, sizeof(int)) != cudaSuccess) return bail(BP_ERR_OOM);
@@ -1461,6 +1536,8 @@ int bp_layer_destroy(bp_layer *L) {
     if (L->h_res) cudaFreeHost(L->h_res);
     if (L->h_tot) cudaFreeHost(L->h_tot);
     if (L->h_err) cudaFreeHost(L->h_err);
+    for (int i = 0; i < 2; ++i)
+        if (L->h_mail[i]) cudaFreeHost(L->h_mail[i]);
     if (L->d_res) cudaFree(L->d_res);
     if (L->d_tot) cudaFree(L->d_tot);
     if (L->d_err) cudaFree(L->d_err);
@@ -1495,7 +1572,7 @@ int bp_layer_clear(bp_layer *L) {
     if (!L) return BP_ERR_INVALID_ARG;
     DeviceGuard g(L->device);
     if (L->pending) { // the result of an extend nobody looked at is discarded with the tree
-        CU(L, cudaEventSynchronize(L->ev_sync));
+        TRY(wait_mail(L, 0, L->pending_seq, L->h_res, sizeof(ExtendResult)));
         L->pending = false;
         L->n_invalid += L->h_res->n_invalid;
     }
