@@ -742,19 +742,18 @@ template <int KIND, class IdT> struct Impl {
 
         // ---- runs ----
         const uint32_t rtiles = (uint32_t)((R + RUNS_TILE - 1) / RUNS_TILE);
-        const size_t sbytes = 64;
-        TRY(ensure(L, L->scratch, sbytes));
         TRY(ensure(L, L->src_idx, R * sizeof(uint32_t)));
         TRY(ensure(L, L->src_off, (R + 1) * sizeof(uint64_t)));
-        CU(L, cudaMemsetAsync(L->scratch.p, 0, sbytes, L->stream));
-        CU(L, cudaMemsetAsync(L->d_tot, 0, sizeof(ScanTotals), L->stream));
+        static_assert(sizeof(ScanTotals) % 8 == 0, "the counters behind the totals must stay 8-byte aligned");
+        char *runs_ctr = (char *)(L->d_tot + 1); // tile counter + packed (sources, work) counter, zeroed with the totals
+        CU(L, cudaMemsetAsync(L->d_tot, 0, sizeof(ScanTotals) + 64, L->stream));
         RunsArgs<T> ra;
         ra.keys = keys(L, L->cur);
         ra.n = (uint32_t)R;
         ra.src_idx = (uint32_t *)L->src_idx.p;
         ra.src_off = (uint64_t *)L->src_off.p;
-        ra.tile_counter = (uint32_t *)L->scratch.p;
-        ra.packed_counter = (unsigned long long *)((char *)L->scratch.p + 8);
+        ra.tile_counter = (uint32_t *)runs_ctr;
+        ra.packed_counter = (unsigned long long *)(runs_ctr + 8);
         ra.totals = L->d_tot;
         ra.err = L->d_err;
         {
@@ -914,8 +913,7 @@ template <int KIND, class IdT> struct Impl {
             const uint32_t ftiles = (uint32_t)((P_raw + FinCfg<IdT>::TILE - 1) / FinCfg<IdT>::TILE);
             const size_t fbytes = 64 + (size_t)ftiles * sizeof(uint64_t);
             TRY(ensure(L, L->scratch, fbytes));
-            CU(L, cudaMemsetAsync(L->scratch.p, 0, fbytes, L->stream));
-            CU(L, cudaMemsetAsync(&L->d_tot->pad, 0, sizeof(unsigned int), L->stream));
+            CU(L, cudaMemsetAsync(L->scratch.p, 0, fbytes, L->stream)); // (d_tot->pad is still zero: every caller cleared *d_tot)
             FinishArgs<IdT> fa;
             fa.in_packed = wide ? nullptr : a0;
             fa.in_a = wide ? a0 : nullptr;
@@ -1485,7 +1483,7 @@ int bp_layer_create(const bp_layer_config *cfg, bp_layer **out) {
         if (cudaHostGetDevicePointer((void **)&L->d_mail[i], L->h_mail[i], 0) != cudaSuccess) return bail(BP_ERR_CUDA);
     }
     if (cudaMalloc((void **)&L->d_res, sizeof(ExtendResult)) != cudaSuccess) return bail(BP_ERR_OOM);
-    if (cudaMalloc((void **)&L->d_tot, sizeof(ScanTotals)) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaMalloc((void **)&L->d_tot, sizeof(ScanTotals) + 64) != cudaSuccess) return bail(BP_ERR_OOM); // + scan_runs_kernel's counters
     if (cudaMalloc((void **)&L->d_err, sizeof(int)) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMalloc((void **)&L->d_last, 16) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMemsetAsync(L->d_err, 0, sizeof(int), L->stream) != cudaSuccess) return bail(BP_ERR_CUDA);
