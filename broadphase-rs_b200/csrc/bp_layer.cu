@@ -293,7 +293,7 @@ void collect_profile(bp_layer *L) {
     static const bool timeline = getenv("BP_TIMELINE") != nullptr;
     if (timeline && !L->prof_events.empty()) {
         static const char *names[BP_K_COUNT] = {"encode", "sort_hist", "sort_pass", "merge", "scan_runs", "scan_emit",
-                                                "pair_hist", "pair_pass", "pair_unique", "misc", "query"};
+                                                "pair_hist", "pair_pass", "pair_unique", "misc", "query", "partition"};
         float prev_end = 0.f;
         for (ProfEvent &pe : L->prof_events) {
             float t0 = 0.f, t1 = 0.f;
@@ -1099,7 +1099,7 @@ template <int KIND, class IdT> struct Impl {
         uint32_t *hist = (uint32_t *)L->scratch.p, *counters = hist + RADIX, *status = counters + 64;
         CU(L, cudaMemsetAsync(L->scratch.p, 0, total, L->stream));
         {
-            LaunchScope ls(L, BP_K_MISC, (double)n * sizeof(PK));
+            LaunchScope ls(L, BP_K_PARTITION, (double)n * sizeof(PK));
             const int blocks = (int)std::min<size_t>((n + 4095) / 4096, 148 * 8);
             partition_hist_kernel<PK, T, false><<<std::max(blocks, 1), 512, 0, L->stream>>>(kin, n, op, hist, nullptr);
         }
@@ -1129,7 +1129,7 @@ template <int KIND, class IdT> struct Impl {
         a.err = L->d_err;
         {
             const double eb = std::is_same<PV, NoVal>::value ? sizeof(PK) : sizeof(PK) + sizeof(PV);
-            LaunchScope ls(L, BP_K_MISC, 2.0 * (double)n * eb);
+            LaunchScope ls(L, BP_K_PARTITION, 2.0 * (double)n * eb);
             kern<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
         }
         TRY(check_launch(L, "radix_pass_kernel<splitters>"));
@@ -1155,7 +1155,7 @@ template <int KIND, class IdT> struct Impl {
         uint32_t *hist = (uint32_t *)L->scratch.p, *halo = hist + 32;
         CU(L, cudaMemsetAsync(L->scratch.p, 0, 256, L->stream));
         {
-            LaunchScope ls(L, BP_K_MISC, (double)n * sizeof(PK));
+            LaunchScope ls(L, BP_K_PARTITION, (double)n * sizeof(PK));
             const int blocks = (int)std::min<size_t>((n + 4095) / 4096, 148 * 8);
             partition_hist_kernel<PK, T, HALO><<<std::max(blocks, 1), 512, 0, L->stream>>>(kin, n, op, hist, halo);
         }
@@ -1210,7 +1210,7 @@ template <int KIND, class IdT> struct Impl {
         a.err = L->d_err;
         {
             const double eb = std::is_same<PV, NoVal>::value ? sizeof(PK) : sizeof(PK) + sizeof(PV);
-            LaunchScope ls(L, BP_K_MISC, 2.0 * (double)n * eb);
+            LaunchScope ls(L, BP_K_PARTITION, 2.0 * (double)n * eb);
             kern<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
         }
         TRY(check_launch(L, "radix_pass_kernel<scatter>"));
@@ -1222,7 +1222,7 @@ template <int KIND, class IdT> struct Impl {
                     hop.vdst[b] = b <= n_spl ? hvdst[b] : 0;
                 }
                 uint32_t *cursor = counters + 32; // zeroed above
-                LaunchScope ls(L, BP_K_MISC, (double)n * sizeof(PK));
+                LaunchScope ls(L, BP_K_PARTITION, (double)n * sizeof(PK));
                 const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
                 halo_scatter_kernel<PK, PV, T><<<std::max(blocks, 1), 256, 0, L->stream>>>(kin, vin, n, hop, cursor);
                 TRY(check_launch(L, "halo_scatter_kernel"));

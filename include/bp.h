@@ -94,7 +94,8 @@ enum {
     BP_K_PAIR_UNIQUE = 8, /* dedup + final pair layout */
     BP_K_MISC = 9,      /* small helpers (histogram scans, masks, gathers) */
     BP_K_QUERY = 10,    /* batched box / ray queries: hierarchy descent (count pass + write pass) */
-    BP_K_COUNT = 11
+    BP_K_PARTITION = 11, /* multi-GPU: splitter counts + the partition pass that stores into the peers' receive buffers */
+    BP_K_COUNT = 12
 };
 
 typedef struct bp_stats {
