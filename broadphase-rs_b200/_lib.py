@@ -55,6 +55,7 @@ SYMBOLS = {
     "bp_layer_scan_device": (_i, [_vp, _P(Filter), _P(_vp), _P(_sz)]),
     "bp_layer_test_box_batch": (_i, [_vp, _vp, _vp, _sz, ctypes.c_int32, _i, _P(_vp), _P(_vp), _P(_sz)]),
     "bp_layer_test_ray_batch": (_i, [_vp, _vp, _vp, _sz, ctypes.c_int32, _i, _P(_vp), _P(_vp), _P(_sz)]),
+    "bp_layer_pick_ray_batch": (_i, [_vp, _vp, _vp, _sz, ctypes.c_float, ctypes.c_int32, ctypes.c_int32, _vp, _sz, _i, _P(_vp)]),
     "bp_layer_records": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
     "bp_layer_records_device": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
     "bp_layer_set_records": (_i, [_vp, _vp, _vp, _sz, _i, _i]),

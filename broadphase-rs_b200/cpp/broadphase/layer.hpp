@@ -18,6 +18,8 @@
 //   layer.test_box(system_bounds, b, d)    src/layer.rs:293 layer.test_box(system_bounds, b, max_depth) -> std::vector<ID>
 //   layer.test_ray(system_bounds, o, v, ..) src/layer.rs:326 layer.test_ray(system_bounds, origin, direction, rmin, rmax, max_depth)
 //   (many geometries in one call)                           layer.test_box_batch(...) / test_ray_batch(...) -> QueryResults<ID>
+//   layer.pick_ray(system_bounds, o, v, max_dist, d, f) src/layer.rs:424 layer.pick_ray(system_bounds, origin, direction, max_dist, Shapes, max_depth)
+//                                                           (get_dist closure -> enumerated shape functor over a table indexed by ID)
 //
 // Errors: the reference never returns errors from these methods; allocation failure aborts.  Here a
 // failed C-ABI call throws broadphase::Error (status + message).
@@ -157,6 +159,15 @@ public:
         ray[2 * Index::DIM] = range_min;
         ray[2 * Index::DIM + 1] = range_max;
         return test_ray_batch(system_bounds, ray, 1, max_depth).ids;
+    }
+
+    // Layer::pick_ray -- src/layer.rs:424-446, batched: rays = n x (origin[DIM], direction[DIM]); shapes = table indexed by ID
+    // (BP_PICK_SPHERE: centre[DIM], radius; BP_PICK_AABB: min[DIM], max[DIM]).  One bp_pick_result per ray (hit == 0: None).
+    std::vector<bp_pick_result> pick_ray_batch(const Bounds<Index::DIM> &system_bounds, const float *rays, size_t n, float max_dist,
+                                               bp_pick_kind kind, const float *shapes, size_t n_shapes, int max_depth = -1) {
+        const bp_pick_result *res = nullptr;
+        ck(bp_layer_pick_ray_batch(h_, system_bounds.min, rays, n, max_dist, max_depth, kind, shapes, n_shapes, 0, &res));
+        return std::vector<bp_pick_result>(res, res + n);
     }
 
     // Layer::iter -- src/layer.rs:79-81

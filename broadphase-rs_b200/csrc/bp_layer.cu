@@ -120,6 +120,9 @@ struct bp_layer {
     DevBuf src_idx, src_off, chunk_src, inactive;
     DevBuf praw[2], praw_b[2];     // raw pairs, ping-pong (u32 IDs: packed; u64 IDs: later / earlier)
     DevBuf pout;                   // final pairs
+    DevBuf pick_shapes, pick_out;  // pick_ray: staged shape table (host callers), one bp_pick_result per ray
+    void *h_pick = nullptr;        // pinned mirror of pick_out
+    size_t h_pick_cap = 0;
     DevBuf query_params, query_counts, query_offsets; // batched queries: geometry parameters, per-query counts, CSR offsets
     void *h_offsets = nullptr;     // pinned mirror of query_offsets
     size_t h_offsets_cap = 0;
@@ -1075,6 +1078,41 @@ template <int KIND, class IdT> struct Impl {
         }
         return check_launch(L, "query_offsets_kernel");
     }
+    // Layer::pick_ray -- src/layer.rs:424-446, batched; results in pick_out (one PickResult per ray)
+    template <class Shape> static int pick_launch(bp_layer *L, PickArgs<T, IdT> &pa, int blocks) {
+        LaunchScope ls(L, BP_K_QUERY, (double)pa.n_queries * (2.0 * T::DIM * 4 + sizeof(PickResult)));
+        pick_kernel<T, IdT, Shape><<<blocks, QUERY_THREADS, 0, L->stream>>>(pa);
+        return BP_OK;
+    }
+    static int pick(bp_layer *L, const float *sysb, const float *d_rays, size_t nq, float max_dist, int max_depth, int shape_kind,
+                    const float *d_shapes, size_t n_shapes) {
+        TRY(sort(L)); // `self.sort()` -- src/layer.rs:375
+        TRY(ensure(L, L->pick_out, std::max<size_t>(nq, 1) * sizeof(PickResult)));
+        if (nq == 0) return BP_OK;
+        PickArgs<T, IdT> pa;
+        pa.keys = keys(L, L->cur);
+        pa.ids = ids(L, L->cur);
+        pa.id_mask = L->ids_flagged ? (IdT)((((IdT)1) << (8 * sizeof(IdT) - 3)) - 1) : (IdT) ~(IdT)0;
+        pa.n = (uint32_t)L->n_records;
+        pa.rays = d_rays;
+        pa.n_queries = (uint32_t)nq;
+        for (int i = 0; i < 6; ++i) pa.sysb[i] = i < 2 * T::DIM ? sysb[i] : 0.f;
+        pa.max_dist = max_dist;
+        pa.max_depth = max_depth;
+        pa.shapes = d_shapes;
+        pa.n_shapes = n_shapes;
+        pa.out = (PickResult *)L->pick_out.p;
+        pa.err = L->d_err;
+        const int blocks = (int)std::min<size_t>((nq + QUERY_WARPS - 1) / QUERY_WARPS, 148 * 16);
+        if (shape_kind == BP_PICK_SPHERE)
+            TRY(pick_launch<PickSphere<T::DIM>>(L, pa, blocks));
+        else if (shape_kind == BP_PICK_AABB)
+            TRY(pick_launch<PickAabb<T::DIM>>(L, pa, blocks));
+        else
+            return fail(L, BP_ERR_INVALID_ARG, "unknown pick shape kind %d", shape_kind);
+        return check_launch(L, "pick_kernel");
+    }
+
     static int query_kind(bp_layer *L, int ray, const float *sysb, const float *d_params, size_t nq, int max_depth) {
         return ray ? query<RayTestGeom<T::DIM>>(L, sysb, d_params, nq, max_depth) : query<BoxTestGeom<T::DIM>>(L, sysb, d_params, nq, max_depth);
     }
@@ -1314,6 +1352,10 @@ int do_sort(bp_layer *L) { DISPATCH(L, sort(L)); }
 int do_scan(bp_layer *L, const bp_filter *f) { DISPATCH(L, scan(L, f)); }
 int do_scan_raw(bp_layer *L, const bp_filter *f, uint64_t *out_raw) { DISPATCH(L, scan_raw(L, f, out_raw)); }
 int do_finish_pairs(bp_layer *L, uint64_t n) { DISPATCH(L, finish_pairs(L, n)); }
+int do_pick(bp_layer *L, const float *sysb, const float *d_rays, size_t nq, float max_dist, int max_depth, int shape_kind,
+            const float *d_shapes, size_t n_shapes) {
+    DISPATCH(L, pick(L, sysb, d_rays, nq, max_dist, max_depth, shape_kind, d_shapes, n_shapes));
+}
 int do_query(bp_layer *L, int ray, const float *sysb, const float *d_params, size_t nq, int max_depth) {
     DISPATCH(L, query_kind(L, ray, sysb, d_params, nq, max_depth));
 }
@@ -1524,11 +1566,14 @@ int bp_layer_destroy(bp_layer *L) {
     release(L->pout);
     release(L->pair_cnt);
     release(L->query_params);
+    release(L->pick_shapes);
+    release(L->pick_out);
     release(L->query_counts);
     release(L->query_offsets);
     release(L->filter_table);
     if (L->h_pairs) cudaFreeHost(L->h_pairs);
     if (L->h_offsets) cudaFreeHost(L->h_offsets);
+    if (L->h_pick) cudaFreeHost(L->h_pick);
     if (L->h_keys) cudaFreeHost(L->h_keys);
     if (L->h_ids) cudaFreeHost(L->h_ids);
     if (L->h_res) cudaFreeHost(L->h_res);
@@ -1736,6 +1781,42 @@ int bp_layer_test_box_batch(bp_layer *L, const float *sysb, const float *boxes, 
 int bp_layer_test_ray_batch(bp_layer *L, const float *sysb, const float *rays, size_t nq, int32_t max_depth, int on_device,
                             const void **out_pairs, const uint32_t **out_offsets, size_t *out_count) {
     return query_batch(L, 1, sysb, rays, nq, max_depth, on_device, out_pairs, out_offsets, out_count);
+}
+
+int bp_layer_pick_ray_batch(bp_layer *L, const float *sysb, const float *rays, size_t nq, float max_dist, int32_t max_depth,
+                            int32_t shape_kind, const float *shapes, size_t n_shapes, int on_device, const bp_pick_result **out_results) {
+    static_assert(sizeof(bp_pick_result) == sizeof(PickResult) && sizeof(PickResult) == 32, "bp_pick_result layout");
+    if (!L || !sysb || (nq && !rays) || (n_shapes && !shapes)) return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_layer_pick_ray_batch");
+    if (nq >= (1ull << 30)) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 rays in one batch");
+    if (shape_kind != BP_PICK_SPHERE && shape_kind != BP_PICK_AABB) return fail(L, BP_ERR_INVALID_ARG, "unknown pick shape kind %d", shape_kind);
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    const float *d_rays = rays, *d_shapes = shapes;
+    if (!on_device) {
+        const size_t rbytes = nq * 2 * L->dim * sizeof(float);
+        const size_t sbytes = n_shapes * (shape_kind == BP_PICK_SPHERE ? L->dim + 1 : 2 * L->dim) * sizeof(float);
+        if (rbytes) {
+            TRY(ensure(L, L->query_params, rbytes));
+            CU(L, cudaMemcpyAsync(L->query_params.p, rays, rbytes, cudaMemcpyHostToDevice, L->stream));
+            d_rays = (const float *)L->query_params.p;
+        }
+        if (sbytes) {
+            TRY(ensure(L, L->pick_shapes, sbytes));
+            CU(L, cudaMemcpyAsync(L->pick_shapes.p, shapes, sbytes, cudaMemcpyHostToDevice, L->stream));
+            d_shapes = (const float *)L->pick_shapes.p;
+        }
+    }
+    TRY(do_pick(L, sysb, d_rays, nq, max_dist, max_depth, shape_kind, d_shapes, n_shapes));
+    const bp_pick_result *res = (const bp_pick_result *)L->pick_out.p;
+    if (!on_device) {
+        const size_t obytes = std::max<size_t>(nq, 1) * sizeof(bp_pick_result);
+        TRY(pinned_ensure(L, &L->h_pick, &L->h_pick_cap, obytes));
+        if (nq) CU(L, cudaMemcpyAsync(L->h_pick, L->pick_out.p, nq * sizeof(bp_pick_result), cudaMemcpyDeviceToHost, L->stream));
+        CU(L, cudaStreamSynchronize(L->stream));
+        res = (const bp_pick_result *)L->h_pick;
+    }
+    if (out_results) *out_results = res;
+    return BP_OK;
 }
 
 int bp_layer_set_halo(bp_layer *L, size_t n_halo) {

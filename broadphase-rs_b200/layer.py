@@ -20,6 +20,7 @@ INDEX_DIM = {Index32_2D: 2, Index64_2D: 2, Index64_3D: 3}
 INDEX_KEY_DTYPE = {Index32_2D: np.uint32, Index64_2D: np.uint64, Index64_3D: np.uint64}
 
 FILTER_NONE, FILTER_ID_PARITY, FILTER_XOR_MASK, FILTER_CATEGORY = 0, 1, 2, 3
+PICK_SPHERE, PICK_AABB = 0, 1
 
 
 class ScanFilter:
@@ -180,6 +181,35 @@ class Layer:
         ray = np.concatenate([np.asarray(origin, dtype=np.float32).reshape(-1), np.asarray(direction, dtype=np.float32).reshape(-1),
                               np.asarray([range_min, range_max], dtype=np.float32)])
         return self.test_ray_batch(system_bounds, ray.reshape(1, -1), max_depth)[1]
+
+    PICK_DTYPE = np.dtype([("dist", np.float32), ("hit", np.uint32), ("id", np.uint64), ("point", np.float32, (3,)),
+                           ("pad", np.uint32)])
+
+    def pick_ray_batch(self, system_bounds, rays, max_dist, shape_kind, shapes, max_depth=None):
+        """Layer::pick_ray (src/layer.rs:424-446) for every row of `rays` ((n, 2*D): origin.., direction..): the nearest
+        object hit within max_dist, with the reference's get_dist closure replaced by a shape functor over `shapes`
+        (rows indexed by ID: PICK_SPHERE centre.., radius; PICK_AABB min.., max..).  Returns a structured array
+        (dist, hit, id, point[3]) with one entry per ray."""
+        sysb = np.ascontiguousarray(system_bounds, dtype=np.float32).reshape(2 * self.dim)
+        r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 2 * self.dim)
+        width = self.dim + 1 if shape_kind == PICK_SPHERE else 2 * self.dim
+        sh = np.ascontiguousarray(shapes, dtype=np.float32).reshape(-1, width)
+        out = ctypes.c_void_p()
+        self._ck(lib().bp_layer_pick_ray_batch(self._h, sysb.ctypes.data, r.ctypes.data, r.shape[0], float(max_dist),
+                                               -1 if max_depth is None else int(max_depth), shape_kind, sh.ctypes.data, sh.shape[0], 0,
+                                               ctypes.byref(out)))
+        if r.shape[0] == 0:
+            return np.zeros(0, dtype=self.PICK_DTYPE)
+        buf = (ctypes.c_char * (r.shape[0] * self.PICK_DTYPE.itemsize)).from_address(out.value)
+        return np.frombuffer(buf, dtype=self.PICK_DTYPE).copy()
+
+    def pick_ray(self, system_bounds, origin, direction, max_dist, shape_kind, shapes, max_depth=None):
+        """Layer::pick_ray: None, or (dist, id, point) of the nearest hit."""
+        ray = np.concatenate([np.asarray(origin, dtype=np.float32).reshape(-1), np.asarray(direction, dtype=np.float32).reshape(-1)])
+        res = self.pick_ray_batch(system_bounds, ray.reshape(1, -1), max_dist, shape_kind, shapes, max_depth)[0]
+        if not res["hit"]:
+            return None
+        return float(res["dist"]), int(res["id"]), res["point"][:self.dim].copy()
 
     def iter(self):
         """Layer::iter: (keys, ids) numpy copies of the tree in its current order."""

@@ -28,6 +28,24 @@ pub struct BpFilter {
 }
 
 #[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct BpPickResult {
+    pub dist: f32,
+    pub hit: u32,
+    pub id: u64,
+    pub point: [f32; 3],
+    pub pad: u32,
+}
+
+/// Device functors standing in for pick_ray's `get_dist` closure (src/layer.rs:431-436): a table of shapes indexed by ID.
+pub enum PickShapes<'a> {
+    /// rows of `DIM + 1` floats: centre.., radius (the closure of examples/main.rs:427-449)
+    Spheres(&'a [f32]),
+    /// rows of `2 * DIM` floats: min.., max..
+    Aabbs(&'a [f32]),
+}
+
+#[repr(C)]
 pub struct BpLayer {
     _private: [u8; 0],
 }
@@ -45,6 +63,9 @@ extern "C" {
                                on_device: c_int, out_pairs: *mut *const c_void, out_offsets: *mut *const u32, out_count: *mut usize) -> c_int;
     fn bp_layer_test_ray_batch(layer: *mut BpLayer, system_bounds: *const f32, rays: *const f32, n_queries: usize, max_depth: i32,
                                on_device: c_int, out_pairs: *mut *const c_void, out_offsets: *mut *const u32, out_count: *mut usize) -> c_int;
+    fn bp_layer_pick_ray_batch(layer: *mut BpLayer, system_bounds: *const f32, rays: *const f32, n_queries: usize, max_dist: f32,
+                               max_depth: i32, shape_kind: i32, shapes: *const f32, n_shapes: usize, on_device: c_int,
+                               out_results: *mut *const BpPickResult) -> c_int;
     fn bp_layer_last_error(layer: *const BpLayer) -> *const c_char;
 }
 
@@ -212,6 +233,24 @@ impl<Index: SpatialIndex, ID: ObjectID> Layer<Index, ID> {
             unsafe { std::slice::from_raw_parts(pairs as *const (ID, ID), n) }.iter().map(|&(_query, id)| id).collect()
         };
         (off, ids)
+    }
+
+    /// src/layer.rs:424-446 for a batch of rays (rows of `2 * DIM` floats: origin.., direction..): per ray
+    /// `Some((dist, id, point))` of the nearest object within `max_dist`, or `None`.
+    pub fn pick_ray_batch(&mut self, system_bounds: Bounds<Index::Point>, rays: &[f32], max_dist: f32, max_depth: Option<u32>,
+                          shapes: PickShapes) -> Vec<Option<(f32, u64, [f32; 3])>> {
+        let nq = rays.len() / (2 * Index::DIM);
+        let (kind, table, width) = match shapes {
+            PickShapes::Spheres(t) => (0, t, Index::DIM + 1),
+            PickShapes::Aabbs(t) => (1, t, 2 * Index::DIM),
+        };
+        let mut res: *const BpPickResult = std::ptr::null();
+        let s = unsafe {
+            bp_layer_pick_ray_batch(self.handle, &system_bounds as *const _ as *const f32, rays.as_ptr(), nq, max_dist,
+                                    max_depth.map_or(-1, |d| d as i32), kind, table.as_ptr(), table.len() / width, 0, &mut res)
+        };
+        self.check(s);
+        unsafe { std::slice::from_raw_parts(res, nq) }.iter().map(|r| if r.hit != 0 { Some((r.dist, r.id, r.point)) } else { None }).collect()
     }
 
     /// src/layer.rs:79-81 (copies the tree back from the device)

@@ -163,12 +163,34 @@ int bp_layer_scan_device(bp_layer *layer, const bp_filter *filter, const void **
  *              1 = device pointers in, device pointers out
  * Result: out_pairs = out_count x {query number, object ID} (two consecutive IDs of id_bytes each), sorted
  * by (query, ID) without duplicates; out_offsets[q] .. out_offsets[q + 1] delimit query q (n_queries + 1
- * entries) -- slice q is exactly the `&Vec<ID>` the reference returns for that geometry.  `pick` / `pick_ray`
- * (src/layer.rs:364-446) take a user closure and are not offered. */
+ * entries) -- slice q is exactly the `&Vec<ID>` the reference returns for that geometry. */
 int bp_layer_test_box_batch(bp_layer *layer, const float *system_bounds, const float *boxes, size_t n_queries, int32_t max_depth,
                             int on_device, const void **out_pairs, const uint32_t **out_offsets, size_t *out_count);
 int bp_layer_test_ray_batch(bp_layer *layer, const float *system_bounds, const float *rays, size_t n_queries, int32_t max_depth,
                             int on_device, const void **out_pairs, const uint32_t **out_offsets, size_t *out_count);
+
+/* Layer::pick_ray -- src/layer.rs:424-446 (through Layer::pick / test_impl, :167-242, 364-408), for a batch of rays:
+ * the nearest object each ray hits within max_dist.  The reference asks a user closure `get_dist(origin, direction,
+ * nearest, id)` for the hit distance of a candidate; a closure cannot cross the ABI, so an enumerated device functor
+ * over a table of shapes indexed by ID stands in (like bp_filter for scan_filtered):
+ *   BP_PICK_SPHERE  shapes = n_shapes x (D + 1) floats (centre.., radius): the ray / sphere distance of the reference's
+ *                   example (examples/main.rs:427-449); 0 when the origin is inside
+ *   BP_PICK_AABB    shapes = n_shapes x 2*D floats (min.., max..): slab test; 0 when the origin is inside
+ * IDs >= n_shapes are never hit.  The walk is the reference's: children in RayTestGeometry::test_order
+ * (src/geom.rs:579-610), cells whose part of the ray starts at or behind the nearest hit so far are skipped, and
+ * between equal distances the ID met first wins.  rays: n_queries x 2*D floats (origin.., direction..);
+ * max_depth < 0 = None; on_device as for the test_* calls (rays, shapes and results).  One bp_pick_result per ray. */
+typedef enum bp_pick_kind { BP_PICK_SPHERE = 0, BP_PICK_AABB = 1 } bp_pick_kind;
+typedef struct bp_pick_result {
+    float dist;     /* Some((dist, id, point)): distance of the nearest hit ... */
+    uint32_t hit;   /* 0 = None */
+    uint64_t id;    /* ... its ID ... */
+    float point[3]; /* ... and origin + direction * dist (point[2] = 0 for the 2-D index types) */
+    uint32_t pad;
+} bp_pick_result;
+int bp_layer_pick_ray_batch(bp_layer *layer, const float *system_bounds, const float *rays, size_t n_queries, float max_dist,
+                            int32_t max_depth, int32_t shape_kind, const float *shapes, size_t n_shapes, int on_device,
+                            const bp_pick_result **out_results);
 
 /* Layer::iter -- src/layer.rs:79-81, and the state PartialEq compares (src/layer.rs:582-585):
  * keys (4 or 8 bytes each) and ids as separate arrays + the sorted flag. */

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstring>
 #include <parallel/algorithm>
+#include <unordered_set>
 #include <utility>
 #include <vector>
 
@@ -351,6 +352,43 @@ template <int DIM> struct RayGeom {
     bool should_test(float nearest) const { return range_min < range_max && range_min < nearest; }
 };
 
+// Distance functors standing in for pick_ray's `get_dist` closure (src/layer.rs:431-436); the same expressions, one
+// IEEE rounding per operation, as csrc/bp_query.cuh PickSphere / PickAabb.  BPO_PICK_SPHERE is the closure of the
+// reference's example (examples/main.rs:427-449); shape = centre.., radius.  BPO_PICK_AABB: slab test, shape = min.., max...
+template <int DIM> inline int shape_width(int kind) { return kind == BPO_PICK_SPHERE ? DIM + 1 : 2 * DIM; }
+template <int DIM> inline float shape_distance(int kind, const float *shape, const float *org, const float *dir) {
+    const float INF = __builtin_inff();
+    if (kind == BPO_PICK_SPHERE) {
+        float proj = 0.f, mag2 = 0.f;
+        for (int i = 0; i < DIM; ++i) {
+            const float b = shape[i] - org[i];
+            const float p = dir[i] * b, m = b * b;
+            proj = i == 0 ? p : proj + p;
+            mag2 = i == 0 ? m : mag2 + m;
+        }
+        const float r = shape[DIM];
+        const float pp = proj * proj, rr = r * r;
+        const float t = pp - mag2;
+        const float ext = __builtin_sqrtf(t + rr);
+        const float lo = proj - ext, hi = proj + ext;
+        if (hi < 0.f) return INF;
+        if (lo < 0.f) return 0.f;
+        return lo;
+    }
+    float t0 = 0.f, t1 = INF;
+    for (int i = 0; i < DIM; ++i) {
+        if (dir[i] != 0.f) {
+            const float na = shape[i] - org[i], nb = shape[DIM + i] - org[i];
+            const float a = na / dir[i], b = nb / dir[i];
+            t0 = f32_max(t0, f32_min(a, b));
+            t1 = f32_min(t1, f32_max(a, b));
+        } else if (org[i] < shape[i] || org[i] > shape[DIM + i]) {
+            return INF;
+        }
+    }
+    return t0 <= t1 ? t0 : INF;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Layer -- src/layer.rs:40-165, 448-573
 // ---------------------------------------------------------------------------------------------
@@ -368,6 +406,8 @@ struct LayerBase {
     virtual void set_records(const uint64_t *keys, const uint64_t *ids, size_t n, bool sorted) = 0;
     virtual size_t test(int ray, const float *sys, const float *params, int max_depth) = 0;
     virtual void test_results_out(uint64_t *ids) const = 0;
+    virtual int pick_ray(const float *sys, const float *ray, float max_dist, int max_depth, int shape_kind, const float *shapes,
+                         size_t n_shapes, float *out, uint64_t *out_id) = 0;
     int kind = 0, id_bytes = 0;
     uint32_t min_depth = 0;
     bool sorted = true; // LayerBuilder::build starts with sorted = true -- src/layer.rs:681
@@ -499,13 +539,13 @@ template <class Ix, class ID> struct LayerT : LayerBase {
 
     // Layer::test_impl -- src/layer.rs:167-242, restated literally (recursion, binary searches, fold order)
     std::vector<ID> test_results;
-    template <class Geom>
-    static float test_impl(const Rec *tree, size_t n, K cell, const Geom &geom, float nearest, int max_depth, std::vector<ID> &results) {
+    template <class Geom, class Callback>
+    static float test_impl(const Rec *tree, size_t n, K cell, const Geom &geom, float nearest, int max_depth, Callback &callback) {
         const int NC = 1 << Ix::DIM;
         if (n == 0 || !geom.should_test(nearest)) return nearest;                         // :180-182
         const uint32_t depth = Ix::depth(cell);
         if (max_depth >= 0 && depth >= (uint32_t)max_depth) {                              // :189-197
-            for (size_t i = 0; i < n; ++i) results.push_back(tree[i].second);              // callback pushes, returns nearest
+            for (size_t i = 0; i < n; ++i) nearest = f32_min(callback(geom, nearest, tree[i].second), nearest); // the fold of :193-196
             return nearest;
         }
         if (depth < (uint32_t)Ix::AXIS_BITS) {                                             // cell.subdivide() -- src/index.rs:251-290
@@ -534,18 +574,18 @@ template <class Ix, class ID> struct LayerT : LayerBase {
             }
             heads[NC] = rest;
             lens[NC] = nrest;
-            for (size_t i = 0; i < lens[0]; ++i) results.push_back(heads[0][i].second);    // :213-217
+            for (size_t i = 0; i < lens[0]; ++i) nearest = f32_min(callback(geom, nearest, heads[0][i].second), nearest); // :213-217
             Geom sub_tests[8];
             geom.subdivide(sub_tests);
             int order[8];
             geom.test_order(order);
             for (int k = 0; k < NC; ++k) {                                                 // :222-230
                 const int i = order[k];
-                nearest = test_impl(heads[i + 1], lens[i + 1], sub_cells[i], sub_tests[i], nearest, max_depth, results);
+                nearest = test_impl(heads[i + 1], lens[i + 1], sub_cells[i], sub_tests[i], nearest, max_depth, callback);
             }
             return nearest;
         }
-        for (size_t i = 0; i < n; ++i) results.push_back(tree[i].second);                  // :236-240
+        for (size_t i = 0; i < n; ++i) nearest = f32_min(callback(geom, nearest, tree[i].second), nearest); // :236-240
         return nearest;
     }
 
@@ -553,17 +593,59 @@ template <class Ix, class ID> struct LayerT : LayerBase {
     size_t test(int ray, const float *sys, const float *params, int max_depth) override {
         sort(false);
         test_results.clear();
+        std::vector<ID> &results = test_results;
         if (ray) {
             const RayGeom<Ix::DIM> g = RayGeom<Ix::DIM>::make(sys, params);
-            test_impl(tree.data(), tree.size(), (K)0, g, __builtin_inff(), max_depth, test_results);
+            auto cb = [&results](const RayGeom<Ix::DIM> &, float nearest, ID id) { results.push_back(id); return nearest; }; // :267-270
+            test_impl(tree.data(), tree.size(), (K)0, g, __builtin_inff(), max_depth, cb);
         } else {
             const BoxGeom<Ix::DIM> g = BoxGeom<Ix::DIM>::make(sys, params);
-            test_impl(tree.data(), tree.size(), (K)0, g, __builtin_inff(), max_depth, test_results);
+            auto cb = [&results](const BoxGeom<Ix::DIM> &, float nearest, ID id) { results.push_back(id); return nearest; };
+            test_impl(tree.data(), tree.size(), (K)0, g, __builtin_inff(), max_depth, cb);
         }
         std::sort(test_results.begin(), test_results.end());
         test_results.erase(std::unique(test_results.begin(), test_results.end()), test_results.end());
         return test_results.size();
     }
+    // Layer::pick -- src/layer.rs:364-408 and pick_ray -- :424-446, with the user's get_dist closure replaced by one of
+    // the enumerated shape functors (a table of shapes indexed by ID; IDs past the table never hit).
+    // out = {dist, point[DIM]}; returns 1 and *out_id if something was hit.
+    int pick_ray(const float *sys, const float *ray, float max_dist, int max_depth, int shape_kind, const float *shapes, size_t n_shapes,
+                 float *out, uint64_t *out_id) override {
+        const int DIM = Ix::DIM;
+        sort(false);                                                                        // :375
+        float params[2 * 3 + 2];
+        for (int i = 0; i < 2 * DIM; ++i) params[i] = ray[i];
+        params[2 * DIM] = 0.0f;                                                             // with_system_bounds(.., 0f32, max_dist) -- :437-442
+        params[2 * DIM + 1] = max_dist;
+        const RayGeom<DIM> g = RayGeom<DIM>::make(sys, params);
+        std::unordered_set<uint64_t> processed;                                             // :377, :384
+        bool have = false;
+        ID result = 0;
+        auto cb = [&](const RayGeom<DIM> &, float nearest, ID id) -> float {                // :383-399
+            if (!processed.insert((uint64_t)id).second) return __builtin_inff();
+            const float dist = (uint64_t)id < n_shapes ? shape_distance<DIM>(shape_kind, shapes + (size_t)id * shape_width<DIM>(shape_kind), ray, ray + DIM)
+                                                       : __builtin_inff();
+            if (is_finite_f32(dist)) {
+                if (dist < nearest) {
+                    result = id;
+                    have = true;
+                }
+                return dist;
+            }
+            return __builtin_inff();
+        };
+        const float dist = test_impl(tree.data(), tree.size(), (K)0, g, max_dist, max_depth, cb);
+        if (!have) return 0;
+        out[0] = dist;
+        for (int i = 0; i < DIM; ++i) {                                                     // origin + direction * dist -- :443-446
+            const float m = ray[DIM + i] * dist;
+            out[1 + i] = ray[i] + m;
+        }
+        *out_id = (uint64_t)result;
+        return 1;
+    }
+
     void test_results_out(uint64_t *ids) const override {
         for (size_t i = 0; i < test_results.size(); ++i) ids[i] = (uint64_t)test_results[i];
     }
@@ -704,6 +786,10 @@ void bpo_to_global(int dim, const float *sys, const uint32_t *local, float *out)
 size_t bpo_layer_test_box(bpo_layer *l, const float *sys, const float *box, int max_depth) { return l->impl->test(0, sys, box, max_depth); }
 size_t bpo_layer_test_ray(bpo_layer *l, const float *sys, const float *ray, int max_depth) { return l->impl->test(1, sys, ray, max_depth); }
 void bpo_layer_test_results(const bpo_layer *l, uint64_t *ids) { l->impl->test_results_out(ids); }
+int bpo_layer_pick_ray(bpo_layer *l, const float *sys, const float *ray, float max_dist, int max_depth, int shape_kind, const float *shapes,
+                       size_t n_shapes, float *out, uint64_t *out_id) {
+    return l->impl->pick_ray(sys, ray, max_dist, max_depth, shape_kind, shapes, n_shapes, out, out_id);
+}
 
 int bpo_max_threads(void) { return omp_get_max_threads(); }
 void bpo_set_threads(int n) { omp_set_num_threads(n); }

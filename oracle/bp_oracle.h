@@ -65,6 +65,12 @@ void bpo_layer_set_records(bpo_layer *, const uint64_t *keys, const uint64_t *id
 size_t bpo_layer_test_box(bpo_layer *, const float *sys_bounds, const float *box, int max_depth);
 size_t bpo_layer_test_ray(bpo_layer *, const float *sys_bounds, const float *ray, int max_depth);
 void bpo_layer_test_results(const bpo_layer *, uint64_t *ids);
+/* Layer::pick_ray (src/layer.rs:424-446) for one ray (2*D floats: origin.., direction..) with an enumerated shape functor
+ * in place of the get_dist closure: shapes = n_shapes x (D + 1) floats (centre.., radius) for BPO_PICK_SPHERE, n_shapes x
+ * 2*D floats (min.., max..) for BPO_PICK_AABB, indexed by ID.  Returns 1 on a hit: out = {dist, point[D]}, *out_id. */
+enum { BPO_PICK_SPHERE = 0, BPO_PICK_AABB = 1 };
+int bpo_layer_pick_ray(bpo_layer *, const float *sys_bounds, const float *ray, float max_dist, int max_depth, int shape_kind,
+                       const float *shapes, size_t n_shapes, float *out, uint64_t *out_id);
 
 /* codec + quantiser, exposed for the known-answer tests */
 uint64_t bpo_encode_axis(int kind, uint32_t v);

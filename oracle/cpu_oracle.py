@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libbp_oracle.so")
 
 INDEX32_2D, INDEX64_2D, INDEX64_3D = 0, 1, 2
+PICK_SPHERE, PICK_AABB = 0, 1
 FILTER_NONE, FILTER_ID_PARITY, FILTER_XOR_MASK, FILTER_CATEGORY = 0, 1, 2, 3
 DIM = {INDEX32_2D: 2, INDEX64_2D: 2, INDEX64_3D: 3}
 
@@ -56,6 +57,7 @@ def lib():
         "bpo_layer_test_box": (sz, [vp, vp, vp, i32]),
         "bpo_layer_test_ray": (sz, [vp, vp, vp, i32]),
         "bpo_layer_test_results": (None, [vp, vp]),
+        "bpo_layer_pick_ray": (i32, [vp, vp, vp, ctypes.c_float, i32, i32, vp, sz, vp, vp]),
         "bpo_encode_axis": (u64, [i32, u32]),
         "bpo_decode_axis": (u32, [i32, u64]),
         "bpo_make_index": (u64, [i32, u32, vp]),
@@ -169,6 +171,18 @@ class OracleLayer:
         ray = np.concatenate([np.asarray(origin, dtype=np.float32).reshape(-1), np.asarray(direction, dtype=np.float32).reshape(-1),
                               np.asarray([range_min, range_max], dtype=np.float32)])
         return self._test(lib().bpo_layer_test_ray, system_bounds, ray, max_depth)
+
+    def pick_ray(self, system_bounds, origin, direction, max_dist, shape_kind, shapes, max_depth=None):
+        """Layer::pick_ray (src/layer.rs:424-446) with a shape functor for get_dist: None or (dist, id, point)."""
+        sysb = np.ascontiguousarray(system_bounds, dtype=np.float32)
+        ray = np.concatenate([np.asarray(origin, dtype=np.float32).reshape(-1), np.asarray(direction, dtype=np.float32).reshape(-1)])
+        sh = np.ascontiguousarray(shapes, dtype=np.float32)
+        dim = ray.shape[0] // 2
+        out = np.zeros(1 + dim, dtype=np.float32)
+        oid = np.zeros(1, dtype=np.uint64)
+        hit = lib().bpo_layer_pick_ray(self._h, _ptr(sysb), _ptr(ray), float(max_dist), -1 if max_depth is None else int(max_depth),
+                                       int(shape_kind), _ptr(sh), sh.shape[0], _ptr(out), _ptr(oid))
+        return (float(out[0]), int(oid[0]), out[1:].copy()) if hit else None
 
     def collisions(self):
         n = lib().bpo_layer_num_collisions(self._h)

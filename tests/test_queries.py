@@ -98,6 +98,99 @@ def test_empty_layer_and_results_are_sorted_unique():
     assert (np.diff(r.astype(np.int64)) > 0).all() and r.shape[0] == np.unique(ids).shape[0]
 
 
+# ---- pick_ray ---------------------------------------------------------------------------------------------------
+
+def _sphere_dist(shape, org, d):
+    """PICK_SPHERE in numpy float32, the same operations in the same order as oracle/bp_oracle.cpp shape_distance."""
+    f = np.float32
+    dim = org.shape[0]
+    b = (shape[:dim] - org).astype(f)
+    p, m = (d * b).astype(f), (b * b).astype(f)
+    proj, mag2 = p[0], m[0]
+    for i in range(1, dim):
+        proj, mag2 = f(proj + p[i]), f(mag2 + m[i])
+    with np.errstate(invalid="ignore"):
+        ext = np.sqrt(f(f(f(proj * proj) - mag2) + f(shape[dim] * shape[dim])), dtype=f)
+    lo, hi = f(proj - ext), f(proj + ext)
+    if hi < 0:
+        return f(np.inf)
+    if lo < 0:
+        return f(0)
+    return lo if np.isfinite(lo) else f(np.inf)
+
+
+def _pick_scene(kind, n, seed):
+    """Disjoint IDs (one bound each); spheres inscribed in the bounds, so a hit point always lies inside the object's cells."""
+    dim = co.DIM[kind]
+    sysb, bounds, _ = _scene(kind, n, seed, span=0.04)
+    bounds = bounds[3:]                                   # (drop the scene-sized objects: their inscribed spheres hide everything)
+    ids = np.arange(bounds.shape[0], dtype=np.uint32)
+    centre = ((bounds[:, :dim] + bounds[:, dim:]) * np.float32(0.5)).astype(np.float32)
+    radius = ((bounds[:, dim:] - bounds[:, :dim]).min(axis=1) * np.float32(0.5)).astype(np.float32)
+    spheres = np.concatenate([centre, radius[:, None]], axis=1).astype(np.float32)
+    return sysb, bounds, ids, spheres
+
+
+def _pick_rays(dim, nq, seed, targets=None):
+    """Rays from random origins; two thirds of them aimed at an object's centre (something gets hit on the way)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    org = (-3.0 + rng.random((nq, dim)) * 8.0).astype(np.float32)
+    d = rng.normal(size=(nq, dim)).astype(np.float32)
+    if targets is not None:
+        aim = targets[rng.integers(0, targets.shape[0], size=nq)] - org
+        sel = np.arange(nq) % 3 != 0
+        d[sel] = aim[sel]
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    d[0, :] = 0.0
+    d[0, 0] = 1.0                                          # axis-parallel
+    return np.concatenate([org, d.astype(np.float32)], axis=1).astype(np.float32)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("max_dist", [np.inf, 4.0])
+def test_oracle_pick_ray_is_the_minimum_over_the_ray_test(kind, max_dist):
+    """pick_ray's pruning must not change the answer: the distance equals the minimum of get_dist over everything
+    test_ray(0, max_dist) reports (independent closed form, pyref), and the ID is one that attains it."""
+    dim = co.DIM[kind]
+    sysb, bounds, ids, spheres = _pick_scene(kind, 1500, 40 + kind)
+    o = co.OracleLayer(kind, 4, 0)
+    o.extend(sysb, bounds, ids)
+    o.sort()
+    keys, rids = o.records()
+    hits = 0
+    for ray in _pick_rays(dim, 60, 50 + kind, spheres[:, :dim]):
+        org, d = ray[:dim], ray[dim:]
+        got = o.pick_ray(sysb, org, d, max_dist, co.PICK_SPHERE, spheres)
+        cand = pyref.test_ray(kind, keys, rids, sysb, org, d, 0.0, max_dist)
+        dists = np.array([_sphere_dist(spheres[int(c)], org, d) for c in cand], dtype=np.float32)
+        best = dists.min() if dists.size else np.float32(np.inf)
+        if not (best < np.float32(max_dist)):
+            assert got is None
+            continue
+        hits += 1
+        assert got is not None and np.float32(got[0]) == best
+        assert got[1] in set(int(c) for c in cand[dists == best])
+        assert (got[2] == (org + d * np.float32(got[0])).astype(np.float32)).all()
+    assert hits > (5 if np.isinf(max_dist) else 0)
+
+
+def test_oracle_pick_ray_aabb_and_ties():
+    """Two identical boxes: the one met first in the walk (smaller ID in the same cell) wins the tie; the slab distance
+    is the entry distance, 0 from inside, None when the ray points away."""
+    sysb = SYS[3]
+    b = np.array([[0, 0, 0, 1, 1, 1], [0, 0, 0, 1, 1, 1], [2, 0, 0, 3, 1, 1]], dtype=np.float32)
+    o = co.OracleLayer(2, 4, 0)
+    o.extend(sysb, b, np.array([5, 4, 9], dtype=np.uint32))
+    shapes = np.zeros((10, 6), dtype=np.float32)
+    shapes[[5, 4, 9]] = b
+    got = o.pick_ray(sysb, [-1, 0.5, 0.5], [1, 0, 0], np.inf, co.PICK_AABB, shapes)
+    assert got is not None and got[0] == 1.0 and got[1] == 4 and got[2].tolist() == [0.0, 0.5, 0.5]
+    assert o.pick_ray(sysb, [0.5, 0.5, 0.5], [1, 0, 0], np.inf, co.PICK_AABB, shapes)[0] == 0.0
+    assert o.pick_ray(sysb, [1.5, 0.5, 0.5], [1, 0, 0], np.inf, co.PICK_AABB, shapes)[1] == 9
+    assert o.pick_ray(sysb, [4, 0.5, 0.5], [1, 0, 0], np.inf, co.PICK_AABB, shapes) is None
+    assert o.pick_ray(sysb, [-1, 0.5, 0.5], [1, 0, 0], 0.5, co.PICK_AABB, shapes) is None      # max_dist
+
+
 # ---- GPU ------------------------------------------------------------------------------------------------------
 
 @pytest.mark.gpu
@@ -152,3 +245,33 @@ def test_gpu_queries_after_a_scan_and_edge_cases(bp):
     assert ray.shape[0] > 0 and (ray.astype(np.uint64) == want).all()
     # the scan still works afterwards and returns the same pairs
     assert (g.par_scan() == pairs).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("id_bytes", [4, 8])
+@pytest.mark.parametrize("shape_kind", [0, 1])
+def test_gpu_pick_ray_matches_the_oracle(bp, kind, id_bytes, shape_kind):
+    dim = co.DIM[kind]
+    sysb, bounds, ids, spheres = _pick_scene(kind, 5000, 60 + kind)
+    shapes = spheres if shape_kind == bp.PICK_SPHERE else bounds     # (IDs are 0..n-1 here, so the table rows line up)
+    g = bp.LayerBuilder().build(kind, "u32" if id_bytes == 4 else "u64")
+    o = co.OracleLayer(kind, id_bytes, 0)
+    g.extend(sysb, bounds, ids.astype(np.uint64 if id_bytes == 8 else np.uint32))
+    o.extend(sysb, bounds, ids.astype(np.uint64 if id_bytes == 8 else np.uint32))
+    rays = _pick_rays(dim, 300, 70 + kind, spheres[:, :dim])
+    for max_dist, max_depth in ((np.inf, None), (2.0, None), (np.inf, 5)):
+        res = g.pick_ray_batch(sysb, rays, max_dist, shape_kind, shapes, max_depth)
+        nhit = 0
+        for q in range(rays.shape[0]):
+            want = o.pick_ray(sysb, rays[q, :dim], rays[q, dim:], max_dist, shape_kind, shapes, max_depth)
+            if want is None:
+                assert res[q]["hit"] == 0, q
+                continue
+            nhit += 1
+            assert res[q]["hit"] == 1 and np.float32(res[q]["dist"]) == np.float32(want[0]) and int(res[q]["id"]) == want[1], q
+            assert (res[q]["point"][:dim] == want[2]).all(), q
+        assert nhit > (10 if np.isinf(max_dist) else 0)
+    single = g.pick_ray(sysb, rays[3, :dim], rays[3, dim:], np.inf, shape_kind, shapes)
+    want = o.pick_ray(sysb, rays[3, :dim], rays[3, dim:], np.inf, shape_kind, shapes)
+    assert (single is None) == (want is None) and (single is None or (single[0] == want[0] and single[1] == want[1]))
