@@ -61,6 +61,11 @@ struct Filter {
     static Filter category(const uint32_t *table, size_t n, bool on_device = false) {
         Filter r; r.f.kind = BP_FILTER_CATEGORY; r.f.table = table; r.f.n_table = n; r.f.table_on_device = on_device; return r;
     }
+    // fused narrow phase: table = n x {x, y, z, r} floats indexed by ID; only pairs whose spheres touch pass
+    static Filter spheres(const float *table, size_t n, bool on_device = false) {
+        Filter r; r.f.kind = BP_FILTER_SPHERES; r.f.table = reinterpret_cast<const uint32_t *>(table); r.f.n_table = n;
+        r.f.table_on_device = on_device; return r;
+    }
 };
 
 // a borrowed view of the layer's result buffer (the reference returns &Vec<(ID, ID)>)

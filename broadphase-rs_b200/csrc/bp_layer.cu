@@ -700,6 +700,7 @@ template <int KIND, class IdT> struct Impl {
         case BP_FILTER_ID_PARITY: TRY((launch_emit<BP_FILTER_ID_PARITY, DEDUP>(L, a, chunks, bytes))); break;
         case BP_FILTER_XOR_MASK: TRY((launch_emit<BP_FILTER_XOR_MASK, DEDUP>(L, a, chunks, bytes))); break;
         case BP_FILTER_CATEGORY: TRY((launch_emit<BP_FILTER_CATEGORY, DEDUP>(L, a, chunks, bytes))); break;
+        case BP_FILTER_SPHERES: TRY((launch_emit<BP_FILTER_SPHERES, DEDUP>(L, a, chunks, bytes))); break;
         default: return fail(L, BP_ERR_INVALID_ARG, "unknown filter kind %d", fk);
         }
         return check_launch(L, "scan_emit_kernel");
@@ -731,14 +732,16 @@ template <int KIND, class IdT> struct Impl {
         fa.arg = f ? f->arg : 0;
         fa.table = nullptr;
         fa.n_table = 0;
-        if (fk == BP_FILTER_CATEGORY) {
-            if (!f->table && f->n_table) return fail(L, BP_ERR_INVALID_ARG, "category filter without a table");
+        if (fk == BP_FILTER_CATEGORY || fk == BP_FILTER_SPHERES) {
+            if (!f->table && f->n_table) return fail(L, BP_ERR_INVALID_ARG, "table filter without a table");
+            const size_t row = fk == BP_FILTER_CATEGORY ? 8 : 16; // {cat, msk} or {x, y, z, r}
             fa.n_table = f->n_table;
             if (f->table_on_device) {
+                if (fk == BP_FILTER_SPHERES && ((uintptr_t)f->table & 15u)) return fail(L, BP_ERR_INVALID_ARG, "the sphere table must be 16-byte aligned");
                 fa.table = f->table;
             } else if (f->n_table) {
-                TRY(ensure(L, L->filter_table, f->n_table * 8));
-                CU(L, cudaMemcpyAsync(L->filter_table.p, f->table, f->n_table * 8, cudaMemcpyHostToDevice, L->stream));
+                TRY(ensure(L, L->filter_table, f->n_table * row));
+                CU(L, cudaMemcpyAsync(L->filter_table.p, f->table, f->n_table * row, cudaMemcpyHostToDevice, L->stream));
                 fa.table = (const uint32_t *)L->filter_table.p;
             }
         }

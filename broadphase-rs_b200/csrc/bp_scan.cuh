@@ -67,6 +67,16 @@ template <> struct FilterFn<BP_FILTER_CATEGORY> {
     }
 };
 
+template <> struct FilterFn<BP_FILTER_SPHERES> { // the narrow phase of examples/main.rs:461-479, one IEEE rounding per operation
+    template <class IdT> __device__ __forceinline__ static bool pass(const FilterArgs &f, IdT a, IdT b) {
+        if ((uint64_t)a >= f.n_table || (uint64_t)b >= f.n_table) return true;
+        const float4 sa = __ldg((const float4 *)f.table + (uint64_t)a), sb = __ldg((const float4 *)f.table + (uint64_t)b);
+        const float dx = __fsub_rn(sb.x, sa.x), dy = __fsub_rn(sb.y, sa.y), dz = __fsub_rn(sb.z, sa.z); // offset = pos1 - pos0
+        const float m = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+        return !(__fsqrt_rn(m) > __fadd_rn(sa.w, sb.w)); // `if dist > dist_min { None }`
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // scan_runs_kernel
 // ---------------------------------------------------------------------------------------------

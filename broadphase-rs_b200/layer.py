@@ -19,7 +19,7 @@ Index32_2D, Index64_2D, Index64_3D = 0, 1, 2
 INDEX_DIM = {Index32_2D: 2, Index64_2D: 2, Index64_3D: 3}
 INDEX_KEY_DTYPE = {Index32_2D: np.uint32, Index64_2D: np.uint64, Index64_3D: np.uint64}
 
-FILTER_NONE, FILTER_ID_PARITY, FILTER_XOR_MASK, FILTER_CATEGORY = 0, 1, 2, 3
+FILTER_NONE, FILTER_ID_PARITY, FILTER_XOR_MASK, FILTER_CATEGORY, FILTER_SPHERES = 0, 1, 2, 3, 4
 PICK_SPHERE, PICK_AABB = 0, 1
 
 
@@ -28,7 +28,12 @@ class ScanFilter:
 
     def __init__(self, kind=FILTER_NONE, arg=0, table=None):
         self.kind, self.arg = kind, arg
-        self.table = None if table is None else np.ascontiguousarray(table, dtype=np.uint32).reshape(-1, 2)
+        if table is None:
+            self.table = None
+        elif kind == FILTER_SPHERES:   # rows of {x, y, z, r}
+            self.table = np.ascontiguousarray(table, dtype=np.float32).reshape(-1, 4)
+        else:                          # rows of {cat, msk}
+            self.table = np.ascontiguousarray(table, dtype=np.uint32).reshape(-1, 2)
 
     @staticmethod
     def none():
@@ -45,6 +50,11 @@ class ScanFilter:
     @staticmethod
     def category(table):
         return ScanFilter(FILTER_CATEGORY, 0, table)
+
+    @staticmethod
+    def spheres(table):
+        """Fused narrow phase: only pairs whose spheres (rows {x, y, z, r} indexed by ID) touch pass."""
+        return ScanFilter(FILTER_SPHERES, 0, table)
 
     def _c(self):
         f = Filter()

@@ -107,6 +107,8 @@ pub enum Filter<'a> {
     IdParity,
     XorMask(u64),
     Category(&'a [[u32; 2]]),
+    /// fused narrow phase: `[x, y, z, r]` per ID; only pairs whose spheres touch pass (examples/main.rs:461-479)
+    Spheres(&'a [[f32; 4]]),
 }
 
 pub struct Layer<Index: SpatialIndex, ID: ObjectID> {
@@ -170,6 +172,7 @@ impl<Index: SpatialIndex, ID: ObjectID> Layer<Index, ID> {
             Filter::IdParity => BpFilter { kind: 1, table_on_device: 0, arg: 0, table: std::ptr::null(), n_table: 0 },
             Filter::XorMask(m) => BpFilter { kind: 2, table_on_device: 0, arg: m, table: std::ptr::null(), n_table: 0 },
             Filter::Category(t) => BpFilter { kind: 3, table_on_device: 0, arg: 0, table: t.as_ptr() as *const u32, n_table: t.len() },
+            Filter::Spheres(t) => BpFilter { kind: 4, table_on_device: 0, arg: 0, table: t.as_ptr() as *const u32, n_table: t.len() },
         };
         let mut pairs: *const c_void = std::ptr::null();
         let mut n: usize = 0;

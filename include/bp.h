@@ -56,8 +56,13 @@ typedef enum bp_filter_kind {
     BP_FILTER_NONE = 0,      /* |_, _| true  (scan / par_scan) */
     BP_FILTER_ID_PARITY = 1, /* ((a ^ b) & 1) == 1 */
     BP_FILTER_XOR_MASK = 2,  /* ((a ^ b) & arg) != 0 */
-    BP_FILTER_CATEGORY = 3   /* (cat[a] & msk[b]) != 0 && (cat[b] & msk[a]) != 0; table = n_table x {u32 cat, u32 msk}
+    BP_FILTER_CATEGORY = 3,  /* (cat[a] & msk[b]) != 0 && (cat[b] & msk[a]) != 0; table = n_table x {u32 cat, u32 msk}
                                 indexed by ID; IDs >= n_table act as all-ones */
+    BP_FILTER_SPHERES = 4    /* fused narrow phase: the pair test of the reference's example,
+                                examples/main.rs:461-479, `!(|c[b] - c[a]| > r[a] + r[b])`, as the scan filter, so that only
+                                touching spheres leave the device.  table = n_table x {f32 x, y, z, r} indexed by ID (z = 0
+                                for the 2-D index types; the same 4 bytes per entry, passed through the u32 pointer);
+                                IDs >= n_table pass */
 } bp_filter_kind;
 
 typedef struct bp_filter {

@@ -215,6 +215,16 @@ struct Filter {
             if (b < n_table) { cb = table[2 * b]; mb = table[2 * b + 1]; }
             return (ca & mb) != 0 && (cb & ma) != 0;
         }
+        case BPO_FILTER_SPHERES: { // the narrow phase of examples/main.rs:461-479; table = n_table x {f32 x, y, z, r}
+            if (a >= n_table || b >= n_table) return true;
+            const float *sa = (const float *)table + 4 * a, *sb = (const float *)table + 4 * b;
+            const float dx = sb[0] - sa[0], dy = sb[1] - sa[1], dz = sb[2] - sa[2];
+            const float xx = dx * dx, yy = dy * dy, zz = dz * dz;
+            const float xy = xx + yy;
+            const float m = xy + zz;
+            const float dist = __builtin_sqrtf(m), dist_min = sa[3] + sb[3];
+            return !(dist > dist_min);
+        }
         default: return true;
         }
     }

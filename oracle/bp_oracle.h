@@ -30,8 +30,10 @@ enum {
     BPO_FILTER_NONE = 0,      /* |_, _| true                                  */
     BPO_FILTER_ID_PARITY = 1, /* ((a ^ b) & 1) == 1                           */
     BPO_FILTER_XOR_MASK = 2,  /* ((a ^ b) & arg) != 0                         */
-    BPO_FILTER_CATEGORY = 3   /* (cat[a] & msk[b]) != 0 && (cat[b] & msk[a]) != 0,
+    BPO_FILTER_CATEGORY = 3,  /* (cat[a] & msk[b]) != 0 && (cat[b] & msk[a]) != 0,
                                  table = n_table x {u32 cat, u32 msk}; ids >= n_table act as all-ones */
+    BPO_FILTER_SPHERES = 4    /* !(|c[b] - c[a]| > r[a] + r[b]), table = n_table x {f32 x, y, z, r} (16 bytes per ID, passed
+                                 through the u32 pointer); ids >= n_table pass */
 };
 
 typedef struct bpo_layer bpo_layer;

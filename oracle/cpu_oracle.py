@@ -14,7 +14,7 @@ _SO = os.path.join(_HERE, "libbp_oracle.so")
 
 INDEX32_2D, INDEX64_2D, INDEX64_3D = 0, 1, 2
 PICK_SPHERE, PICK_AABB = 0, 1
-FILTER_NONE, FILTER_ID_PARITY, FILTER_XOR_MASK, FILTER_CATEGORY = 0, 1, 2, 3
+FILTER_NONE, FILTER_ID_PARITY, FILTER_XOR_MASK, FILTER_CATEGORY, FILTER_SPHERES = 0, 1, 2, 3, 4
 DIM = {INDEX32_2D: 2, INDEX64_2D: 2, INDEX64_3D: 3}
 
 _lib = None
@@ -115,7 +115,12 @@ class OracleLayer:
         lib().bpo_layer_par_sort(self._h)
 
     def _scan(self, fn, filter_kind, filter_arg, table):
-        t = None if table is None else np.ascontiguousarray(table, dtype=np.uint32).reshape(-1, 2)
+        if table is None:
+            t = None
+        elif filter_kind == FILTER_SPHERES:
+            t = np.ascontiguousarray(table, dtype=np.float32).reshape(-1, 4)
+        else:
+            t = np.ascontiguousarray(table, dtype=np.uint32).reshape(-1, 2)
         fn(self._h, filter_kind, filter_arg, None if t is None else _ptr(t), 0 if t is None else t.shape[0])
         return self.collisions()
 

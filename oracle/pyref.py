@@ -21,7 +21,7 @@ KINDS = {
 }
 INDEX32_2D, INDEX64_2D, INDEX64_3D = 0, 1, 2
 
-FILTER_NONE, FILTER_ID_PARITY, FILTER_XOR_MASK, FILTER_CATEGORY = 0, 1, 2, 3
+FILTER_NONE, FILTER_ID_PARITY, FILTER_XOR_MASK, FILTER_CATEGORY, FILTER_SPHERES = 0, 1, 2, 3, 4
 
 RANGE = np.float32(4294967040.0)  # 0xffff_ff00 as f32 -- src/geom.rs:152-154
 
@@ -198,6 +198,15 @@ def _filter(kind, arg, table, a, b):
             out[inr] = table[x[inr].astype(np.int64), col]
             return out
         return ((look(a, 0) & look(b, 1)) != 0) & ((look(b, 0) & look(a, 1)) != 0)
+    if kind == FILTER_SPHERES:  # the narrow phase of examples/main.rs:461-479 in float32, one rounding per operation
+        t = np.asarray(table, dtype=np.float32).reshape(-1, 4)
+        n = t.shape[0]
+        inr = (a < n) & (b < n)
+        ia, ib = np.where(inr, a, 0).astype(np.int64), np.where(inr, b, 0).astype(np.int64)
+        d = (t[ib, :3] - t[ia, :3]).astype(np.float32)
+        sq = (d * d).astype(np.float32)
+        m = ((sq[:, 0] + sq[:, 1]).astype(np.float32) + sq[:, 2]).astype(np.float32)
+        return ~inr | ~(np.sqrt(m, dtype=np.float32) > (t[ia, 3] + t[ib, 3]).astype(np.float32))
     raise ValueError(kind)
 
 

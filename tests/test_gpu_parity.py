@@ -93,7 +93,12 @@ def test_filters(bp, kind):
     o.extend(sysb, bounds, ids)
     rng = np.random.Generator(np.random.Philox(5))
     table = rng.integers(0, 16, size=(3000, 2)).astype(np.uint32)  # ids >= 3000 act as all-ones
+    dim = co.DIM[kind]                                               # spheres around the objects (fused narrow phase)
+    spheres = np.zeros((3500, 4), dtype=np.float32)
+    spheres[ids[ids < 3500], :dim] = ((bounds[:, :dim] + bounds[:, dim:]) * np.float32(0.5))[ids < 3500]
+    spheres[ids[ids < 3500], 3] = ((bounds[:, dim:] - bounds[:, :dim]).max(axis=1) * np.float32(0.45))[ids < 3500]
     for gf, of in [(bp.ScanFilter.id_parity(), (co.FILTER_ID_PARITY, 0, None)),
+                   (bp.ScanFilter.spheres(spheres), (co.FILTER_SPHERES, 0, spheres)),
                    (bp.ScanFilter.xor_mask(6), (co.FILTER_XOR_MASK, 6, None)),
                    (bp.ScanFilter.category(table), (co.FILTER_CATEGORY, 0, table)),
                    (None, (co.FILTER_NONE, 0, None))]:

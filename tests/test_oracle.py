@@ -178,6 +178,26 @@ def test_category_filter():
     assert got.shape == want.shape and (got == want).all() and got.shape[0] > 0
 
 
+def test_sphere_filter_is_the_narrow_phase():
+    """FILTER_SPHERES = the pair test of the reference's example (examples/main.rs:461-479) as the scan filter: oracle vs
+    pyref, and against the plain scan post-filtered the way the example does it."""
+    sysb, bounds, ids = _random_scene(2, 3000, 11, False, span=0.1)
+    centre = ((bounds[:, :3] + bounds[:, 3:]) * np.float32(0.5)).astype(np.float32)
+    radius = ((bounds[:, 3:] - bounds[:, :3]).max(axis=1) * np.float32(0.5)).astype(np.float32)
+    table = np.zeros((int(ids.max()) + 1, 4), dtype=np.float32)
+    table[ids] = np.concatenate([centre, radius[:, None]], axis=1)
+    table = table[:2500]                                    # ids >= 2500 pass unconditionally
+    L = co.OracleLayer(2, 4, 0)
+    L.extend(sysb, bounds, ids)
+    got = L.scan(co.FILTER_SPHERES, 0, table)
+    k, i = L.records()
+    want, _ = pyref.scan(2, k, i, pyref.FILTER_SPHERES, 0, table)
+    assert got.shape == want.shape and (got == want).all()
+    every = L.scan()
+    keep = pyref._filter(pyref.FILTER_SPHERES, 0, table, every[:, 0], every[:, 1])
+    assert (every[keep] == got).all() and 0 < got.shape[0] < every.shape[0]
+
+
 def test_u64_ids_and_merge():
     sysb, bounds, ids = _random_scene(2, 1500, 9, True, span=0.1)
     big = ids.astype(np.uint64) * np.uint64(0x1_0000_0001) + np.uint64(1 << 40)
