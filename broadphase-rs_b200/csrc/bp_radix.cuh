@@ -167,6 +167,34 @@ __device__ __forceinline__ unsigned match_digit(uint32_t d) {
 
 constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_INC = 2u << 30, RS_VALUE_MASK = (1u << 30) - 1;
 
+// One round of the per-digit look-back: B predecessor tiles t, t-1, .. of digit `tid`, loaded together.
+template <int B>
+__device__ __forceinline__ void lookback_round(const uint32_t *status, unsigned tid, int64_t &t, uint32_t &excl, bool &done, int *err) {
+    uint32_t sv[B];
+#pragma unroll
+    for (int b = 0; b < B; ++b) sv[b] = (t - b >= 0) ? ld_volatile_u32(status + (size_t)(t - b) * RADIX + tid) : RS_FLAG_INC;
+#pragma unroll
+    for (int b = 0; b < B; ++b) {
+        if (done) break;
+        uint32_t sb = sv[b];
+        if ((sb >> 30) == 0) { // not published yet: poll this one
+            const uint32_t *ps = status + (size_t)(t - b) * RADIX + tid;
+            uint32_t spins = 0;
+            do {
+                if (++spins > BP_SPIN_LIMIT) {
+                    *err = 1;
+                    sb = RS_FLAG_INC;
+                    break;
+                }
+                sb = ld_volatile_u32(ps);
+            } while ((sb >> 30) == 0);
+        }
+        excl += sb & RS_VALUE_MASK;
+        if ((sb >> 30) == 2) done = true;
+    }
+    t -= B;
+}
+
 template <class K, class V, int THREADS, int ITEMS> struct RadixPassCfg {
     static constexpr bool HAS_V = !std::is_same<V, NoVal>::value;
     static constexpr int TILE = THREADS * ITEMS;
@@ -300,39 +328,17 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
         if (tile != 0) {
             uint32_t count = count_full;
             if (!FULL && tid == dmax) count -= (uint32_t)(TILE - tile_n);
-            // Walk back over the predecessors LB_BATCH tiles at a time: the status loads of one batch are
+            // Walk back over the predecessors a batch of tiles at a time: the status loads of one batch are
             // independent, so a batch costs one L2 round trip.  The batch size sets how fast the first
             // wave of tiles (none of which has an inclusive prefix to offer yet) resolves: about
-            // tile / (2 * LB_BATCH) round trips for tile number `tile`.
-            constexpr int LB_BATCH = 16;
+            // tile / (2 * LB_BATCH) round trips for tile number `tile`.  In the steady state an inclusive prefix
+            // sits a few tiles back, so the first batch is short (the look-back loads were 12 % of the kernel's
+            // instructions, profiles/r1_cfg3_sort_pass.txt).
+            constexpr int LB_FIRST = 4, LB_BATCH = 16;
             int64_t t = (int64_t)tile - 1;
             bool done = false;
-            while (!done && t >= 0) {
-                uint32_t sv[LB_BATCH];
-#pragma unroll
-                for (int b = 0; b < LB_BATCH; ++b)
-                    sv[b] = (t - b >= 0) ? ld_volatile_u32(a.status + (size_t)(t - b) * RADIX + tid) : RS_FLAG_INC;
-#pragma unroll
-                for (int b = 0; b < LB_BATCH; ++b) {
-                    if (done) break;
-                    uint32_t sb = sv[b];
-                    if ((sb >> 30) == 0) { // not published yet: poll this one
-                        const uint32_t *ps = a.status + (size_t)(t - b) * RADIX + tid;
-                        uint32_t spins = 0;
-                        do {
-                            if (++spins > BP_SPIN_LIMIT) {
-                                *a.err = 1;
-                                sb = RS_FLAG_INC;
-                                break;
-                            }
-                            sb = ld_volatile_u32(ps);
-                        } while ((sb >> 30) == 0);
-                    }
-                    excl += sb & RS_VALUE_MASK;
-                    if ((sb >> 30) == 2) done = true;
-                }
-                t -= LB_BATCH;
-            }
+            lookback_round<LB_FIRST>(a.status, tid, t, excl, done, a.err);
+            while (!done && t >= 0) lookback_round<LB_BATCH>(a.status, tid, t, excl, done, a.err);
             st_volatile_u32(a.status + (size_t)tile * RADIX + tid, RS_FLAG_INC | ((excl + count) & RS_VALUE_MASK));
         }
         gbase[tid] = a.ghist_excl[tid] + excl - dstart[tid];
