@@ -333,8 +333,11 @@ _REAL_STDOUT = None
 def emit_line(line):
     """The one JSON line goes to the process's original stdout."""
     data = (json.dumps(line) + "\n").encode()
-    if _REAL_STDOUT is not None:
-        os.write(_REAL_STDOUT, data)
+    # (under torchrun this file runs as __main__ while dist_bench imports it again as `bench`: the second copy of
+    # the module finds the descriptor in the environment)
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else int(os.environ.get("BP_BENCH_STDOUT_FD", "-1"))
+    if fd >= 0:
+        os.write(fd, data)
     else:
         sys.stdout.write(data.decode())
         sys.stdout.flush()
@@ -346,6 +349,7 @@ def main():
     global _REAL_STDOUT
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
+    os.environ["BP_BENCH_STDOUT_FD"] = str(_REAL_STDOUT)
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
