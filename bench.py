@@ -151,6 +151,13 @@ def run_reference(args):
     n = WORKLOADS[wl]["n"]
     sample_n = min(n, 1 << 20)  # bounded sample: at most 2^20 objects per step
     sc = make_scene(bp, wl, sample_n)
+    # all the host threads there are: torchrun exports OMP_NUM_THREADS=1 to its workers, which would make this a
+    # single-threaded run at N > 1
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    co.lib().bpo_set_threads(avail)
     cores = co.lib().bpo_max_threads()
     times, pairs = cpu_frames(co, sc, wl == "cfg3", args.steps, args.warmup)
     ms = 1e3 * sum(times) / len(times)
@@ -304,6 +311,14 @@ def run_ours(args):
             }
         except Exception as e:  # never lose the headline line to the extra measurement
             extra["cfg3_error"] = repr(e)
+        try:  # the per-GPU shape of BASELINE config 5 (2^25 uniform cubes) on ONE GPU: the base of the N > 1 arm's large shape
+            m5, _ = time_workload(bp, torch, "cfg2", 3, 2, n=1 << 25, with_e2e=False, with_profile=False)
+            extra["cfg5_shape_2^25_objects_per_gpu"] = {
+                "objects_total": m5["n"], "ms_per_step": m5["ms"], "objects_per_s": m5["n"] / (m5["ms"] * 1e-3),
+                "pairs": m5["pairs"], "pairs_per_s": m5["pairs"] / (m5["ms"] * 1e-3), "steps": 3,
+                "records": m5["stats"]["n_records"], "sort_passes": m5["stats"]["sort_passes"]}
+        except Exception as e:
+            extra["cfg5_error"] = repr(e)
 
     st = m["stats"]
     line = {
