@@ -1182,7 +1182,27 @@ template <int KIND, class IdT> struct Impl {
     // Bucket sizes of a splitter partition (and, for records, the halo copies every bucket will receive).
     template <class PK, bool HALO>
     static int partition_count(bp_layer *L, const PK *kin, uint32_t n, const uint64_t *spl, int n_spl, uint32_t shift,
-                               uint64_t *counts_out, uint64_t *halo_out) {
+                               uint64_t *counts_out, uint64_t *halo_out, uint64_t *d_row = nullptr, uint64_t tag = 0) {
+        if (d_row) { // counts stay on the device (a row of a peer-visible matrix): no host round trip
+            SplitterDigit<PK> op;
+            for (int i = 0; i < MAX_SPLITTERS; ++i) op.spl[i] = i < n_spl ? spl[i] : ~0ull;
+            op.n = (uint32_t)n_spl;
+            op.shift = shift;
+            TRY(ensure(L, L->scratch, 256));
+            uint32_t *hist = (uint32_t *)L->scratch.p, *halo = hist + 32;
+            CU(L, cudaMemsetAsync(L->scratch.p, 0, 256, L->stream));
+            if (n) {
+                LaunchScope ls(L, BP_K_PARTITION, (double)n * sizeof(PK));
+                const int blocks = (int)std::min<size_t>((n + 4095) / 4096, 148 * 8);
+                partition_hist_kernel<PK, T, HALO><<<std::max(blocks, 1), 512, 0, L->stream>>>(kin, n, op, hist, halo);
+            }
+            TRY(check_launch(L, "partition_hist_kernel"));
+            {
+                LaunchScope ls(L, BP_K_MISC, 0);
+                count_row_kernel<<<1, 32, 0, L->stream>>>(hist, HALO ? halo : nullptr, (uint32_t)n_spl + 1, tag, d_row);
+            }
+            return check_launch(L, "count_row_kernel");
+        }
         for (int b = 0; b <= n_spl; ++b) {
             counts_out[b] = 0;
             if (halo_out) halo_out[b] = 0;
@@ -1274,6 +1294,9 @@ template <int KIND, class IdT> struct Impl {
 
     static int count_records(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *counts, uint64_t *halo) {
         return partition_count<K, true>(L, (const K *)kin, (uint32_t)n, spl, n_spl, 0, counts, halo);
+    }
+    static int count_records_row(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t tag, uint64_t *d_row) {
+        return partition_count<K, true>(L, (const K *)kin, (uint32_t)n, spl, n_spl, 0, nullptr, nullptr, d_row, tag);
     }
     static int scatter_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl,
                                const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst) {
@@ -1376,6 +1399,12 @@ int do_count_records(bp_layer *L, const void *kin, size_t n, const uint64_t *spl
 int do_scatter_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl, const uint64_t *kdst,
                        const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst) {
     DISPATCH(L, scatter_records(L, kin, vin, n, spl, n_spl, kdst, vdst, hkdst, hvdst));
+}
+int do_count_records_row(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t tag, uint64_t *d_row) {
+    DISPATCH(L, count_records_row(L, kin, n, spl, n_spl, tag, d_row));
+}
+int do_count_pairs_row(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t tag, uint64_t *d_row) {
+    return Impl<BP_INDEX64_3D, uint32_t>::partition_count<uint64_t, false>(L, kin, (uint32_t)n, spl, n_spl, 32, nullptr, nullptr, d_row, tag);
 }
 int do_count_pairs(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *counts) {
     return Impl<BP_INDEX64_3D, uint32_t>::partition_count<uint64_t, false>(L, kin, (uint32_t)n, spl, n_spl, 32, counts, nullptr);
@@ -1915,6 +1944,24 @@ int bp_dist_count_pairs(bp_layer *L, const void *d_pairs, size_t n, const uint64
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
     return do_count_pairs(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, out_counts);
+}
+
+int bp_dist_count_records_device(bp_layer *L, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
+                                 void *d_out_row) {
+    if (!L || !d_out_row || bad_splitters(splitters, n_splitters)) return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_records_device");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_count_records_row(L, d_keys, n, splitters, n_splitters, tag, (uint64_t *)d_out_row);
+}
+
+int bp_dist_count_pairs_device(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
+                               void *d_out_row) {
+    if (!L || !d_out_row || bad_splitters(splitters, n_splitters)) return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_pairs_device");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 pairs");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_count_pairs_row(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, tag, (uint64_t *)d_out_row);
 }
 
 int bp_dist_scatter_pairs(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,

@@ -447,6 +447,18 @@ __global__ void __launch_bounds__(512) partition_hist_kernel(const K *__restrict
         atomicAdd(&ghalo[threadIdx.x], sh[MAX_SPLITTERS + 1 + threadIdx.x]);
 }
 
+// The bucket (and halo) counts of partition_hist_kernel as one row of 64-bit words for a peer-visible count
+// matrix: [counts 0..nb) | halo 0..nb) (if any) | tag] -- written on the device so that no host round trip is needed.
+__global__ void count_row_kernel(const uint32_t *__restrict__ hist, const uint32_t *__restrict__ halo, uint32_t nb, uint64_t tag,
+                                 uint64_t *__restrict__ row) {
+    const uint32_t i = threadIdx.x;
+    if (i < nb) {
+        row[i] = hist[i];
+        if (halo) row[nb + i] = halo[i];
+    }
+    if (i == 0) row[halo ? 2 * nb : nb] = tag;
+}
+
 // Writes the halo copies counted above into their destinations (slots handed out by atomics: the
 // receiver sorts its records anyway).
 template <class K, class V, class T>

@@ -112,6 +112,27 @@ class _SymmBuffer:
         self.hdl.barrier()
 
 
+class _CountMatrix:
+    """A g x row matrix of 64-bit counts in symmetric memory.  Rank r's count kernel writes row r of r's own copy
+    (no host round trip); one small peer copy per peer puts it into row r of their copies; after one barrier every
+    rank holds the whole matrix.  Replaces count -> host -> device -> NCCL all_gather -> host (two synchronisations
+    and a collective launch per exchange: ~0.2 ms of the 1.5 ms frame at 2^20 objects per GPU)."""
+
+    def __init__(self, g, me, row, device, group):
+        self.g, self.me, self.row = g, me, row
+        self.buf = _SymmBuffer(g * row * 8, device, group)
+        self.local = self.buf.t.view(torch.int64).view(g, row)
+        self.my_row_ptr = self.buf.ptrs[me] + me * row * 8
+        self.peer_rows = {p: self.buf.hdl.get_buffer(p, (g, row), torch.int64)[me] for p in range(g) if p != me}
+
+    def gather(self):
+        mine = self.local[self.me]
+        for p, dst in self.peer_rows.items():
+            dst.copy_(mine, non_blocking=True)
+        self.buf.barrier()  # every rank's row has landed everywhere
+        return self.local.cpu().numpy()
+
+
 class CudaOps:
     """The shard-local operations on one B200, every one a call through the C ABI; the exchanges are
     partition passes that store directly into the peers' symmetric receive buffers."""
@@ -129,6 +150,7 @@ class CudaOps:
             l.set_stream(stream)
         self.rec_cap = self.pair_cap = 0
         self.rk = self.ri = self.rp = None
+        self._cm_rec = self._cm_pair = None
 
     def layers(self):
         return (self.enc, self.shard, self.static)
@@ -143,6 +165,20 @@ class CudaOps:
     def count_records(self, keys, splitters):
         c, h = self.enc.count_records(keys, keys.shape[0], splitters)
         return [int(x) for x in c], [int(x) for x in h]
+
+    def count_records_matrix(self, keys, splitters, tag):
+        """count_records + the exchange of the count matrix, without leaving the device until the matrix is complete:
+        returns the [source, 2 g + 1] matrix (owned counts | halo counts | tag) as host numpy."""
+        if self._cm_rec is None:
+            self._cm_rec = _CountMatrix(self.world, self.rank, 2 * self.world + 1, self.device, self.group)
+        self.enc.count_records_device(keys, keys.shape[0], splitters, tag, self._cm_rec.my_row_ptr)
+        return self._cm_rec.gather()
+
+    def count_pairs_matrix(self, raw, splitters):
+        if self._cm_pair is None:
+            self._cm_pair = _CountMatrix(self.world, self.rank, self.world + 1, self.device, self.group)
+        self.shard.count_pairs_device(raw, raw.shape[0], splitters, 0, self._cm_pair.my_row_ptr)
+        return self._cm_pair.gather()[:, :self.world]
 
     def exchange_records(self, keys, ids, splitters, m_own, m_halo):
         me, g = self.rank, self.world
@@ -303,8 +339,11 @@ class DistLayer:
         mark("splitters")
 
         # 3. count, all-gather the count matrix, scatter straight into the owners' receive buffers
-        counts, halo = ops.count_records(keys, splitters)
-        mat = self._gather_rows(counts + halo + [id_or], dev)
+        if hasattr(ops, "count_records_matrix"):  # the product: counts stay on the device, the matrix travels over NVLink
+            mat = ops.count_records_matrix(keys, splitters, id_or)
+        else:                                      # CPU test double: host counts + all_gather (gloo)
+            counts, halo = ops.count_records(keys, splitters)
+            mat = self._gather_rows(counts + halo + [id_or], dev)
         m_own, m_halo = mat[:, :g], mat[:, g:2 * g]
         id_bits = 0
         for v in mat[:, 2 * g]:
@@ -337,8 +376,11 @@ class DistLayer:
             gathered = self._all_gather(ps).cpu().numpy().reshape(-1)
             self._a_splitters = choose_splitters(gathered[gathered >= 0].astype(np.uint64), g)
         a_splitters = self._a_splitters
-        pc = ops.count_pairs(raw, a_splitters)
-        pm = self._gather_rows(pc, dev)
+        if hasattr(ops, "count_pairs_matrix"):
+            pm = ops.count_pairs_matrix(raw, a_splitters)
+        else:
+            pc = ops.count_pairs(raw, a_splitters)
+            pm = self._gather_rows(pc, dev)
         mark("pair_counts")
         rp = ops.exchange_pairs(raw, a_splitters, pm)
         mark("pair_exchange")

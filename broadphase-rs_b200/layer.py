@@ -286,6 +286,17 @@ class Layer:
                                              halo.ctypes.data))
         return counts, halo
 
+    def count_records_device(self, d_keys, n, splitters, tag, d_out_row):
+        """count_records with the result left on the device: row = [counts | halo counts | tag] (u64), asynchronous."""
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        self._ck(lib().bp_dist_count_records_device(self._h, _dev_ptr(d_keys), n, spl.ctypes.data, spl.shape[0], int(tag),
+                                                    _dev_ptr(d_out_row)))
+
+    def count_pairs_device(self, d_pairs, n, splitters, tag, d_out_row):
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        self._ck(lib().bp_dist_count_pairs_device(self._h, _dev_ptr(d_pairs), n, spl.ctypes.data, spl.shape[0], int(tag),
+                                                  _dev_ptr(d_out_row)))
+
     def scatter_records(self, d_keys, d_ids, n, splitters, dst_keys, dst_ids, halo_dst_keys=None, halo_dst_ids=None):
         """Partition pass writing bucket b to the device addresses dst_keys[b] / dst_ids[b]."""
         spl = np.ascontiguousarray(splitters, dtype=np.uint64)

@@ -240,6 +240,14 @@ int bp_dist_count_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint
                         uint64_t *out_counts);
 int bp_dist_scatter_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
                           const uint64_t *dst_pairs);
+/* The counts of bp_dist_count_records / _pairs left ON THE DEVICE as one row of 64-bit words -- [bucket sizes
+ * 0..n_splitters] [halo copies 0..n_splitters] (records only) [tag] -- at d_out_row, typically this rank's row of a count
+ * matrix in every peer's symmetric memory: the matrix is then exchanged by peer copies and one barrier instead of a
+ * host round trip plus an NCCL all-gather.  Asynchronous on the layer's stream. */
+int bp_dist_count_records_device(bp_layer *ctx, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
+                                 uint64_t tag, void *d_out_row);
+int bp_dist_count_pairs_device(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
+                               void *d_out_row);
 /* Equal range [lo, hi) of every query key in a sorted device key array (halo look-ups). */
 int bp_dist_lookup_ranges(bp_layer *ctx, const void *d_sorted_keys, size_t n, const uint64_t *queries, int n_queries,
                           uint64_t *out_lo, uint64_t *out_hi);
