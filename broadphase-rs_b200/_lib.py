@@ -59,6 +59,8 @@ SYMBOLS = {
     "bp_layer_records": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
     "bp_layer_records_device": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
     "bp_layer_set_records": (_i, [_vp, _vp, _vp, _sz, _i, _i]),
+    "bp_layer_set_records_flagged": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i]),
+    "bp_layer_fold_cell_flags": (_i, [_vp, _P(_i)]),
     "bp_dist_count_records_device": (_i, [_vp, _vp, _sz, _vp, _i, _u64, _vp]),
     "bp_dist_count_pairs_device": (_i, [_vp, _vp, _sz, _vp, _i, _u64, _vp]),
     "bp_dist_partition_records": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),

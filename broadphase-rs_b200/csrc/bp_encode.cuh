@@ -326,16 +326,16 @@ template <class IdT> __global__ void __launch_bounds__(256) flags_strip_kernel(I
 // (bp_layer_set_records).  result must be pre-initialised like for encode_kernel.
 template <class K, class IdT>
 __global__ void __launch_bounds__(256) record_masks_kernel(const K *__restrict__ keys, const IdT *__restrict__ ids,
-                                                           uint32_t n, ExtendResult *result) {
+                                                           uint32_t n, IdT id_mask /* removes cell flags */, ExtendResult *result) {
     unsigned long long key_or = 0, key_and = ~0ull, id_or = 0, id_and = ~0ull;
     unsigned nonmono = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const unsigned long long k = (unsigned long long)keys[i], v = (unsigned long long)ids[i];
+        const unsigned long long k = (unsigned long long)keys[i], v = (unsigned long long)(ids[i] & id_mask);
         key_or |= k;
         key_and &= k;
         id_or |= v;
         id_and &= v;
-        if (i > 0 && ids[i - 1] > ids[i]) nonmono = 1;
+        if (i > 0 && (ids[i - 1] & id_mask) > (ids[i] & id_mask)) nonmono = 1;
     }
     key_or = warp_or(key_or);
     key_and = warp_and(key_and);

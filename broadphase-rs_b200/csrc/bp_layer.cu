@@ -493,6 +493,24 @@ template <int KIND, class IdT> struct Impl {
         return BP_OK;
     }
 
+    // Moves the cell flags of an encoded, not yet sorted tree into the IDs' top 3 bits now (the multi-GPU exchange
+    // ships the records before they are sorted).  *folded = 0 if the flags are gone or the IDs leave no room.
+    static int fold_flags(bp_layer *L, int *folded) {
+        *folded = L->ids_flagged ? 1 : 0;
+        if (L->ids_flagged || !L->flags_valid || L->n_records == 0) return BP_OK;
+        const int id_bits = 64 - (L->id_or ? __builtin_clzll(L->id_or) : 64);
+        if (id_bits > (int)(8 * sizeof(IdT)) - 3) return BP_OK;
+        {
+            LaunchScope ls(L, BP_K_MISC, (double)L->n_records * (2.0 * sizeof(IdT) + 1.0));
+            const int blocks = (int)std::min<uint64_t>((L->n_records + 1023) / 1024, 148 * 8);
+            flags_merge_kernel<IdT><<<blocks, 256, 0, L->stream>>>(ids(L, L->cur), (const uint8_t *)L->cell_flags.p, (uint32_t)L->n_records);
+        }
+        TRY(check_launch(L, "flags_merge_kernel"));
+        L->ids_flagged = true;
+        *folded = 1;
+        return BP_OK;
+    }
+
     // ---- extend ------------------------------------------------------------------------------------------
     static int launch_encode(bp_layer *L, const float *sysb, const float *d_bounds, const IdT *d_ids, uint32_t n) {
         EncodeArgs<T, IdT> a;
@@ -1343,7 +1361,8 @@ template <int KIND, class IdT> struct Impl {
         if (n) {
             LaunchScope ls(L, BP_K_MISC, 0);
             const int blocks = (int)std::min<uint64_t>((n + 255) / 256, 148 * 8);
-            record_masks_kernel<K, IdT><<<blocks, 256, 0, L->stream>>>(keys(L, L->cur), ids(L, L->cur), (uint32_t)n, L->d_res);
+            const IdT id_mask = L->ids_flagged ? (IdT)((((IdT)1) << (8 * sizeof(IdT) - 3)) - 1) : (IdT) ~(IdT)0;
+            record_masks_kernel<K, IdT><<<blocks, 256, 0, L->stream>>>(keys(L, L->cur), ids(L, L->cur), (uint32_t)n, id_mask, L->d_res);
         }
         TRY(check_launch(L, "record_masks_kernel"));
         CU(L, cudaMemcpyAsync(L->h_res, L->d_res, sizeof(ExtendResult), cudaMemcpyDeviceToHost, L->stream));
@@ -1418,6 +1437,7 @@ int do_lookup_ranges(bp_layer *L, const void *keys, size_t n, const uint64_t *q,
 }
 int do_masks(bp_layer *L, uint64_t n) { DISPATCH(L, masks_from_records(L, n)); }
 int do_strip_flags(bp_layer *L) { DISPATCH(L, strip_flags(L)); }
+int do_fold_flags(bp_layer *L, int *folded) { DISPATCH(L, fold_flags(L, folded)); }
 
 // Folds the result of the last (still asynchronous) extend into the host-side state.
 int resolve_pending(bp_layer *L) {
@@ -2018,7 +2038,21 @@ int bp_layer_records(bp_layer *L, const void **out_keys, const void **out_ids, s
     return BP_OK;
 }
 
+int bp_layer_fold_cell_flags(bp_layer *L, int *out_folded) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    int folded = 0;
+    TRY(do_fold_flags(L, &folded));
+    if (out_folded) *out_folded = folded;
+    return BP_OK;
+}
+
 int bp_layer_set_records(bp_layer *L, const void *keys, const void *ids, size_t n, int sorted, int on_device) {
+    return bp_layer_set_records_flagged(L, keys, ids, n, sorted, on_device, 0);
+}
+
+int bp_layer_set_records_flagged(bp_layer *L, const void *keys, const void *ids, size_t n, int sorted, int on_device, int flagged) {
     if (!L || (n && (!keys || !ids))) return fail(L, BP_ERR_INVALID_ARG, "null argument to set_records");
     if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
     DeviceGuard g(L->device);
@@ -2030,7 +2064,8 @@ int bp_layer_set_records(bp_layer *L, const void *keys, const void *ids, size_t 
         CU(L, cudaMemcpyAsync(L->ids[L->cur].p, ids, n * L->id_bytes, kind, L->stream));
     }
     L->n_records = n;
-    L->flags_valid = false; // foreign records: no cell flags
+    L->flags_valid = false;        // foreign records: no separate cell flags ...
+    L->ids_flagged = flagged != 0; // ... but they may ride in the IDs' top 3 bits (bp_layer_fold_cell_flags on the sender)
     TRY(do_masks(L, n));
     L->key_or = L->h_res->key_or;
     L->key_and = L->h_res->key_and;

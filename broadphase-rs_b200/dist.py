@@ -197,9 +197,17 @@ class CudaOps:
         n_recv = int((m_own + m_halo)[:, me].sum())
         return self.rk.t.view(torch.int64)[:n_recv], self.ri.t.view(torch.int32)[:n_recv]
 
-    def sort_records(self, keys, ids):
-        self.shard.set_records(keys, ids, sorted_=False, on_device=True, n=keys.shape[0])
+    def fold_flags(self):
+        """Moves the cell flags of the freshly encoded records into their IDs' top 3 bits, in place (the views encode()
+        returned see them): they travel with the records, and the receiving shard can emit every ID pair from its
+        canonical shared cell only -- fewer raw pairs to exchange and to sort."""
+        return self.enc.fold_cell_flags()
+
+    def sort_records(self, keys, ids, flagged=False):
+        self.shard.set_records(keys, ids, sorted_=False, on_device=True, n=keys.shape[0], flagged=flagged)
         self.shard.sort()
+        if flagged:  # (records_device would strip the flags again; the scan below reads the shard layer itself)
+            return None, None
         kp, ip, r, _ = self.shard.records_device()
         return _view(kp, r, torch.int64, self.device), _view(ip, r, torch.int32, self.device)
 
@@ -339,16 +347,24 @@ class DistLayer:
         mark("splitters")
 
         # 3. count, all-gather the count matrix, scatter straight into the owners' receive buffers
+        # bit 63 of the tag: "my IDs leave their top 3 bits free" (dedup at the source across the exchange, below)
+        can_fold = hasattr(ops, "fold_flags") and self._static_halo is None and int(id_or) < (1 << 29)
         if hasattr(ops, "count_records_matrix"):  # the product: counts stay on the device, the matrix travels over NVLink
-            mat = ops.count_records_matrix(keys, splitters, id_or)
+            mat = ops.count_records_matrix(keys, splitters, int(id_or) | ((1 << 63) if can_fold else 0))
         else:                                      # CPU test double: host counts + all_gather (gloo)
             counts, halo = ops.count_records(keys, splitters)
             mat = self._gather_rows(counts + halo + [id_or], dev)
         m_own, m_halo = mat[:, :g], mat[:, g:2 * g]
         id_bits = 0
+        flagged = hasattr(ops, "count_records_matrix")
         for v in mat[:, 2 * g]:
-            id_bits |= int(v)
+            v = int(v) & 0xFFFFFFFFFFFFFFFF
+            flagged = flagged and bool(v >> 63)
+            id_bits |= v & ~(1 << 63)
         id_bits |= self._static_id_bits
+        if flagged:  # every rank can: the cell flags ride in the IDs (in place, before the scatter ships them)
+            folded = ops.fold_flags()
+            assert folded or r_loc == 0
         self._id_mask |= (1 << max(1, id_bits.bit_length())) - 1  # IDs seen since the splitters were cached
         mark("counts")
         rk, ri = ops.exchange_records(keys, rids, splitters, m_own, m_halo)
@@ -356,7 +372,7 @@ class DistLayer:
         mark("exchange")
 
         # 4. local sort: the halo records (all < my lower splitter) end up in front
-        sk, si = ops.sort_records(rk, ri)
+        sk, si = ops.sort_records(rk, ri, flagged) if flagged else ops.sort_records(rk, ri)
         if self._static_halo is not None:  # Layer::merge of the resident static shard (sorted runs: merge path)
             ops.merge_static()
             n_halo += self._static_halo

@@ -238,9 +238,15 @@ class Layer:
         self._ck(lib().bp_layer_records_device(self._h, ctypes.byref(k), ctypes.byref(i), ctypes.byref(n), ctypes.byref(s)))
         return k.value, i.value, n.value, bool(s.value)
 
-    def set_records(self, keys, ids, sorted_=False, on_device=False, n=None):
+    def fold_cell_flags(self):
+        """Moves the cell flags of a freshly extended tree into the IDs' top 3 bits (include/bp.h); True if it did."""
+        f = ctypes.c_int()
+        self._ck(lib().bp_layer_fold_cell_flags(self._h, ctypes.byref(f)))
+        return bool(f.value)
+
+    def set_records(self, keys, ids, sorted_=False, on_device=False, n=None, flagged=False):
         if on_device:
-            self._ck(lib().bp_layer_set_records(self._h, _dev_ptr(keys), _dev_ptr(ids), n, int(sorted_), 1))
+            self._ck(lib().bp_layer_set_records_flagged(self._h, _dev_ptr(keys), _dev_ptr(ids), n, int(sorted_), 1, int(flagged)))
         else:
             k = np.ascontiguousarray(keys, dtype=self.key_dtype)
             i = np.ascontiguousarray(ids, dtype=self.id_dtype)

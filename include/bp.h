@@ -204,6 +204,14 @@ int bp_layer_records_device(bp_layer *layer, const void **out_d_keys, const void
 /* Replaces the tree (the serde Deserialize path of Layer, src/layer.rs:41; also how a
  * multi-GPU exchange hands a shard its records).  Host or device pointers per `on_device`. */
 int bp_layer_set_records(bp_layer *layer, const void *keys, const void *ids, size_t n, int sorted, int on_device);
+/* Dedup at the source across an exchange (multi-GPU).  bp_layer_fold_cell_flags moves the 3 cell flags encode_kernel
+ * wrote for every record of a freshly extended, unsorted tree into the top 3 bits of its ID, in place (*out_folded = 0
+ * and nothing happens if the IDs use more than id_bits - 3 bits, or the flags are gone); the records read through
+ * bp_layer_records_device BEFORE this call then carry them.  bp_layer_set_records_flagged(.., flagged = 1) loads such
+ * records: the scan of that layer emits every ID pair from its canonical shared cell only, and every accessor strips
+ * the flags before IDs are shown. */
+int bp_layer_fold_cell_flags(bp_layer *layer, int *out_folded);
+int bp_layer_set_records_flagged(bp_layer *layer, const void *keys, const void *ids, size_t n, int sorted, int on_device, int flagged);
 
 int bp_layer_len(bp_layer *layer, size_t *out_n);
 int bp_layer_is_sorted(bp_layer *layer, int *out_sorted);
