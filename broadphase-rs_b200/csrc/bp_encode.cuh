@@ -24,6 +24,7 @@ struct ExtendResult {
     unsigned long long key_or, key_and, id_or, id_and;
     unsigned int nonmono;  // 1 if an ID smaller than its predecessor was seen
     unsigned int too_many; // 1 if one object wanted more than ENCODE_MAX_CELLS cells
+    unsigned long long id_first, id_last; // IDs of the first / last object of the call (valid or not): with !nonmono, the ID range
 };
 
 constexpr uint32_t ENCODE_MAX_CELLS = 1u << 20;
@@ -306,8 +307,10 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
     }
     if (obj0 + tile_objs == a.n && tid == 0) { // last tile: totals + the tail's last ID
         a.result->total_records = tile_base + tile_total;
+        a.result->id_last = (unsigned long long)a.ids[a.n - 1];
         if (a.next_last_id) *a.next_last_id = a.ids[a.n - 1];
     }
+    if (obj0 == 0 && tid == 0) a.result->id_first = (unsigned long long)a.ids[0];
 }
 
 // The cell flags ride through the sort in the unused top 3 bits of the ID payload (the host checks that

@@ -91,6 +91,7 @@ struct bp_layer {
     bool tail_has_last = false;
     int last_slot = 0;
     uint64_t key_or = 0, key_and = ~0ull, id_or = 0, id_and = ~0ull;
+    uint64_t id_first = 0, id_last = 0; // IDs of the first / last object extended since the last clear (bp_layer_id_order)
     uint64_t n_invalid = 0;
     uint64_t n_halo = 0; // records [0, n_halo) only act as ancestors in scan (multi-GPU halos)
     // dedup at the source: encode writes 3 cell flags per record (cell_flags); a full sort of a tree that
@@ -126,6 +127,7 @@ struct bp_layer {
     DevBuf query_params, query_counts, query_offsets; // batched queries: geometry parameters, per-query counts, CSR offsets
     void *h_offsets = nullptr;     // pinned mirror of query_offsets
     size_t h_offsets_cap = 0;
+    void *pairs_src = nullptr;     // finish_pairs: the raw pairs live here instead of praw[0] (bp_layer_unique_pairs_inplace_device)
     bool pairs_grouped = false;    // finish_pairs: the raw pairs are already grouped by their first ID, in order
     DevBuf pair_cnt;               // pairs per later ID (counting sort of the pairs; dense 32-bit IDs only)
     bool want_pair_counts = false; // the caller of scan_raw will finish the pairs itself (scan), not hand them out raw
@@ -372,7 +374,10 @@ struct RadixScratch {
 
 template <class K, class V>
 int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32_t *n_dev, uint64_t mask, int cls_hist,
-               int cls_pass, int *out_passes, bool *out_in_alt, size_t elem_bytes, const uint8_t *first_pass_vflags = nullptr) {
+               int cls_pass, int *out_passes, bool *out_in_alt, size_t elem_bytes, const uint8_t *first_pass_vflags = nullptr,
+               const K *k_src = nullptr, const V *v_src = nullptr) {
+    // k_src / v_src: the first pass (and the histograms) read these arrays instead of k0 / v0 and write k1 / v1 as usual --
+    // sorting straight out of a buffer the layer does not own (a multi-GPU receive buffer) without a staging copy
     typedef PassTune<K, V> Tune;
     typedef RadixPassCfg<K, V, Tune::THREADS, Tune::ITEMS> Cfg;
     *out_in_alt = false;
@@ -394,7 +399,7 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
     {
         LaunchScope ls(L, cls_hist, (double)n * sizeof(K));
         const int blocks = (int)std::min<size_t>((n + 512 * 8 - 1) / (512 * 8), 148 * 8);
-        radix_hist_kernel<K><<<std::max(blocks, 1), 512, 0, L->stream>>>(k0, n, n_dev, plan, hist);
+        radix_hist_kernel<K><<<std::max(blocks, 1), 512, 0, L->stream>>>(k_src ? k_src : k0, n, n_dev, plan, hist);
     }
     TRY(check_launch(L, "radix_hist_kernel"));
     {
@@ -406,8 +411,10 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
     auto kern2 = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS, Tune::MINB, ShiftMaskDigit<K>>;
     CU(L, cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     CU(L, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-    K *kin = k0, *kout = k1;
-    V *vin = v0, *vout = v1;
+    const K *kin = k_src ? k_src : k0;
+    const V *vin = k_src ? v_src : v0;
+    K *kout = k1;
+    V *vout = v1;
     for (int p = 0; p < np; ++p) {
         LaunchScope ls(L, cls_pass, 2.0 * (double)n * (double)elem_bytes);
         if (plan.bits2[p] == 0) {
@@ -448,8 +455,10 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(L, BP_ERR_CUDA, "launch of radix_pass_kernel failed: %s", cudaGetErrorString(e));
-        std::swap(kin, kout);
-        std::swap(vin, vout);
+        kin = kout;
+        vin = vout;
+        kout = (p & 1) ? k1 : k0;
+        vout = (p & 1) ? v1 : v0;
     }
     *out_passes = np;
     *out_in_alt = (np & 1) != 0;
@@ -586,8 +595,10 @@ template <int KIND, class IdT> struct Impl {
     // ---- sort --------------------------------------------------------------------------------------------------
     // Sorts records [off, off + cnt) of the current buffer by (key, id); the result is left in the
     // current buffer.
+    // src_k / src_v (whole-tree sorts only): the records are read from these arrays instead of the current buffer; if no
+    // pass runs at all they are copied into it.
     static int sort_range(bp_layer *L, uint64_t off, uint64_t cnt, bool need_id_passes, const uint8_t *fold_flags = nullptr,
-                          bool *flags_folded = nullptr) {
+                          bool *flags_folded = nullptr, const K *src_k = nullptr, const IdT *src_v = nullptr) {
         const int c = L->cur, o = c ^ 1;
         K *k0 = keys(L, c) + off, *k1 = keys(L, o) + off;
         IdT *v0 = ids(L, c) + off, *v1 = ids(L, o) + off;
@@ -596,8 +607,9 @@ template <int KIND, class IdT> struct Impl {
         int passes = 0, total_passes = 0;
         if (need_id_passes && imask) { // secondary key first (LSD): IDs as the sort key, Index as the payload
             TRY((radix_sort<IdT, K>(L, v0, k0, v1, k1, (uint32_t)cnt, nullptr, imask, BP_K_SORT_HIST, BP_K_SORT_PASS,
-                                    &passes, &in_alt, sizeof(K) + sizeof(IdT))));
+                                    &passes, &in_alt, sizeof(K) + sizeof(IdT), nullptr, src_v, src_k)));
             total_passes += passes;
+            if (passes) src_k = nullptr, src_v = nullptr; // consumed
             if (in_alt) {
                 std::swap(k0, k1);
                 std::swap(v0, v1);
@@ -607,9 +619,13 @@ template <int KIND, class IdT> struct Impl {
         // (the flags can only ride along when the key passes are the first thing that touches the records)
         const uint8_t *vf = (fold_flags && !(need_id_passes && imask)) ? fold_flags + off : nullptr;
         TRY((radix_sort<K, IdT>(L, k0, v0, k1, v1, (uint32_t)cnt, nullptr, kmask, BP_K_SORT_HIST, BP_K_SORT_PASS, &passes,
-                                &in_alt2, sizeof(K) + sizeof(IdT), vf)));
+                                &in_alt2, sizeof(K) + sizeof(IdT), vf, src_k, src_v)));
         if (flags_folded) *flags_folded = vf != nullptr && passes > 0;
         total_passes += passes;
+        if (src_k && !passes) { // nothing to sort by: the records still have to arrive in the tree
+            CU(L, cudaMemcpyAsync(k0, src_k, cnt * sizeof(K), cudaMemcpyDeviceToDevice, L->stream));
+            CU(L, cudaMemcpyAsync(v0, src_v, cnt * sizeof(IdT), cudaMemcpyDeviceToDevice, L->stream));
+        }
         const bool final_in_alt = in_alt != in_alt2;
         L->stats.sort_passes = (uint32_t)total_passes;
         if (final_in_alt) {
@@ -705,6 +721,15 @@ template <int KIND, class IdT> struct Impl {
     }
 
     // ---- scan ---------------------------------------------------------------------------------------------------
+    // set_records + sort in one step for records that live in somebody else's buffer (a multi-GPU receive buffer): the first
+    // radix pass reads them where they are (no staging copy), the digit plan comes from the caller's masks (no mask pass).
+    static int sort_from(bp_layer *L, const void *src_k, const void *src_v, uint64_t n, bool ids_ascending) {
+        L->stats.sort_passes = 0;
+        L->stats.merged = 0;
+        if (n) TRY(sort_range(L, 0, n, !ids_ascending, nullptr, nullptr, (const K *)src_k, (const IdT *)src_v));
+        return BP_OK;
+    }
+
     template <int FK, bool DEDUP> static int launch_emit(bp_layer *L, EmitArgs<IdT> &a, uint32_t chunks, double bytes) {
         auto kern = scan_emit_kernel<IdT, FK, T, DEDUP>;
         CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EmitSmem<IdT>::BYTES));
@@ -894,7 +919,7 @@ template <int KIND, class IdT> struct Impl {
         // deduplicates the (tiny) groups of equal later IDs.  Fallback (a group larger than the finish
         // kernel's window): the remaining passes over all bits, then pair_unique_kernel.
         const uint64_t imask = L->id_or & ~L->id_and;
-        uint64_t *a0 = (uint64_t *)L->praw[0].p, *a1 = (uint64_t *)L->praw[1].p;
+        uint64_t *a0 = (uint64_t *)(L->pairs_src ? L->pairs_src : L->praw[0].p), *a1 = (uint64_t *)L->praw[1].p;
         uint64_t *b0 = wide ? (uint64_t *)L->praw_b[0].p : nullptr, *b1 = wide ? (uint64_t *)L->praw_b[1].p : nullptr;
         int passes = 0, total_passes = 0;
         bool in_alt = false;
@@ -1200,7 +1225,8 @@ template <int KIND, class IdT> struct Impl {
     // Bucket sizes of a splitter partition (and, for records, the halo copies every bucket will receive).
     template <class PK, bool HALO>
     static int partition_count(bp_layer *L, const PK *kin, uint32_t n, const uint64_t *spl, int n_spl, uint32_t shift,
-                               uint64_t *counts_out, uint64_t *halo_out, uint64_t *d_row = nullptr, uint64_t tag = 0) {
+                               uint64_t *counts_out, uint64_t *halo_out, uint64_t *d_row = nullptr, const uint64_t *tags = nullptr,
+                               int n_tags = 0) {
         if (d_row) { // counts stay on the device (a row of a peer-visible matrix): no host round trip
             SplitterDigit<PK> op;
             for (int i = 0; i < MAX_SPLITTERS; ++i) op.spl[i] = i < n_spl ? spl[i] : ~0ull;
@@ -1217,7 +1243,10 @@ template <int KIND, class IdT> struct Impl {
             TRY(check_launch(L, "partition_hist_kernel"));
             {
                 LaunchScope ls(L, BP_K_MISC, 0);
-                count_row_kernel<<<1, 32, 0, L->stream>>>(hist, HALO ? halo : nullptr, (uint32_t)n_spl + 1, tag, d_row);
+                RowTags rt;
+                rt.n = (uint32_t)std::min(n_tags, MAX_ROW_TAGS);
+                for (uint32_t i = 0; i < (uint32_t)MAX_ROW_TAGS; ++i) rt.v[i] = i < rt.n ? tags[i] : 0;
+                count_row_kernel<<<1, 32, 0, L->stream>>>(hist, HALO ? halo : nullptr, (uint32_t)n_spl + 1, rt, d_row);
             }
             return check_launch(L, "count_row_kernel");
         }
@@ -1255,7 +1284,7 @@ template <int KIND, class IdT> struct Impl {
     template <class PK, class PV>
     static int partition_scatter(bp_layer *L, const PK *kin, const PV *vin, uint32_t n, const uint64_t *spl, int n_spl,
                                  uint32_t shift, const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst,
-                                 const uint64_t *hvdst) {
+                                 const uint64_t *hvdst, const uint8_t *vflags = nullptr) {
         typedef PassTune<PK, PV> Tune;
         typedef RadixPassCfg<PK, PV, Tune::THREADS, Tune::ITEMS> Cfg;
         if (n == 0) return BP_OK;
@@ -1284,7 +1313,7 @@ template <int KIND, class IdT> struct Impl {
         a.ghist_excl = zero_hist; // every bucket starts at offset 0 of its own destination
         a.status = status;
         a.tile_counter = counters;
-        a.vflags = nullptr;
+        a.vflags = vflags; // dedup at the source across the exchange: the cell flags leave inside the IDs
         a.op = op;
         a.err = L->d_err;
         {
@@ -1303,7 +1332,7 @@ template <int KIND, class IdT> struct Impl {
                 uint32_t *cursor = counters + 32; // zeroed above
                 LaunchScope ls(L, BP_K_PARTITION, (double)n * sizeof(PK));
                 const int blocks = (int)std::min<size_t>((n + 1023) / 1024, 148 * 8);
-                halo_scatter_kernel<PK, PV, T><<<std::max(blocks, 1), 256, 0, L->stream>>>(kin, vin, n, hop, cursor);
+                halo_scatter_kernel<PK, PV, T><<<std::max(blocks, 1), 256, 0, L->stream>>>(kin, vin, n, hop, cursor, vflags);
                 TRY(check_launch(L, "halo_scatter_kernel"));
             }
         }
@@ -1313,12 +1342,21 @@ template <int KIND, class IdT> struct Impl {
     static int count_records(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *counts, uint64_t *halo) {
         return partition_count<K, true>(L, (const K *)kin, (uint32_t)n, spl, n_spl, 0, counts, halo);
     }
-    static int count_records_row(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t tag, uint64_t *d_row) {
-        return partition_count<K, true>(L, (const K *)kin, (uint32_t)n, spl, n_spl, 0, nullptr, nullptr, d_row, tag);
+    static int count_records_row(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, const uint64_t *tags, int n_tags,
+                                 uint64_t *d_row) {
+        return partition_count<K, true>(L, (const K *)kin, (uint32_t)n, spl, n_spl, 0, nullptr, nullptr, d_row, tags, n_tags);
     }
     static int scatter_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl,
-                               const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst) {
-        return partition_scatter<K, IdT>(L, (const K *)kin, (const IdT *)vin, (uint32_t)n, spl, n_spl, 0, kdst, vdst, hkdst, hvdst);
+                               const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst, bool fold) {
+        const uint8_t *vflags = nullptr;
+        if (fold) { // only the layer's own freshly encoded records have cell flags, and only small enough IDs leave room
+            const int id_bits = 64 - (L->id_or ? __builtin_clzll(L->id_or) : 64);
+            if (kin != (const void *)keys(L, L->cur) || n != L->n_records || !L->flags_valid || L->ids_flagged ||
+                id_bits > (int)(8 * sizeof(IdT)) - 3)
+                return fail(L, BP_ERR_INVALID_ARG, "scatter_records: cell flags can only be folded into the layer's own encoded records");
+            vflags = (const uint8_t *)L->cell_flags.p;
+        }
+        return partition_scatter<K, IdT>(L, (const K *)kin, (const IdT *)vin, (uint32_t)n, spl, n_spl, 0, kdst, vdst, hkdst, hvdst, vflags);
     }
 
     static int partition_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl,
@@ -1416,14 +1454,15 @@ int do_count_records(bp_layer *L, const void *kin, size_t n, const uint64_t *spl
     DISPATCH(L, count_records(L, kin, n, spl, n_spl, counts, halo));
 }
 int do_scatter_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl, const uint64_t *kdst,
-                       const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst) {
-    DISPATCH(L, scatter_records(L, kin, vin, n, spl, n_spl, kdst, vdst, hkdst, hvdst));
+                       const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst, bool fold) {
+    DISPATCH(L, scatter_records(L, kin, vin, n, spl, n_spl, kdst, vdst, hkdst, hvdst, fold));
 }
-int do_count_records_row(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t tag, uint64_t *d_row) {
-    DISPATCH(L, count_records_row(L, kin, n, spl, n_spl, tag, d_row));
+int do_count_records_row(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, const uint64_t *tags, int n_tags,
+                         uint64_t *d_row) {
+    DISPATCH(L, count_records_row(L, kin, n, spl, n_spl, tags, n_tags, d_row));
 }
 int do_count_pairs_row(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t tag, uint64_t *d_row) {
-    return Impl<BP_INDEX64_3D, uint32_t>::partition_count<uint64_t, false>(L, kin, (uint32_t)n, spl, n_spl, 32, nullptr, nullptr, d_row, tag);
+    return Impl<BP_INDEX64_3D, uint32_t>::partition_count<uint64_t, false>(L, kin, (uint32_t)n, spl, n_spl, 32, nullptr, nullptr, d_row, &tag, 1);
 }
 int do_count_pairs(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *counts) {
     return Impl<BP_INDEX64_3D, uint32_t>::partition_count<uint64_t, false>(L, kin, (uint32_t)n, spl, n_spl, 32, counts, nullptr);
@@ -1435,6 +1474,7 @@ int do_scatter_pairs(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t 
 int do_lookup_ranges(bp_layer *L, const void *keys, size_t n, const uint64_t *q, int nq, uint64_t *lo, uint64_t *hi) {
     DISPATCH(L, lookup_ranges(L, keys, n, q, nq, lo, hi));
 }
+int do_sort_from(bp_layer *L, const void *k, const void *v, uint64_t n, bool asc) { DISPATCH(L, sort_from(L, k, v, n, asc)); }
 int do_masks(bp_layer *L, uint64_t n) { DISPATCH(L, masks_from_records(L, n)); }
 int do_strip_flags(bp_layer *L) { DISPATCH(L, strip_flags(L)); }
 int do_fold_flags(bp_layer *L, int *folded) { DISPATCH(L, fold_flags(L, folded)); }
@@ -1460,6 +1500,8 @@ int resolve_pending(bp_layer *L) {
         }
         L->tail_sorted = false;
         if (r.nonmono) L->tail_nonmono = true;
+        if (L->pending_base == 0) L->id_first = r.id_first;
+        L->id_last = r.id_last;
         L->n_records = L->pending_base + added;
         L->key_or |= r.key_or;
         L->key_and &= r.key_and;
@@ -1889,13 +1931,27 @@ int bp_layer_scan_raw_device(bp_layer *L, const bp_filter *f, const void **out_r
     return BP_OK;
 }
 
+static int unique_pairs_impl(bp_layer *L, const void *d_raw, size_t n, uint64_t id_mask, const void **out_pairs, size_t *out_count,
+                             bool in_place);
+
 int bp_layer_unique_pairs_device(bp_layer *L, const void *d_raw, size_t n, uint64_t id_mask, const void **out_pairs, size_t *out_count) {
+    return unique_pairs_impl(L, d_raw, n, id_mask, out_pairs, out_count, false);
+}
+
+int bp_layer_unique_pairs_inplace_device(bp_layer *L, void *d_raw, size_t n, uint64_t id_mask, const void **out_pairs, size_t *out_count) {
+    return unique_pairs_impl(L, d_raw, n, id_mask, out_pairs, out_count, true);
+}
+
+static int unique_pairs_impl(bp_layer *L, const void *d_raw, size_t n, uint64_t id_mask, const void **out_pairs, size_t *out_count,
+                             bool in_place) {
     if (!L || (n && !d_raw)) return BP_ERR_INVALID_ARG;
     if (L->id_bytes != 4) return fail(L, BP_ERR_INVALID_ARG, "raw pairs are exposed for 32-bit IDs only");
     if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 pairs");
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
-    if (n) {
+    if (n && in_place && d_raw != L->praw[0].p) {
+        L->pairs_src = (void *)d_raw; // sorted where they are: the caller's array is one side of the ping-pong
+    } else if (n) {
         TRY(ensure(L, L->praw[0], n * sizeof(uint64_t)));
         if (d_raw != L->praw[0].p)
             CU(L, cudaMemcpyAsync(L->praw[0].p, d_raw, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, L->stream));
@@ -1908,6 +1964,7 @@ int bp_layer_unique_pairs_device(bp_layer *L, const void *d_raw, size_t n, uint6
     }
     CU(L, cudaMemsetAsync(L->d_tot, 0, sizeof(ScanTotals), L->stream));
     const int st = do_finish_pairs(L, n);
+    L->pairs_src = nullptr;
     L->id_or = keep_or;
     L->id_and = keep_and;
     TRY(st);
@@ -1950,12 +2007,19 @@ int bp_dist_count_records(bp_layer *L, const void *d_keys, size_t n, const uint6
 int bp_dist_scatter_records(bp_layer *L, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
                             int n_splitters, const uint64_t *dst_keys, const uint64_t *dst_ids, const uint64_t *halo_dst_keys,
                             const uint64_t *halo_dst_ids) {
+    return bp_dist_scatter_records_flagged(L, d_keys, d_ids, n, splitters, n_splitters, dst_keys, dst_ids, halo_dst_keys, halo_dst_ids, 0);
+}
+
+int bp_dist_scatter_records_flagged(bp_layer *L, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
+                                    int n_splitters, const uint64_t *dst_keys, const uint64_t *dst_ids, const uint64_t *halo_dst_keys,
+                                    const uint64_t *halo_dst_ids, int fold_cell_flags) {
     if (!L || !dst_keys || !dst_ids || bad_splitters(splitters, n_splitters))
         return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_scatter_records");
     if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
-    return do_scatter_records(L, d_keys, d_ids, n, splitters, n_splitters, dst_keys, dst_ids, halo_dst_keys, halo_dst_ids);
+    return do_scatter_records(L, d_keys, d_ids, n, splitters, n_splitters, dst_keys, dst_ids, halo_dst_keys, halo_dst_ids,
+                              fold_cell_flags != 0 && n > 0);
 }
 
 int bp_dist_count_pairs(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t *out_counts) {
@@ -1972,7 +2036,17 @@ int bp_dist_count_records_device(bp_layer *L, const void *d_keys, size_t n, cons
     if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
-    return do_count_records_row(L, d_keys, n, splitters, n_splitters, tag, (uint64_t *)d_out_row);
+    return do_count_records_row(L, d_keys, n, splitters, n_splitters, &tag, 1, (uint64_t *)d_out_row);
+}
+
+int bp_dist_count_records_device_tags(bp_layer *L, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
+                                      const uint64_t *tags, int n_tags, void *d_out_row) {
+    if (!L || !d_out_row || bad_splitters(splitters, n_splitters) || n_tags < 0 || n_tags > MAX_ROW_TAGS || (n_tags && !tags))
+        return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_records_device_tags");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_count_records_row(L, d_keys, n, splitters, n_splitters, tags, n_tags, (uint64_t *)d_out_row);
 }
 
 int bp_dist_count_pairs_device(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
@@ -2076,6 +2150,37 @@ int bp_layer_set_records_flagged(bp_layer *L, const void *keys, const void *ids,
     L->tail_sorted = false;
     L->tail_nonmono = L->h_res->nonmono != 0;
     L->stats.n_records = n;
+    return BP_OK;
+}
+
+int bp_layer_sort_from_device(bp_layer *L, const void *d_keys, const void *d_ids, size_t n, int flagged, uint64_t key_or,
+                              uint64_t key_and, uint64_t id_or, uint64_t id_and, int ids_ascending) {
+    if (!L || (n && (!d_keys || !d_ids))) return fail(L, BP_ERR_INVALID_ARG, "null argument to sort_from_device");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
+    DeviceGuard g(L->device);
+    TRY(bp_layer_clear(L));
+    if (n) TRY(do_ensure_tree(L, n));
+    L->n_records = n;
+    L->flags_valid = false;
+    L->ids_flagged = flagged != 0;
+    L->key_or = key_or;
+    L->key_and = key_and;
+    L->id_or = id_or;
+    L->id_and = id_and;
+    L->stats.n_records = n;
+    TRY(do_sort_from(L, d_keys, d_ids, n, ids_ascending != 0));
+    L->dirty = false;
+    return BP_OK;
+}
+
+int bp_layer_id_order(bp_layer *L, uint64_t *out_first, uint64_t *out_last, int *out_ascending) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    const bool from_extends = L->n_records > 0 && L->dirty && L->prefix == 0 && !L->tail_sorted;
+    if (out_first) *out_first = from_extends ? L->id_first : ~0ull;
+    if (out_last) *out_last = from_extends ? L->id_last : 0;
+    if (out_ascending) *out_ascending = (L->n_records == 0 || (from_extends && !L->tail_nonmono)) ? 1 : 0;
     return BP_OK;
 }
 

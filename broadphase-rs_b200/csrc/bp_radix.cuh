@@ -419,23 +419,33 @@ __global__ void __launch_bounds__(512) partition_hist_kernel(const K *__restrict
     const uint32_t nb = op.n + 1; // buckets in use
     const unsigned lane = threadIdx.x & 31u;
     uint32_t mine = 0; // lane b of every warp accumulates bucket b
+    constexpr int U = 4; // independent key loads in flight per thread
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const size_t nround = ((size_t)n + stride - 1) / stride * stride; // whole warps stay in the loop together
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        const bool live = i < n;
-        const K k = live ? ld_stream(keys + i) : (K)0;
-        const uint32_t d = live ? op(k) : 0xffffffffu;
-        for (uint32_t b = 0; b < nb; ++b) { // one ballot per bucket in use (2..16), warp-uniform trip count
-            const uint32_t c = __popc(__ballot_sync(BP_FULL_MASK, d == b));
-            if (lane == b) mine += c;
+    const size_t nround = ((size_t)n + U * stride - 1) / (U * stride) * (U * stride); // whole warps stay in the loop together
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < nround; i0 += U * stride) {
+        K kk[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = i0 + (size_t)u * stride;
+            kk[u] = i < n ? ld_stream(keys + i) : (K)0;
         }
-        if constexpr (HALO) {
-            // common case: the cell ends before the next splitter -- one comparison
-            if (live && d < op.n) {
-                const K hi = run_upper_key<T>(k);
-                if (((uint64_t)hi >> op.shift) >= op.spl[d]) {
-                    const uint32_t last = op(hi);
-                    for (uint32_t s = d + 1; s <= last; ++s) atomicAdd(&sh[MAX_SPLITTERS + 1 + s], 1u); // rare
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool live = i0 + (size_t)u * stride < n;
+            const K k = kk[u];
+            const uint32_t d = live ? op(k) : 0xffffffffu;
+            for (uint32_t b = 0; b < nb; ++b) { // one ballot per bucket in use (2..16), warp-uniform trip count
+                const uint32_t c = __popc(__ballot_sync(BP_FULL_MASK, d == b));
+                if (lane == b) mine += c;
+            }
+            if constexpr (HALO) {
+                // common case: the cell ends before the next splitter -- one comparison
+                if (live && d < op.n) {
+                    const K hi = run_upper_key<T>(k);
+                    if (((uint64_t)hi >> op.shift) >= op.spl[d]) {
+                        const uint32_t last = op(hi);
+                        for (uint32_t s = d + 1; s <= last; ++s) atomicAdd(&sh[MAX_SPLITTERS + 1 + s], 1u); // rare
+                    }
                 }
             }
         }
@@ -449,21 +459,27 @@ __global__ void __launch_bounds__(512) partition_hist_kernel(const K *__restrict
 
 // The bucket (and halo) counts of partition_hist_kernel as one row of 64-bit words for a peer-visible count
 // matrix: [counts 0..nb) | halo 0..nb) (if any) | tag] -- written on the device so that no host round trip is needed.
-__global__ void count_row_kernel(const uint32_t *__restrict__ hist, const uint32_t *__restrict__ halo, uint32_t nb, uint64_t tag,
+constexpr int MAX_ROW_TAGS = 8;
+struct RowTags {
+    uint64_t v[MAX_ROW_TAGS];
+    uint32_t n;
+};
+__global__ void count_row_kernel(const uint32_t *__restrict__ hist, const uint32_t *__restrict__ halo, uint32_t nb, RowTags tags,
                                  uint64_t *__restrict__ row) {
     const uint32_t i = threadIdx.x;
     if (i < nb) {
         row[i] = hist[i];
         if (halo) row[nb + i] = halo[i];
     }
-    if (i == 0) row[halo ? 2 * nb : nb] = tag;
+    if (i < tags.n) row[(halo ? 2 * nb : nb) + i] = tags.v[i];
 }
 
 // Writes the halo copies counted above into their destinations (slots handed out by atomics: the
 // receiver sorts its records anyway).
 template <class K, class V, class T>
 __global__ void __launch_bounds__(256) halo_scatter_kernel(const K *__restrict__ keys, const V *__restrict__ vals, uint32_t n,
-                                                            SplitterScatterDigit<K> op, uint32_t *__restrict__ cursor) {
+                                                            SplitterScatterDigit<K> op, uint32_t *__restrict__ cursor,
+                                                            const uint8_t *__restrict__ vflags) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const K k = ld_stream(keys + i);
         const uint32_t d = op(k);
@@ -472,7 +488,8 @@ __global__ void __launch_bounds__(256) halo_scatter_kernel(const K *__restrict__
         if (((uint64_t)hi >> op.shift) < op.spl[d]) continue; // the cell ends before the next splitter
         const uint32_t last = op(hi);
         if (last > d) {
-            const V v = vals[i];
+            V v = vals[i];
+            if (vflags) v |= (V)vflags[i] << (8 * sizeof(V) - 3);
             for (uint32_t s = d + 1; s <= last; ++s) {
                 const uint32_t slot = atomicAdd(&cursor[s], 1u);
                 ((K *)op.kdst[s])[slot] = k;

@@ -39,6 +39,7 @@ import torch.distributed as dist
 KIND_PARAMS = {0: (32, 2, 4, 14), 1: (64, 2, 5, 29), 2: (64, 3, 5, 19)}
 SAMPLES_PER_RANK = 2048
 U64_MAX = np.uint64(0xFFFFFFFFFFFFFFFF)
+N_TAGS = 7  # words a rank appends to its row of the record count matrix: id_or | fold bit, then CudaOps.sort_tags()
 REBALANCE_AT = 1.15  # recompute cached splitters when the fullest shard exceeds the mean by this factor
 
 
@@ -72,6 +73,26 @@ def choose_splitters(sample, parts):
         return np.full(parts - 1, U64_MAX, dtype=np.uint64)
     q = [s[min(s.shape[0] - 1, (i * s.shape[0]) // parts)] for i in range(1, parts)]
     return np.asarray(q, dtype=np.uint64)
+
+
+def sort_plan(tags, id_or, n_halo):
+    """(key_or, key_and, id_or, id_and, ids_ascending) for the sort of a receive buffer, from the tag words every source
+    sent with its counts (N_TAGS per source: id_or | fold bit, key_or, key_and, id_and, first ID, last ID, ascending).
+    The buffer holds the sources' chunks in rank order, each a stable partition of the source's records: its IDs ascend
+    iff every source's do, the sources' ID ranges follow each other in rank order, and no (unordered) halo copies came."""
+    full = 0xFFFFFFFFFFFFFFFF
+    key_or, key_and, id_and = 0, full, full
+    ascending, prev_last = n_halo == 0, -1
+    for t in tags:
+        key_or |= t[1]
+        key_and &= t[2]
+        id_and &= t[3]
+        first, last, asc = t[4], t[5], t[6]
+        if first > last and asc:  # an empty source
+            continue
+        ascending = ascending and bool(asc) and first >= prev_last
+        prev_last = max(prev_last, last)
+    return key_or, key_and, id_or, id_and, ascending
 
 
 def chunk_offsets(m_own, m_halo, me):
@@ -166,12 +187,20 @@ class CudaOps:
         c, h = self.enc.count_records(keys, keys.shape[0], splitters)
         return [int(x) for x in c], [int(x) for x in h]
 
-    def count_records_matrix(self, keys, splitters, tag):
+    def sort_tags(self):
+        """What the receivers of this rank's records need to plan their sort without a pass over the records:
+        [key_or, key_and, id_and, first ID, last ID, IDs ascending] of the freshly encoded tree (N_TAGS - 1 words)."""
+        key_or, key_and, _, id_and = self.enc.masks()
+        first, last, asc = self.enc.id_order()
+        return [key_or, key_and, id_and, first, last, int(asc)]
+
+    def count_records_matrix(self, keys, splitters, tags):
         """count_records + the exchange of the count matrix, without leaving the device until the matrix is complete:
-        returns the [source, 2 g + 1] matrix (owned counts | halo counts | tag) as host numpy."""
+        returns the [source, 2 g + N_TAGS] matrix (owned counts | halo counts | tags) as host numpy."""
         if self._cm_rec is None:
-            self._cm_rec = _CountMatrix(self.world, self.rank, 2 * self.world + 1, self.device, self.group)
-        self.enc.count_records_device(keys, keys.shape[0], splitters, tag, self._cm_rec.my_row_ptr)
+            self._cm_rec = _CountMatrix(self.world, self.rank, 2 * self.world + N_TAGS, self.device, self.group)
+        assert len(tags) == N_TAGS
+        self.enc.count_records_device_tags(keys, keys.shape[0], splitters, tags, self._cm_rec.my_row_ptr)
         return self._cm_rec.gather()
 
     def count_pairs_matrix(self, raw, splitters):
@@ -180,7 +209,9 @@ class CudaOps:
         self.shard.count_pairs_device(raw, raw.shape[0], splitters, 0, self._cm_pair.my_row_ptr)
         return self._cm_pair.gather()[:, :self.world]
 
-    def exchange_records(self, keys, ids, splitters, m_own, m_halo):
+    def exchange_records(self, keys, ids, splitters, m_own, m_halo, fold=False):
+        """fold: the cell flags of the encoded records leave in the top 3 bits of their IDs (dedup at the source across
+        the exchange: the receiving shard emits every ID pair from its canonical shared cell only)."""
         me, g = self.rank, self.world
         need = int((m_own + m_halo).sum(axis=0).max())
         if need > self.rec_cap:  # the matrices are global, so every rank grows (collectively) at the same time
@@ -190,22 +221,23 @@ class CudaOps:
         own_off, halo_off = chunk_offsets(m_own, m_halo, me)
         dk = [self.rk.ptrs[d] + 8 * own_off[d] for d in range(g)]
         di = [self.ri.ptrs[d] + 4 * own_off[d] for d in range(g)]
-        hk = [self.rk.ptrs[d] + 8 * halo_off[d] for d in range(g)]
-        hi = [self.ri.ptrs[d] + 4 * halo_off[d] for d in range(g)]
-        self.enc.scatter_records(keys, ids, keys.shape[0], splitters, dk, di, hk, hi)
+        hk = hi = None  # no halo copies leave this rank (the usual case): no second pass over the keys
+        if int(m_halo[me].sum()):
+            hk = [self.rk.ptrs[d] + 8 * halo_off[d] for d in range(g)]
+            hi = [self.ri.ptrs[d] + 4 * halo_off[d] for d in range(g)]
+        self.enc.scatter_records(keys, ids, keys.shape[0], splitters, dk, di, hk, hi, fold_cell_flags=fold)
         self.rk.barrier()  # every rank's stores have landed before anybody reads its receive buffer
         n_recv = int((m_own + m_halo)[:, me].sum())
         return self.rk.t.view(torch.int64)[:n_recv], self.ri.t.view(torch.int32)[:n_recv]
 
-    def fold_flags(self):
-        """Moves the cell flags of the freshly encoded records into their IDs' top 3 bits, in place (the views encode()
-        returned see them): they travel with the records, and the receiving shard can emit every ID pair from its
-        canonical shared cell only -- fewer raw pairs to exchange and to sort."""
-        return self.enc.fold_cell_flags()
-
-    def sort_records(self, keys, ids, flagged=False):
-        self.shard.set_records(keys, ids, sorted_=False, on_device=True, n=keys.shape[0], flagged=flagged)
-        self.shard.sort()
+    def sort_records(self, keys, ids, flagged=False, plan=None):
+        """plan = (key_or, key_and, id_or, id_and, ids_ascending) gathered with the count matrix: the sort then reads the
+        receive buffer directly, with neither a staging copy nor a mask pass."""
+        if plan is not None:
+            self.shard.sort_from_device(keys, ids, keys.shape[0], flagged, *plan)
+        else:
+            self.shard.set_records(keys, ids, sorted_=False, on_device=True, n=keys.shape[0], flagged=flagged)
+            self.shard.sort()
         if flagged:  # (records_device would strip the flags again; the scan below reads the shard layer itself)
             return None, None
         kp, ip, r, _ = self.shard.records_device()
@@ -246,7 +278,7 @@ class CudaOps:
         return self.rp.t.view(torch.int64)[:int(m[:, me].sum())]
 
     def unique_pairs(self, raw, id_mask):
-        ptr, n = self.shard.unique_pairs_device(raw, raw.shape[0], id_mask)
+        ptr, n = self.shard.unique_pairs_inplace_device(raw, raw.shape[0], id_mask)  # raw = our receive buffer: sort scratch
         return _view(ptr, 2 * n, torch.int32, self.device).view(-1, 2)
 
 
@@ -348,31 +380,33 @@ class DistLayer:
 
         # 3. count, all-gather the count matrix, scatter straight into the owners' receive buffers
         # bit 63 of the tag: "my IDs leave their top 3 bits free" (dedup at the source across the exchange, below)
-        can_fold = hasattr(ops, "fold_flags") and self._static_halo is None and int(id_or) < (1 << 29)
-        if hasattr(ops, "count_records_matrix"):  # the product: counts stay on the device, the matrix travels over NVLink
-            mat = ops.count_records_matrix(keys, splitters, int(id_or) | ((1 << 63) if can_fold else 0))
-        else:                                      # CPU test double: host counts + all_gather (gloo)
+        product = hasattr(ops, "count_records_matrix")
+        can_fold = product and self._static_halo is None and int(id_or) < (1 << 29)
+        if product:  # counts stay on the device, the matrix travels over NVLink
+            mat = ops.count_records_matrix(keys, splitters, [int(id_or) | ((1 << 63) if can_fold else 0)] + ops.sort_tags())
+        else:        # CPU test double: host counts + all_gather (gloo)
             counts, halo = ops.count_records(keys, splitters)
             mat = self._gather_rows(counts + halo + [id_or], dev)
         m_own, m_halo = mat[:, :g], mat[:, g:2 * g]
-        id_bits = 0
-        flagged = hasattr(ops, "count_records_matrix")
-        for v in mat[:, 2 * g]:
-            v = int(v) & 0xFFFFFFFFFFFFFFFF
-            flagged = flagged and bool(v >> 63)
-            id_bits |= v & ~(1 << 63)
+        n_halo = int(m_halo[:, me].sum())
+        tags = [[int(v) & 0xFFFFFFFFFFFFFFFF for v in row] for row in mat[:, 2 * g:]]
+        flagged, id_bits, plan = product, 0, None
+        for t in tags:
+            flagged = flagged and bool(t[0] >> 63)  # every rank can: the cell flags ride in the IDs across the exchange
+            id_bits |= t[0] & ~(1 << 63)
+        if product:
+            plan = sort_plan(tags, id_bits, n_halo)
         id_bits |= self._static_id_bits
-        if flagged:  # every rank can: the cell flags ride in the IDs (in place, before the scatter ships them)
-            folded = ops.fold_flags()
-            assert folded or r_loc == 0
         self._id_mask |= (1 << max(1, id_bits.bit_length())) - 1  # IDs seen since the splitters were cached
         mark("counts")
-        rk, ri = ops.exchange_records(keys, rids, splitters, m_own, m_halo)
-        n_halo = int(m_halo[:, me].sum())
+        if product:
+            rk, ri = ops.exchange_records(keys, rids, splitters, m_own, m_halo, fold=flagged)
+        else:
+            rk, ri = ops.exchange_records(keys, rids, splitters, m_own, m_halo)
         mark("exchange")
 
         # 4. local sort: the halo records (all < my lower splitter) end up in front
-        sk, si = ops.sort_records(rk, ri, flagged) if flagged else ops.sort_records(rk, ri)
+        sk, si = ops.sort_records(rk, ri, flagged, plan) if product else ops.sort_records(rk, ri)
         if self._static_halo is not None:  # Layer::merge of the resident static shard (sorted runs: merge path)
             ops.merge_static()
             n_halo += self._static_halo

@@ -269,6 +269,24 @@ class Layer:
         self._ck(lib().bp_layer_unique_pairs_device(self._h, _dev_ptr(d_raw), n, id_mask, ctypes.byref(out), ctypes.byref(cnt)))
         return out.value, cnt.value
 
+    def unique_pairs_inplace_device(self, d_raw, n, id_mask=0):
+        """unique_pairs_device without the staging copy: d_raw is sort scratch afterwards."""
+        out, cnt = ctypes.c_void_p(), ctypes.c_size_t()
+        self._ck(lib().bp_layer_unique_pairs_inplace_device(self._h, _dev_ptr(d_raw), n, id_mask, ctypes.byref(out), ctypes.byref(cnt)))
+        return out.value, cnt.value
+
+    def sort_from_device(self, d_keys, d_ids, n, flagged, key_or, key_and, id_or, id_and, ids_ascending):
+        """set_records + sort straight out of d_keys / d_ids with a caller-supplied digit plan (include/bp.h)."""
+        m = 0xFFFFFFFFFFFFFFFF
+        self._ck(lib().bp_layer_sort_from_device(self._h, _dev_ptr(d_keys), _dev_ptr(d_ids), n, int(flagged), int(key_or) & m,
+                                                 int(key_and) & m, int(id_or) & m, int(id_and) & m, int(ids_ascending)))
+
+    def id_order(self):
+        """(first ID, last ID, ascending) of a tree built by extend calls since the last clear (include/bp.h)."""
+        a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int()
+        self._ck(lib().bp_layer_id_order(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, bool(c.value)
+
     def partition_records(self, d_keys, d_ids, n, splitters, d_out_keys, d_out_ids):
         spl = np.ascontiguousarray(splitters, dtype=np.uint64)
         counts = np.zeros(spl.shape[0] + 1, dtype=np.uint64)
@@ -298,20 +316,29 @@ class Layer:
         self._ck(lib().bp_dist_count_records_device(self._h, _dev_ptr(d_keys), n, spl.ctypes.data, spl.shape[0], int(tag),
                                                     _dev_ptr(d_out_row)))
 
+    def count_records_device_tags(self, d_keys, n, splitters, tags, d_out_row):
+        """count_records_device with up to 8 tag words: row = [counts | halo counts | tags...]."""
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        t = np.asarray([int(x) & 0xFFFFFFFFFFFFFFFF for x in tags], dtype=np.uint64)
+        self._ck(lib().bp_dist_count_records_device_tags(self._h, _dev_ptr(d_keys), n, spl.ctypes.data, spl.shape[0],
+                                                         t.ctypes.data, t.shape[0], _dev_ptr(d_out_row)))
+
     def count_pairs_device(self, d_pairs, n, splitters, tag, d_out_row):
         spl = np.ascontiguousarray(splitters, dtype=np.uint64)
         self._ck(lib().bp_dist_count_pairs_device(self._h, _dev_ptr(d_pairs), n, spl.ctypes.data, spl.shape[0], int(tag),
                                                   _dev_ptr(d_out_row)))
 
-    def scatter_records(self, d_keys, d_ids, n, splitters, dst_keys, dst_ids, halo_dst_keys=None, halo_dst_ids=None):
-        """Partition pass writing bucket b to the device addresses dst_keys[b] / dst_ids[b]."""
+    def scatter_records(self, d_keys, d_ids, n, splitters, dst_keys, dst_ids, halo_dst_keys=None, halo_dst_ids=None,
+                        fold_cell_flags=False):
+        """Partition pass writing bucket b to the device addresses dst_keys[b] / dst_ids[b]; fold_cell_flags: the layer's
+        cell flags leave in the top 3 bits of the IDs (bp_dist_scatter_records_flagged)."""
         spl = np.ascontiguousarray(splitters, dtype=np.uint64)
         arrs = [np.ascontiguousarray(x, dtype=np.uint64) for x in (dst_keys, dst_ids)]
         h = [None if x is None else np.ascontiguousarray(x, dtype=np.uint64) for x in (halo_dst_keys, halo_dst_ids)]
-        self._ck(lib().bp_dist_scatter_records(self._h, _dev_ptr(d_keys), _dev_ptr(d_ids), n, spl.ctypes.data, spl.shape[0],
-                                               arrs[0].ctypes.data, arrs[1].ctypes.data,
-                                               None if h[0] is None else h[0].ctypes.data,
-                                               None if h[1] is None else h[1].ctypes.data))
+        self._ck(lib().bp_dist_scatter_records_flagged(self._h, _dev_ptr(d_keys), _dev_ptr(d_ids), n, spl.ctypes.data, spl.shape[0],
+                                                       arrs[0].ctypes.data, arrs[1].ctypes.data,
+                                                       None if h[0] is None else h[0].ctypes.data,
+                                                       None if h[1] is None else h[1].ctypes.data, int(fold_cell_flags)))
 
     def count_pairs(self, d_pairs, n, splitters):
         spl = np.ascontiguousarray(splitters, dtype=np.uint64)

@@ -213,6 +213,21 @@ int bp_layer_set_records(bp_layer *layer, const void *keys, const void *ids, siz
 int bp_layer_fold_cell_flags(bp_layer *layer, int *out_folded);
 int bp_layer_set_records_flagged(bp_layer *layer, const void *keys, const void *ids, size_t n, int sorted, int on_device, int flagged);
 
+/* bp_layer_set_records_flagged(.., sorted = 0, on_device = 1) followed by bp_layer_sort, as one step and without the two
+ * passes over the records that combination spends before the sort starts: the first radix pass reads d_keys / d_ids where
+ * they are (e.g. a multi-GPU receive buffer; not modified, no staging copy), and the digit plan comes from the caller's
+ * masks instead of a mask pass -- key_or / id_or may have extra bits set and key_and / id_and extra bits clear (a plan
+ * with idle digits, never a wrong order); ids_ascending must only be non-zero if the IDs do not decrease in record order
+ * (then equal keys keep their order and no ID digits are sorted).  The masks describe the IDs without cell flags. */
+int bp_layer_sort_from_device(bp_layer *layer, const void *d_keys, const void *d_ids, size_t n, int flagged, uint64_t key_or,
+                              uint64_t key_and, uint64_t id_or, uint64_t id_and, int ids_ascending);
+/* What a sender knows about the order of the IDs of a tree built by extend calls since the last clear: the IDs of the
+ * first and the last object passed in (valid or not) and whether no ID was smaller than its predecessor.  With
+ * *out_ascending set, [first, last] bounds the tree's IDs; several such trees concatenated in an order in which these
+ * ranges do not overlap are ascending again (what bp_layer_sort_from_device wants to hear).  An empty tree reports
+ * first = 2^64 - 1, last = 0, ascending = 1. */
+int bp_layer_id_order(bp_layer *layer, uint64_t *out_first, uint64_t *out_last, int *out_ascending);
+
 int bp_layer_len(bp_layer *layer, size_t *out_n);
 int bp_layer_is_sorted(bp_layer *layer, int *out_sorted);
 int bp_layer_min_depth(const bp_layer *layer, uint32_t *out_min_depth);
@@ -244,6 +259,12 @@ int bp_dist_count_records(bp_layer *ctx, const void *d_keys, size_t n, const uin
 int bp_dist_scatter_records(bp_layer *ctx, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
                             int n_splitters, const uint64_t *dst_keys, const uint64_t *dst_ids, const uint64_t *halo_dst_keys,
                             const uint64_t *halo_dst_ids);
+/* bp_dist_scatter_records with the layer's cell flags (see bp_layer_fold_cell_flags) OR-ed into the top 3 bits of every
+ * ID as the pass loads it -- no separate folding pass, the layer's own records stay unflagged.  d_keys / d_ids must be the
+ * layer's own record arrays (bp_layer_records_device) of a freshly extended tree whose IDs leave those bits free. */
+int bp_dist_scatter_records_flagged(bp_layer *ctx, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
+                                    int n_splitters, const uint64_t *dst_keys, const uint64_t *dst_ids,
+                                    const uint64_t *halo_dst_keys, const uint64_t *halo_dst_ids, int fold_cell_flags);
 int bp_dist_count_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
                         uint64_t *out_counts);
 int bp_dist_scatter_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
@@ -256,6 +277,10 @@ int bp_dist_count_records_device(bp_layer *ctx, const void *d_keys, size_t n, co
                                  uint64_t tag, void *d_out_row);
 int bp_dist_count_pairs_device(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
                                void *d_out_row);
+/* The same with up to 8 tag words at the end of the row (the sort masks and ID order of the sender travel with its counts,
+ * so that the receivers can plan their sort without looking at the records: bp_layer_sort_from_device). */
+int bp_dist_count_records_device_tags(bp_layer *ctx, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
+                                      const uint64_t *tags, int n_tags, void *d_out_row);
 /* Equal range [lo, hi) of every query key in a sorted device key array (halo look-ups). */
 int bp_dist_lookup_ranges(bp_layer *ctx, const void *d_sorted_keys, size_t n, const uint64_t *queries, int n_queries,
                           uint64_t *out_lo, uint64_t *out_hi);
@@ -268,6 +293,9 @@ int bp_layer_scan_raw_device(bp_layer *layer, const bp_filter *filter, const voi
  * (later, earlier) layout.  id_mask: OR of all bits in which two IDs may differ (0: use the layer's own). */
 int bp_layer_unique_pairs_device(bp_layer *layer, const void *d_raw, size_t n, uint64_t id_mask, const void **out_d_pairs,
                                  size_t *out_count);
+/* The same without the staging copy: d_raw itself is one side of the sort's ping-pong (its contents are destroyed). */
+int bp_layer_unique_pairs_inplace_device(bp_layer *layer, void *d_raw, size_t n, uint64_t id_mask, const void **out_d_pairs,
+                                         size_t *out_count);
 
 /* ---- instrumentation -------------------------------------------------------------------------- */
 int bp_layer_set_profiling(bp_layer *layer, int enabled); /* CUDA-event timing of every kernel launch */

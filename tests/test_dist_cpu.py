@@ -55,3 +55,20 @@ def test_ancestor_keys_and_splitters(bp):
     m_halo = np.array([[0, 3], [0, 0]])
     assert bpd.chunk_offsets(m_own, m_halo, 0) == ([0, 0], [5, 1])
     assert bpd.chunk_offsets(m_own, m_halo, 1) == ([5, 4], [7, 11])
+
+
+def test_sort_plan_from_tag_words(bp):
+    """The receivers' sort plan from the senders' tag words: masks OR / AND over the sources, IDs ascending only if every
+    source's are, the ID ranges follow each other in rank order and no halo copies arrived."""
+    from broadphase_rs_b200.dist import sort_plan
+    full = (1 << 64) - 1
+    empty = [0, 0, full, full, full, 0, 1]
+    a = [0xFF | (1 << 63), 0xF0F0, 0x1010, 0x01, 0, 99, 1]
+    b = [0x1FF, 0x0F0F, 0x0101, 0x100, 100, 250, 1]
+    assert sort_plan([a, b], 0x1FF, 0) == (0xFFFF, 0, 0x1FF, 0, True)
+    assert sort_plan([a, empty, b], 0x1FF, 0)[4] is True
+    assert sort_plan([b, a], 0x1FF, 0)[4] is False            # ranges out of rank order
+    assert sort_plan([a, b], 0x1FF, 3)[4] is False            # halo copies are unordered
+    assert sort_plan([a, b[:6] + [0]], 0x1FF, 0)[4] is False  # a source whose own IDs do not ascend
+    assert sort_plan([a, [0x1FF, 0, full, full, 99, 250, 1]], 0x1FF, 0)[4] is True   # equal IDs may meet at the seam
+    assert sort_plan([empty, empty], 0, 0) == (0, full, 0, full, True)

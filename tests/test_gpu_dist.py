@@ -149,6 +149,89 @@ def test_count_and_scatter_pairs(bp):
     assert (out.cpu().numpy().view(np.uint64) == raw[np.argsort(bucket, kind="stable")]).all()
 
 
+def test_sort_from_device_equals_set_records_then_sort(bp):
+    """bp_layer_sort_from_device: the first radix pass reads the caller's buffer, the plan comes from the caller's masks
+    (exact or loose); every combination must leave the tree set_records + sort leaves, and must not touch the source."""
+    import torch
+    sc, k, i = _records(bp, 120_000, 7)
+    full = (1 << 64) - 1
+    rng = np.random.Generator(np.random.Philox(5))
+    perm = rng.permutation(k.shape[0])
+    for name, kk, ii, asc in (("ascending ids", k, i, True), ("shuffled", k[perm], i[perm], False),
+                              ("equal keys", np.full(1000, k[0]), i[:1000][::-1].copy(), False),
+                              ("one record", k[:1], i[:1], True), ("empty", k[:0], i[:0], True)):
+        n = kk.shape[0]
+        dk = torch.from_numpy(kk.view(np.int64).copy()).cuda()
+        di = torch.from_numpy(ii.view(np.int32).copy()).cuda()
+        want_k, want_i = pyref.sort_records(kk, ii)
+        key_or = int(np.bitwise_or.reduce(kk)) if n else 0
+        key_and = int(np.bitwise_and.reduce(kk)) if n else full
+        id_or = int(np.bitwise_or.reduce(ii)) if n else 0
+        id_and = int(np.bitwise_and.reduce(ii)) if n else full
+        for plan in ((key_or, key_and, id_or, id_and, asc), (key_or | (0xFF << 40), 0, id_or | 0xF, 0, False)):
+            L = bp.Layer(2, "u32")
+            L.sort_from_device(dk, di, n, False, *plan)
+            gk, gi = L.iter()
+            assert (gk == want_k).all() and (gi == want_i).all(), (name, plan)
+            assert L.sorted
+            assert (dk.cpu().numpy().view(np.uint64) == kk).all() and (di.cpu().numpy().view(np.uint32) == ii).all()
+            if n > 1:
+                assert (L.scan().astype(np.uint64) == pyref.scan(2, want_k, want_i)[0]).all(), name
+
+
+def test_id_order_and_flagged_scatter(bp):
+    """bp_layer_id_order reports what the receivers of a rank's records need; bp_dist_scatter_records_flagged ships the cell
+    flags inside the IDs, and a shard sorted from such a buffer scans to the same pairs with no duplicate raw pair."""
+    import torch
+    from broadphase_rs_b200.dist import _view, sort_plan
+    sc = bp.scenes.uniform_cubes(60_000, 4)
+    L = bp.Layer(2, "u32")
+    assert L.id_order() == ((1 << 64) - 1, 0, True)
+    db = torch.from_numpy(sc["bounds"]).cuda()
+    di = torch.from_numpy(sc["ids"].view(np.int32)).cuda()
+    L.extend_device(sc["sys_bounds"], db, di, 60_000)
+    assert L.id_order() == (0, 59_999, True)
+    kp, ip, r, _ = L.records_device()
+    key_or, key_and, id_or, id_and = L.masks()
+    spl = np.array([1 << 60], dtype=np.uint64)
+    counts, halo = L.count_records(_view(kp, r, torch.int64, torch.device("cuda")), r, spl)
+    assert int(halo.sum()) == 0
+    ok = torch.zeros(r, dtype=torch.int64, device="cuda")
+    oi = torch.zeros(r, dtype=torch.int32, device="cuda")
+    dst_k = [ok.data_ptr(), ok.data_ptr() + 8 * int(counts[0])]
+    dst_i = [oi.data_ptr(), oi.data_ptr() + 4 * int(counts[0])]
+    L.scatter_records(kp, ip, r, spl, dst_k, dst_i, None, None, fold_cell_flags=True)
+    torch.cuda.synchronize()
+    ids_out = oi.cpu().numpy().view(np.uint32)
+    assert (ids_out >> 29).any() and ((ids_out & ((1 << 29) - 1)) < 60_000).all()
+    o = co.OracleLayer(2, 4, 0)
+    o.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    want = o.par_scan().astype(np.uint32)
+    # both buckets together are the whole scene again: sort them as one flagged shard
+    S = bp.Layer(2, "u32")
+    tags = [[id_or | (1 << 63), key_or, key_and, id_and, 0, 59_999, 1]]
+    plan = list(sort_plan(tags, id_or, 0))
+    assert plan == [key_or, key_and, id_or, id_and, True]
+    plan[4] = False  # two buckets of the same source side by side: the IDs start over at the seam
+    S.sort_from_device(ok, oi, r, True, *plan)
+    ptr, n_raw = S.scan_raw_device(None)
+    raw = _view(ptr, n_raw, torch.int64, torch.device("cuda")).clone()
+    assert n_raw == want.shape[0]                     # dedup at the source: every ID pair exactly once
+    ptr, n = S.unique_pairs_inplace_device(raw, n_raw, (1 << 16) - 1)
+    got = _view(ptr, 2 * n, torch.int32, torch.device("cuda")).cpu().numpy().view(np.uint32).reshape(n, 2)
+    assert got.shape == want.shape and (got == want).all()
+    gk, gi = S.iter()                                  # accessors strip the flags
+    ok_, oi_ = o.records()
+    sk, si = pyref.sort_records(ok_, oi_.astype(np.uint32))
+    assert (gk == sk).all() and (gi == si).all()
+    # an unsorted / foreign buffer cannot be folded
+    with pytest.raises(Exception):
+        L.scatter_records(ok, oi, r, spl, dst_k, dst_i, None, None, fold_cell_flags=True)
+    # a second extend with smaller IDs: not ascending any more
+    L.extend_device(sc["sys_bounds"], db[:10], di[:10], 10)
+    assert L.id_order() == (0, 9, False)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
