@@ -30,6 +30,7 @@ def _time_frames(bp, bpd, dl, ops, sc, n_local, steps, warmup, device, host_path
     if host_path:
         h_bounds = torch.from_numpy(sc["bounds"]).pin_memory()
         h_ids = torch.from_numpy(sc["ids"].view(np.int32)).pin_memory()
+        h_pairs = torch.empty((0, 2), dtype=torch.int32).pin_memory()  # pinned landing buffer for the rank's pair slice
     times, pairs_local = [], 0
     for s in range(warmup + steps):
         flush.fill_(s & 0xFF)
@@ -43,8 +44,10 @@ def _time_frames(bp, bpd, dl, ops, sc, n_local, steps, warmup, device, host_path
             d_ids.copy_(h_ids, non_blocking=True)
         pairs = dl.frame(sc["sys_bounds"], d_bounds, d_ids, n_local, None)
         if host_path:
-            host_pairs = pairs.cpu()
-            pairs_local = host_pairs.shape[0]
+            pairs_local = pairs.shape[0]
+            if pairs_local > h_pairs.shape[0]:  # (grows during the warm-up step)
+                h_pairs = torch.empty((pairs_local + pairs_local // 4, 2), dtype=torch.int32).pin_memory()
+            h_pairs[:pairs_local].copy_(pairs, non_blocking=True)
         else:
             pairs_local = pairs.shape[0]
         e1.record(stream)
