@@ -1225,9 +1225,9 @@ template <int KIND, class IdT> struct Impl {
     // Bucket sizes of a splitter partition (and, for records, the halo copies every bucket will receive).
     template <class PK, bool HALO>
     static int partition_count(bp_layer *L, const PK *kin, uint32_t n, const uint64_t *spl, int n_spl, uint32_t shift,
-                               uint64_t *counts_out, uint64_t *halo_out, uint64_t *d_row = nullptr, const uint64_t *tags = nullptr,
-                               int n_tags = 0) {
-        if (d_row) { // counts stay on the device (a row of a peer-visible matrix): no host round trip
+                               uint64_t *counts_out, uint64_t *halo_out, const uint64_t *d_rows = nullptr, int n_rows = 0,
+                               const uint64_t *tags = nullptr, int n_tags = 0) {
+        if (d_rows) { // counts stay on the device (a row of a peer-visible matrix): no host round trip
             SplitterDigit<PK> op;
             for (int i = 0; i < MAX_SPLITTERS; ++i) op.spl[i] = i < n_spl ? spl[i] : ~0ull;
             op.n = (uint32_t)n_spl;
@@ -1246,7 +1246,10 @@ template <int KIND, class IdT> struct Impl {
                 RowTags rt;
                 rt.n = (uint32_t)std::min(n_tags, MAX_ROW_TAGS);
                 for (uint32_t i = 0; i < (uint32_t)MAX_ROW_TAGS; ++i) rt.v[i] = i < rt.n ? tags[i] : 0;
-                count_row_kernel<<<1, 32, 0, L->stream>>>(hist, HALO ? halo : nullptr, (uint32_t)n_spl + 1, rt, d_row);
+                RowDst rd;
+                rd.n = (uint32_t)std::min(n_rows, MAX_ROW_COPIES);
+                for (uint32_t i = 0; i < (uint32_t)MAX_ROW_COPIES; ++i) rd.p[i] = i < rd.n ? (uint64_t *)d_rows[i] : nullptr;
+                count_row_kernel<<<1, 32, 0, L->stream>>>(hist, HALO ? halo : nullptr, (uint32_t)n_spl + 1, rt, rd);
             }
             return check_launch(L, "count_row_kernel");
         }
@@ -1343,8 +1346,8 @@ template <int KIND, class IdT> struct Impl {
         return partition_count<K, true>(L, (const K *)kin, (uint32_t)n, spl, n_spl, 0, counts, halo);
     }
     static int count_records_row(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, const uint64_t *tags, int n_tags,
-                                 uint64_t *d_row) {
-        return partition_count<K, true>(L, (const K *)kin, (uint32_t)n, spl, n_spl, 0, nullptr, nullptr, d_row, tags, n_tags);
+                                 const uint64_t *d_rows, int n_rows) {
+        return partition_count<K, true>(L, (const K *)kin, (uint32_t)n, spl, n_spl, 0, nullptr, nullptr, d_rows, n_rows, tags, n_tags);
     }
     static int scatter_records(bp_layer *L, const void *kin, const void *vin, size_t n, const uint64_t *spl, int n_spl,
                                const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst, bool fold) {
@@ -1458,11 +1461,13 @@ int do_scatter_records(bp_layer *L, const void *kin, const void *vin, size_t n, 
     DISPATCH(L, scatter_records(L, kin, vin, n, spl, n_spl, kdst, vdst, hkdst, hvdst, fold));
 }
 int do_count_records_row(bp_layer *L, const void *kin, size_t n, const uint64_t *spl, int n_spl, const uint64_t *tags, int n_tags,
-                         uint64_t *d_row) {
-    DISPATCH(L, count_records_row(L, kin, n, spl, n_spl, tags, n_tags, d_row));
+                         const uint64_t *d_rows, int n_rows) {
+    DISPATCH(L, count_records_row(L, kin, n, spl, n_spl, tags, n_tags, d_rows, n_rows));
 }
-int do_count_pairs_row(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t tag, uint64_t *d_row) {
-    return Impl<BP_INDEX64_3D, uint32_t>::partition_count<uint64_t, false>(L, kin, (uint32_t)n, spl, n_spl, 32, nullptr, nullptr, d_row, &tag, 1);
+int do_count_pairs_row(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, const uint64_t *tags, int n_tags,
+                       const uint64_t *d_rows, int n_rows) {
+    return Impl<BP_INDEX64_3D, uint32_t>::partition_count<uint64_t, false>(L, kin, (uint32_t)n, spl, n_spl, 32, nullptr, nullptr, d_rows,
+                                                                           n_rows, tags, n_tags);
 }
 int do_count_pairs(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t *spl, int n_spl, uint64_t *counts) {
     return Impl<BP_INDEX64_3D, uint32_t>::partition_count<uint64_t, false>(L, kin, (uint32_t)n, spl, n_spl, 32, counts, nullptr);
@@ -2036,17 +2041,32 @@ int bp_dist_count_records_device(bp_layer *L, const void *d_keys, size_t n, cons
     if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
-    return do_count_records_row(L, d_keys, n, splitters, n_splitters, &tag, 1, (uint64_t *)d_out_row);
+    const uint64_t row = (uint64_t)(uintptr_t)d_out_row;
+    return do_count_records_row(L, d_keys, n, splitters, n_splitters, &tag, 1, &row, 1);
 }
 
-int bp_dist_count_records_device_tags(bp_layer *L, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
-                                      const uint64_t *tags, int n_tags, void *d_out_row) {
-    if (!L || !d_out_row || bad_splitters(splitters, n_splitters) || n_tags < 0 || n_tags > MAX_ROW_TAGS || (n_tags && !tags))
-        return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_records_device_tags");
+static bool bad_rows(const uint64_t *tags, int n_tags, const uint64_t *rows, int n_rows) {
+    return n_tags < 0 || n_tags > MAX_ROW_TAGS || (n_tags && !tags) || n_rows < 1 || n_rows > MAX_ROW_COPIES || !rows;
+}
+
+int bp_dist_count_records_rows(bp_layer *L, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
+                               const uint64_t *tags, int n_tags, const uint64_t *d_out_rows, int n_out_rows) {
+    if (!L || bad_splitters(splitters, n_splitters) || bad_rows(tags, n_tags, d_out_rows, n_out_rows))
+        return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_records_rows");
     if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
-    return do_count_records_row(L, d_keys, n, splitters, n_splitters, tags, n_tags, (uint64_t *)d_out_row);
+    return do_count_records_row(L, d_keys, n, splitters, n_splitters, tags, n_tags, d_out_rows, n_out_rows);
+}
+
+int bp_dist_count_pairs_rows(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
+                             const uint64_t *tags, int n_tags, const uint64_t *d_out_rows, int n_out_rows) {
+    if (!L || bad_splitters(splitters, n_splitters) || bad_rows(tags, n_tags, d_out_rows, n_out_rows))
+        return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_pairs_rows");
+    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 pairs");
+    DeviceGuard g(L->device);
+    TRY(resolve_pending(L));
+    return do_count_pairs_row(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, tags, n_tags, d_out_rows, n_out_rows);
 }
 
 int bp_dist_count_pairs_device(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
@@ -2055,7 +2075,8 @@ int bp_dist_count_pairs_device(bp_layer *L, const void *d_pairs, size_t n, const
     if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 pairs");
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
-    return do_count_pairs_row(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, tag, (uint64_t *)d_out_row);
+    const uint64_t row = (uint64_t)(uintptr_t)d_out_row;
+    return do_count_pairs_row(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, &tag, 1, &row, 1);
 }
 
 int bp_dist_scatter_pairs(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,

@@ -464,14 +464,23 @@ struct RowTags {
     uint64_t v[MAX_ROW_TAGS];
     uint32_t n;
 };
+constexpr int MAX_ROW_COPIES = 16;
+struct RowDst { // the same row goes to every rank's copy of the count matrix (peer stores: no copy engine, no extra launches)
+    uint64_t *p[MAX_ROW_COPIES];
+    uint32_t n;
+};
 __global__ void count_row_kernel(const uint32_t *__restrict__ hist, const uint32_t *__restrict__ halo, uint32_t nb, RowTags tags,
-                                 uint64_t *__restrict__ row) {
+                                 RowDst dst) {
     const uint32_t i = threadIdx.x;
-    if (i < nb) {
-        row[i] = hist[i];
-        if (halo) row[nb + i] = halo[i];
+    const uint64_t c = i < nb ? hist[i] : 0, h = (halo && i < nb) ? halo[i] : 0;
+    for (uint32_t r = 0; r < dst.n; ++r) {
+        uint64_t *row = dst.p[r];
+        if (i < nb) {
+            row[i] = c;
+            if (halo) row[nb + i] = h;
+        }
+        if (i < tags.n) row[(halo ? 2 * nb : nb) + i] = tags.v[i];
     }
-    if (i < tags.n) row[(halo ? 2 * nb : nb) + i] = tags.v[i];
 }
 
 // Writes the halo copies counted above into their destinations (slots handed out by atomics: the

@@ -134,22 +134,19 @@ class _SymmBuffer:
 
 
 class _CountMatrix:
-    """A g x row matrix of 64-bit counts in symmetric memory.  Rank r's count kernel writes row r of r's own copy
-    (no host round trip); one small peer copy per peer puts it into row r of their copies; after one barrier every
-    rank holds the whole matrix.  Replaces count -> host -> device -> NCCL all_gather -> host (two synchronisations
-    and a collective launch per exchange: ~0.2 ms of the 1.5 ms frame at 2^20 objects per GPU)."""
+    """A g x row matrix of 64-bit counts in symmetric memory.  The kernel that finishes rank r's counts stores them as
+    row r of EVERY rank's copy (its own, and the peers' through NVLink: self.row_ptrs); after one barrier every rank
+    holds the whole matrix.  Replaces count -> host -> device -> NCCL all_gather -> host (two synchronisations and a
+    collective launch per exchange: ~0.2 ms of the 1.5 ms frame at 2^20 objects per GPU), and the g - 1 copy-engine
+    transfers per gather of the first symmetric-memory version (serialised in the stream: ~0.1 ms per frame at g = 8)."""
 
     def __init__(self, g, me, row, device, group):
         self.g, self.me, self.row = g, me, row
         self.buf = _SymmBuffer(g * row * 8, device, group)
         self.local = self.buf.t.view(torch.int64).view(g, row)
-        self.my_row_ptr = self.buf.ptrs[me] + me * row * 8
-        self.peer_rows = {p: self.buf.hdl.get_buffer(p, (g, row), torch.int64)[me] for p in range(g) if p != me}
+        self.row_ptrs = [self.buf.ptrs[p] + me * row * 8 for p in range(g)]
 
     def gather(self):
-        mine = self.local[self.me]
-        for p, dst in self.peer_rows.items():
-            dst.copy_(mine, non_blocking=True)
         self.buf.barrier()  # every rank's row has landed everywhere
         return self.local.cpu().numpy()
 
@@ -200,13 +197,13 @@ class CudaOps:
         if self._cm_rec is None:
             self._cm_rec = _CountMatrix(self.world, self.rank, 2 * self.world + N_TAGS, self.device, self.group)
         assert len(tags) == N_TAGS
-        self.enc.count_records_device_tags(keys, keys.shape[0], splitters, tags, self._cm_rec.my_row_ptr)
+        self.enc.count_records_rows(keys, keys.shape[0], splitters, tags, self._cm_rec.row_ptrs)
         return self._cm_rec.gather()
 
     def count_pairs_matrix(self, raw, splitters):
         if self._cm_pair is None:
             self._cm_pair = _CountMatrix(self.world, self.rank, self.world + 1, self.device, self.group)
-        self.shard.count_pairs_device(raw, raw.shape[0], splitters, 0, self._cm_pair.my_row_ptr)
+        self.shard.count_pairs_rows(raw, raw.shape[0], splitters, [0], self._cm_pair.row_ptrs)
         return self._cm_pair.gather()[:, :self.world]
 
     def exchange_records(self, keys, ids, splitters, m_own, m_halo, fold=False):

@@ -316,12 +316,21 @@ class Layer:
         self._ck(lib().bp_dist_count_records_device(self._h, _dev_ptr(d_keys), n, spl.ctypes.data, spl.shape[0], int(tag),
                                                     _dev_ptr(d_out_row)))
 
-    def count_records_device_tags(self, d_keys, n, splitters, tags, d_out_row):
-        """count_records_device with up to 8 tag words: row = [counts | halo counts | tags...]."""
+    def count_records_rows(self, d_keys, n, splitters, tags, out_rows):
+        """count_records_device with up to 8 tag words, row = [counts | halo counts | tags...], stored to every device
+        address in out_rows (this rank's row in every rank's count matrix)."""
         spl = np.ascontiguousarray(splitters, dtype=np.uint64)
         t = np.asarray([int(x) & 0xFFFFFFFFFFFFFFFF for x in tags], dtype=np.uint64)
-        self._ck(lib().bp_dist_count_records_device_tags(self._h, _dev_ptr(d_keys), n, spl.ctypes.data, spl.shape[0],
-                                                         t.ctypes.data, t.shape[0], _dev_ptr(d_out_row)))
+        rows = np.asarray(out_rows, dtype=np.uint64)
+        self._ck(lib().bp_dist_count_records_rows(self._h, _dev_ptr(d_keys), n, spl.ctypes.data, spl.shape[0],
+                                                  t.ctypes.data, t.shape[0], rows.ctypes.data, rows.shape[0]))
+
+    def count_pairs_rows(self, d_pairs, n, splitters, tags, out_rows):
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        t = np.asarray([int(x) & 0xFFFFFFFFFFFFFFFF for x in tags], dtype=np.uint64)
+        rows = np.asarray(out_rows, dtype=np.uint64)
+        self._ck(lib().bp_dist_count_pairs_rows(self._h, _dev_ptr(d_pairs), n, spl.ctypes.data, spl.shape[0],
+                                                t.ctypes.data, t.shape[0], rows.ctypes.data, rows.shape[0]))
 
     def count_pairs_device(self, d_pairs, n, splitters, tag, d_out_row):
         spl = np.ascontiguousarray(splitters, dtype=np.uint64)

@@ -278,9 +278,13 @@ int bp_dist_count_records_device(bp_layer *ctx, const void *d_keys, size_t n, co
 int bp_dist_count_pairs_device(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
                                void *d_out_row);
 /* The same with up to 8 tag words at the end of the row (the sort masks and ID order of the sender travel with its counts,
- * so that the receivers can plan their sort without looking at the records: bp_layer_sort_from_device). */
-int bp_dist_count_records_device_tags(bp_layer *ctx, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
-                                      const uint64_t *tags, int n_tags, void *d_out_row);
+ * so that the receivers can plan their sort without looking at the records: bp_layer_sort_from_device), and with the row
+ * stored to up to 16 device ADDRESSES at once -- this rank's row inside every rank's copy of the matrix, peers' through
+ * NVLink: the kernel that finishes the counts also distributes them, no copy-engine transfers in between. */
+int bp_dist_count_records_rows(bp_layer *ctx, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
+                               const uint64_t *tags, int n_tags, const uint64_t *d_out_rows, int n_out_rows);
+int bp_dist_count_pairs_rows(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
+                             const uint64_t *tags, int n_tags, const uint64_t *d_out_rows, int n_out_rows);
 /* Equal range [lo, hi) of every query key in a sorted device key array (halo look-ups). */
 int bp_dist_lookup_ranges(bp_layer *ctx, const void *d_sorted_keys, size_t n, const uint64_t *queries, int n_queries,
                           uint64_t *out_lo, uint64_t *out_hi);
