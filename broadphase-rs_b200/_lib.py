@@ -64,6 +64,7 @@ SYMBOLS = {
     "bp_layer_sort_from_device": (_i, [_vp, _vp, _vp, _sz, _i, _u64, _u64, _u64, _u64, _i]),
     "bp_layer_id_order": (_i, [_vp, _P(_u64), _P(_u64), _P(_i)]),
     "bp_dist_count_records_rows": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _i, _vp, _i]),
+    "bp_dist_extend_count_rows": (_i, [_vp, _vp, _vp, _vp, _sz, _vp, _i, _i, _vp, _i]),
     "bp_dist_count_pairs_rows": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _i, _vp, _i]),
     "bp_dist_scatter_records_flagged": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _vp, _i]),
     "bp_layer_unique_pairs_inplace_device": (_i, [_vp, _vp, _sz, _u64, _P(_vp), _P(_sz)]),

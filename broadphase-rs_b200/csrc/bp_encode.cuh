@@ -34,6 +34,17 @@ constexpr int ENCODE_TILE = ENCODE_THREADS * ENCODE_OPT;
 constexpr int ENCODE_ROUND = 8192; // records generated per round (= ENCODE_TILE * 2^3: one round at natural depth)
 constexpr int ENCODE_LUT_BITS = 10;
 
+// Optional by-product for the multi-GPU frame: while the splitters of the previous frame are still good, the records are
+// counted per destination shard (and per halo copy) as they are generated -- the separate counting pass over the keys
+// (partition_hist_kernel) and its launch disappear.  Same definition: home = #splitters <= key, halo copies for the
+// shards home+1 .. #splitters <= run_upper_key(key).
+constexpr int ENCODE_MAX_SPLITTERS = 15;
+struct EncodeCount {
+    uint64_t spl[ENCODE_MAX_SPLITTERS];
+    uint32_t n_spl;
+    uint32_t *cnt; // [0, 16): records per home shard, [16, 32): halo copies per shard; zeroed by the host
+};
+
 template <class T, class IdT> struct EncodeArgs {
     const float *bounds; // n x 2*DIM
     const IdT *ids;      // n
@@ -51,6 +62,7 @@ template <class T, class IdT> struct EncodeArgs {
     const IdT *prev_last_id; // last ID of the previous extend since the tail began (or null)
     IdT *next_last_id;
     int *err;
+    EncodeCount count; // used by encode_kernel<.., COUNT = true> only
 };
 
 // Shared-memory layout.  The staged AABBs are dead once every thread has quantised its objects, so the
@@ -87,9 +99,11 @@ template <int DIM> __device__ __forceinline__ uint64_t spread_lut(const uint32_t
     return r;
 }
 
-template <class T, class IdT>
+template <class T, class IdT, bool COUNT = false>
 __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs<T, IdT> a) {
     typedef typename T::key_t K;
+    __shared__ uint32_t scount[COUNT ? 32 : 1];
+    if (COUNT && threadIdx.x < 32) scount[threadIdx.x] = 0; // (published by the barriers below, long before its first use)
     constexpr int DIM = T::DIM;
     constexpr int FPO = 2 * DIM; // floats per object
     typedef EncodeSmem<T, IdT> S;
@@ -282,6 +296,26 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
                 a.ids_out[gi] = sid[o];
                 if (a.cell_flags_out) a.cell_flags_out[gi] = (uint8_t)((ix ? 1u : 0u) | (iy ? 2u : 0u) | (iz ? 4u : 0u));
             }
+            if constexpr (COUNT) {
+                // the threads of the warp that are still in the loop vote bucket by bucket; their first lane books the counts
+                const unsigned act = __activemask();
+                const unsigned leader = (unsigned)__ffs((int)act) - 1u;
+                const uint32_t ns = a.count.n_spl;
+                uint32_t home = 0;
+                for (uint32_t i = 0; i < ns; ++i) home += (a.count.spl[i] <= (uint64_t)key) ? 1u : 0u;
+                for (uint32_t b = 0; b <= ns; ++b) {
+                    const uint32_t c = (uint32_t)__popc(__ballot_sync(act, home == b));
+                    if (lane == leader && c) atomicAdd(&scount[b], c);
+                }
+                if (home < ns) { // common case: the cell ends before the next splitter -- one comparison
+                    const uint64_t hi = (uint64_t)run_upper_key<T>(key);
+                    if (hi >= a.count.spl[home]) {
+                        uint32_t last = 0;
+                        for (uint32_t i = 0; i < ns; ++i) last += (a.count.spl[i] <= hi) ? 1u : 0u;
+                        for (uint32_t s2 = home + 1; s2 <= last; ++s2) atomicAdd(&scount[16 + s2], 1u); // rare
+                    }
+                }
+            }
         }
         __syncthreads();
     }
@@ -304,6 +338,10 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
         if (n_invalid) atomicAdd(&a.result->n_invalid, (unsigned long long)n_invalid);
         if (nonmono) atomicOr(&a.result->nonmono, 1u);
         if (too_many) atomicOr(&a.result->too_many, 1u);
+    }
+    if constexpr (COUNT) {
+        __syncthreads();
+        if (tid < 32 && scount[tid]) atomicAdd(&a.count.cnt[tid], scount[tid]);
     }
     if (obj0 + tile_objs == a.n && tid == 0) { // last tile: totals + the tail's last ID
         a.result->total_records = tile_base + tile_total;

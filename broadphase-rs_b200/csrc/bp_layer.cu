@@ -72,6 +72,36 @@ __global__ void post_kernel(const unsigned long long *__restrict__ src, int nwor
 
 } // namespace
 
+// The count row of a counting extend (Impl::extend_count_rows): per-shard counts from encode_kernel<.., COUNT>, then the tag
+// words broadphase-rs_b200/dist.py expects (N_TAGS = 7), built from the extend's result block without leaving the device:
+// id_or | (bit 63: the IDs leave their top 3 bits free and the caller allows folding), key_or, key_and, id_and, first ID,
+// last ID, IDs ascending -- an empty tree reports first = 2^64 - 1, last = 0, ascending = 1 like bp_layer_id_order.
+__global__ void count_row_result_kernel(const uint32_t *__restrict__ cnt, uint32_t nb, const bp::ExtendResult *__restrict__ res,
+                                        int allow_fold, int id_bits, bp::RowDst dst) {
+    const uint32_t i = threadIdx.x;
+    const bool empty = res->total_records == 0;
+    uint64_t tag = 0;
+    switch (i) {
+    case 0: tag = res->id_or | ((allow_fold && (res->id_or >> (id_bits - 3)) == 0) ? (1ull << 63) : 0ull); break;
+    case 1: tag = res->key_or; break;
+    case 2: tag = res->key_and; break;
+    case 3: tag = res->id_and; break;
+    case 4: tag = empty ? ~0ull : res->id_first; break;
+    case 5: tag = empty ? 0ull : res->id_last; break;
+    case 6: tag = (empty || !res->nonmono) ? 1ull : 0ull; break;
+    default: break;
+    }
+    const uint64_t c = i < nb ? cnt[i] : 0, h = i < nb ? cnt[16 + i] : 0;
+    for (uint32_t r = 0; r < dst.n; ++r) {
+        uint64_t *row = dst.p[r];
+        if (i < nb) {
+            row[i] = c;
+            row[nb + i] = h;
+        }
+        if (i < 7) row[2 * nb + i] = tag;
+    }
+}
+
 struct bp_layer {
     bp_layer_config cfg;
     int kind, id_bytes, key_bytes, dim, device;
@@ -107,6 +137,7 @@ struct bp_layer {
     cudaEvent_t ev_sync = nullptr;
     ExtendResult *h_res = nullptr; // pinned
     ExtendResult *d_res = nullptr;
+    uint32_t *d_cnt = nullptr;     // 32 words: per-shard record / halo counts taken by encode_kernel<.., COUNT> (multi-GPU)
     void *d_last = nullptr;        // 2 x u64 slots
     ScanTotals *h_tot = nullptr;   // pinned
     ScanTotals *d_tot = nullptr;
@@ -521,8 +552,11 @@ template <int KIND, class IdT> struct Impl {
     }
 
     // ---- extend ------------------------------------------------------------------------------------------
-    static int launch_encode(bp_layer *L, const float *sysb, const float *d_bounds, const IdT *d_ids, uint32_t n) {
+    static int launch_encode(bp_layer *L, const float *sysb, const float *d_bounds, const IdT *d_ids, uint32_t n,
+                             const EncodeCount *count = nullptr) {
         EncodeArgs<T, IdT> a;
+        memset(&a.count, 0, sizeof a.count);
+        if (count) a.count = *count;
         a.bounds = d_bounds;
         a.ids = d_ids;
         a.n = n;
@@ -558,7 +592,7 @@ template <int KIND, class IdT> struct Impl {
         a.next_last_id = (IdT *)((char *)slots + 8 * (L->last_slot ^ 1));
         a.err = L->d_err;
         typedef EncodeSmem<T, IdT> S;
-        auto kern = encode_kernel<T, IdT>;
+        auto kern = count ? encode_kernel<T, IdT, true> : encode_kernel<T, IdT, false>;
         CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
         {
             // algorithmic bytes: input AABBs + IDs; the record bytes are added when the count is known
@@ -572,15 +606,17 @@ template <int KIND, class IdT> struct Impl {
         return BP_OK;
     }
 
-    static int extend_device(bp_layer *L, const float *sysb, const float *d_bounds, const void *d_ids, size_t n) {
+    static int extend_device(bp_layer *L, const float *sysb, const float *d_bounds, const void *d_ids, size_t n,
+                             const EncodeCount *count = nullptr) {
         if (n == 0) return BP_OK;
         TRY(strip_flags(L));
         if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "too many objects in one extend");
         const uint64_t per_obj = 1ull << T::DIM;
         TRY(ensure_tree(L, std::min<uint64_t>(L->n_records + n * per_obj, MAX_RECORDS)));
         for (int attempt = 0; attempt < 2; ++attempt) {
-            TRY(launch_encode(L, sysb, d_bounds, (const IdT *)d_ids, (uint32_t)n));
+            TRY(launch_encode(L, sysb, d_bounds, (const IdT *)d_ids, (uint32_t)n, count));
             if (L->min_depth == 0 && L->n_records + n * per_obj <= L->cap_records) return BP_OK; // cannot overflow: stays async
+            if (count) return fail(L, BP_ERR_INTERNAL, "counting extend needs min_depth 0 (the counts of a repeated call would add up)");
             // min_depth can push objects below their natural depth: the record count is only
             // known after the kernel, so check it now and redo the call once with enough room
             TRY(wait_mail(L, 0, L->pending_seq, L->h_res, sizeof(ExtendResult)));
@@ -590,6 +626,36 @@ template <int KIND, class IdT> struct Impl {
             TRY(ensure_tree(L, L->pending_base + total));
         }
         return fail(L, BP_ERR_INTERNAL, "extend did not converge");
+    }
+
+    // clear + extend with the per-shard counts taken by the encode kernel itself, then the count row (counts, halo counts
+    // and the 7 tag words of the multi-GPU frame, all read from device memory) stored to every rank's matrix: the first
+    // host round trip of the frame is the one that fetches the finished matrix.
+    static int extend_count_rows(bp_layer *L, const float *sysb, const float *d_bounds, const void *d_ids, size_t n,
+                                 const uint64_t *spl, int n_spl, bool allow_fold, const uint64_t *d_rows, int n_rows) {
+        EncodeCount ec;
+        for (int i = 0; i < ENCODE_MAX_SPLITTERS; ++i) ec.spl[i] = i < n_spl ? spl[i] : ~0ull;
+        ec.n_spl = (uint32_t)n_spl;
+        ec.cnt = L->d_cnt;
+        CU(L, cudaMemsetAsync(L->d_cnt, 0, 32 * sizeof(uint32_t), L->stream));
+        if (n == 0) { // no kernel will initialise the result block: an empty tree
+            ExtendResult init;
+            memset(&init, 0, sizeof init);
+            init.key_and = ~0ull;
+            init.id_and = ~0ull;
+            *L->h_res = init;
+            CU(L, cudaMemcpyAsync(L->d_res, L->h_res, sizeof init, cudaMemcpyHostToDevice, L->stream));
+        }
+        TRY(extend_device(L, sysb, d_bounds, d_ids, n, &ec));
+        RowDst rd;
+        rd.n = (uint32_t)std::min(n_rows, MAX_ROW_COPIES);
+        for (uint32_t i = 0; i < (uint32_t)MAX_ROW_COPIES; ++i) rd.p[i] = i < rd.n ? (uint64_t *)d_rows[i] : nullptr;
+        {
+            LaunchScope ls(L, BP_K_MISC, 0);
+            count_row_result_kernel<<<1, 32, 0, L->stream>>>(L->d_cnt, (uint32_t)n_spl + 1, L->d_res, allow_fold ? 1 : 0,
+                                                            (int)(8 * sizeof(IdT)), rd);
+        }
+        return check_launch(L, "count_row_result_kernel");
     }
 
     // ---- sort --------------------------------------------------------------------------------------------------
@@ -1479,6 +1545,10 @@ int do_scatter_pairs(bp_layer *L, const uint64_t *kin, size_t n, const uint64_t 
 int do_lookup_ranges(bp_layer *L, const void *keys, size_t n, const uint64_t *q, int nq, uint64_t *lo, uint64_t *hi) {
     DISPATCH(L, lookup_ranges(L, keys, n, q, nq, lo, hi));
 }
+int do_extend_count_rows(bp_layer *L, const float *sysb, const float *d_bounds, const void *d_ids, size_t n, const uint64_t *spl,
+                         int n_spl, bool allow_fold, const uint64_t *d_rows, int n_rows) {
+    DISPATCH(L, extend_count_rows(L, sysb, d_bounds, d_ids, n, spl, n_spl, allow_fold, d_rows, n_rows));
+}
 int do_sort_from(bp_layer *L, const void *k, const void *v, uint64_t n, bool asc) { DISPATCH(L, sort_from(L, k, v, n, asc)); }
 int do_masks(bp_layer *L, uint64_t n) { DISPATCH(L, masks_from_records(L, n)); }
 int do_strip_flags(bp_layer *L) { DISPATCH(L, strip_flags(L)); }
@@ -1624,6 +1694,7 @@ int bp_layer_create(const bp_layer_config *cfg, bp_layer **out) {
         if (cudaHostGetDevicePointer((void **)&L->d_mail[i], L->h_mail[i], 0) != cudaSuccess) return bail(BP_ERR_CUDA);
     }
     if (cudaMalloc((void **)&L->d_res, sizeof(ExtendResult)) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaMalloc((void **)&L->d_cnt, 32 * sizeof(uint32_t)) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMalloc((void **)&L->d_tot, sizeof(ScanTotals) + 64) != cudaSuccess) return bail(BP_ERR_OOM); // + scan_runs_kernel's counters
     if (cudaMalloc((void **)&L->d_err, sizeof(int)) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMalloc((void **)&L->d_last, 16) != cudaSuccess) return bail(BP_ERR_OOM);
@@ -1681,6 +1752,7 @@ int bp_layer_destroy(bp_layer *L) {
     for (int i = 0; i < 2; ++i)
         if (L->h_mail[i]) cudaFreeHost(L->h_mail[i]);
     if (L->d_res) cudaFree(L->d_res);
+    if (L->d_cnt) cudaFree(L->d_cnt);
     if (L->d_tot) cudaFree(L->d_tot);
     if (L->d_err) cudaFree(L->d_err);
     if (L->d_last) cudaFree(L->d_last);
@@ -2057,6 +2129,17 @@ int bp_dist_count_records_rows(bp_layer *L, const void *d_keys, size_t n, const 
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
     return do_count_records_row(L, d_keys, n, splitters, n_splitters, tags, n_tags, d_out_rows, n_out_rows);
+}
+
+int bp_dist_extend_count_rows(bp_layer *L, const float *sysb, const float *d_bounds, const void *d_ids, size_t n,
+                              const uint64_t *splitters, int n_splitters, int allow_fold, const uint64_t *d_out_rows, int n_out_rows) {
+    if (!L || !sysb || (n && (!d_bounds || !d_ids)) || bad_splitters(splitters, n_splitters) || n_out_rows < 1 ||
+        n_out_rows > MAX_ROW_COPIES || !d_out_rows)
+        return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_extend_count_rows");
+    if (L->min_depth != 0) return fail(L, BP_ERR_INVALID_ARG, "bp_dist_extend_count_rows needs a layer with min_depth 0");
+    DeviceGuard g(L->device);
+    TRY(bp_layer_clear(L));
+    return do_extend_count_rows(L, sysb, d_bounds, d_ids, n, splitters, n_splitters, allow_fold != 0, d_out_rows, n_out_rows);
 }
 
 int bp_dist_count_pairs_rows(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,

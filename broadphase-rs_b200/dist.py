@@ -180,6 +180,18 @@ class CudaOps:
         id_or = self.enc.masks()[2]
         return _view(kp, r, torch.int64, self.device), _view(ip, r, torch.int32, self.device), id_or
 
+    def encode_count_matrix(self, sys_bounds, bounds, ids, n, splitters, allow_fold):
+        """encode + count_records_matrix in one step for frames whose splitters are cached: the encode kernel counts the
+        records per destination shard as it generates them (no counting pass over the keys), the row with its tag words is
+        put together on the device, and the first host synchronisation of the frame is the one that fetches the finished
+        matrix.  Returns (keys, ids, matrix)."""
+        if self._cm_rec is None:
+            self._cm_rec = _CountMatrix(self.world, self.rank, 2 * self.world + N_TAGS, self.device, self.group)
+        self.enc.extend_count_rows(sys_bounds, bounds, ids, n, splitters, allow_fold, self._cm_rec.row_ptrs)
+        mat = self._cm_rec.gather()
+        kp, ip, r, _ = self.enc.records_device()
+        return _view(kp, r, torch.int64, self.device), _view(ip, r, torch.int32, self.device), mat
+
     def count_records(self, keys, splitters):
         c, h = self.enc.count_records(keys, keys.shape[0], splitters)
         return [int(x) for x in c], [int(x) for x in h]
@@ -288,6 +300,7 @@ class DistLayer:
         self.world = dist.get_world_size(group)
         self.trace = trace  # per-phase wall times (device-synchronised) in self.last["phases_ms"]; for tuning only
         self.reuse_splitters = reuse_splitters
+        self.fuse_counts = True  # frames with cached splitters: counts taken by the encode kernel (CudaOps.encode_count_matrix)
         self._splitters = self._a_splitters = None
         self._id_mask = 0
         self._static_halo = None  # halo records at the front of the resident static shard (None: no static layer)
@@ -352,14 +365,22 @@ class DistLayer:
                 phases.append((name, time.perf_counter()))
 
         mark("start")
-        # 1. encode
-        keys, rids, id_or = ops.encode(sys_bounds, bounds, ids, n)
+        # 1. encode -- together with step 3's counts when the splitters are already known (cached from the last frame)
+        m = SAMPLES_PER_RANK
+        product = hasattr(ops, "count_records_matrix")
+        need_splitters = self._splitters is None or (not self.reuse_splitters and self._static_halo is None)
+        fused = product and not need_splitters and self.fuse_counts and ops.enc.min_depth == 0
+        mat = None
+        if fused:
+            keys, rids, mat = ops.encode_count_matrix(sys_bounds, bounds, ids, n, self._splitters, self._static_halo is None)
+            id_or = None
+        else:
+            keys, rids, id_or = ops.encode(sys_bounds, bounds, ids, n)
         r_loc = keys.shape[0]
         mark("encode")
 
         # 2. key splitters (+ the ID bits, piggybacked) from an all-gathered sample
-        m = SAMPLES_PER_RANK
-        if self._splitters is None or (not self.reuse_splitters and self._static_halo is None):
+        if need_splitters:
             meta = torch.full((m + 1,), -1, dtype=torch.int64, device=dev)
             if r_loc:
                 ks = keys[::max(1, r_loc // m)][:m]
@@ -377,9 +398,10 @@ class DistLayer:
 
         # 3. count, all-gather the count matrix, scatter straight into the owners' receive buffers
         # bit 63 of the tag: "my IDs leave their top 3 bits free" (dedup at the source across the exchange, below)
-        product = hasattr(ops, "count_records_matrix")
-        can_fold = product and self._static_halo is None and int(id_or) < (1 << 29)
-        if product:  # counts stay on the device, the matrix travels over NVLink
+        can_fold = product and not fused and self._static_halo is None and int(id_or) < (1 << 29)
+        if fused:    # (already there)
+            pass
+        elif product:  # counts stay on the device, the matrix travels over NVLink
             mat = ops.count_records_matrix(keys, splitters, [int(id_or) | ((1 << 63) if can_fold else 0)] + ops.sort_tags())
         else:        # CPU test double: host counts + all_gather (gloo)
             counts, halo = ops.count_records(keys, splitters)

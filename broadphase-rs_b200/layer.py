@@ -123,6 +123,15 @@ class Layer:
         sysb = np.ascontiguousarray(system_bounds, dtype=np.float32).reshape(2 * self.dim)
         self._ck(lib().bp_layer_extend_device(self._h, sysb.ctypes.data, _dev_ptr(d_bounds), _dev_ptr(d_ids), n))
 
+    def extend_count_rows(self, system_bounds, d_bounds, d_ids, n, splitters, allow_fold, out_rows):
+        """clear + extend_device with the per-shard counts taken by the encode kernel, and the count row (counts, halo
+        counts, 7 tag words) stored to every device address in out_rows -- asynchronous (bp_dist_extend_count_rows)."""
+        sysb = np.ascontiguousarray(system_bounds, dtype=np.float32).reshape(2 * self.dim)
+        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
+        rows = np.asarray(out_rows, dtype=np.uint64)
+        self._ck(lib().bp_dist_extend_count_rows(self._h, sysb.ctypes.data, _dev_ptr(d_bounds), _dev_ptr(d_ids), n, spl.ctypes.data,
+                                                 spl.shape[0], int(allow_fold), rows.ctypes.data, rows.shape[0]))
+
     def merge(self, other):
         self._ck(lib().bp_layer_merge(self._h, other._h))
 

@@ -283,6 +283,16 @@ int bp_dist_count_pairs_device(bp_layer *ctx, const void *d_pairs, size_t n, con
  * NVLink: the kernel that finishes the counts also distributes them, no copy-engine transfers in between. */
 int bp_dist_count_records_rows(bp_layer *ctx, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
                                const uint64_t *tags, int n_tags, const uint64_t *d_out_rows, int n_out_rows);
+/* bp_layer_clear + bp_layer_extend_device + bp_dist_count_records_rows in one asynchronous step, for frames whose
+ * splitters are known before the objects are encoded (cached from the previous frame): encode_kernel counts every
+ * record it generates per destination shard (and per halo copy), so no counting pass over the keys runs, and the row --
+ * [counts | halo counts | 7 tag words: id_or (| 1 << 63 if allow_fold and the IDs leave their top 3 bits free), key_or,
+ * key_and, id_and, first ID, last ID, IDs ascending (bp_layer_masks / bp_layer_id_order)] -- is assembled on the device
+ * and stored to every address in d_out_rows.  Nothing returns to the host: the caller's first synchronisation is the one
+ * that fetches the finished count matrix.  The layer must have min_depth 0. */
+int bp_dist_extend_count_rows(bp_layer *layer, const float *system_bounds, const float *d_bounds, const void *d_ids, size_t n,
+                              const uint64_t *splitters, int n_splitters, int allow_fold, const uint64_t *d_out_rows,
+                              int n_out_rows);
 int bp_dist_count_pairs_rows(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
                              const uint64_t *tags, int n_tags, const uint64_t *d_out_rows, int n_out_rows);
 /* Equal range [lo, hi) of every query key in a sorted device key array (halo look-ups). */

@@ -232,6 +232,51 @@ def test_id_order_and_flagged_scatter(bp):
     assert L.id_order() == (0, 9, False)
 
 
+def test_extend_count_rows_equals_the_separate_steps(bp):
+    """bp_dist_extend_count_rows: the counts the encode kernel takes while it generates the records, and the tag words the
+    row kernel reads from the extend's result block on the device, equal count_records + masks + id_order."""
+    import torch
+    from broadphase_rs_b200.dist import _view, N_TAGS
+    sc = bp.scenes.lognormal_cubes(150_000, 13)
+    big = bp.scenes.uniform_cubes(64, 5, id_base=1_000_000, edge_factor=0.4 * 64 ** (1.0 / 3.0) * 0.9)  # halo copies exist
+    bounds = np.concatenate([sc["bounds"], big["bounds"]])
+    ids = np.concatenate([sc["ids"], big["ids"]]).astype(np.uint32)
+    n = bounds.shape[0]
+    db = torch.from_numpy(bounds).cuda()
+    di = torch.from_numpy(ids.view(np.int32)).cuda()
+    o = co.OracleLayer(2, 4, 0)
+    o.extend(sc["sys_bounds"], bounds, ids)
+    k, _ = o.records()
+    full = (1 << 64) - 1
+    for nspl, allow_fold, n_obj in ((1, True, n), (3, False, n), (7, True, n), (15, True, n), (3, True, 0)):
+        spl = np.sort(np.random.Generator(np.random.Philox(nspl)).choice(k, nspl, replace=False)).astype(np.uint64)
+        g = nspl + 1
+        rows = torch.full((2, 2 * g + N_TAGS), -7, dtype=torch.int64, device="cuda")
+        L = bp.Layer(2, "u32")
+        L.extend_count_rows(sc["sys_bounds"], db, di, n_obj, spl, allow_fold, [rows[0].data_ptr(), rows[1].data_ptr()])
+        torch.cuda.synchronize()
+        got = rows.cpu().numpy().view(np.uint64)
+        assert (got[0] == got[1]).all()
+        kp, ip, r, _ = L.records_device()
+        if n_obj:
+            counts, halo = L.count_records(_view(kp, r, torch.int64, torch.device("cuda")), r, spl)
+            assert int(halo.sum()) > 0
+            gk, gi = L.iter()
+            ok, oi = o.records()
+            assert (gk == ok).all() and (gi == oi).all()      # the records themselves are those of a plain extend
+        else:
+            counts, halo = np.zeros(g, dtype=np.uint64), np.zeros(g, dtype=np.uint64)
+        assert (got[0, :g] == counts).all() and (got[0, g:2 * g] == halo).all() and int(counts.sum()) == r
+        key_or, key_and, id_or, id_and = L.masks()
+        first, last, asc = L.id_order()
+        fold = allow_fold and id_or < (1 << 29)
+        want = [id_or | ((1 << 63) if fold else 0), key_or, key_and, id_and, first, last, int(asc)]
+        assert [int(x) for x in got[0, 2 * g:]] == [w & full for w in want], (nspl, n_obj)
+    # a layer with min_depth != 0 is refused (its extend may have to run twice)
+    with pytest.raises(Exception):
+        bp.Layer(2, "u32", min_depth=3).extend_count_rows(sc["sys_bounds"], db, di, n, spl, True, [rows[0].data_ptr()])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
