@@ -136,6 +136,76 @@ class CpuOps:
         return torch.from_numpy(out.view(np.int32).copy())
 
 
+def _s64(v):
+    v = int(v) & 0xFFFFFFFFFFFFFFFF
+    return v - (1 << 64) if v >> 63 else v
+
+
+class _EncInfo:
+    def __init__(self, min_depth):
+        self.min_depth = min_depth
+
+
+class CpuOpsProduct(CpuOps):
+    """The same double behind the PRODUCT-side protocol of DistLayer.frame (what dist.CudaOps speaks): the count matrix
+    carries every sender's tag words, the receivers plan their sort from them (dist.sort_plan), frames with cached splitters
+    take the counts together with the encode.  sort_records CHECKS the plan it is handed against the records that actually
+    arrived -- the masks must cover them, and "IDs ascending" must be true of the receive buffer, because the GPU sort then
+    skips the ID digits and relies on stability.  (The cell flags of the fold are a device-side matter: ignored here.)"""
+
+    def __init__(self, kind, min_depth):
+        super().__init__(kind, min_depth)
+        self.enc = _EncInfo(min_depth)
+        self.fused_frames = 0
+        self.plans = []  # (ids_ascending, n_records) of every planned sort
+
+    def encode(self, sys_bounds, bounds, ids, n):
+        k, i, id_or = super().encode(sys_bounds, bounds, ids, n)
+        ku, iu = _u64(k), _u32(i)
+        full = (1 << 64) - 1
+        obj = np.asarray(ids[:n]).astype(np.int64)
+        empty = ku.size == 0
+        self._tags = [int(np.bitwise_or.reduce(ku)) if not empty else 0, int(np.bitwise_and.reduce(ku)) if not empty else full,
+                      int(np.bitwise_and.reduce(iu)) if not empty else full,
+                      full if empty else int(obj[0]), 0 if empty else int(obj[-1]),
+                      1 if empty else int(bool((np.diff(obj) >= 0).all()))]
+        return k, i, id_or
+
+    def sort_tags(self):
+        return list(self._tags)
+
+    def count_records_matrix(self, keys, splitters, tags):
+        counts, halo = self.count_records(keys, splitters)
+        row = torch.tensor([_s64(v) for v in counts + halo + list(tags)], dtype=torch.int64)
+        out = [torch.empty_like(row) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, row)
+        return torch.stack(out).numpy()
+
+    def encode_count_matrix(self, sys_bounds, bounds, ids, n, splitters, allow_fold):
+        k, i, id_or = self.encode(sys_bounds, bounds, ids, n)
+        tag0 = id_or | ((1 << 63) if (allow_fold and id_or < (1 << 29)) else 0)
+        self.fused_frames += 1
+        return k, i, self.count_records_matrix(k, splitters, [tag0] + self.sort_tags())
+
+    def exchange_records(self, keys, ids, splitters, m_own, m_halo, fold=False):
+        return super().exchange_records(keys, ids, splitters, m_own, m_halo)
+
+    def sort_records(self, keys, ids, flagged=False, plan=None):
+        assert plan is not None, "the product path always plans the shard sort from the tag words"
+        k, i = _u64(keys), _u32(ids)
+        key_or, key_and, id_or, id_and, asc = plan
+        if k.size:
+            assert int(np.bitwise_or.reduce(k)) & ~key_or == 0 and key_and & ~int(np.bitwise_and.reduce(k)) == 0
+            assert int(np.bitwise_or.reduce(i)) & ~id_or == 0 and id_and & ~int(np.bitwise_and.reduce(i)) == 0
+        want_k, want_i = pyref.sort_records(k, i)
+        if asc:  # what the GPU does with this plan: a stable sort on the key alone
+            assert (np.diff(i.astype(np.int64)) >= 0).all(), "plan says the IDs ascend in the receive buffer, they do not"
+            order = np.argsort(k, kind="stable")
+            assert (k[order] == want_k).all() and (i[order] == want_i).all()
+        self.plans.append((bool(asc), int(k.size)))
+        return _i64(want_k), _i32(want_i)
+
+
 def make_case(name):
     """Deterministic scenes that stress the distributed logic.  Returns (kind, min_depth, sys, bounds, ids, filter)."""
     rng = np.random.Generator(np.random.Philox(abs(hash(name)) % (1 << 31) if False else sum(map(ord, name))))
@@ -190,7 +260,9 @@ def reference_static_dynamic(frame):
     return D.scan().astype(np.uint32)
 
 
-def worker(rank, world, port, cases, empty_rank, out_dir):
+def worker(rank, world, port, cases, empty_rank, out_dir, product=False):
+    Ops = CpuOpsProduct if product else CpuOps
+    stats = []
     try:
         os.environ["MASTER_ADDR"] = "127.0.0.1"
         os.environ["MASTER_PORT"] = str(port)
@@ -209,7 +281,8 @@ def worker(rank, world, port, cases, empty_rank, out_dir):
                 lo, hi = cuts[h], cuts[h + 1]
             else:
                 lo, hi = 0, 0
-            dl = bpd.DistLayer(CpuOps(kind, md), kind)
+            dl = bpd.DistLayer(Ops(kind, md), kind)
+            stats.append(dl.ops)
             dl.frame(sysb, bounds[lo:hi], ids[lo:hi], hi - lo, flt)  # first frame computes the splitters
             pairs = dl.frame(sysb, bounds[lo:hi], ids[lo:hi], hi - lo, flt)  # second frame reuses them
             allp = dl.gather_pairs(pairs)
@@ -226,7 +299,8 @@ def worker(rank, world, port, cases, empty_rank, out_dir):
         dids = (dids + np.uint32(100_000)).astype(np.uint32)
         cs = np.linspace(0, sb.shape[0], world + 1).astype(int)
         cd = np.linspace(0, db.shape[0], world + 1).astype(int)
-        dl = bpd.DistLayer(CpuOps(kind, md), kind)
+        dl = bpd.DistLayer(Ops(kind, md), kind)
+        stats.append(dl.ops)
         dl.set_static(sysb, sb[cs[rank]:cs[rank + 1]], sids[cs[rank]:cs[rank + 1]], cs[rank + 1] - cs[rank])
         for frame in range(2):
             shift = np.float32(0.001 * frame)
@@ -235,6 +309,14 @@ def worker(rank, world, port, cases, empty_rank, out_dir):
             allp = dl.gather_pairs(pairs)
             if rank == 0:
                 np.save(os.path.join(out_dir, "static_dynamic_%d.npy" % frame), allp)
+        if product:  # every DistLayer ran frames with cached splitters (fused counts) and planned sorts of both kinds
+            mine = [(o.fused_frames, o.plans) for o in stats]
+            everyone = [None] * world
+            dist.all_gather_object(everyone, mine)
+            if rank == 0:
+                import json
+                with open(os.path.join(out_dir, "product_stats.json"), "w") as f:
+                    json.dump(everyone, f)
         dist.barrier()
         dist.destroy_process_group()
     except Exception:

@@ -38,6 +38,27 @@ def test_distributed_frame_equals_single_process_oracle(tmp_path, world, empty_r
         assert halos[0] == 0 and halos[1:].sum() > 0  # scene-sized objects must have produced halo records
 
 
+@pytest.mark.parametrize("world,empty_rank", [(2, -1), (3, 1)])
+def test_product_protocol_plans_hold_on_the_received_records(tmp_path, world, empty_rank):
+    """DistLayer.frame through the protocol the CUDA path speaks (tag words in the count matrix, sort planned from them,
+    counts fused with the encode once the splitters are cached), on the CPU double: the double checks every plan against the
+    records that actually arrived (masks cover them; "IDs ascending" is true of the buffer), and the pairs are the oracle's."""
+    import json
+    mp.spawn(dco.worker, args=(world, _free_port(), CASES, empty_rank, str(tmp_path), True), nprocs=world, join=True)
+    for case in CASES:
+        got = np.load(os.path.join(str(tmp_path), "%s.npy" % case))
+        want = dco.reference_pairs(case)
+        assert got.shape == want.shape and (got == want).all(), case
+    for frame in range(2):
+        got = np.load(os.path.join(str(tmp_path), "static_dynamic_%d.npy" % frame))
+        want = dco.reference_static_dynamic(frame)
+        assert got.shape == want.shape and (got == want).all(), ("static+dynamic", frame)
+    stats = json.load(open(os.path.join(str(tmp_path), "product_stats.json")))
+    plans = [p for rank in stats for fused, ps in rank for p in ps if p[1] > 0]
+    assert all(fused >= 1 for rank in stats for fused, _ in rank)          # cached splitters -> counts came with the encode
+    assert any(asc for asc, _ in plans) and any(not asc for asc, _ in plans)  # both kinds of plan were exercised
+
+
 def test_ancestor_keys_and_splitters(bp):
     from broadphase_rs_b200 import dist as bpd
     from oracle import cpu_oracle as co
