@@ -60,7 +60,6 @@ SYMBOLS = {
     "bp_layer_records_device": (_i, [_vp, _P(_vp), _P(_vp), _P(_sz), _P(_i)]),
     "bp_layer_set_records": (_i, [_vp, _vp, _vp, _sz, _i, _i]),
     "bp_layer_set_records_flagged": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i]),
-    "bp_layer_fold_cell_flags": (_i, [_vp, _P(_i)]),
     "bp_layer_sort_from_device": (_i, [_vp, _vp, _vp, _sz, _i, _u64, _u64, _u64, _u64, _i]),
     "bp_layer_id_order": (_i, [_vp, _P(_u64), _P(_u64), _P(_i)]),
     "bp_dist_count_records_rows": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _i, _vp, _i]),
@@ -68,8 +67,6 @@ SYMBOLS = {
     "bp_dist_count_pairs_rows": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _i, _vp, _i]),
     "bp_dist_scatter_records_flagged": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _vp, _i]),
     "bp_layer_unique_pairs_inplace_device": (_i, [_vp, _vp, _sz, _u64, _P(_vp), _P(_sz)]),
-    "bp_dist_count_records_device": (_i, [_vp, _vp, _sz, _vp, _i, _u64, _vp]),
-    "bp_dist_count_pairs_device": (_i, [_vp, _vp, _sz, _vp, _i, _u64, _vp]),
     "bp_dist_partition_records": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp]),
     "bp_dist_partition_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),
     "bp_dist_lookup_ranges": (_i, [_vp, _vp, _sz, _vp, _i, _vp, _vp]),

@@ -533,24 +533,6 @@ template <int KIND, class IdT> struct Impl {
         return BP_OK;
     }
 
-    // Moves the cell flags of an encoded, not yet sorted tree into the IDs' top 3 bits now (the multi-GPU exchange
-    // ships the records before they are sorted).  *folded = 0 if the flags are gone or the IDs leave no room.
-    static int fold_flags(bp_layer *L, int *folded) {
-        *folded = L->ids_flagged ? 1 : 0;
-        if (L->ids_flagged || !L->flags_valid || L->n_records == 0) return BP_OK;
-        const int id_bits = 64 - (L->id_or ? __builtin_clzll(L->id_or) : 64);
-        if (id_bits > (int)(8 * sizeof(IdT)) - 3) return BP_OK;
-        {
-            LaunchScope ls(L, BP_K_MISC, (double)L->n_records * (2.0 * sizeof(IdT) + 1.0));
-            const int blocks = (int)std::min<uint64_t>((L->n_records + 1023) / 1024, 148 * 8);
-            flags_merge_kernel<IdT><<<blocks, 256, 0, L->stream>>>(ids(L, L->cur), (const uint8_t *)L->cell_flags.p, (uint32_t)L->n_records);
-        }
-        TRY(check_launch(L, "flags_merge_kernel"));
-        L->ids_flagged = true;
-        *folded = 1;
-        return BP_OK;
-    }
-
     // ---- extend ------------------------------------------------------------------------------------------
     static int launch_encode(bp_layer *L, const float *sysb, const float *d_bounds, const IdT *d_ids, uint32_t n,
                              const EncodeCount *count = nullptr) {
@@ -1552,7 +1534,6 @@ int do_extend_count_rows(bp_layer *L, const float *sysb, const float *d_bounds, 
 int do_sort_from(bp_layer *L, const void *k, const void *v, uint64_t n, bool asc) { DISPATCH(L, sort_from(L, k, v, n, asc)); }
 int do_masks(bp_layer *L, uint64_t n) { DISPATCH(L, masks_from_records(L, n)); }
 int do_strip_flags(bp_layer *L) { DISPATCH(L, strip_flags(L)); }
-int do_fold_flags(bp_layer *L, int *folded) { DISPATCH(L, fold_flags(L, folded)); }
 
 // Folds the result of the last (still asynchronous) extend into the host-side state.
 int resolve_pending(bp_layer *L) {
@@ -2107,16 +2088,6 @@ int bp_dist_count_pairs(bp_layer *L, const void *d_pairs, size_t n, const uint64
     return do_count_pairs(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, out_counts);
 }
 
-int bp_dist_count_records_device(bp_layer *L, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
-                                 void *d_out_row) {
-    if (!L || !d_out_row || bad_splitters(splitters, n_splitters)) return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_records_device");
-    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 records");
-    DeviceGuard g(L->device);
-    TRY(resolve_pending(L));
-    const uint64_t row = (uint64_t)(uintptr_t)d_out_row;
-    return do_count_records_row(L, d_keys, n, splitters, n_splitters, &tag, 1, &row, 1);
-}
-
 static bool bad_rows(const uint64_t *tags, int n_tags, const uint64_t *rows, int n_rows) {
     return n_tags < 0 || n_tags > MAX_ROW_TAGS || (n_tags && !tags) || n_rows < 1 || n_rows > MAX_ROW_COPIES || !rows;
 }
@@ -2150,16 +2121,6 @@ int bp_dist_count_pairs_rows(bp_layer *L, const void *d_pairs, size_t n, const u
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
     return do_count_pairs_row(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, tags, n_tags, d_out_rows, n_out_rows);
-}
-
-int bp_dist_count_pairs_device(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
-                               void *d_out_row) {
-    if (!L || !d_out_row || bad_splitters(splitters, n_splitters)) return fail(L, BP_ERR_INVALID_ARG, "bad arguments to bp_dist_count_pairs_device");
-    if (n > MAX_RECORDS) return fail(L, BP_ERR_TOO_LARGE, "more than 2^30 pairs");
-    DeviceGuard g(L->device);
-    TRY(resolve_pending(L));
-    const uint64_t row = (uint64_t)(uintptr_t)d_out_row;
-    return do_count_pairs_row(L, (const uint64_t *)d_pairs, n, splitters, n_splitters, &tag, 1, &row, 1);
 }
 
 int bp_dist_scatter_pairs(bp_layer *L, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
@@ -2216,16 +2177,6 @@ int bp_layer_records(bp_layer *L, const void **out_keys, const void **out_ids, s
     return BP_OK;
 }
 
-int bp_layer_fold_cell_flags(bp_layer *L, int *out_folded) {
-    if (!L) return BP_ERR_INVALID_ARG;
-    DeviceGuard g(L->device);
-    TRY(resolve_pending(L));
-    int folded = 0;
-    TRY(do_fold_flags(L, &folded));
-    if (out_folded) *out_folded = folded;
-    return BP_OK;
-}
-
 int bp_layer_set_records(bp_layer *L, const void *keys, const void *ids, size_t n, int sorted, int on_device) {
     return bp_layer_set_records_flagged(L, keys, ids, n, sorted, on_device, 0);
 }
@@ -2243,7 +2194,7 @@ int bp_layer_set_records_flagged(bp_layer *L, const void *keys, const void *ids,
     }
     L->n_records = n;
     L->flags_valid = false;        // foreign records: no separate cell flags ...
-    L->ids_flagged = flagged != 0; // ... but they may ride in the IDs' top 3 bits (bp_layer_fold_cell_flags on the sender)
+    L->ids_flagged = flagged != 0; // ... but they may ride in the IDs' top 3 bits (bp_dist_scatter_records_flagged on the sender)
     TRY(do_masks(L, n));
     L->key_or = L->h_res->key_or;
     L->key_and = L->h_res->key_and;

@@ -247,12 +247,6 @@ class Layer:
         self._ck(lib().bp_layer_records_device(self._h, ctypes.byref(k), ctypes.byref(i), ctypes.byref(n), ctypes.byref(s)))
         return k.value, i.value, n.value, bool(s.value)
 
-    def fold_cell_flags(self):
-        """Moves the cell flags of a freshly extended tree into the IDs' top 3 bits (include/bp.h); True if it did."""
-        f = ctypes.c_int()
-        self._ck(lib().bp_layer_fold_cell_flags(self._h, ctypes.byref(f)))
-        return bool(f.value)
-
     def set_records(self, keys, ids, sorted_=False, on_device=False, n=None, flagged=False):
         if on_device:
             self._ck(lib().bp_layer_set_records_flagged(self._h, _dev_ptr(keys), _dev_ptr(ids), n, int(sorted_), 1, int(flagged)))
@@ -319,15 +313,9 @@ class Layer:
                                              halo.ctypes.data))
         return counts, halo
 
-    def count_records_device(self, d_keys, n, splitters, tag, d_out_row):
-        """count_records with the result left on the device: row = [counts | halo counts | tag] (u64), asynchronous."""
-        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
-        self._ck(lib().bp_dist_count_records_device(self._h, _dev_ptr(d_keys), n, spl.ctypes.data, spl.shape[0], int(tag),
-                                                    _dev_ptr(d_out_row)))
-
     def count_records_rows(self, d_keys, n, splitters, tags, out_rows):
-        """count_records_device with up to 8 tag words, row = [counts | halo counts | tags...], stored to every device
-        address in out_rows (this rank's row in every rank's count matrix)."""
+        """count_records with the result left on the device: row = [counts | halo counts | up to 8 tag words] (u64), stored
+        to every device address in out_rows (this rank's row in every rank's count matrix); asynchronous."""
         spl = np.ascontiguousarray(splitters, dtype=np.uint64)
         t = np.asarray([int(x) & 0xFFFFFFFFFFFFFFFF for x in tags], dtype=np.uint64)
         rows = np.asarray(out_rows, dtype=np.uint64)
@@ -340,11 +328,6 @@ class Layer:
         rows = np.asarray(out_rows, dtype=np.uint64)
         self._ck(lib().bp_dist_count_pairs_rows(self._h, _dev_ptr(d_pairs), n, spl.ctypes.data, spl.shape[0],
                                                 t.ctypes.data, t.shape[0], rows.ctypes.data, rows.shape[0]))
-
-    def count_pairs_device(self, d_pairs, n, splitters, tag, d_out_row):
-        spl = np.ascontiguousarray(splitters, dtype=np.uint64)
-        self._ck(lib().bp_dist_count_pairs_device(self._h, _dev_ptr(d_pairs), n, spl.ctypes.data, spl.shape[0], int(tag),
-                                                  _dev_ptr(d_out_row)))
 
     def scatter_records(self, d_keys, d_ids, n, splitters, dst_keys, dst_ids, halo_dst_keys=None, halo_dst_ids=None,
                         fold_cell_flags=False):

@@ -204,13 +204,11 @@ int bp_layer_records_device(bp_layer *layer, const void **out_d_keys, const void
 /* Replaces the tree (the serde Deserialize path of Layer, src/layer.rs:41; also how a
  * multi-GPU exchange hands a shard its records).  Host or device pointers per `on_device`. */
 int bp_layer_set_records(bp_layer *layer, const void *keys, const void *ids, size_t n, int sorted, int on_device);
-/* Dedup at the source across an exchange (multi-GPU).  bp_layer_fold_cell_flags moves the 3 cell flags encode_kernel
- * wrote for every record of a freshly extended, unsorted tree into the top 3 bits of its ID, in place (*out_folded = 0
- * and nothing happens if the IDs use more than id_bits - 3 bits, or the flags are gone); the records read through
- * bp_layer_records_device BEFORE this call then carry them.  bp_layer_set_records_flagged(.., flagged = 1) loads such
+/* Dedup at the source across an exchange (multi-GPU).  encode_kernel writes 3 cell flags for every record of a freshly
+ * extended tree; bp_dist_scatter_records_flagged ships them inside the top 3 bits of the IDs (if the IDs leave those
+ * bits free).  bp_layer_set_records_flagged(.., flagged = 1) / bp_layer_sort_from_device(.., flagged = 1) load such
  * records: the scan of that layer emits every ID pair from its canonical shared cell only, and every accessor strips
  * the flags before IDs are shown. */
-int bp_layer_fold_cell_flags(bp_layer *layer, int *out_folded);
 int bp_layer_set_records_flagged(bp_layer *layer, const void *keys, const void *ids, size_t n, int sorted, int on_device, int flagged);
 
 /* bp_layer_set_records_flagged(.., sorted = 0, on_device = 1) followed by bp_layer_sort, as one step and without the two
@@ -259,7 +257,7 @@ int bp_dist_count_records(bp_layer *ctx, const void *d_keys, size_t n, const uin
 int bp_dist_scatter_records(bp_layer *ctx, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
                             int n_splitters, const uint64_t *dst_keys, const uint64_t *dst_ids, const uint64_t *halo_dst_keys,
                             const uint64_t *halo_dst_ids);
-/* bp_dist_scatter_records with the layer's cell flags (see bp_layer_fold_cell_flags) OR-ed into the top 3 bits of every
+/* bp_dist_scatter_records with the layer's cell flags (see bp_layer_set_records_flagged) OR-ed into the top 3 bits of every
  * ID as the pass loads it -- no separate folding pass, the layer's own records stay unflagged.  d_keys / d_ids must be the
  * layer's own record arrays (bp_layer_records_device) of a freshly extended tree whose IDs leave those bits free. */
 int bp_dist_scatter_records_flagged(bp_layer *ctx, const void *d_keys, const void *d_ids, size_t n, const uint64_t *splitters,
@@ -270,17 +268,13 @@ int bp_dist_count_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint
 int bp_dist_scatter_pairs(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters,
                           const uint64_t *dst_pairs);
 /* The counts of bp_dist_count_records / _pairs left ON THE DEVICE as one row of 64-bit words -- [bucket sizes
- * 0..n_splitters] [halo copies 0..n_splitters] (records only) [tag] -- at d_out_row, typically this rank's row of a count
- * matrix in every peer's symmetric memory: the matrix is then exchanged by peer copies and one barrier instead of a
- * host round trip plus an NCCL all-gather.  Asynchronous on the layer's stream. */
-int bp_dist_count_records_device(bp_layer *ctx, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
-                                 uint64_t tag, void *d_out_row);
-int bp_dist_count_pairs_device(bp_layer *ctx, const void *d_pairs, size_t n, const uint64_t *splitters, int n_splitters, uint64_t tag,
-                               void *d_out_row);
-/* The same with up to 8 tag words at the end of the row (the sort masks and ID order of the sender travel with its counts,
- * so that the receivers can plan their sort without looking at the records: bp_layer_sort_from_device), and with the row
- * stored to up to 16 device ADDRESSES at once -- this rank's row inside every rank's copy of the matrix, peers' through
- * NVLink: the kernel that finishes the counts also distributes them, no copy-engine transfers in between. */
+ * 0..n_splitters] [halo copies 0..n_splitters] (records only) [tags] -- typically this rank's row of a count matrix in
+ * symmetric memory: the matrix is then complete after one barrier instead of a host round trip plus an NCCL
+ * all-gather.  Asynchronous on the layer's stream.  Up to 8 tag words close the row (the sort masks and ID order of the
+ * sender travel with its counts, so that the receivers can plan their sort without looking at the records:
+ * bp_layer_sort_from_device), and the row is stored to up to 16 device ADDRESSES at once -- this rank's row inside
+ * every rank's copy of the matrix, the peers' through NVLink: the kernel that finishes the counts also distributes
+ * them, no copy-engine transfers in between. */
 int bp_dist_count_records_rows(bp_layer *ctx, const void *d_keys, size_t n, const uint64_t *splitters, int n_splitters,
                                const uint64_t *tags, int n_tags, const uint64_t *d_out_rows, int n_out_rows);
 /* bp_layer_clear + bp_layer_extend_device + bp_dist_count_records_rows in one asynchronous step, for frames whose
