@@ -98,11 +98,23 @@ def sort_plan(tags, id_or, n_halo):
 def chunk_offsets(m_own, m_halo, me):
     """Where this rank's chunks start inside every destination's receive buffer.  The buffer of
     destination d is laid out source by source: [owned from 0 | halo from 0 | owned from 1 | ...]."""
-    g = m_own.shape[0]
-    both = m_own + m_halo
-    own_off = [int(both[:me, d].sum()) for d in range(g)]
-    halo_off = [own_off[d] + int(m_own[me, d]) for d in range(g)]
-    return own_off, halo_off
+    own_off = (m_own[:me] + m_halo[:me]).sum(axis=0)
+    return own_off.tolist(), (own_off + m_own[me]).tolist()
+
+
+def scatter_destinations(key_ptrs, id_ptrs, m_own, m_halo, me):
+    """Device addresses (uint64 arrays, one entry per destination rank) at which this rank's owned chunk and its halo
+    chunk start inside every receive buffer: (keys, ids, halo keys, halo ids); the halo arrays are None when no halo
+    copy leaves this rank.  key_ptrs / id_ptrs: base addresses of every rank's receive buffers (uint64 arrays).  This runs
+    between the host's look at the count matrix and the launch of the scatter, with the GPU idle: array arithmetic, no
+    Python loops."""
+    own_off = (m_own[:me] + m_halo[:me]).sum(axis=0).astype(np.uint64)
+    dk = key_ptrs + np.uint64(8) * own_off
+    di = id_ptrs + np.uint64(4) * own_off
+    if not m_halo[me].any():
+        return dk, di, None, None
+    halo_off = own_off + m_own[me].astype(np.uint64)
+    return dk, di, key_ptrs + np.uint64(8) * halo_off, id_ptrs + np.uint64(4) * halo_off
 
 
 class _CudaView:
@@ -221,22 +233,20 @@ class CudaOps:
     def exchange_records(self, keys, ids, splitters, m_own, m_halo, fold=False):
         """fold: the cell flags of the encoded records leave in the top 3 bits of their IDs (dedup at the source across
         the exchange: the receiving shard emits every ID pair from its canonical shared cell only)."""
-        me, g = self.rank, self.world
-        need = int((m_own + m_halo).sum(axis=0).max())
-        if need > self.rec_cap:  # the matrices are global, so every rank grows (collectively) at the same time
+        me = self.rank
+        recv = (m_own + m_halo).sum(axis=0)  # records every rank receives
+        need = int(recv.max())
+        if need > self.rec_cap or self.rk is None:  # the matrices are global, so every rank grows (collectively) at the same time
             self.rec_cap = int(need * 1.25) + 1024
             self.rk = _SymmBuffer(self.rec_cap * 8, self.device, self.group)
             self.ri = _SymmBuffer(self.rec_cap * 4, self.device, self.group)
-        own_off, halo_off = chunk_offsets(m_own, m_halo, me)
-        dk = [self.rk.ptrs[d] + 8 * own_off[d] for d in range(g)]
-        di = [self.ri.ptrs[d] + 4 * own_off[d] for d in range(g)]
-        hk = hi = None  # no halo copies leave this rank (the usual case): no second pass over the keys
-        if int(m_halo[me].sum()):
-            hk = [self.rk.ptrs[d] + 8 * halo_off[d] for d in range(g)]
-            hi = [self.ri.ptrs[d] + 4 * halo_off[d] for d in range(g)]
+            self._rk_ptrs = np.asarray(self.rk.ptrs, dtype=np.uint64)
+            self._ri_ptrs = np.asarray(self.ri.ptrs, dtype=np.uint64)
+        # (no halo arrays = no halo copies leave this rank, the usual case: no second pass over the keys)
+        dk, di, hk, hi = scatter_destinations(self._rk_ptrs, self._ri_ptrs, m_own, m_halo, me)
         self.enc.scatter_records(keys, ids, keys.shape[0], splitters, dk, di, hk, hi, fold_cell_flags=fold)
         self.rk.barrier()  # every rank's stores have landed before anybody reads its receive buffer
-        n_recv = int((m_own + m_halo)[:, me].sum())
+        n_recv = int(recv[me])
         return self.rk.t.view(torch.int64)[:n_recv], self.ri.t.view(torch.int32)[:n_recv]
 
     def sort_records(self, keys, ids, flagged=False, plan=None):
@@ -276,15 +286,17 @@ class CudaOps:
         return [int(x) for x in self.shard.count_pairs(raw, raw.shape[0], splitters)]
 
     def exchange_pairs(self, raw, splitters, m):
-        me, g = self.rank, self.world
-        need = int(m.sum(axis=0).max())
-        if need > self.pair_cap:
+        me = self.rank
+        recv = m.sum(axis=0)
+        need = int(recv.max())
+        if need > self.pair_cap or self.rp is None:
             self.pair_cap = int(need * 1.25) + 1024
             self.rp = _SymmBuffer(self.pair_cap * 8, self.device, self.group)
-        dst = [self.rp.ptrs[d] + 8 * int(m[:me, d].sum()) for d in range(g)]
+            self._rp_ptrs = np.asarray(self.rp.ptrs, dtype=np.uint64)
+        dst = self._rp_ptrs + np.uint64(8) * m[:me].sum(axis=0).astype(np.uint64)
         self.shard.scatter_pairs(raw, raw.shape[0], splitters, dst)
         self.rp.barrier()
-        return self.rp.t.view(torch.int64)[:int(m[:, me].sum())]
+        return self.rp.t.view(torch.int64)[:int(recv[me])]
 
     def unique_pairs(self, raw, id_mask):
         ptr, n = self.shard.unique_pairs_inplace_device(raw, raw.shape[0], id_mask)  # raw = our receive buffer: sort scratch
@@ -408,7 +420,7 @@ class DistLayer:
             mat = self._gather_rows(counts + halo + [id_or], dev)
         m_own, m_halo = mat[:, :g], mat[:, g:2 * g]
         n_halo = int(m_halo[:, me].sum())
-        tags = [[int(v) & 0xFFFFFFFFFFFFFFFF for v in row] for row in mat[:, 2 * g:]]
+        tags = np.ascontiguousarray(mat[:, 2 * g:]).view(np.uint64).tolist()  # Python ints, unsigned
         flagged, id_bits, plan = product, 0, None
         for t in tags:
             flagged = flagged and bool(t[0] >> 63)  # every rank can: the cell flags ride in the IDs across the exchange

@@ -93,3 +93,31 @@ def test_sort_plan_from_tag_words(bp):
     assert sort_plan([a, b[:6] + [0]], 0x1FF, 0)[4] is False  # a source whose own IDs do not ascend
     assert sort_plan([a, [0x1FF, 0, full, full, 99, 250, 1]], 0x1FF, 0)[4] is True   # equal IDs may meet at the seam
     assert sort_plan([empty, empty], 0, 0) == (0, full, 0, full, True)
+
+
+def test_scatter_destinations_equal_the_per_destination_sums(bp):
+    """The array arithmetic that runs between the count matrix and the scatter launch (GPU idle) against the plain
+    per-destination sums it replaced; addresses stay exact 64-bit integers."""
+    from broadphase_rs_b200 import dist as bpd
+    rng = np.random.Generator(np.random.Philox(77))
+    for g in (1, 2, 3, 8, 16):
+        kp = (np.uint64(0x7F00_0000_0000) + np.arange(g, dtype=np.uint64) * np.uint64(1 << 36))
+        ip = kp + np.uint64(1 << 35)
+        for with_halo in (False, True):
+            m_own = rng.integers(0, 1 << 28, size=(g, g)).astype(np.int64)
+            m_halo = (rng.integers(0, 50, size=(g, g)) * np.triu(np.ones((g, g), dtype=np.int64), 1)).astype(np.int64)
+            if not with_halo:
+                m_halo[:] = 0
+            for me in range(g):
+                dk, di, hk, hi = bpd.scatter_destinations(kp, ip, m_own, m_halo, me)
+                own = [sum(int(m_own[s, d]) + int(m_halo[s, d]) for s in range(me)) for d in range(g)]
+                assert dk.dtype == np.uint64 and di.dtype == np.uint64
+                assert dk.tolist() == [int(kp[d]) + 8 * own[d] for d in range(g)]
+                assert di.tolist() == [int(ip[d]) + 4 * own[d] for d in range(g)]
+                assert bpd.chunk_offsets(m_own, m_halo, me) == (own, [own[d] + int(m_own[me, d]) for d in range(g)])
+                if m_halo[me].any():
+                    assert hk.dtype == np.uint64 and hi.dtype == np.uint64
+                    assert hk.tolist() == [int(kp[d]) + 8 * (own[d] + int(m_own[me, d])) for d in range(g)]
+                    assert hi.tolist() == [int(ip[d]) + 4 * (own[d] + int(m_own[me, d])) for d in range(g)]
+                else:
+                    assert hk is None and hi is None
