@@ -245,6 +245,13 @@ def reference_pairs(case):
     return L.scan(fk, arg).astype(np.uint32)
 
 
+def reference_pairs_unfiltered(case):
+    kind, md, sysb, bounds, ids, _ = make_case(case)
+    L = co.OracleLayer(kind, 4, md)
+    L.extend(sysb, bounds, ids)
+    return L.scan().astype(np.uint32)
+
+
 def reference_static_dynamic(frame):
     kind, md, sysb, sb, sids, _ = make_case("big_objects3d")
     _, _, _, db, dids, _ = make_case("uniform3d")
@@ -309,6 +316,21 @@ def worker(rank, world, port, cases, empty_rank, out_dir, product=False):
             allp = dl.gather_pairs(pairs)
             if rank == 0:
                 np.save(os.path.join(out_dir, "static_dynamic_%d.npy" % frame), allp)
+        if product:
+            # the scene changes under cached splitters: the frame with the stale splitters is still exact, notices the
+            # imbalance and drops them; the next frame samples new ones (plain counts), the one after is fused again
+            kind, md, sysb, ba, ia, _ = make_case("uniform3d")
+            _, _, _, bb, ib, _ = make_case("skewed3d")
+            ca = np.linspace(0, ba.shape[0], world + 1).astype(int)
+            cb = np.linspace(0, bb.shape[0], world + 1).astype(int)
+            dl = bpd.DistLayer(Ops(kind, md), kind)
+            for f, (b, i, c) in enumerate([(ba, ia, ca), (ba, ia, ca), (bb, ib, cb), (bb, ib, cb), (bb, ib, cb)]):
+                pairs = dl.frame(sysb, b[c[rank]:c[rank + 1]], i[c[rank]:c[rank + 1]], c[rank + 1] - c[rank], None)
+                allp = dl.gather_pairs(pairs)
+                if rank == 0:
+                    np.save(os.path.join(out_dir, "rebalance_%d.npy" % f), allp)
+            if rank == 0:
+                np.save(os.path.join(out_dir, "rebalance_fused.npy"), np.array([dl.ops.fused_frames]))
         if product:  # every DistLayer ran frames with cached splitters (fused counts) and planned sorts of both kinds
             mine = [(o.fused_frames, o.plans) for o in stats]
             everyone = [None] * world

@@ -53,6 +53,14 @@ def test_product_protocol_plans_hold_on_the_received_records(tmp_path, world, em
         got = np.load(os.path.join(str(tmp_path), "static_dynamic_%d.npy" % frame))
         want = dco.reference_static_dynamic(frame)
         assert got.shape == want.shape and (got == want).all(), ("static+dynamic", frame)
+    # a scene change under cached splitters: frames 0-1 scene A, frames 2-4 scene B; frame 2 runs on stale splitters
+    want_a, want_b = dco.reference_pairs_unfiltered("uniform3d"), dco.reference_pairs_unfiltered("skewed3d")
+    for f in range(5):
+        got = np.load(os.path.join(str(tmp_path), "rebalance_%d.npy" % f))
+        want = want_a if f < 2 else want_b
+        assert got.shape == want.shape and (got == want).all(), ("rebalance frame", f)
+    # fused: frames 1, 2 and 4 -- frame 3 had to sample new splitters (so the imbalance was noticed and acted on)
+    assert int(np.load(os.path.join(str(tmp_path), "rebalance_fused.npy"))[0]) == 3
     stats = json.load(open(os.path.join(str(tmp_path), "product_stats.json")))
     plans = [p for rank in stats for fused, ps in rank for p in ps if p[1] > 0]
     assert all(fused >= 1 for rank in stats for fused, _ in rank)          # cached splitters -> counts came with the encode
