@@ -70,6 +70,22 @@ def gen_boxes(n=10_000, seed=0, density=1e-3, size_range=(1.0, 10.0)):
     return dict(kind=INDEX64_3D, min_depth=0, sys_bounds=sys_bounds, bounds=bounds, ids=ids)
 
 
+def gen_boxes_reference(n=10_000, seed=0, density=1e-3, size_range=(1.0, 10.0)):
+    """The same recipe on the reference's OWN random stream (ChaChaRng::seed_from_u64 + gen_range, restated in
+    rust_rand.py): for seed 0 / density 0.001 / sizes 1..10 these are, bit for bit, the scenes of the reference's
+    tests/data/inputs/*.br_scene (SHA-256 checked in tests/test_reference_fixtures.py)."""
+    try:
+        from . import rust_rand
+    except ImportError:      # loaded by path (tests, bench reference arm), not as a package member
+        import importlib.util
+        import os
+        spec = importlib.util.spec_from_file_location("bp_rust_rand", os.path.join(os.path.dirname(os.path.abspath(__file__)), "rust_rand.py"))
+        rust_rand = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(rust_rand)
+    sys_bounds, bounds, ids = rust_rand.gen_boxes_reference(n, seed, density, size_range)
+    return dict(kind=INDEX64_3D, min_depth=0, sys_bounds=sys_bounds, bounds=bounds, ids=ids)
+
+
 def edge_cases_3d():
     """Hand-picked boxes in the [-64, 64]^3 system of the reference's own unit test
     (src/geom.rs:696-706) that exercise the quantiser's corner cases."""

@@ -2,9 +2,11 @@
 //
 // TEST INFRASTRUCTURE ONLY (see bp_oracle.h).  Never linked into or called by the product.
 //
-// PARITY STATUS: codec/quantiser pinned by the reference's in-source KATs; extend/sort/scan
-// end-to-end "parity unpinned" (no Rust toolchain, LFS-stub fixtures) -- cross-checked against
-// the independent numpy restatement in oracle/pyref.py.
+// PARITY STATUS: pinned.  Codec/quantiser by the reference's in-source KATs; extend/sort/scan end to end by
+// the SHA-256 of the reference's three validation files (tests/data/validation/*, LFS pointers), which this
+// restatement reproduces byte for byte from the regenerated n = 10 000 input scene
+// (tests/test_reference_fixtures.py); additionally cross-checked against the independent numpy restatement
+// in oracle/pyref.py.  The query functions (test_box / test_ray / pick_ray) remain unpinned.
 //
 // Every function cites the reference file:line (relative to /root/reference) that it follows.
 // Build: g++ -O3 -march=x86-64-v3 -fopenmp -ffp-contract=off (never -ffast-math), see Makefile.

@@ -6,11 +6,14 @@
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it;
  * the product (libbroadphase_b200.so) never links, loads or calls anything in oracle/.
  *
- * PARITY STATUS: the codec and quantiser are pinned by the reference's in-source
- * known-answer tests (src/index.rs:343-374, src/geom.rs:696-706).  The end-to-end
- * extend/sort/scan results are "parity unpinned": the reference's golden fixtures are
- * Git-LFS pointer stubs and no Rust toolchain exists in this image, so they are pinned only by
- * agreement between this restatement and an independent numpy restatement (oracle/pyref.py).
+ * PARITY STATUS: PINNED by reference-produced data.  The codec and quantiser are pinned by the reference's
+ * in-source known-answer tests (src/index.rs:343-374, src/geom.rs:696-706).  extend / sort / scan end to end
+ * are pinned by the reference's own golden files: tests/data/ holds Git-LFS pointers (SHA-256 + size) of the
+ * seven gen_boxes input scenes and of the three validation files tests/test_layer.rs:25-124 compares against;
+ * the inputs are regenerated bit for bit (rand_core 0.5 seed_from_u64 + ChaCha20 + rand 0.7 gen_range restated in
+ * broadphase-rs_b200/rust_rand.py, all seven hashes equal), and this oracle's extend, sort and scan of the
+ * n = 10 000 scene serialise to files with exactly the three validation hashes (tests/test_reference_fixtures.py).
+ * Still unpinned: the queries (test_box / test_ray / pick_ray) -- the reference holds no vector for them.
  */
 #ifndef BP_ORACLE_H
 #define BP_ORACLE_H

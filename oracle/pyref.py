@@ -1,8 +1,9 @@
 """pyref.py -- an independent numpy restatement of the broadphase-rs hot path.
 
-TEST INFRASTRUCTURE ONLY.  It exists to cross-check the C++ oracle (bp_oracle.cpp), because the
-Rust reference cannot be built in this image and its golden fixtures are Git-LFS stubs ("parity
-unpinned" for extend/sort/scan; the codec and quantiser are pinned by the reference's KATs).
+TEST INFRASTRUCTURE ONLY.  It exists to cross-check the C++ oracle (bp_oracle.cpp) with a second,
+independent formulation.  Parity status: pinned -- like the C++ oracle it reproduces the reference's three
+validation files (SHA-256 in the LFS pointers of tests/data/validation/) from the regenerated n = 10 000
+gen_boxes scene (tests/test_reference_fixtures.py); the codec and quantiser are pinned by the reference's KATs.
 
 It deliberately uses different formulations from the C++ oracle:
   * Morton spreading is a plain bit loop (the definition "axis bit i -> origin bit DIM*i + axis",
