@@ -124,6 +124,7 @@ struct bp_layer {
     uint64_t id_first = 0, id_last = 0; // IDs of the first / last object extended since the last clear (bp_layer_id_order)
     uint64_t n_invalid = 0;
     uint64_t n_halo = 0; // records [0, n_halo) only act as ancestors in scan (multi-GPU halos)
+    bool scan_dedup = true; // bp_layer_set_scan_dedup: the scan may emit every ID pair from its canonical shared cell only
     // dedup at the source: encode writes 3 cell flags per record (cell_flags); a full sort of a tree that
     // only holds encoded records moves them into the top 3 bits of the IDs (ids_flagged) so that they
     // travel with the records; any other mutation strips them again
@@ -889,7 +890,7 @@ template <int KIND, class IdT> struct Impl {
         ea.ids = ids(L, L->cur);
         ea.keys = keys(L, L->cur);
         ea.id_mask = L->ids_flagged ? (IdT)((((IdT)1) << (8 * sizeof(IdT) - 3)) - 1) : (IdT) ~(IdT)0;
-        const bool dedup = L->ids_flagged && L->n_halo == 0;
+        const bool dedup = L->ids_flagged && L->n_halo == 0 && L->scan_dedup;
         ea.src_idx = (const uint32_t *)L->src_idx.p;
         ea.src_off = (const uint64_t *)L->src_off.p;
         ea.chunk_src = (const uint32_t *)L->chunk_src.p;
@@ -1974,6 +1975,12 @@ int bp_layer_pick_ray_batch(bp_layer *L, const float *sysb, const float *rays, s
 int bp_layer_set_halo(bp_layer *L, size_t n_halo) {
     if (!L) return BP_ERR_INVALID_ARG;
     L->n_halo = n_halo;
+    return BP_OK;
+}
+
+int bp_layer_set_scan_dedup(bp_layer *L, int enabled) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    L->scan_dedup = enabled != 0;
     return BP_OK;
 }
 

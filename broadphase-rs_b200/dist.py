@@ -224,11 +224,13 @@ class CudaOps:
         self.enc.count_records_rows(keys, keys.shape[0], splitters, tags, self._cm_rec.row_ptrs)
         return self._cm_rec.gather()
 
-    def count_pairs_matrix(self, raw, splitters):
+    def count_pairs_matrix(self, raw, splitters, tag=0):
+        """-> (count matrix [source, destination], the tag word every source sent along)."""
         if self._cm_pair is None:
             self._cm_pair = _CountMatrix(self.world, self.rank, self.world + 1, self.device, self.group)
-        self.shard.count_pairs_rows(raw, raw.shape[0], splitters, [0], self._cm_pair.row_ptrs)
-        return self._cm_pair.gather()[:, :self.world]
+        self.shard.count_pairs_rows(raw, raw.shape[0], splitters, [int(tag)], self._cm_pair.row_ptrs)
+        mat = self._cm_pair.gather()
+        return mat[:, :self.world], mat[:, self.world]
 
     def exchange_records(self, keys, ids, splitters, m_own, m_halo, fold=False):
         """fold: the cell flags of the encoded records leave in the top 3 bits of their IDs (dedup at the source across
@@ -275,11 +277,15 @@ class CudaOps:
         self.shard.merge(self.static)
         return len(self.shard)
 
-    def scan_raw(self, keys, ids, n_halo, flt):
-        """The sorted records live in self.shard; its first n_halo records are halo."""
+    def scan_raw(self, keys, ids, n_halo, flt, dedup=True):
+        """The sorted records live in self.shard; its first n_halo records are halo.  dedup = False: every ID pair is
+        emitted from every cell the two objects share (bp_layer_set_scan_dedup)."""
         self.shard.set_halo(n_halo)
+        self.shard.set_scan_dedup(dedup)
         ptr, n = self.shard.scan_raw_device(flt)
+        self.shard.set_scan_dedup(True)
         self.shard.set_halo(0)
+        self.saw_same_id = self.shard.stats()["rescans"] != 0   # an ID owns nested bounds here: some record is inactive
         return _view(ptr, n, torch.int64, self.device)
 
     def count_pairs(self, raw, splitters):
@@ -306,8 +312,9 @@ class CudaOps:
 class DistLayer:
     """The distributed counterpart of clear -> extend -> par_sort -> par_scan(_filtered) for one frame."""
 
-    def __init__(self, ops, kind, group=None, trace=False, reuse_splitters=True):
+    def __init__(self, ops, kind, group=None, trace=False, reuse_splitters=True, global_dedup_decision=True):
         self.ops, self.kind, self.group = ops, kind, group
+        self.global_dedup_decision = global_dedup_decision  # (False only in a test that shows what the decision prevents)
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.trace = trace  # per-phase wall times (device-synchronised) in self.last["phases_ms"]; for tuning only
@@ -458,7 +465,19 @@ class DistLayer:
             self._a_splitters = choose_splitters(gathered[gathered >= 0].astype(np.uint64), g)
         a_splitters = self._a_splitters
         if hasattr(ops, "count_pairs_matrix"):
-            pm = ops.count_pairs_matrix(raw, a_splitters)
+            # Dedup at the source (every ID pair emitted from its canonical shared cell only) is valid only while NO record
+            # of the whole scene is inactive: the shard holding a pair's canonical cell skips it there if that record's ID
+            # owns an enclosing bound (src/layer.rs:562-564), and the reference then reports the pair from another shared
+            # cell -- possibly in a neighbouring shard, which must not have suppressed its copy.  A shard knows only its
+            # own records, so the flag travels with the pair counts, and when ANY shard saw an inactive record, every
+            # shard whose scan ran with the dedup scans again without it (a rare path: IDs owning nested bounds).
+            same = bool(getattr(ops, "saw_same_id", False))
+            pm, seen = ops.count_pairs_matrix(raw, a_splitters, int(same))
+            if flagged and self.global_dedup_decision and bool(np.any(seen != 0)):
+                if not same and n_halo == 0:
+                    raw = ops.scan_raw(sk, si, n_halo, flt, dedup=False)
+                    p_raw = raw.shape[0]
+                pm, _ = ops.count_pairs_matrix(raw, a_splitters, int(same))
         else:
             pc = ops.count_pairs(raw, a_splitters)
             pm = self._gather_rows(pc, dev)

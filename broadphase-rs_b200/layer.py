@@ -259,6 +259,9 @@ class Layer:
     def set_halo(self, n_halo):
         self._ck(lib().bp_layer_set_halo(self._h, n_halo))
 
+    def set_scan_dedup(self, enabled):
+        self._ck(lib().bp_layer_set_scan_dedup(self._h, int(enabled)))
+
     def scan_raw_device(self, flt=None):
         """Raw (filtered, unsorted, duplicate-carrying) packed pairs: (device pointer, count)."""
         f = None if flt is None else flt._c()

@@ -295,6 +295,12 @@ int bp_dist_lookup_ranges(bp_layer *ctx, const void *d_sorted_keys, size_t n, co
 /* Records [0, n_halo) of the tree are halo: they are ancestors only, never the later record of an
  * emitted pair.  Reset to 0 by bp_layer_clear / bp_layer_set_records. */
 int bp_layer_set_halo(bp_layer *layer, size_t n_halo);
+/* Dedup at the source (the scan emits an ID pair from the canonical one of the cells two objects share, DESIGN.md
+ * section 4) is only valid while NO record of the whole scene is inactive (an ID owning nested bounds,
+ * src/layer.rs:562-564).  A single layer decides that by itself; shards of a distributed scene must decide it
+ * together: a shard that saw such a record (bp_stats.rescans != 0 after the scan) tells the others, and every shard
+ * whose scan ran with the dedup scans again with it switched off (enabled = 0).  Default: enabled. */
+int bp_layer_set_scan_dedup(bp_layer *layer, int enabled);
 /* scan up to the raw pairs (filtered, not yet sorted / deduplicated), packed (later << 32) | earlier. */
 int bp_layer_scan_raw_device(bp_layer *layer, const bp_filter *filter, const void **out_d_raw, size_t *out_count);
 /* Sorts + deduplicates n packed raw pairs (possibly received from other shards) into the final

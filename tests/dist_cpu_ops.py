@@ -219,6 +219,9 @@ def make_case(name):
     elif name == "multibounds2d":  # several (nested) bounds per ID: inactive records across shard borders
         n, kind, dim = 5000, 1, 2
         size = (0.2 * rng.random((n, dim)) ** 3).astype(np.float32)
+    elif name == "multibounds3d":  # Index64_3D, several nested bounds per ID, multi-cell objects: with the cell flags riding
+        n, kind, dim = 6000, 2, 3  # across the exchange (dedup at the source) a skipped inactive record in one shard must
+        size = (0.25 * rng.random((n, dim)) ** 3).astype(np.float32)  # switch the dedup off in every other shard too
     elif name == "skewed3d":  # almost everything in one corner: very uneven key distribution
         n, kind, dim = 5000, 2, 3
         size = (0.01 * rng.random((n, dim))).astype(np.float32)
@@ -231,6 +234,8 @@ def make_case(name):
     bounds = np.concatenate([mn, np.minimum(mn + size, 1.0)], axis=1).astype(np.float32)
     if name == "multibounds2d":
         ids = np.sort(rng.integers(0, n // 4, size=n)).astype(np.uint32)
+    elif name == "multibounds3d":   # unsorted: an ID's bounds sit on different ranks
+        ids = rng.integers(0, n // 3, size=n).astype(np.uint32)
     else:
         ids = np.arange(n, dtype=np.uint32)
     flt = (1, 0) if name == "uniform3d" else None  # ID-parity filter on one case

@@ -10,7 +10,7 @@ import torch.multiprocessing as mp
 
 from tests import dist_cpu_ops as dco
 
-CASES = ["uniform3d", "big_objects3d", "multibounds2d", "skewed3d"]
+CASES = ["uniform3d", "big_objects3d", "multibounds2d", "multibounds3d", "skewed3d"]
 
 
 def _free_port():

@@ -10,6 +10,7 @@ from oracle import cpu_oracle as co
 from oracle import pyref
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _records(bp, n=200_000, seed=3):
@@ -296,13 +297,15 @@ def _nccl_worker(rank, world, port, out_dir):
     bp = _loadpkg.load()
     from broadphase_rs_b200 import dist as bpd
     from tests import dist_cpu_ops as dco
-    for case in ("uniform3d", "big_objects3d", "skewed3d"):
-        kind, md, sysb, bounds, ids, flt = dco.make_case(case)
+    for case in ("uniform3d", "big_objects3d", "skewed3d", "multibounds3d", "multibounds3d_local_decision"):
+        kind, md, sysb, bounds, ids, flt = dco.make_case(case.replace("_local_decision", ""))
         n = bounds.shape[0]
         cuts = np.linspace(0, n, world + 1).astype(int)
         lo, hi = cuts[rank], cuts[rank + 1]
         ops = bpd.CudaOps(bp, kind, md, rank)
-        dl = bpd.DistLayer(ops, kind)
+        # (the "_local_decision" run switches the global dedup decision off: it shows what the decision prevents and is
+        # only recorded, not asserted)
+        dl = bpd.DistLayer(ops, kind, global_dedup_decision=not case.endswith("_local_decision"))
         db = torch.from_numpy(bounds[lo:hi].copy()).cuda()
         di = torch.from_numpy(ids[lo:hi].copy().view(np.int32)).cuda()
         gflt = bp.ScanFilter.id_parity() if flt else None
@@ -353,10 +356,17 @@ def test_nccl_frame_equals_oracle(bp, tmp_path):
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     from tests import dist_cpu_ops as dco
-    for case in ("uniform3d", "big_objects3d", "skewed3d"):
+    for case in ("uniform3d", "big_objects3d", "skewed3d", "multibounds3d"):
         got = np.load(os.path.join(str(tmp_path), "%s.npy" % case))
         want = dco.reference_pairs(case)
         assert got.shape == want.shape and (got == want).all(), case
+    # with every shard deciding "dedup at the source" on its own, pairs whose canonical cell holds an
+    # inactive record are lost when a neighbouring shard suppresses its copy; the global decision (above) keeps them
+    lost = dco.reference_pairs("multibounds3d").shape[0] - np.load(os.path.join(str(tmp_path), "multibounds3d_local_decision.npy")).shape[0]
+    print("pairs lost without the global dedup decision: %d" % lost)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "dedup_decision.txt"), "w") as f:
+        f.write("world=%d pairs lost with per-shard decision: %d (0 with the global decision: asserted)\n" % (world, lost))
     for frame in range(2):
         got = np.load(os.path.join(str(tmp_path), "static_dynamic_%d.npy" % frame))
         want = dco.reference_static_dynamic(frame)

@@ -419,6 +419,65 @@ def test_non_ascending_ids_need_id_passes(bp):
     assert g.stats()["sort_passes"] >= 4
 
 
+# ---- BASELINE configs at FULL size against the oracle (about a minute of host time each) -------------------
+
+def _full_size(bp, sc, flt=None, oflt=(0, 0, None)):
+    """extend -> par_sort -> par_scan(_filtered) from device-resident inputs; records after the sort and the pair list
+    compared bit for bit with the oracle (tests/test_layer.rs:57-124's equalities at BASELINE's sizes)."""
+    import torch
+    n = sc["bounds"].shape[0]
+    g = bp.LayerBuilder().with_min_depth(sc["min_depth"]).build(sc["kind"], "u32")
+    o = co.OracleLayer(sc["kind"], 4, sc["min_depth"])
+    db = torch.from_numpy(sc["bounds"]).cuda()
+    di = torch.from_numpy(sc["ids"].view(np.int32)).cuda()
+    g.extend_device(sc["sys_bounds"], db, di, n)
+    o.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    g.par_sort()
+    o.par_sort()
+    _assert_records_equal(g, o)
+    gp = g.par_scan_filtered(flt)
+    op = o.par_scan(*oflt)
+    _assert_pairs_equal(gp, op)
+    assert _is_strictly_increasing(gp)
+    return g, gp
+
+
+def test_config3_full_size_against_oracle(bp):
+    """BASELINE config 3 as quoted: 2^24 log-normal cubes, Index64_3D, scan_filtered with the ID-parity filter."""
+    g, gp = _full_size(bp, bp.scenes.lognormal_cubes(1 << 24, 3), bp.ScanFilter.id_parity(), (co.FILTER_ID_PARITY, 0, None))
+    assert gp.shape[0] > (1 << 23) and ((gp[:, 0] ^ gp[:, 1]) & 1).all()
+    assert g.stats()["n_records"] > 4 * (1 << 24)
+
+
+def test_config5_per_gpu_shape_full_size_against_oracle(bp):
+    """The bench's headline shape on one GPU: 2^25 uniform cubes (BASELINE config 5's per-GPU share)."""
+    g, gp = _full_size(bp, bp.scenes.uniform_cubes(1 << 25, 6))
+    assert gp.shape[0] > (1 << 25)
+
+
+def test_config4_static_plus_dynamic_large(bp):
+    """BASELINE config 4 at 1/16 of its size: 2^22 static objects sorted once + 2^20 dynamic objects per frame through
+    Layer::merge (the reference appends and re-sorts; here one merge-path merge), two frames."""
+    import torch
+    ns, nd = 1 << 22, 1 << 20
+    st = bp.scenes.uniform_cubes(ns, 4)
+    gs = bp.Layer(2, "u32"); os_ = co.OracleLayer(2, 4, 0)
+    gs.extend(st["sys_bounds"], st["bounds"], st["ids"]); os_.extend(st["sys_bounds"], st["bounds"], st["ids"])
+    gs.sort(); os_.par_sort()
+    gd = bp.Layer(2, "u32"); od = co.OracleLayer(2, 4, 0)
+    for frame in range(2):
+        dy = bp.scenes.uniform_cubes(nd, 5 + frame, id_base=ns, edge_factor=0.4 * (ns / nd) ** (-1.0 / 3.0))
+        gd.clear(); od.clear()
+        gd.extend_device(dy["sys_bounds"], torch.from_numpy(dy["bounds"]).cuda(), torch.from_numpy(dy["ids"].view(np.int32)).cuda(), nd)
+        od.extend(dy["sys_bounds"], dy["bounds"], dy["ids"])
+        gd.sort(); od.par_sort()
+        gd.merge(gs); od.merge(os_)
+        gp = gd.par_scan(); op = od.par_scan()
+        _assert_pairs_equal(gp, op)
+        _assert_records_equal(gd, od)
+        assert gd.stats()["merged"] == 1
+
+
 # ---- full-size properties (no oracle): BASELINE config 3 at 2^24 objects -----------------------------
 
 def test_config3_full_size_properties(bp):
