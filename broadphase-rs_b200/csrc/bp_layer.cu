@@ -21,6 +21,7 @@
 #include "bp_merge.cuh"
 #include "bp_query.cuh"
 #include "bp_radix.cuh"
+#include "bp_exchange.cuh"
 #include "bp_scan.cuh"
 
 using namespace bp;
@@ -36,6 +37,13 @@ template <> struct PassTune<uint64_t, uint32_t> { static constexpr int THREADS =
 template <> struct PassTune<uint32_t, uint32_t> { static constexpr int THREADS = 512, ITEMS = 16, MINB = 2; };
 template <> struct PassTune<uint64_t, NoVal> { static constexpr int THREADS = 384, ITEMS = 12, MINB = 3; };
 template <> struct PassTune<uint64_t, uint64_t> { static constexpr int THREADS = 256, ITEMS = 12, MINB = 3; };
+// Shapes per digit width.  A 9-bit pass has half as many keys per (tile, digit) run as an 8-bit pass, and the write-out is
+// what it pays for (profiles/r2_sortbench_*.log: 384 x 12 x 3: 1.34 ms against 1.07 ms per pass on 146 M records); the larger
+// tile of 384 x 16 (2 CTAs / SM, 80 registers: fewer spills) brings it to 1.24 ms, so a 9-bit plan wins whenever it saves
+// a pass out of at most seven.  10-bit passes (1.6-1.8 ms) never pay.
+template <class K, class V, int RB> struct PassTuneRB : PassTune<K, V> {};
+template <> struct PassTuneRB<uint64_t, uint32_t, 9> { static constexpr int THREADS = 384, ITEMS = 16, MINB = 2; };
+template <> struct PassTuneRB<uint64_t, NoVal, 9> { static constexpr int THREADS = 384, ITEMS = 16, MINB = 2; };
 
 constexpr uint64_t MAX_RECORDS = (1ull << 30) - 1;
 
@@ -124,6 +132,7 @@ struct bp_layer {
     uint64_t id_first = 0, id_last = 0; // IDs of the first / last object extended since the last clear (bp_layer_id_order)
     uint64_t n_invalid = 0;
     uint64_t n_halo = 0; // records [0, n_halo) only act as ancestors in scan (multi-GPU halos)
+    int radix_bits_cap = 0; // BP_RADIX_BITS (tuning aid): widest radix digit the sorts may use; 0 = no cap
     bool scan_dedup = true; // bp_layer_set_scan_dedup: the scan may emit every ID pair from its canonical shared cell only
     // dedup at the source: encode writes 3 cell flags per record (cell_flags); a full sort of a tree that
     // only holds encoded records moves them into the top 3 bits of the IDs (ids_flagged) so that they
@@ -352,11 +361,13 @@ template <class T> inline T *ptr(DevBuf &b, size_t off = 0) { return (T *)b.p + 
 
 // ---- radix planning --------------------------------------------------------------------------------------
 // Digits for an LSD sort over the bits set in `mask` (bits that differ between keys).  Each pass
-// takes whichever covers more of the remaining bits: one 8-bit window starting at the lowest
+// takes whichever covers more of the remaining bits: one W-bit window starting at the lowest
 // remaining bit, or two runs of consecutive set bits (the lowest run, then the next one after a
-// gap) of 8 bits in total.
-int plan_passes(uint64_t mask, RadixPlan &plan, int first = 0) {
+// gap) of W bits in total.  W = 8 by default; the record sort takes 9- or 10-bit digits when that saves a
+// whole pass (27 varying bits: 3 passes instead of 4; 43: 5 instead of 6).
+int plan_passes(uint64_t mask, RadixPlan &plan, int first = 0, int W = 8) {
     int np = first;
+    const uint64_t wmask = (1ull << W) - 1ull;
     auto run_len = [](uint64_t m, int from, int cap) {
         int n = 0;
         while (n < cap && from + n < 64 && ((m >> (from + n)) & 1ull)) ++n;
@@ -365,17 +376,17 @@ int plan_passes(uint64_t mask, RadixPlan &plan, int first = 0) {
     while (mask && np < RADIX_MAX_PASSES) {
         const int s0 = __builtin_ctzll(mask);
         // option A: one window
-        const uint64_t window = (mask >> s0) & 0xffull;
+        const uint64_t window = (mask >> s0) & wmask;
         const int bitsA = 64 - __builtin_clzll(window);
         const int coverA = __builtin_popcountll(window);
         // option B: two runs
-        const int len0 = run_len(mask, s0, 8);
+        const int len0 = run_len(mask, s0, W);
         int s1 = 0, len1 = 0;
-        if (len0 < 8) {
+        if (len0 < W) {
             const uint64_t rest = (s0 + len0 >= 64) ? 0 : (mask >> (s0 + len0)) << (s0 + len0);
             if (rest) {
                 s1 = __builtin_ctzll(rest);
-                len1 = run_len(mask, s1, 8 - len0);
+                len1 = run_len(mask, s1, W - len0);
             }
         }
         if (len0 + len1 > coverA) {
@@ -390,7 +401,7 @@ int plan_passes(uint64_t mask, RadixPlan &plan, int first = 0) {
             plan.bits[np] = (unsigned char)bitsA;
             plan.shift2[np] = 0;
             plan.bits2[np] = 0;
-            mask &= ~(0xffull << s0);
+            mask &= ~(wmask << s0);
         }
         ++np;
     }
@@ -404,43 +415,82 @@ struct RadixScratch {
     size_t bytes;
 };
 
+// Which (key, payload) sorts may use digits wider than 8 bits (each width is another set of kernel instantiations).
+template <class K, class V> struct WideDigits { static constexpr int MAX_BITS = 8; };
+template <> struct WideDigits<uint64_t, uint32_t> { static constexpr int MAX_BITS = 9; }; // records
+template <> struct WideDigits<uint64_t, NoVal> { static constexpr int MAX_BITS = 9; };    // packed pairs
+
+template <class K, class V, int RB>
+int radix_sort_rb(bp_layer *L, const RadixPlan &plan, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32_t *n_dev, int cls_hist,
+                  int cls_pass, int *out_passes, bool *out_in_alt, size_t elem_bytes, const uint8_t *first_pass_vflags, const K *k_src,
+                  const V *v_src);
+
 template <class K, class V>
 int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32_t *n_dev, uint64_t mask, int cls_hist,
                int cls_pass, int *out_passes, bool *out_in_alt, size_t elem_bytes, const uint8_t *first_pass_vflags = nullptr,
                const K *k_src = nullptr, const V *v_src = nullptr) {
     // k_src / v_src: the first pass (and the histograms) read these arrays instead of k0 / v0 and write k1 / v1 as usual --
     // sorting straight out of a buffer the layer does not own (a multi-GPU receive buffer) without a staging copy
-    typedef PassTune<K, V> Tune;
-    typedef RadixPassCfg<K, V, Tune::THREADS, Tune::ITEMS> Cfg;
     *out_in_alt = false;
     *out_passes = 0;
+    if (n < 2) return BP_OK;
+    // the narrowest digit that reaches the smallest number of passes
     RadixPlan plan;
     memset(&plan, 0, sizeof plan);
-    const int np = plan_passes(mask, plan);
-    if (np == 0 || n < 2) return BP_OK;
+    int rb = 8, np = plan_passes(mask, plan, 0, 8);
+    if (np == 0) return BP_OK;
+    const int max_bits = L->radix_bits_cap ? std::min(L->radix_bits_cap, WideDigits<K, V>::MAX_BITS) : WideDigits<K, V>::MAX_BITS;
+    for (int w = 9; w <= max_bits; ++w) {
+        RadixPlan pw;
+        memset(&pw, 0, sizeof pw);
+        const int npw = plan_passes(mask, pw, 0, w);
+        if (npw < np && npw * 7 <= np * 6) { // a wider pass costs about 1.17 x an 8-bit pass
+            np = npw;
+            rb = w;
+            plan = pw;
+        }
+    }
+    if constexpr (WideDigits<K, V>::MAX_BITS >= 9) {
+        if (rb == 9)
+            return radix_sort_rb<K, V, 9>(L, plan, k0, v0, k1, v1, n, n_dev, cls_hist, cls_pass, out_passes, out_in_alt, elem_bytes,
+                                          first_pass_vflags, k_src, v_src);
+    }
+    return radix_sort_rb<K, V, 8>(L, plan, k0, v0, k1, v1, n, n_dev, cls_hist, cls_pass, out_passes, out_in_alt, elem_bytes,
+                                  first_pass_vflags, k_src, v_src);
+}
+
+template <class K, class V, int RB>
+int radix_sort_rb(bp_layer *L, const RadixPlan &plan, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32_t *n_dev, int cls_hist,
+                  int cls_pass, int *out_passes, bool *out_in_alt, size_t elem_bytes, const uint8_t *first_pass_vflags, const K *k_src,
+                  const V *v_src) {
+    typedef PassTuneRB<K, V, RB> Tune;
+    typedef RadixPassCfg<K, V, Tune::THREADS, Tune::ITEMS, RB> Cfg;
+    constexpr int NB = Cfg::NB;
+    const int np = plan.npasses;
     const uint32_t tiles = (n + Cfg::TILE - 1) / Cfg::TILE;
-    const size_t hist_bytes = (size_t)RADIX_MAX_PASSES * RADIX * sizeof(uint32_t);
+    const size_t hist_bytes = (size_t)RADIX_MAX_PASSES * NB * sizeof(uint32_t);
     const size_t ctr_bytes = 64 * sizeof(uint32_t);
-    const size_t status_bytes = (size_t)np * tiles * RADIX * sizeof(uint32_t);
+    const size_t status_bytes = (size_t)np * tiles * NB * sizeof(uint32_t);
     const size_t total = hist_bytes + ctr_bytes + status_bytes;
     TRY(ensure(L, L->scratch, total));
     uint32_t *hist = (uint32_t *)L->scratch.p;
-    uint32_t *counters = hist + RADIX_MAX_PASSES * RADIX;
+    uint32_t *counters = hist + RADIX_MAX_PASSES * NB;
     uint32_t *status = counters + 64;
     CU(L, cudaMemsetAsync(L->scratch.p, 0, total, L->stream));
     {
         LaunchScope ls(L, cls_hist, (double)n * sizeof(K));
         const int blocks = (int)std::min<size_t>((n + 512 * 8 - 1) / (512 * 8), 148 * 8);
-        radix_hist_kernel<K><<<std::max(blocks, 1), 512, 0, L->stream>>>(k_src ? k_src : k0, n, n_dev, plan, hist);
+        radix_hist_kernel<K><<<std::max(blocks, 1), 512, (size_t)np * NB * sizeof(uint32_t), L->stream>>>(k_src ? k_src : k0, n, n_dev, plan,
+                                                                                                         hist, NB);
     }
     TRY(check_launch(L, "radix_hist_kernel"));
     {
         LaunchScope ls(L, BP_K_MISC, 0);
-        radix_scan_hist_kernel<<<np, RADIX, 0, L->stream>>>(hist);
+        radix_scan_hist_kernel<NB><<<np, NB, 0, L->stream>>>(hist);
     }
     TRY(check_launch(L, "radix_scan_hist_kernel"));
-    auto kern1 = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS, Tune::MINB, OneFieldDigit<K>>;
-    auto kern2 = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS, Tune::MINB, ShiftMaskDigit<K>>;
+    auto kern1 = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS, Tune::MINB, OneFieldDigit<K>, RB>;
+    auto kern2 = radix_pass_kernel<K, V, Tune::THREADS, Tune::ITEMS, Tune::MINB, ShiftMaskDigit<K>, RB>;
     CU(L, cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     CU(L, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
     const K *kin = k_src ? k_src : k0;
@@ -457,8 +507,8 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
             a.vout = vout;
             a.n_host = n;
             a.n_dev = n_dev;
-            a.ghist_excl = hist + (size_t)p * RADIX;
-            a.status = status + (size_t)p * tiles * RADIX;
+            a.ghist_excl = hist + (size_t)p * NB;
+            a.status = status + (size_t)p * tiles * NB;
             a.tile_counter = counters + p;
             a.op.shift = plan.shift[p];
             a.op.mask = (1u << plan.bits[p]) - 1u;
@@ -473,8 +523,8 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
             a.vout = vout;
             a.n_host = n;
             a.n_dev = n_dev;
-            a.ghist_excl = hist + (size_t)p * RADIX;
-            a.status = status + (size_t)p * tiles * RADIX;
+            a.ghist_excl = hist + (size_t)p * NB;
+            a.status = status + (size_t)p * tiles * NB;
             a.tile_counter = counters + p;
             a.op.shift = plan.shift[p];
             a.op.mask = (1u << plan.bits[p]) - 1u;
@@ -1337,10 +1387,10 @@ template <int KIND, class IdT> struct Impl {
     static int partition_scatter(bp_layer *L, const PK *kin, const PV *vin, uint32_t n, const uint64_t *spl, int n_spl,
                                  uint32_t shift, const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst,
                                  const uint64_t *hvdst, const uint8_t *vflags = nullptr) {
-        typedef PassTune<PK, PV> Tune;
-        typedef RadixPassCfg<PK, PV, Tune::THREADS, Tune::ITEMS> Cfg;
+        constexpr int XT = 384, XI = 12, XMINB = 3;
+        typedef ExchangeCfg<PK, PV, XT, XI> Cfg;
         if (n == 0) return BP_OK;
-        SplitterScatterDigit<PK> op;
+        SplitterScatterDigit<PK> op; // (the halo copies below still go through the splitter functor)
         for (int i = 0; i < MAX_SPLITTERS; ++i) op.spl[i] = i < n_spl ? spl[i] : ~0ull;
         op.n = (uint32_t)n_spl;
         op.shift = shift;
@@ -1349,31 +1399,36 @@ template <int KIND, class IdT> struct Impl {
             op.vdst[b] = (b <= n_spl && vdst) ? vdst[b] : 0;
         }
         const uint32_t tiles = (n + Cfg::TILE - 1) / Cfg::TILE;
-        const size_t total = (size_t)(RADIX + 64 + (size_t)tiles * RADIX) * sizeof(uint32_t);
+        const size_t total = (size_t)(64 + (size_t)tiles * XCH_BUCKETS) * sizeof(uint32_t);
         TRY(ensure(L, L->scratch, total));
-        uint32_t *zero_hist = (uint32_t *)L->scratch.p, *counters = zero_hist + RADIX, *status = counters + 64;
+        uint32_t *counters = (uint32_t *)L->scratch.p, *status = counters + 64;
         CU(L, cudaMemsetAsync(L->scratch.p, 0, total, L->stream));
-        auto kern = radix_pass_kernel<PK, PV, Tune::THREADS, Tune::ITEMS, Tune::MINB, SplitterScatterDigit<PK>>;
-        CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-        RadixPassArgs<PK, PV, SplitterScatterDigit<PK>> a;
+        ExchangeArgs<PK, PV> a;
         a.kin = kin;
-        a.kout = nullptr;
         a.vin = vin;
-        a.vout = nullptr;
-        a.n_host = n;
-        a.n_dev = nullptr;
-        a.ghist_excl = zero_hist; // every bucket starts at offset 0 of its own destination
+        a.vflags = vflags; // dedup at the source across the exchange: the cell flags leave inside the IDs
+        a.n = n;
+        a.n_spl = (uint32_t)n_spl;
+        a.shift = shift;
+        for (int i = 0; i < MAX_SPLITTERS; ++i) a.spl[i] = op.spl[i];
+        for (int b = 0; b < XCH_BUCKETS; ++b) {
+            a.kdst[b] = op.kdst[b];
+            a.vdst[b] = op.vdst[b];
+        }
         a.status = status;
         a.tile_counter = counters;
-        a.vflags = vflags; // dedup at the source across the exchange: the cell flags leave inside the IDs
-        a.op = op;
         a.err = L->d_err;
         {
+            static const bool use_tma = !(getenv("BP_EXCHANGE_TMA") && atoi(getenv("BP_EXCHANGE_TMA")) == 0);
+            auto kern_tma = exchange_pass_kernel<PK, PV, XT, XI, XMINB, true>;
+            auto kern_st = exchange_pass_kernel<PK, PV, XT, XI, XMINB, false>;
+            auto kern = use_tma ? kern_tma : kern_st;
+            CU(L, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
             const double eb = std::is_same<PV, NoVal>::value ? sizeof(PK) : sizeof(PK) + sizeof(PV);
             LaunchScope ls(L, BP_K_PARTITION, 2.0 * (double)n * eb);
-            kern<<<tiles, Tune::THREADS, Cfg::SMEM_BYTES, L->stream>>>(a);
+            kern<<<tiles, XT, Cfg::SMEM_BYTES, L->stream>>>(a);
         }
-        TRY(check_launch(L, "radix_pass_kernel<scatter>"));
+        TRY(check_launch(L, "exchange_pass_kernel"));
         if constexpr (!std::is_same<PV, NoVal>::value) {
             if (hkdst && hvdst) {
                 SplitterScatterDigit<PK> hop = op;
@@ -1659,6 +1714,7 @@ int bp_layer_create(const bp_layer_config *cfg, bp_layer **out) {
     L->device = dev;
     L->min_depth = cfg->min_depth;
     memset(&L->stats, 0, sizeof L->stats);
+    if (const char *e = getenv("BP_RADIX_BITS")) L->radix_bits_cap = atoi(e); // tuning aid: 8 = the 8-bit pass everywhere
     DeviceGuard g(dev);
     auto bail = [&](int st) {
         bp_layer_destroy(L);

@@ -20,7 +20,8 @@ namespace bp {
 struct NoVal {};
 
 constexpr int RADIX_MAX_PASSES = 16;
-constexpr int RADIX = 256;
+constexpr int RADIX = 256;      // bins of an 8-bit digit (the default digit width)
+constexpr int RADIX_MAX_BITS = 10; // widest digit a pass kernel is instantiated for (record sort: 9 or 10 bits when that saves a pass)
 
 // One digit = up to two bit-fields of the key: (key >> shift) & ((1 << bits) - 1), with the second field
 // (shift2, bits2; bits2 may be 0) stacked above the first.  Two fields let the planner skip a gap of
@@ -40,13 +41,14 @@ template <class K> __host__ __device__ __forceinline__ uint32_t plan_digit(const
 }
 
 // ---- histograms for every planned digit in one read of the keys ---------------------------------
+// NB = bins per pass (a power of two >= 2^bits of every planned digit); dynamic shared memory: np * NB counters.
 template <class K>
 __global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ keys, uint32_t n_host,
                                                           const uint32_t *__restrict__ n_dev, RadixPlan plan,
-                                                          uint32_t *__restrict__ ghist) {
-    __shared__ uint32_t sh[RADIX_MAX_PASSES * RADIX];
+                                                          uint32_t *__restrict__ ghist, int NB = RADIX) {
+    extern __shared__ uint32_t sh[];
     const int np = plan.npasses;
-    for (int i = threadIdx.x; i < np * RADIX; i += blockDim.x) sh[i] = 0;
+    for (int i = threadIdx.x; i < np * NB; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const uint32_t n = n_dev ? *n_dev : n_host;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ k
         for (int p = 0; p < np; ++p) {
             const uint32_t s0 = plan.shift[p], m0 = (1u << plan.bits[p]) - 1u, b0 = plan.bits[p];
             const uint32_t s1 = plan.shift2[p], m1 = (1u << plan.bits2[p]) - 1u;
-            uint32_t *h = sh + p * RADIX;
+            uint32_t *h = sh + p * NB;
 #pragma unroll
             for (int u = 0; u < UNROLL; ++u)
                 atomicAdd(&h[((uint32_t)(k[u] >> s0) & m0) | (((uint32_t)(k[u] >> s1) & m1) << b0)], 1u);
@@ -69,22 +71,22 @@ __global__ void __launch_bounds__(512) radix_hist_kernel(const K *__restrict__ k
     }
     for (; i < n; i += stride) {
         const K k = ld_stream(keys + i);
-        for (int p = 0; p < np; ++p) atomicAdd(&sh[p * RADIX + plan_digit<K>(plan, p, k)], 1u);
+        for (int p = 0; p < np; ++p) atomicAdd(&sh[p * NB + plan_digit<K>(plan, p, k)], 1u);
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < np * RADIX; j += blockDim.x) {
+    for (int j = threadIdx.x; j < np * NB; j += blockDim.x) {
         const uint32_t c = sh[j];
         if (c) atomicAdd(&ghist[j], c);
     }
 }
 
-// ---- exclusive scan of each pass's 256-bin histogram (one CTA of 256 threads per pass) -----------
-__global__ void __launch_bounds__(RADIX) radix_scan_hist_kernel(uint32_t *__restrict__ ghist) {
-    __shared__ uint32_t wt[RADIX / 32 + 1];
-    uint32_t *h = ghist + (size_t)blockIdx.x * RADIX;
+// ---- exclusive scan of each pass's NB-bin histogram (one CTA of NB threads per pass) -----------
+template <int NB = RADIX> __global__ void __launch_bounds__(NB) radix_scan_hist_kernel(uint32_t *__restrict__ ghist) {
+    __shared__ uint32_t wt[NB / 32 + 1];
+    uint32_t *h = ghist + (size_t)blockIdx.x * NB;
     const uint32_t c = h[threadIdx.x];
     uint32_t total;
-    const uint32_t ex = block_exclusive_sum<RADIX, uint32_t>(c, wt, &total);
+    const uint32_t ex = block_exclusive_sum<NB, uint32_t>(c, wt, &total);
     h[threadIdx.x] = ex;
 }
 
@@ -133,8 +135,8 @@ template <class K, class V, class Op = ShiftMaskDigit<K>> struct RadixPassArgs {
     V *vout;
     uint32_t n_host;
     const uint32_t *n_dev;      // optional: element count in device memory (grid sized by n_host >= *n_dev)
-    const uint32_t *ghist_excl; // [RADIX] exclusive digit offsets of this pass
-    uint32_t *status;           // [tiles][RADIX], zeroed; bits 31..30 flag, 29..0 count
+    const uint32_t *ghist_excl; // [NB] exclusive digit offsets of this pass (NB = 2^RB bins)
+    uint32_t *status;           // [tiles][NB], zeroed; bits 31..30 flag, 29..0 count
     uint32_t *tile_counter;     // zeroed
     const uint8_t *vflags;      // optional: 3 flag bits per input element, OR-ed into the top bits of the payload as it is loaded
     Op op;
@@ -145,10 +147,10 @@ template <class K, class V, class Op = ShiftMaskDigit<K>> struct RadixPassArgs {
 // sm_100a MATCH runs on the ADU pipe at a rate that drops with the number of distinct values in
 // the warp -- the ncu capture profiles/r1_sortpass_before.txt shows it at 56% of peak, the top
 // unit, on high-entropy digits -- while VOTE does not depend on the data.
-__device__ __forceinline__ unsigned match_digit(uint32_t d) {
+template <int RB = 8> __device__ __forceinline__ unsigned match_digit(uint32_t d) {
     unsigned m = BP_FULL_MASK;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < RB; ++b) {
         // m &= (bit b of d) ? ballot : ~ballot, as  m & ~(ballot ^ e)  with e = all-ones iff the bit is set
         asm("{\n\t"
             ".reg .pred p;\n\t"
@@ -167,58 +169,126 @@ __device__ __forceinline__ unsigned match_digit(uint32_t d) {
 
 constexpr uint32_t RS_FLAG_AGG = 1u << 30, RS_FLAG_INC = 2u << 30, RS_VALUE_MASK = (1u << 30) - 1;
 
-// One round of the per-digit look-back: B predecessor tiles t, t-1, .. of digit `tid`, loaded together.
-template <int B>
-__device__ __forceinline__ void lookback_round(const uint32_t *status, unsigned tid, int64_t &t, uint32_t &excl, bool &done, int *err) {
-    uint32_t sv[B];
-#pragma unroll
-    for (int b = 0; b < B; ++b) sv[b] = (t - b >= 0) ? ld_volatile_u32(status + (size_t)(t - b) * RADIX + tid) : RS_FLAG_INC;
+// DPT consecutive status words (the digits one look-back thread owns) with one volatile vector load / store.  Every word
+// carries its own flag, so tearing between the words of a vector is harmless.
+template <int DPT> struct StatusVec { uint32_t w[DPT]; };
+template <int DPT> __device__ __forceinline__ StatusVec<DPT> ld_status(const uint32_t *p) {
+    StatusVec<DPT> v;
+    if constexpr (DPT == 1) {
+        v.w[0] = ld_volatile_u32(p);
+    } else if constexpr (DPT == 2) {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.w[0]), "=r"(v.w[1]) : "l"(p) : "memory");
+    } else {
+        static_assert(DPT == 4, "1, 2 or 4 digits per look-back thread");
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.w[0]), "=r"(v.w[1]), "=r"(v.w[2]), "=r"(v.w[3]) : "l"(p) : "memory");
+    }
+    return v;
+}
+template <int DPT> __device__ __forceinline__ void st_status(uint32_t *p, const StatusVec<DPT> &v) {
+    if constexpr (DPT == 1) {
+        st_volatile_u32(p, v.w[0]);
+    } else if constexpr (DPT == 2) {
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]) : "memory");
+    } else {
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]), "r"(v.w[2]), "r"(v.w[3]) : "memory");
+    }
+}
+
+// One round of the per-digit look-back: B predecessor tiles t, t-1, .. of the DPT digits starting at `d0`, loaded together.
+// NB = status words per tile.
+template <int B, int DPT>
+__device__ __forceinline__ void lookback_round(const uint32_t *status, int NB, unsigned d0, int64_t &t, uint32_t (&excl)[DPT],
+                                               unsigned &done, int *err) {
+    StatusVec<DPT> sv[B];
 #pragma unroll
     for (int b = 0; b < B; ++b) {
-        if (done) break;
-        uint32_t sb = sv[b];
-        if ((sb >> 30) == 0) { // not published yet: poll this one
-            const uint32_t *ps = status + (size_t)(t - b) * RADIX + tid;
-            uint32_t spins = 0;
-            do {
-                if (++spins > BP_SPIN_LIMIT) {
-                    *err = 1;
-                    sb = RS_FLAG_INC;
-                    break;
-                }
-                sb = ld_volatile_u32(ps);
-            } while ((sb >> 30) == 0);
+        if (t - b >= 0) {
+            sv[b] = ld_status<DPT>(status + (size_t)(t - b) * NB + d0);
+        } else {
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) sv[b].w[j] = RS_FLAG_INC;
         }
-        excl += sb & RS_VALUE_MASK;
-        if ((sb >> 30) == 2) done = true;
+    }
+    if constexpr (DPT == 1) { // the 8-bit pass: one digit per thread, leave the batch at the first inclusive prefix
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+            if (done) break;
+            uint32_t sb = sv[b].w[0];
+            if ((sb >> 30) == 0) { // not published yet: poll this one
+                const uint32_t *ps = status + (size_t)(t - b) * NB + d0;
+                uint32_t spins = 0;
+                do {
+                    if (++spins > BP_SPIN_LIMIT) {
+                        *err = 1;
+                        sb = RS_FLAG_INC;
+                        break;
+                    }
+                    sb = ld_volatile_u32(ps);
+                } while ((sb >> 30) == 0);
+            }
+            excl[0] += sb & RS_VALUE_MASK;
+            if ((sb >> 30) == 2) done = 1u;
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < B; ++b) {
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) {
+                uint32_t sb = sv[b].w[j];
+                const bool live = !(done & (1u << j));
+                if (live && (sb >> 30) == 0) { // not published yet: poll this one
+                    const uint32_t *ps = status + (size_t)(t - b) * NB + d0 + j;
+                    uint32_t spins = 0;
+                    do {
+                        if (++spins > BP_SPIN_LIMIT) {
+                            *err = 1;
+                            sb = RS_FLAG_INC;
+                            break;
+                        }
+                        sb = ld_volatile_u32(ps);
+                    } while ((sb >> 30) == 0);
+                }
+                excl[j] += live ? (sb & RS_VALUE_MASK) : 0u; // branch-free apart from the (rare) poll
+                done |= (live && (sb >> 30) == 2) ? (1u << j) : 0u;
+            }
+        }
     }
     t -= B;
 }
 
-template <class K, class V, int THREADS, int ITEMS> struct RadixPassCfg {
+// RB = digit width in bits: NB = 2^RB bins.  The 256 threads that own the digits (publish, look-back, digit offsets) own
+// DPT = NB / 256 consecutive digits each; above 8 bits the per-warp digit counters are packed 16-bit halves (a warp ranks
+// 32 * ITEMS < 2^16 keys), so the shared-memory footprint -- and with it 3 CTAs per SM -- stays that of the 8-bit pass.
+template <class K, class V, int THREADS, int ITEMS, int RB = 8> struct RadixPassCfg {
     static constexpr bool HAS_V = !std::is_same<V, NoVal>::value;
+    static constexpr int NB = 1 << RB;
+    static constexpr int DPT = NB / 256;
+    static constexpr bool PACK = RB > 8;
     static constexpr int TILE = THREADS * ITEMS;
     static constexpr int WARPS = THREADS / 32;
     static constexpr size_t ELEM = HAS_V ? (sizeof(K) > sizeof(V) ? sizeof(K) : sizeof(V)) : sizeof(K);
     static constexpr size_t STAGE_BYTES = (size_t)TILE * ELEM;
-    static constexpr size_t SMEM_BYTES = STAGE_BYTES + (size_t)(WARPS * RADIX + 2 * RADIX + 16) * sizeof(uint32_t);
-    static_assert(THREADS >= RADIX && THREADS % 32 == 0, "one thread per digit is needed");
+    static constexpr size_t WHIST_WORDS = (size_t)WARPS * NB / (PACK ? 2 : 1);
+    static constexpr size_t SMEM_BYTES = STAGE_BYTES + (WHIST_WORDS + 2 * NB + 16) * sizeof(uint32_t);
+    static_assert(RB >= 8 && RB <= RADIX_MAX_BITS, "digit width");
+    static_assert(THREADS >= 256 && THREADS % 32 == 0, "256 threads own the digits");
     static_assert(TILE < 65536, "ranks are packed in 16 bits");
 };
 
 // The body of one tile.  FULL = the tile has exactly TILE elements: every bounds check disappears.
-template <class K, class V, class Op, int THREADS, int ITEMS, bool FULL>
+template <class K, class V, class Op, int THREADS, int ITEMS, bool FULL, int RB>
 __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a, unsigned char *smem_raw, const uint32_t tile,
                                                 const uint32_t tile_n) {
-    typedef RadixPassCfg<K, V, THREADS, ITEMS> Cfg;
-    constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS;
-    constexpr bool HAS_V = Cfg::HAS_V;
+    typedef RadixPassCfg<K, V, THREADS, ITEMS, RB> Cfg;
+    constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS, NB = Cfg::NB, DPT = Cfg::DPT;
+    constexpr bool HAS_V = Cfg::HAS_V, PACK = Cfg::PACK;
 
     unsigned char *stage = smem_raw;
-    uint32_t *whist = (uint32_t *)(smem_raw + Cfg::STAGE_BYTES); // [WARPS][RADIX]
-    uint32_t *dstart = whist + WARPS * RADIX;                    // [RADIX] first block rank of each digit
-    uint32_t *gbase = dstart + RADIX;                            // [RADIX] global offset minus dstart
-    uint32_t *misc = gbase + RADIX;                              // [0] tile, [1..9] warp totals
+    uint32_t *whist = (uint32_t *)(smem_raw + Cfg::STAGE_BYTES); // [WARPS][NB] counters (u32, or u16 pairs when PACK)
+    uint32_t *dstart = whist + Cfg::WHIST_WORDS;                 // [NB] first block rank of each digit
+    uint32_t *gbase = dstart + NB;                               // [NB] global offset minus dstart
+    uint32_t *misc = gbase + NB;                                 // [0] tile, [1..9] warp totals
+    constexpr int WROW = NB / (PACK ? 2 : 1);                    // words per warp row
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t tile_begin = (uint64_t)tile * TILE;
@@ -243,20 +313,27 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
     // old counter values are broadcast with shuffles.
     const Op op = a.op;
     const uint32_t dmax = op.max();
-    uint32_t *wrow = whist + warp * RADIX;
+    uint32_t *wrow = whist + warp * WROW;
     const unsigned lt = lanemask_lt();
     unsigned mm[ITEMS];
     uint32_t rd[ITEMS]; // low 16 bits: rank, high 16 bits: digit
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t d = op(key[k]);
-        mm[k] = match_digit(d);
+        mm[k] = match_digit<RB>(d);
         rd[k] = d;
     }
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         uint32_t old = 0;
-        if ((mm[k] & lt) == 0) old = atomicAdd(&wrow[rd[k]], (uint32_t)__popc(mm[k])); // lowest lane of its group
+        if ((mm[k] & lt) == 0) { // lowest lane of its group
+            if constexpr (PACK) {
+                const uint32_t sh = (rd[k] & 1u) << 4;
+                old = (atomicAdd(&wrow[rd[k] >> 1], (uint32_t)__popc(mm[k]) << sh) >> sh) & 0xffffu;
+            } else {
+                old = atomicAdd(&wrow[rd[k]], (uint32_t)__popc(mm[k]));
+            }
+        }
         rd[k] |= old << 16; // parked in the high half until the broadcast below
     }
 #pragma unroll
@@ -269,28 +346,54 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
     __syncthreads();
 
     // ---- per digit: exclusive scan over the warps, publish the tile count ----------------------------
-    uint32_t count_full = 0, incl = 0;
-    if (tid < RADIX) {
-        uint32_t sum = 0;
+    const unsigned d0 = tid * DPT; // first of this thread's digits (tid < 256)
+    uint32_t count_full[DPT];
+    uint32_t incl = 0, mine = 0;
+    if (tid < 256) {
+        if constexpr (PACK) { // two digits per word: the packed halves add independently (a tile holds < 2^16 keys)
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const uint32_t c = whist[w * RADIX + tid];
-            whist[w * RADIX + tid] = sum;
-            sum += c;
+            for (int j = 0; j < DPT / 2; ++j) {
+                uint32_t sum = 0;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) {
+                    const uint32_t c = whist[w * WROW + tid * (DPT / 2) + j];
+                    whist[w * WROW + tid * (DPT / 2) + j] = sum;
+                    sum += c;
+                }
+                count_full[2 * j] = sum & 0xffffu;
+                count_full[2 * j + 1] = sum >> 16;
+            }
+        } else {
+            uint32_t sum = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = whist[w * WROW + tid];
+                whist[w * WROW + tid] = sum;
+                sum += c;
+            }
+            count_full[0] = sum;
         }
-        count_full = sum;
-        uint32_t count = sum;
-        if (!FULL && tid == dmax) count -= (uint32_t)(TILE - tile_n); // pads carry the largest digit
-        uint32_t *st = a.status + (size_t)tile * RADIX + tid;
-        st_volatile_u32(st, (tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG) | count);
-        incl = warp_inclusive_sum(count_full);
+        StatusVec<DPT> st;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            uint32_t count = count_full[j];
+            if (!FULL && d0 + j == dmax) count -= (uint32_t)(TILE - tile_n); // pads carry the largest digit
+            st.w[j] = (tile == 0 ? RS_FLAG_INC : RS_FLAG_AGG) | count;
+            mine += count_full[j];
+        }
+        st_status<DPT>(a.status + (size_t)tile * NB + d0, st);
+        incl = warp_inclusive_sum(mine);
         if (lane == 31) misc[1 + warp] = incl;
     }
     __syncthreads();
-    if (tid < RADIX) {
-        uint32_t off = 0;
+    if (tid < 256) {
+        uint32_t off = incl - mine;
         for (unsigned w = 0; w < warp; ++w) off += misc[1 + w];
-        dstart[tid] = off + incl - count_full;
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) {
+            dstart[d0 + j] = off;
+            off += count_full[j];
+        }
     }
     __syncthreads();
 
@@ -299,7 +402,12 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t d = rd[k] >> 16;
-        const uint32_t r = (rd[k] & 0xffffu) + whist[warp * RADIX + d] + dstart[d];
+        uint32_t wex; // keys of this digit in the warps before this one
+        if constexpr (PACK)
+            wex = (wrow[d >> 1] >> ((d & 1u) << 4)) & 0xffffu;
+        else
+            wex = wrow[d];
+        const uint32_t r = (rd[k] & 0xffffu) + wex + dstart[d];
         rd[k] = r;
         skeys[r] = key[k];
     }
@@ -323,25 +431,34 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
     }
 
     // ---- look back: global offset of every digit run of this tile ------------------------------------
-    if (tid < RADIX) {
-        uint32_t excl = 0;
+    if (tid < 256) {
+        uint32_t excl[DPT];
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) excl[j] = 0;
         if (tile != 0) {
-            uint32_t count = count_full;
-            if (!FULL && tid == dmax) count -= (uint32_t)(TILE - tile_n);
             // Walk back over the predecessors a batch of tiles at a time: the status loads of one batch are
             // independent, so a batch costs one L2 round trip.  The batch size sets how fast the first
             // wave of tiles (none of which has an inclusive prefix to offer yet) resolves: about
             // tile / (2 * LB_BATCH) round trips for tile number `tile`.  In the steady state an inclusive prefix
             // sits a few tiles back, so the first batch is short (the look-back loads were 12 % of the kernel's
             // instructions, profiles/r1_cfg3_sort_pass.txt).
-            constexpr int LB_FIRST = 4, LB_BATCH = 16;
+            constexpr int LB_FIRST = 4, LB_BATCH = 16 / DPT;
             int64_t t = (int64_t)tile - 1;
-            bool done = false;
-            lookback_round<LB_FIRST>(a.status, tid, t, excl, done, a.err);
-            while (!done && t >= 0) lookback_round<LB_BATCH>(a.status, tid, t, excl, done, a.err);
-            st_volatile_u32(a.status + (size_t)tile * RADIX + tid, RS_FLAG_INC | ((excl + count) & RS_VALUE_MASK));
+            unsigned done = 0;
+            constexpr unsigned ALL = (1u << DPT) - 1u;
+            lookback_round<LB_FIRST, DPT>(a.status, NB, d0, t, excl, done, a.err);
+            while (done != ALL && t >= 0) lookback_round<LB_BATCH, DPT>(a.status, NB, d0, t, excl, done, a.err);
+            StatusVec<DPT> st;
+#pragma unroll
+            for (int j = 0; j < DPT; ++j) {
+                uint32_t count = count_full[j];
+                if (!FULL && d0 + j == dmax) count -= (uint32_t)(TILE - tile_n);
+                st.w[j] = RS_FLAG_INC | ((excl[j] + count) & RS_VALUE_MASK);
+            }
+            st_status<DPT>(a.status + (size_t)tile * NB + d0, st);
         }
-        gbase[tid] = a.ghist_excl[tid] + excl - dstart[tid];
+#pragma unroll
+        for (int j = 0; j < DPT; ++j) gbase[d0 + j] = a.ghist_excl[d0 + j] + excl[j] - dstart[d0 + j];
     }
     __syncthreads();
     uint32_t dst[ITEMS];
@@ -383,17 +500,17 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
     }
 }
 
-template <class K, class V, int THREADS, int ITEMS, int MINB = 1, class Op = ShiftMaskDigit<K>>
+template <class K, class V, int THREADS, int ITEMS, int MINB = 1, class Op = ShiftMaskDigit<K>, int RB = 8>
 __global__ void __launch_bounds__(THREADS, MINB) radix_pass_kernel(const RadixPassArgs<K, V, Op> a) {
-    typedef RadixPassCfg<K, V, THREADS, ITEMS> Cfg;
-    constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS;
+    typedef RadixPassCfg<K, V, THREADS, ITEMS, RB> Cfg;
+    constexpr int TILE = Cfg::TILE;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *whist = (uint32_t *)(smem_raw + Cfg::STAGE_BYTES);
-    uint32_t *misc = whist + WARPS * RADIX + 2 * RADIX;
+    uint32_t *misc = whist + Cfg::WHIST_WORDS + 2 * Cfg::NB;
 
     const unsigned tid = threadIdx.x;
     if (tid == 0) misc[0] = atomicAdd(a.tile_counter, 1u);
-    for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
+    for (int i = tid; i < (int)Cfg::WHIST_WORDS; i += THREADS) whist[i] = 0;
     __syncthreads();
     const uint32_t tile = misc[0];
     const uint32_t n = a.n_dev ? *a.n_dev : a.n_host;
@@ -401,9 +518,9 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_pass_kernel(const RadixPa
     if (tile_begin >= n) return;
     const uint32_t tile_n = (uint32_t)min((uint64_t)TILE, (uint64_t)n - tile_begin);
     if (tile_n == (uint32_t)TILE)
-        radix_pass_tile<K, V, Op, THREADS, ITEMS, true>(a, smem_raw, tile, tile_n);
+        radix_pass_tile<K, V, Op, THREADS, ITEMS, true, RB>(a, smem_raw, tile, tile_n);
     else
-        radix_pass_tile<K, V, Op, THREADS, ITEMS, false>(a, smem_raw, tile, tile_n);
+        radix_pass_tile<K, V, Op, THREADS, ITEMS, false, RB>(a, smem_raw, tile, tile_n);
 }
 
 // ---- bucket counts for a splitter partition (one read of the keys) --------------------------------------
