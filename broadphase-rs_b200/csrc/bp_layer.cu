@@ -132,6 +132,13 @@ struct bp_layer {
     uint64_t id_first = 0, id_last = 0; // IDs of the first / last object extended since the last clear (bp_layer_id_order)
     uint64_t n_invalid = 0;
     uint64_t n_halo = 0; // records [0, n_halo) only act as ancestors in scan (multi-GPU halos)
+    // Layer::merge of a sorted layer into a sorted layer is deferred: the other layer's records are not copied behind ours,
+    // the next sort merges the two runs straight out of the two layers' buffers (one read of the other tree instead of
+    // copy + read).  Every other access to this layer's records, and every call that may change the other layer,
+    // materialises the copy first (resolve_pending), so nothing observable differs from the eager append.
+    bp_layer *lazy_src = nullptr;           // the layer whose records logically sit at [n_records - lazy_n, n_records)
+    uint64_t lazy_n = 0;
+    std::vector<bp_layer *> lazy_readers;   // layers holding a deferred merge from this one
     int radix_bits_cap = 0; // BP_RADIX_BITS (tuning aid): widest radix digit the sorts may use; 0 = no cap
     bool scan_dedup = true; // bp_layer_set_scan_dedup: the scan may emit every ID pair from its canonical shared cell only
     // dedup at the source: encode writes 3 cell flags per record (cell_flags); a full sort of a tree that
@@ -145,6 +152,8 @@ struct bp_layer {
     bool pending = false;
     uint64_t pending_base = 0;
     cudaEvent_t ev_sync = nullptr;
+    cudaStream_t copy_stream = nullptr;     // bp_layer_extend_host: chunked H2D copies run here, the encodes trail behind them
+    cudaEvent_t ev_chunk[16] = {};
     ExtendResult *h_res = nullptr; // pinned
     ExtendResult *d_res = nullptr;
     uint32_t *d_cnt = nullptr;     // 32 words: per-shard record / halo counts taken by encode_kernel<.., COUNT> (multi-GPU)
@@ -291,6 +300,10 @@ struct LaunchScope {
     }
 };
 
+void detach_lazy(bp_layer *L);
+int materialize_lazy(bp_layer *L);
+int resolve_pending(bp_layer *L, bool keep_lazy = false);
+
 int check_launch(bp_layer *L, const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(L, BP_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
@@ -419,6 +432,10 @@ struct RadixScratch {
 template <class K, class V> struct WideDigits { static constexpr int MAX_BITS = 8; };
 template <> struct WideDigits<uint64_t, uint32_t> { static constexpr int MAX_BITS = 9; }; // records
 template <> struct WideDigits<uint64_t, NoVal> { static constexpr int MAX_BITS = 9; };    // packed pairs
+// Measured on B200 (profiles/r2_sortbench_*.log, r2_bench_digit_width.txt): a 9-bit pass costs 1.24-1.32 ms where the 8-bit pass
+// costs 1.02 ms (146 M records), so 3 x 9 bits beat 4 x 8 bits by only 3 % on the 2^25-object frame while the pass falls from
+// 52 % to 41 % of the HBM roofline; the 8-bit plan stays the default, BP_RADIX_BITS=9 switches the wide digits on.
+constexpr int DEFAULT_RADIX_BITS = 8;
 
 template <class K, class V, int RB>
 int radix_sort_rb(bp_layer *L, const RadixPlan &plan, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32_t *n_dev, int cls_hist,
@@ -439,7 +456,7 @@ int radix_sort(bp_layer *L, K *k0, V *v0, K *k1, V *v1, uint32_t n, const uint32
     memset(&plan, 0, sizeof plan);
     int rb = 8, np = plan_passes(mask, plan, 0, 8);
     if (np == 0) return BP_OK;
-    const int max_bits = L->radix_bits_cap ? std::min(L->radix_bits_cap, WideDigits<K, V>::MAX_BITS) : WideDigits<K, V>::MAX_BITS;
+    const int max_bits = std::min(L->radix_bits_cap ? L->radix_bits_cap : DEFAULT_RADIX_BITS, WideDigits<K, V>::MAX_BITS);
     for (int w = 9; w <= max_bits; ++w) {
         RadixPlan pw;
         memset(&pw, 0, sizeof pw);
@@ -738,17 +755,23 @@ template <int KIND, class IdT> struct Impl {
         return BP_OK;
     }
 
-    static int merge_runs(bp_layer *L, uint64_t na, uint64_t nb) {
+    static int merge_runs(bp_layer *L, uint64_t na, uint64_t nb, bp_layer *B = nullptr) {
+        // B: the second run is the (sorted) tree of another layer, read where it is (deferred Layer::merge)
         const int c = L->cur, o = c ^ 1;
         MergeArgs<K, IdT> a;
         a.ka = keys(L, c);
         a.va = ids(L, c);
         a.na = (uint32_t)na;
-        a.kb = keys(L, c) + na;
-        a.vb = ids(L, c) + na;
+        a.kb = B ? keys(B, B->cur) : keys(L, c) + na;
+        a.vb = B ? ids(B, B->cur) : ids(L, c) + na;
         a.nb = (uint32_t)nb;
         a.kout = keys(L, o);
         a.vout = ids(L, o);
+        a.id_mask = L->ids_flagged ? (IdT)((((IdT)1) << (8 * sizeof(IdT) - 3)) - 1) : (IdT) ~(IdT)0;
+        if (B && B->stream != L->stream) { // after everything queued on the other layer's stream
+            CU(L, cudaEventRecord(B->ev_sync, B->stream));
+            CU(L, cudaStreamWaitEvent(L->stream, B->ev_sync, 0));
+        }
         const uint32_t tiles = (uint32_t)((na + nb + MERGE_TILE - 1) / MERGE_TILE);
         TRY(ensure(L, L->scratch, (size_t)(tiles + 1) * sizeof(uint32_t)));
         a.partition = (uint32_t *)L->scratch.p;
@@ -763,6 +786,10 @@ template <int KIND, class IdT> struct Impl {
             merge_tiles_kernel<K, IdT><<<tiles, MERGE_THREADS, 0, L->stream>>>(a);
         }
         TRY(check_launch(L, "merge_tiles_kernel"));
+        if (B && B->stream != L->stream) { // and keep the other layer from touching its tree before the merge has read it
+            CU(L, cudaEventRecord(L->ev_sync, L->stream));
+            CU(L, cudaStreamWaitEvent(B->stream, L->ev_sync, 0));
+        }
         L->cur = o;
         L->stats.merged = 1;
         return BP_OK;
@@ -802,6 +829,11 @@ template <int KIND, class IdT> struct Impl {
                     }
                     TRY(check_launch(L, "flags_merge_kernel"));
                 }
+            } else if (L->lazy_src) {
+                // deferred Layer::merge of a sorted layer into this sorted layer: merge straight out of both trees
+                bp_layer *B = L->lazy_src;
+                TRY(merge_runs(L, prefix, tail, B));
+                detach_lazy(L);
             } else if (L->tail_sorted || prefix * 8 >= R) {
                 // two sorted runs: one linear merge.  An unsorted tail is radix-sorted on its own first,
                 // unless the sorted prefix is so short that re-sorting everything is cheaper.
@@ -1591,8 +1623,42 @@ int do_sort_from(bp_layer *L, const void *k, const void *v, uint64_t n, bool asc
 int do_masks(bp_layer *L, uint64_t n) { DISPATCH(L, masks_from_records(L, n)); }
 int do_strip_flags(bp_layer *L) { DISPATCH(L, strip_flags(L)); }
 
-// Folds the result of the last (still asynchronous) extend into the host-side state.
-int resolve_pending(bp_layer *L) {
+void detach_lazy(bp_layer *L) {
+    if (!L->lazy_src) return;
+    auto &rd = L->lazy_src->lazy_readers;
+    rd.erase(std::remove(rd.begin(), rd.end(), L), rd.end());
+    L->lazy_src = nullptr;
+    L->lazy_n = 0;
+}
+
+// Performs a deferred Layer::merge as the plain append it stands for: the other layer's records are copied behind ours.
+int materialize_lazy(bp_layer *L) {
+    bp_layer *O = L->lazy_src;
+    if (!O) return BP_OK;
+    const uint64_t add = L->lazy_n, base = L->n_records - add;
+    DeviceGuard g(L->device);
+    if (O->stream != L->stream) {
+        CU(L, cudaEventRecord(O->ev_sync, O->stream));
+        CU(L, cudaStreamWaitEvent(L->stream, O->ev_sync, 0));
+    }
+    CU(L, cudaMemcpyAsync((char *)L->keys[L->cur].p + base * L->key_bytes, O->keys[O->cur].p, add * L->key_bytes,
+                          cudaMemcpyDeviceToDevice, L->stream));
+    CU(L, cudaMemcpyAsync((char *)L->ids[L->cur].p + base * L->id_bytes, O->ids[O->cur].p, add * L->id_bytes,
+                          cudaMemcpyDeviceToDevice, L->stream));
+    if (O->stream != L->stream) { // and keep the other layer from overwriting its tree before the copy ran
+        CU(L, cudaEventRecord(L->ev_sync, L->stream));
+        CU(L, cudaStreamWaitEvent(O->stream, L->ev_sync, 0));
+    }
+    detach_lazy(L);
+    return BP_OK;
+}
+
+// Folds the result of the last (still asynchronous) extend into the host-side state.  Every entry point calls this
+// first; unless keep_lazy (the sort / scan entry points, which merge a deferred Layer::merge out of both trees), a
+// deferred merge INTO this layer is materialised, and so is every deferred merge FROM this layer (the call may change it).
+int resolve_pending(bp_layer *L, bool keep_lazy) {
+    if (!keep_lazy && L->lazy_src) TRY(materialize_lazy(L));
+    while (!L->lazy_readers.empty()) TRY(materialize_lazy(L->lazy_readers.back()));
     if (!L->pending) return BP_OK;
     TRY(wait_mail(L, 0, L->pending_seq, L->h_res, sizeof(ExtendResult)));
     L->pending = false;
@@ -1755,6 +1821,8 @@ int bp_layer_create(const bp_layer_config *cfg, bp_layer **out) {
 
 int bp_layer_destroy(bp_layer *L) {
     if (!L) return BP_OK;
+    while (!L->lazy_readers.empty()) materialize_lazy(L->lazy_readers.back()); // deferred merges from this layer: copy now
+    detach_lazy(L);
     DeviceGuard g(L->device);
     if (L->stream) cudaStreamSynchronize(L->stream);
     for (int i = 0; i < 2; ++i) {
@@ -1803,6 +1871,9 @@ int bp_layer_destroy(bp_layer *L) {
         cudaEventDestroy(pe.stop);
     }
     if (L->ev_sync) cudaEventDestroy(L->ev_sync);
+    for (cudaEvent_t e : L->ev_chunk)
+        if (e) cudaEventDestroy(e);
+    if (L->copy_stream) cudaStreamDestroy(L->copy_stream);
     if (L->own_stream && L->stream) cudaStreamDestroy(L->stream);
     cudaGetLastError();
     delete L;
@@ -1856,11 +1927,68 @@ int bp_layer_extend_host(bp_layer *L, const float *sysb, const float *bounds, co
     TRY(resolve_pending(L));
     if (n == 0) return BP_OK;
     const size_t bbytes = n * 2 * L->dim * sizeof(float), ibytes = n * L->id_bytes;
-    TRY(ensure(L, L->stage_bounds, bbytes));
-    TRY(ensure(L, L->stage_ids, ibytes));
-    CU(L, cudaMemcpyAsync(L->stage_bounds.p, bounds, bbytes, cudaMemcpyHostToDevice, L->stream));
-    CU(L, cudaMemcpyAsync(L->stage_ids.p, ids, ibytes, cudaMemcpyHostToDevice, L->stream));
-    TRY(do_extend_device(L, sysb, (const float *)L->stage_bounds.p, L->stage_ids.p, n));
+    // Pinned (page-locked, device-mapped) host buffers are read by the encode kernel where they are: every AABB and ID is
+    // read exactly once, so the PCIe transfer IS the kernel's input stream and the encode hides under it, instead of a
+    // staging copy followed by the encode.  Pageable memory still goes through the staging buffers.
+    const void *d_b = nullptr, *d_i = nullptr;
+    {
+        static const bool zero_copy = !(getenv("BP_EXTEND_ZERO_COPY") && atoi(getenv("BP_EXTEND_ZERO_COPY")) == 0);
+        cudaPointerAttributes ab, ai;
+        if (zero_copy && cudaPointerGetAttributes(&ab, bounds) == cudaSuccess && cudaPointerGetAttributes(&ai, ids) == cudaSuccess &&
+            ab.type == cudaMemoryTypeHost && ai.type == cudaMemoryTypeHost && ab.devicePointer && ai.devicePointer &&
+            ((uintptr_t)ab.devicePointer & 15u) == 0 && ((uintptr_t)ai.devicePointer & 15u) == 0) {
+            d_b = ab.devicePointer;
+            d_i = ai.devicePointer;
+        }
+        cudaGetLastError(); // (a failed attribute query on a plain malloc pointer leaves an error behind on old drivers)
+    }
+    const size_t obj_bytes = 2 * L->dim * sizeof(float) + L->id_bytes;
+    constexpr size_t ZERO_COPY_MAX = 64u << 20; // beyond this the copy engine's DMA beats the SMs' PCIe reads (measured: 2^25 objects)
+    if (d_b && n * obj_bytes <= ZERO_COPY_MAX) {
+        TRY(do_extend_device(L, sysb, (const float *)d_b, d_i, n));
+    } else {
+        TRY(ensure(L, L->stage_bounds, bbytes));
+        TRY(ensure(L, L->stage_ids, ibytes));
+        // Chunked: every chunk's copy is queued on the copy stream up front, the encode of chunk c starts when its copy
+        // has landed -- extend + extend + ... of consecutive object ranges, i.e. the same records in the same order, with
+        // the encode hidden under the next chunk's transfer.
+        const size_t min_chunk = (size_t)1 << 20; // objects
+        int chunks = (int)std::min<size_t>(16, std::max<size_t>(1, n / min_chunk));
+        if (!d_b) chunks = 1;                     // pageable memory: cudaMemcpyAsync is synchronous with the host anyway
+        if (chunks > 1 && !L->copy_stream) {
+            if (cudaStreamCreateWithFlags(&L->copy_stream, cudaStreamNonBlocking) != cudaSuccess) chunks = 1;
+            for (int c = 0; c < 16 && chunks > 1; ++c)
+                if (cudaEventCreateWithFlags(&L->ev_chunk[c], cudaEventDisableTiming) != cudaSuccess) chunks = 1;
+        }
+        if (chunks == 1) {
+            CU(L, cudaMemcpyAsync(L->stage_bounds.p, bounds, bbytes, cudaMemcpyHostToDevice, L->stream));
+            CU(L, cudaMemcpyAsync(L->stage_ids.p, ids, ibytes, cudaMemcpyHostToDevice, L->stream));
+            TRY(do_extend_device(L, sysb, (const float *)L->stage_bounds.p, L->stage_ids.p, n));
+        } else {
+            const size_t per = ((n + chunks - 1) / chunks + 3) & ~(size_t)3; // 16-byte aligned ID chunks
+            const size_t bstride = 2 * L->dim * sizeof(float);
+            CU(L, cudaEventRecord(L->ev_sync, L->stream)); // the staging buffers may still be read by an earlier extend
+            CU(L, cudaStreamWaitEvent(L->copy_stream, L->ev_sync, 0));
+            for (int c = 0; c < chunks; ++c) {
+                const size_t o = std::min(n, per * c), m = std::min(n, per * (c + 1)) - o;
+                if (m) {
+                    CU(L, cudaMemcpyAsync((char *)L->stage_bounds.p + o * bstride, (const char *)bounds + o * bstride, m * bstride,
+                                          cudaMemcpyHostToDevice, L->copy_stream));
+                    CU(L, cudaMemcpyAsync((char *)L->stage_ids.p + o * L->id_bytes, (const char *)ids + o * L->id_bytes, m * L->id_bytes,
+                                          cudaMemcpyHostToDevice, L->copy_stream));
+                }
+                CU(L, cudaEventRecord(L->ev_chunk[c], L->copy_stream));
+            }
+            for (int c = 0; c < chunks; ++c) {
+                const size_t o = std::min(n, per * c), m = std::min(n, per * (c + 1)) - o;
+                CU(L, cudaStreamWaitEvent(L->stream, L->ev_chunk[c], 0));
+                if (!m) continue;
+                TRY(do_extend_device(L, sysb, (const float *)((char *)L->stage_bounds.p + o * bstride),
+                                      (char *)L->stage_ids.p + o * L->id_bytes, m));
+                if (c + 1 < chunks) TRY(resolve_pending(L)); // the next chunk appends behind this one's records
+            }
+        }
+    }
     // the caller may reuse its buffers as soon as we return
     return resolve_pending(L);
 }
@@ -1874,27 +2002,41 @@ int bp_layer_merge(bp_layer *L, const bp_layer *O_) {
     DeviceGuard g(L->device);
     TRY(resolve_pending(L));
     TRY(resolve_pending(O));
-    TRY(do_strip_flags(L));
-    TRY(do_strip_flags(O));
-    L->flags_valid = false; // the appended records carry no cell flags
+    // Two sorted layers whose cell flags ride in their IDs (dedup at the source) keep them through the merge: the merged
+    // tree is flagged too, and the scan emits every ID pair from its canonical cell only.  Anything else: strip, as before.
+    const uint64_t id_all = L->id_or | O->id_or;
+    const int id_bits = 64 - (id_all ? __builtin_clzll(id_all) : 64);
+    const bool keep_flags = !L->dirty && !O->dirty && L->n_records && O->n_records && L->ids_flagged && O->ids_flagged &&
+                            id_bits <= 8 * L->id_bytes - 3;
+    if (!keep_flags) {
+        TRY(do_strip_flags(L));
+        TRY(do_strip_flags(O));
+    }
+    L->flags_valid = false; // the appended records carry no separate cell flags
     if (O->min_depth < L->min_depth) L->min_depth = O->min_depth; // src/layer.rs:131-134
     const uint64_t base = L->n_records, add = O->n_records;
     if (add) {
         TRY(do_ensure_tree(L, base + add));
-        // order the copy after everything queued on the other layer's stream
-        if (O->stream != L->stream) {
-            CU(L, cudaEventRecord(O->ev_sync, O->stream));
-            CU(L, cudaStreamWaitEvent(L->stream, O->ev_sync, 0));
+        if (!L->dirty && !O->dirty && base > 0 && O->lazy_src == nullptr) {
+            // sorted into sorted: defer the append, the next sort merges straight out of both trees
+            L->lazy_src = O;
+            L->lazy_n = add;
+            O->lazy_readers.push_back(L);
+        } else {
+            // order the copy after everything queued on the other layer's stream
+            if (O->stream != L->stream) {
+                CU(L, cudaEventRecord(O->ev_sync, O->stream));
+                CU(L, cudaStreamWaitEvent(L->stream, O->ev_sync, 0));
+            }
+            CU(L, cudaMemcpyAsync((char *)L->keys[L->cur].p + base * L->key_bytes, O->keys[O->cur].p, add * L->key_bytes,
+                                  cudaMemcpyDeviceToDevice, L->stream));
+            CU(L, cudaMemcpyAsync((char *)L->ids[L->cur].p + base * L->id_bytes, O->ids[O->cur].p, add * L->id_bytes,
+                                  cudaMemcpyDeviceToDevice, L->stream));
+            if (O->stream != L->stream) { // and keep the other layer from overwriting its tree before the copy ran
+                CU(L, cudaEventRecord(L->ev_sync, L->stream));
+                CU(L, cudaStreamWaitEvent(O->stream, L->ev_sync, 0));
+            }
         }
-        CU(L, cudaMemcpyAsync((char *)L->keys[L->cur].p + base * L->key_bytes, O->keys[O->cur].p, add * L->key_bytes,
-                              cudaMemcpyDeviceToDevice, L->stream));
-        CU(L, cudaMemcpyAsync((char *)L->ids[L->cur].p + base * L->id_bytes, O->ids[O->cur].p, add * L->id_bytes,
-                              cudaMemcpyDeviceToDevice, L->stream));
-        if (O->stream != L->stream) { // and keep the other layer from overwriting its tree before the copy ran
-            CU(L, cudaEventRecord(L->ev_sync, L->stream));
-            CU(L, cudaStreamWaitEvent(O->stream, L->ev_sync, 0));
-        }
-        L->stats.launches_total += 0;
     }
     if (!L->dirty) {
         L->prefix = base;
@@ -1918,14 +2060,14 @@ int bp_layer_merge(bp_layer *L, const bp_layer *O_) {
 int bp_layer_sort(bp_layer *L) {
     if (!L) return BP_ERR_INVALID_ARG;
     DeviceGuard g(L->device);
-    TRY(resolve_pending(L));
+    TRY(resolve_pending(L, true));
     return do_sort(L);
 }
 
 int bp_layer_scan_device(bp_layer *L, const bp_filter *f, const void **out_pairs, size_t *out_count) {
     if (!L) return BP_ERR_INVALID_ARG;
     DeviceGuard g(L->device);
-    TRY(resolve_pending(L));
+    TRY(resolve_pending(L, true));
     TRY(do_scan(L, f));
     if (out_pairs) *out_pairs = L->n_pairs ? L->pout.p : nullptr;
     if (out_count) *out_count = (size_t)L->n_pairs;
@@ -1935,7 +2077,7 @@ int bp_layer_scan_device(bp_layer *L, const bp_filter *f, const void **out_pairs
 int bp_layer_scan(bp_layer *L, const bp_filter *f, const void **out_pairs, size_t *out_count) {
     if (!L) return BP_ERR_INVALID_ARG;
     DeviceGuard g(L->device);
-    TRY(resolve_pending(L));
+    TRY(resolve_pending(L, true));
     TRY(do_scan(L, f));
     const size_t bytes = (size_t)L->n_pairs * 2 * L->id_bytes;
     if (bytes) {
@@ -2044,7 +2186,7 @@ int bp_layer_scan_raw_device(bp_layer *L, const bp_filter *f, const void **out_r
     if (!L) return BP_ERR_INVALID_ARG;
     if (L->id_bytes != 4) return fail(L, BP_ERR_INVALID_ARG, "raw pairs are exposed for 32-bit IDs only");
     DeviceGuard g(L->device);
-    TRY(resolve_pending(L));
+    TRY(resolve_pending(L, true));
     uint64_t n = 0;
     TRY(do_scan_raw(L, f, &n));
     if (out_raw) *out_raw = n ? L->praw[0].p : nullptr;

@@ -32,6 +32,7 @@ template <class K, class V> struct MergeArgs {
     K *kout;
     V *vout;
     uint32_t *partition; // [tiles + 1]
+    V id_mask;           // IDs compare under this mask (cell flags may ride in their top 3 bits: dedup at the source)
 };
 
 // (ka, va) sorts strictly before (kb, vb)
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(256) merge_partition_kernel(const MergeArgs<K,
     while (lo < hi) {
         const uint32_t mid = lo + ((hi - lo) >> 1);
         const uint32_t bi = (uint32_t)(diag - 1 - mid);
-        if (!rec_less(a.kb[bi], a.vb[bi], a.ka[mid], a.va[mid]))
+        if (!rec_less(a.kb[bi], (V)(a.vb[bi] & a.id_mask), a.ka[mid], (V)(a.va[mid] & a.id_mask)))
             lo = mid + 1;
         else
             hi = mid;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_tiles_kernel(const MergeA
     while (lo < hi) {
         const uint32_t mid = (lo + hi) >> 1;
         const uint32_t bi = la + (diag - 1 - mid);
-        if (!rec_less(sk[bi], sv[bi], sk[mid], sv[mid]))
+        if (!rec_less(sk[bi], (V)(sv[bi] & a.id_mask), sk[mid], (V)(sv[mid] & a.id_mask)))
             lo = mid + 1;
         else
             hi = mid;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_tiles_kernel(const MergeA
     for (int q = 0; q < MERGE_IPT; ++q) {
         const bool has_a = ai < la, has_b = bi < tile_n;
         bool take_a = has_a;
-        if (has_a && has_b) take_a = !rec_less(sk[bi], sv[bi], sk[ai], sv[ai]);
+        if (has_a && has_b) take_a = !rec_less(sk[bi], (V)(sv[bi] & a.id_mask), sk[ai], (V)(sv[ai] & a.id_mask));
         if (has_a || has_b) {
             const uint32_t s = take_a ? ai : bi;
             rk[q] = sk[s];

@@ -409,6 +409,70 @@ def test_config4_static_plus_dynamic_frames(bp):
         assert gd.stats()["merged"] == 1
 
 
+@pytest.mark.parametrize("mutation", ["none", "clear_other", "extend_other", "destroy_other", "merge_twice", "iter_first"])
+def test_deferred_merge_is_unobservable(bp, mutation):
+    """Layer::merge of a sorted layer into a sorted layer is deferred (the next sort merges straight out of both trees,
+    the cell flags of dedup-at-the-source stay in the IDs).  Whatever happens to the other layer in between, the
+    result is that of the reference's eager append (src/layer.rs:127-138)."""
+    sc = bp.scenes.uniform_cubes(60_000, 21)
+    a, b = slice(0, 45_000), slice(45_000, 60_000)
+    gs, os_ = _pair(bp, 2, 4, 0)
+    gd, od = _pair(bp, 2, 4, 0)
+    gs.extend(sc["sys_bounds"], sc["bounds"][a], sc["ids"][a]); os_.extend(sc["sys_bounds"], sc["bounds"][a], sc["ids"][a])
+    gd.extend(sc["sys_bounds"], sc["bounds"][b], sc["ids"][b]); od.extend(sc["sys_bounds"], sc["bounds"][b], sc["ids"][b])
+    gs.sort(); os_.sort(); gd.sort(); od.sort()
+    gd.merge(gs); od.merge(os_)
+    assert len(gd) == len(od) and not gd.sorted
+    extra = bp.scenes.uniform_cubes(5_000, 22, id_base=100_000)
+    if mutation == "clear_other":
+        gs.clear()
+    elif mutation == "extend_other":
+        gs.extend(extra["sys_bounds"], extra["bounds"], extra["ids"])
+    elif mutation == "destroy_other":
+        gs.close()
+    elif mutation == "merge_twice":
+        g2, o2 = _pair(bp, 2, 4, 0)
+        g2.extend(extra["sys_bounds"], extra["bounds"], extra["ids"]); o2.extend(extra["sys_bounds"], extra["bounds"], extra["ids"])
+        g2.sort(); o2.sort()
+        gd.merge(g2); od.merge(o2)
+    elif mutation == "iter_first":
+        _assert_records_equal(gd, od)          # the appended, still unsorted tree
+    gp, op = gd.par_scan(), od.par_scan()
+    _assert_pairs_equal(gp, op)
+    _assert_records_equal(gd, od)
+    if mutation in ("none",):
+        st = gd.stats()
+        assert st["merged"] == 1 and st["n_raw_pairs"] == gp.shape[0]   # flags kept: no duplicate reached the pair sort
+
+
+def test_extend_from_pinned_host_buffers(bp):
+    """bp_layer_extend_host reads page-locked buffers in place (the encode kernel streams them over PCIe); pageable
+    buffers go through a staging copy.  Same records either way."""
+    import torch
+    sc = bp.scenes.lognormal_cubes(300_001, 8)
+    hb = torch.from_numpy(sc["bounds"]).pin_memory().numpy()
+    hi = torch.from_numpy(sc["ids"].view(np.int32)).pin_memory().numpy().view(np.uint32)
+    g, o = _pair(bp, 2, 4, 0)
+    g.extend(sc["sys_bounds"], hb, hi)
+    o.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    _assert_records_equal(g, o)
+    g.extend(sc["sys_bounds"], hb[1:1001], hi[1:1001])       # a misaligned slice of the pinned buffer: staged
+    o.extend(sc["sys_bounds"], sc["bounds"][1:1001], sc["ids"][1:1001])
+    _assert_records_equal(g, o)
+    _assert_pairs_equal(g.par_scan(), o.par_scan())
+    # beyond 64 MB the copy engine takes over: chunked copies on a second stream, one encode per chunk behind them
+    big = bp.scenes.uniform_cubes(3_000_003, 12)
+    hb = torch.from_numpy(big["bounds"]).pin_memory().numpy()
+    hi = torch.from_numpy(big["ids"].view(np.int32)).pin_memory().numpy().view(np.uint32)
+    g, o = _pair(bp, 2, 4, 0)
+    for _ in range(2):                                       # twice: the staging buffers are reused
+        g.clear(); o.clear()
+        g.extend(big["sys_bounds"], hb, hi)
+        o.extend(big["sys_bounds"], big["bounds"], big["ids"])
+        _assert_records_equal(g, o)
+    _assert_pairs_equal(g.par_scan(), o.par_scan())
+
+
 def test_non_ascending_ids_need_id_passes(bp):
     """IDs in random order: the sort must order equal keys by ID (derived Ord of (Index, ID))."""
     sc = bp.scenes.uniform_cubes(200_000, 9)
