@@ -39,6 +39,25 @@ class Stats(ctypes.Structure):
                 ("kernel_ms", ctypes.c_double * BP_K_COUNT), ("algo_bytes", ctypes.c_double * BP_K_COUNT)]
 
 
+BP_DIST_PHASES = 9
+DIST_PHASE_NAMES = ["encode", "splitters", "counts", "exchange", "sort", "scan", "pair_counts", "pair_exchange", "unique"]
+DIST_OPT_REUSE_SPLITTERS, DIST_OPT_FUSE_COUNTS, DIST_OPT_GLOBAL_DEDUP_DECISION, DIST_OPT_TRACE = 0, 1, 2, 3
+
+
+class DistConfig(ctypes.Structure):
+    _fields_ = [("index_kind", ctypes.c_int32), ("min_depth", ctypes.c_uint32), ("device", ctypes.c_int32),
+                ("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("record_capacity", ctypes.c_size_t),
+                ("pair_capacity", ctypes.c_size_t)]
+
+
+class DistInfo(ctypes.Structure):
+    _fields_ = [("records_local", ctypes.c_uint64), ("records_owned", ctypes.c_uint64), ("n_halo", ctypes.c_uint64),
+                ("raw_pairs", ctypes.c_uint64), ("pairs", ctypes.c_uint64), ("records_needed", ctypes.c_uint64),
+                ("pairs_needed", ctypes.c_uint64), ("fused", ctypes.c_int32), ("rescanned", ctypes.c_int32),
+                ("rebalance_records", ctypes.c_int32), ("rebalance_pairs", ctypes.c_int32),
+                ("phase_ms", ctypes.c_double * BP_DIST_PHASES)]
+
+
 # every symbol include/bp.h declares: name -> (restype, argtypes)
 _vp, _sz, _i, _u32, _u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64
 _P = ctypes.POINTER
@@ -74,6 +93,18 @@ SYMBOLS = {
     "bp_dist_scatter_records": (_i, [_vp, _vp, _vp, _sz, _vp, _i, _vp, _vp, _vp, _vp]),
     "bp_dist_count_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp]),
     "bp_dist_scatter_pairs": (_i, [_vp, _vp, _sz, _vp, _i, _vp]),
+    "bp_dist_create": (_i, [_P(DistConfig), _P(_vp)]),
+    "bp_dist_destroy": (_i, [_vp]),
+    "bp_dist_handle_bytes": (_sz, []),
+    "bp_dist_export": (_i, [_vp, _vp]),
+    "bp_dist_connect": (_i, [_vp, _vp]),
+    "bp_dist_set_stream": (_i, [_vp, _vp]),
+    "bp_dist_set_option": (_i, [_vp, _i, _i]),
+    "bp_dist_set_static": (_i, [_vp, _vp, _vp, _vp, _sz]),
+    "bp_dist_frame": (_i, [_vp, _vp, _vp, _vp, _sz, _P(Filter), _P(_vp), _P(_sz)]),
+    "bp_dist_last_info": (_i, [_vp, _P(DistInfo)]),
+    "bp_dist_layer": (_vp, [_vp, _i]),
+    "bp_dist_last_error": (ctypes.c_char_p, [_vp]),
     "bp_layer_set_halo": (_i, [_vp, _sz]),
     "bp_layer_set_scan_dedup": (_i, [_vp, _i]),
     "bp_layer_scan_raw_device": (_i, [_vp, _P(Filter), _P(_vp), _P(_sz)]),

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libbroadphase_b200.so")
-SOURCES = ["bp_layer.cu"]
+SOURCES = ["bp_layer.cu", "bp_dist.cu"]
 HEADERS = ["bp_common.cuh", "bp_encode.cuh", "bp_radix.cuh", "bp_exchange.cuh", "bp_scan.cuh", "bp_merge.cuh", "bp_query.cuh", "../../include/bp.h"]
 
 NVCC_FLAGS = [

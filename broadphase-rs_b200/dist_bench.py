@@ -1,7 +1,7 @@
 """bench.py's N > 1 arm: one process per GPU (torchrun), NCCL over NVLink, weak scaling.
 
 Every rank owns `objects_per_gpu` objects of one global scene (block-distributed by ID, like SURVEY.md
-section 8d config 5).  A step is one distributed frame of dist.DistLayer: encode -> sample sort +
+section 8d config 5).  A step is one distributed frame, ONE C-ABI call (bp_dist_frame through dist.DistContext): encode -> sample sort +
 all-to-all of the records -> local sort -> halos -> shard-local scan -> all-to-all of the raw pairs ->
 sort + dedup.  The result (left sharded on the devices, in rank order) is exactly the reference's
 globally sorted, deduplicated pair vector.
@@ -104,6 +104,12 @@ def _host_inputs(frames):
     return [(torch.from_numpy(sc["bounds"]).pin_memory(), torch.from_numpy(sc["ids"].view(np.int32)).pin_memory()) for sc in frames]
 
 
+def _context(bp, bpd, kind, device, n_local):
+    """A bp_dist context sized for n_local objects per rank: at most 8 records per object at min_depth 0, some imbalance
+    allowed; the pair buffers grow on demand (collectively, during the warm-up)."""
+    return bpd.DistContext(bp, kind, 0, device, record_capacity=int(n_local * 8 * 1.3) + 4096, pair_capacity=6 * n_local + 4096)
+
+
 def _profile(ops, fn):
     """Runs fn() with per-launch CUDA events on every layer of `ops`; -> summed per-class stats."""
     for l in ops.layers():
@@ -121,7 +127,7 @@ def _profile(ops, fn):
 
 
 # ---- self-checks (untimed) -----------------------------------------------------------------------------------------
-def _oracle_check(bp, bpd, scenes, ops, kind, world, rank, device):
+def _oracle_check(bp, bpd, scenes, kind, world, rank, device):
     """One frame of a 2^22-object scene against the CPU oracle's par_scan, bit for bit (rank 0 compares)."""
     n_total = 1 << 22
     n_local = n_total // world
@@ -132,10 +138,11 @@ def _oracle_check(bp, bpd, scenes, ops, kind, world, rank, device):
     mn = (big.random((k, 3)) * 0.6).astype(np.float32)
     sc["bounds"][:k, :3] = mn
     sc["bounds"][:k, 3:] = mn + np.float32(0.3)
-    dl = bpd.DistLayer(ops, kind)
+    dl = _context(bp, bpd, kind, device, n_local)
     d_bounds = torch.from_numpy(sc["bounds"]).cuda(device)
     d_ids = torch.from_numpy(sc["ids"].view(np.int32)).cuda(device)
-    pairs = dl.frame(sc["sys_bounds"], d_bounds, d_ids, n_local, None)
+    dl.frame(sc["sys_bounds"], d_bounds, d_ids, n_local, None)          # samples the splitters
+    pairs = dl.frame(sc["sys_bounds"], d_bounds, d_ids, n_local, None)  # cached splitters, counts fused with the encode
     halo = torch.tensor([dl.last["halo"]], dtype=torch.int64, device=d_bounds.device)
     dist.all_reduce(halo, op=dist.ReduceOp.SUM)
     got = dl.gather_pairs(pairs)
@@ -158,6 +165,7 @@ def _oracle_check(bp, bpd, scenes, ops, kind, world, rank, device):
         info["oracle_pairs"] = int(want.shape[0])
     flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=d_bounds.device)
     dist.broadcast(flag, 0)
+    dl.close()
     return bool(flag.item()), info
 
 
@@ -246,23 +254,22 @@ def run(args, bp):
     scenes = bench.load_scenes()
     kind = bp.Index64_3D
     wl = "cfg5"
-    ops = bpd.CudaOps(bp, kind, 0, local)
 
     # ---- self-checks, untimed ----
     parity = {"checked": False}
     if not args.no_parity:
-        ok_o, info_o = _oracle_check(bp, bpd, scenes, ops, kind, world, rank, local)
+        ok_o, info_o = _oracle_check(bp, bpd, scenes, kind, world, rank, local)
         parity = {"checked": True, "oracle_equal": ok_o, "oracle_scene": info_o}
 
     inp = bench.make_inputs(scenes, wl, 0, world=world, rank=rank)
     frames = inp["frames"]
     n_local = inp["n"]
     dev_in = _device_inputs(frames, local)
-    dl = bpd.DistLayer(ops, kind)
+    dl = ops = _context(bp, bpd, kind, local, n_local)   # the whole frame is one C-ABI call: bp_dist_frame
+    dl.set_stream(torch.cuda.current_stream(local).cuda_stream)
     if not args.no_parity:
         ok_h, info_h = _hash_check(bp, dl, frames, dev_in, world, rank, local, kind)
         parity.update(hash_equal=ok_h, timed_shape=info_h)
-        dl = bpd.DistLayer(ops, kind)      # fresh splitters for the timed run
 
     # ---- the timed shape ----
     with bench.ClockSampler(local) as clocks:
@@ -282,8 +289,10 @@ def run(args, bp):
         try:
             inp_s = bench.make_inputs(scenes, "cfg2", 0, world=world, rank=rank)
             dev_s = _device_inputs(inp_s["frames"], local)
-            dl_s = bpd.DistLayer(ops, kind)
+            dl_s = _context(bp, bpd, kind, local, inp_s["n"])
+            dl_s.set_stream(torch.cuda.current_stream(local).cuda_stream)
             ms_s, pairs_s, _, _ = _time_frames(dl_s, inp_s["frames"], dev_s, None, 20, 3, local)
+            dl_s.close()
             extra["2^20_objects_per_gpu"] = {
                 "objects_per_step": inp_s["n"] * world, "ms_per_step": ms_s, "value": inp_s["n"] * world / (ms_s * 1e-3),
                 "unit": "objects/s", "pairs": pairs_s, "pairs_per_s": pairs_s / (ms_s * 1e-3), "steps": 20}

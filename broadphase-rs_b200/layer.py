@@ -88,9 +88,23 @@ class Layer:
         check(lib().bp_layer_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
 
+    @classmethod
+    def borrow(cls, handle, index, id_type="u32"):
+        """A view of a layer somebody else owns (the layers inside a bp_dist context): never destroyed from here."""
+        self = cls.__new__(cls)
+        self.index = index
+        self.dim = INDEX_DIM[index]
+        self.id_bytes = {"u32": 4, "u64": 8, 4: 4, 8: 8}[id_type]
+        self.id_dtype = np.uint32 if self.id_bytes == 4 else np.uint64
+        self.key_dtype = INDEX_KEY_DTYPE[index]
+        self._h = ctypes.c_void_p(handle)
+        self._borrowed = True
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
-            lib().bp_layer_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                lib().bp_layer_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -311,6 +311,62 @@ int bp_layer_unique_pairs_device(bp_layer *layer, const void *d_raw, size_t n, u
 int bp_layer_unique_pairs_inplace_device(bp_layer *layer, void *d_raw, size_t n, uint64_t id_mask, const void **out_d_pairs,
                                          size_t *out_count);
 
+/* ---- the sharded frame as one call ---------------------------------------------------------------
+ * A bp_dist context runs the whole multi-GPU frame -- clear -> extend -> par_sort -> [merge] -> par_scan(_filtered) of
+ * one scene spread over `world` GPUs of one NVLink domain, one process (or thread) per GPU -- in C++ on top of the
+ * building blocks above (csrc/bp_dist.cu).  No reference counterpart: the crate is single-process;
+ * the calls mirror Layer::clear / extend / merge / scan_filtered (src/layer.rs:84-138, 449-520) for the distributed scene.
+ *
+ * Peer memory: every rank owns ONE device arena (barrier flags, sample and count matrices, receive buffers of
+ * record_capacity records and pair_capacity raw pairs).  bp_dist_export writes an opaque blob of bp_dist_handle_bytes()
+ * bytes (a CUDA IPC handle); the caller all-gathers the blobs with whatever transport it has (MPI, torch.distributed, a
+ * file) and passes all `world` of them, in rank order, to bp_dist_connect.  world == 1 needs neither call.
+ * Every rank must call bp_dist_set_static / bp_dist_frame the same number of times in the same order (they contain
+ * device-side barriers).  BP_ERR_TOO_LARGE: a receive buffer is too small -- the same on every rank, because the count
+ * matrices are global; bp_dist_last_info tells the sizes needed, recreate the contexts with larger capacities. */
+typedef struct bp_dist bp_dist;
+typedef struct bp_dist_config {
+    int32_t index_kind;     /* BP_INDEX64_2D or BP_INDEX64_3D; IDs are u32 */
+    uint32_t min_depth;     /* LayerBuilder::with_min_depth, src/layer.rs:646-649 */
+    int32_t device;         /* CUDA device ordinal; -1 = current device */
+    int32_t rank, world;    /* world <= 16 */
+    size_t record_capacity; /* records one rank can RECEIVE in a frame (owned + halo copies) */
+    size_t pair_capacity;   /* raw pairs one rank can receive in a frame */
+} bp_dist_config;
+enum { BP_DIST_PHASES = 9 }; /* encode, splitters, counts, exchange, sort, scan, pair_counts, pair_exchange, unique */
+typedef struct bp_dist_info { /* the last frame on this rank */
+    uint64_t records_local;  /* records encoded from this rank's objects */
+    uint64_t records_owned;  /* records of this rank's Morton range after the exchange */
+    uint64_t n_halo;         /* ancestor (halo) records in front of them, static halo included */
+    uint64_t raw_pairs, pairs;
+    uint64_t records_needed, pairs_needed; /* fullest receive buffer of the frame (what the capacities must hold) */
+    int32_t fused;           /* counts taken by the encode kernel (cached splitters) */
+    int32_t rescanned;       /* the scan ran again without dedup at the source (another shard saw an inactive record) */
+    int32_t rebalance_records, rebalance_pairs; /* cached splitters dropped after this frame */
+    double phase_ms[BP_DIST_PHASES]; /* with BP_DIST_OPT_TRACE: device-synchronised wall time of every phase */
+} bp_dist_info;
+enum { BP_DIST_OPT_REUSE_SPLITTERS = 0, BP_DIST_OPT_FUSE_COUNTS = 1, BP_DIST_OPT_GLOBAL_DEDUP_DECISION = 2, BP_DIST_OPT_TRACE = 3 };
+
+int bp_dist_create(const bp_dist_config *config, bp_dist **out);
+int bp_dist_destroy(bp_dist *ctx);
+size_t bp_dist_handle_bytes(void);
+int bp_dist_export(bp_dist *ctx, void *out_blob);
+int bp_dist_connect(bp_dist *ctx, const void *all_blobs);
+int bp_dist_set_stream(bp_dist *ctx, void *cuda_stream);
+int bp_dist_set_option(bp_dist *ctx, int option, int value);
+/* Shards a static scene once: sorted, kept resident, merged into every frame (the reference's "static scene layer"
+ * use of Layer::merge, README + src/layer.rs:127-138).  Its splitters stay fixed from then on. */
+int bp_dist_set_static(bp_dist *ctx, const float *system_bounds, const float *d_bounds, const void *d_ids, size_t n);
+/* One frame on this rank's n objects (device pointers).  *out_d_pairs: this rank's slice of the globally sorted,
+ * duplicate-free (later, earlier) pair list (u32 IDs), on the device, valid until the next call; the slices of ranks
+ * 0 .. world-1 concatenated are exactly the reference's scan() vector of the whole scene. */
+int bp_dist_frame(bp_dist *ctx, const float *system_bounds, const float *d_bounds, const void *d_ids, size_t n,
+                  const bp_filter *filter, const void **out_d_pairs, size_t *out_count);
+int bp_dist_last_info(const bp_dist *ctx, bp_dist_info *out);
+/* The context's layers, for bp_layer_stats / bp_layer_set_profiling: 0 = encode, 1 = shard, 2 = static. */
+bp_layer *bp_dist_layer(bp_dist *ctx, int which);
+const char *bp_dist_last_error(const bp_dist *ctx);
+
 /* ---- instrumentation -------------------------------------------------------------------------- */
 int bp_layer_set_profiling(bp_layer *layer, int enabled); /* CUDA-event timing of every kernel launch */
 int bp_layer_reset_stats(bp_layer *layer);

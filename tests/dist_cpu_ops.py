@@ -1,7 +1,7 @@
-"""CPU test double of dist.CudaOps (numpy + the CPU oracle) and the gloo worker that drives
-dist.DistLayer with it.  TEST INFRASTRUCTURE ONLY: lets world_size > 1 tests check the splitter /
+"""CPU test double of the device operations (numpy + the CPU oracle) and the gloo worker that drives the protocol
+model tests/dist_protocol.DistLayer with it (the product runs the same protocol in C++: csrc/bp_dist.cu).  TEST INFRASTRUCTURE ONLY: lets world_size > 1 tests check the splitter /
 halo / ownership / global-dedup choreography of the multi-GPU path on a CPU-only box.  The product
-path (dist.CudaOps) never touches any of this."""
+path (bp_dist_frame) never touches any of this."""
 import os
 import sys
 import traceback
@@ -147,7 +147,7 @@ class _EncInfo:
 
 
 class CpuOpsProduct(CpuOps):
-    """The same double behind the PRODUCT-side protocol of DistLayer.frame (what dist.CudaOps speaks): the count matrix
+    """The same double behind the PRODUCT-side protocol of DistLayer.frame (what bp_dist_frame speaks): the count matrix
     carries every sender's tag words, the receivers plan their sort from them (dist.sort_plan), frames with cached splitters
     take the counts together with the encode.  sort_records CHECKS the plan it is handed against the records that actually
     arrived -- the masks must cover them, and "IDs ascending" must be true of the receive buffer, because the GPU sort then
@@ -288,7 +288,7 @@ def worker(rank, world, port, cases, empty_rank, out_dir, product=False):
         dist.init_process_group("gloo", rank=rank, world_size=world)
         import _loadpkg
         bp = _loadpkg.load()
-        from broadphase_rs_b200 import dist as bpd
+        from tests import dist_protocol as bpd
         for case in cases:
             kind, md, sysb, bounds, ids, flt = make_case(case)
             n = bounds.shape[0]

@@ -1,4 +1,4 @@
-"""world_size > 1 tests of the multi-GPU choreography (dist.DistLayer) on CPU: gloo backend, the
+"""world_size > 1 tests of the multi-GPU choreography (tests/dist_protocol.DistLayer, the executable model of bp_dist_frame's protocol) on CPU: gloo backend, the
 numpy/oracle test double for the shard-local operations.  The concatenation of the ranks' results
 must equal the single-process oracle scan bit for bit."""
 import os
@@ -68,7 +68,7 @@ def test_product_protocol_plans_hold_on_the_received_records(tmp_path, world, em
 
 
 def test_ancestor_keys_and_splitters(bp):
-    from broadphase_rs_b200 import dist as bpd
+    from tests import dist_protocol as bpd
     from oracle import cpu_oracle as co
     key = co.make_index(2, 5, [0x12345678 & 0xF8000000, 0x9abcdef0 & 0xF8000000, 0x0fedcba9 & 0xF8000000])  # origin truncated to depth 5
     anc = bpd.ancestor_keys(2, key)
@@ -106,7 +106,7 @@ def test_sort_plan_from_tag_words(bp):
 def test_scatter_destinations_equal_the_per_destination_sums(bp):
     """The array arithmetic that runs between the count matrix and the scatter launch (GPU idle) against the plain
     per-destination sums it replaced; addresses stay exact 64-bit integers."""
-    from broadphase_rs_b200 import dist as bpd
+    from tests import dist_protocol as bpd
     rng = np.random.Generator(np.random.Philox(77))
     for g in (1, 2, 3, 8, 16):
         kp = (np.uint64(0x7F00_0000_0000) + np.arange(g, dtype=np.uint64) * np.uint64(1 << 36))

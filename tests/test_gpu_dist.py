@@ -278,6 +278,66 @@ def test_extend_count_rows_equals_the_separate_steps(bp):
         bp.Layer(2, "u32", min_depth=3).extend_count_rows(sc["sys_bounds"], db, di, n, spl, True, [rows[0].data_ptr()])
 
 
+@pytest.mark.parametrize("case", ["uniform3d", "big_objects3d", "multibounds2d", "multibounds3d", "skewed3d"])
+def test_dist_context_world_1_equals_oracle(bp, case):
+    """bp_dist_frame with a single rank: the whole C++ frame (count row, exchange kernel into its own receive buffer, sort
+    out of it, scan, pair exchange, dedup) on one GPU -- cached splitters and fused counts from the second frame on."""
+    import torch
+    from broadphase_rs_b200 import dist as bpd
+    from tests import dist_cpu_ops as dco
+    kind, md, sysb, bounds, ids, flt = dco.make_case(case)
+    n = bounds.shape[0]
+    ctx = bpd.DistContext(bp, kind, md, 0, record_capacity=16 * n, pair_capacity=1 << 22)
+    db = torch.from_numpy(bounds).cuda()
+    di = torch.from_numpy(ids.view(np.int32)).cuda()
+    gflt = bp.ScanFilter.id_parity() if flt else None
+    want = dco.reference_pairs(case)
+    if case == "uniform3d":      # on the caller's stream (torch's current one, then a side stream), with phase tracing
+        from broadphase_rs_b200 import _lib
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        ctx.set_stream(side.cuda_stream)
+        ctx.set_option(_lib.DIST_OPT_TRACE, 1)
+    for frame in range(3):
+        got = ctx.frame(sysb, db, di, n, gflt).cpu().numpy().view(np.uint32)
+        assert got.shape == want.shape and (got == want).all(), (case, frame)
+        assert ctx.last["fused"] == (1 if frame > 0 and md == 0 else 0)
+    if case == "uniform3d":
+        assert sum(ctx.last["phases_ms"].values()) > 0
+    # an empty frame, then the scene again
+    assert ctx.frame(sysb, db, di, 0, gflt).shape[0] == 0
+    got = ctx.frame(sysb, db, di, n, gflt).cpu().numpy().view(np.uint32)
+    assert (got == want).all()
+    ctx.close()
+
+
+def test_dist_context_world_1_static_plus_dynamic_and_regrow(bp):
+    import torch
+    from broadphase_rs_b200 import dist as bpd
+    from tests import dist_cpu_ops as dco
+    kind, md, sysb, sb, sids, _ = dco.make_case("big_objects3d")
+    _, _, _, dbn, dids, _ = dco.make_case("uniform3d")
+    dids = (dids + np.uint32(100_000)).astype(np.uint32)
+    ctx = bpd.DistContext(bp, kind, md, 0, record_capacity=1 << 20, pair_capacity=1 << 22)
+    ctx.set_static(sysb, torch.from_numpy(sb).cuda(), torch.from_numpy(sids.view(np.int32)).cuda(), sb.shape[0])
+    for frame in range(2):
+        moved = np.clip(dbn + np.float32(0.001 * frame), 0.0, 1.0).astype(np.float32)
+        got = ctx.frame(sysb, torch.from_numpy(moved).cuda(), torch.from_numpy(dids.view(np.int32)).cuda(), moved.shape[0], None)
+        want = dco.reference_static_dynamic(frame)
+        got = got.cpu().numpy().view(np.uint32)
+        assert got.shape == want.shape and (got == want).all(), frame
+    assert ctx.layers()[1].stats()["merged"] == 1
+    ctx.close()
+    # receive buffers far too small: the frame grows them (collectively; here alone) and runs again
+    kind, md, sysb, bounds, ids, _ = dco.make_case("uniform3d")
+    ctx = bpd.DistContext(bp, kind, md, 0, record_capacity=1000, pair_capacity=10)
+    got = ctx.frame(sysb, torch.from_numpy(bounds).cuda(), torch.from_numpy(ids.view(np.int32)).cuda(), bounds.shape[0], None)
+    want = dco.reference_pairs_unfiltered("uniform3d")
+    assert (got.cpu().numpy().view(np.uint32) == want).all() and ctx.record_capacity > 1000 and ctx.pair_capacity > 10
+    ctx.close()
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -297,53 +357,55 @@ def _nccl_worker(rank, world, port, out_dir):
     bp = _loadpkg.load()
     from broadphase_rs_b200 import dist as bpd
     from tests import dist_cpu_ops as dco
+    # the same scenes through the C-ABI context (bp_dist_frame): the product path
     for case in ("uniform3d", "big_objects3d", "skewed3d", "multibounds3d", "multibounds3d_local_decision"):
         kind, md, sysb, bounds, ids, flt = dco.make_case(case.replace("_local_decision", ""))
         n = bounds.shape[0]
         cuts = np.linspace(0, n, world + 1).astype(int)
         lo, hi = cuts[rank], cuts[rank + 1]
-        ops = bpd.CudaOps(bp, kind, md, rank)
-        # (the "_local_decision" run switches the global dedup decision off: it shows what the decision prevents and is
-        # only recorded, not asserted)
-        dl = bpd.DistLayer(ops, kind, global_dedup_decision=not case.endswith("_local_decision"))
+        ctx = bpd.DistContext(bp, kind, md, rank, record_capacity=16 * n, pair_capacity=1 << 22)
+        if case.endswith("_local_decision"):
+            from broadphase_rs_b200 import _lib
+            ctx.set_option(_lib.DIST_OPT_GLOBAL_DEDUP_DECISION, 0)
         db = torch.from_numpy(bounds[lo:hi].copy()).cuda()
         di = torch.from_numpy(ids[lo:hi].copy().view(np.int32)).cuda()
         gflt = bp.ScanFilter.id_parity() if flt else None
-        for _ in range(2):  # twice: buffers are reused across frames
-            pairs = dl.frame(sysb, db, di, hi - lo, gflt)
-        allp = dl.gather_pairs(pairs)
+        for _ in range(3):  # the first frame samples splitters, the later ones reuse them with fused counts
+            pairs = ctx.frame(sysb, db, di, hi - lo, gflt)
+        allp = ctx.gather_pairs(pairs)
         if rank == 0:
-            np.save(os.path.join(out_dir, "%s.npy" % case), allp)
-    # config-4 shape: static scene sharded once, dynamic layer merged in per frame (Layer::merge)
+            np.save(os.path.join(out_dir, "ctx_%s.npy" % case), allp)
+            np.save(os.path.join(out_dir, "ctx_%s.fused.npy" % case), np.array([ctx.last["fused"]]))
+        ctx.close()
     kind, md, sysb, sb, sids, _ = dco.make_case("big_objects3d")
     _, _, _, dbn, dids, _ = dco.make_case("uniform3d")
     dids = (dids + np.uint32(100_000)).astype(np.uint32)
     cs = np.linspace(0, sb.shape[0], world + 1).astype(int)
     cd = np.linspace(0, dbn.shape[0], world + 1).astype(int)
-    ops = bpd.CudaOps(bp, kind, md, rank)
-    dl = bpd.DistLayer(ops, kind)
-    dl.set_static(sysb, torch.from_numpy(sb[cs[rank]:cs[rank + 1]].copy()).cuda(),
-                  torch.from_numpy(sids[cs[rank]:cs[rank + 1]].copy().view(np.int32)).cuda(), cs[rank + 1] - cs[rank])
+    ctx = bpd.DistContext(bp, kind, md, rank, record_capacity=1 << 20, pair_capacity=1 << 22)
+    ctx.set_static(sysb, torch.from_numpy(sb[cs[rank]:cs[rank + 1]].copy()).cuda(),
+                   torch.from_numpy(sids[cs[rank]:cs[rank + 1]].copy().view(np.int32)).cuda(), cs[rank + 1] - cs[rank])
     for frame in range(2):
         moved = np.clip(dbn + np.float32(0.001 * frame), 0.0, 1.0).astype(np.float32)
-        pairs = dl.frame(sysb, torch.from_numpy(moved[cd[rank]:cd[rank + 1]].copy()).cuda(),
-                         torch.from_numpy(dids[cd[rank]:cd[rank + 1]].copy().view(np.int32)).cuda(), cd[rank + 1] - cd[rank], None)
-        allp = dl.gather_pairs(pairs)
+        pairs = ctx.frame(sysb, torch.from_numpy(moved[cd[rank]:cd[rank + 1]].copy()).cuda(),
+                          torch.from_numpy(dids[cd[rank]:cd[rank + 1]].copy().view(np.int32)).cuda(), cd[rank + 1] - cd[rank], None)
+        allp = ctx.gather_pairs(pairs)
         if rank == 0:
-            np.save(os.path.join(out_dir, "static_dynamic_%d.npy" % frame), allp)
-    assert ops.shard.stats()["merged"] == 1
+            np.save(os.path.join(out_dir, "ctx_static_dynamic_%d.npy" % frame), allp)
+    ctx.close()
     # the BASELINE config-2 recipe, 2^18 objects per rank
     import importlib
     dbm = importlib.import_module("broadphase_rs_b200.dist_bench")
     sc = dbm._scene_slice(bp, 1 << 18, world, rank, 6)
-    ops = bpd.CudaOps(bp, 2, 0, rank)
-    dl = bpd.DistLayer(ops, 2)
+    ctx = dbm._context(bp, bpd, 2, rank, 1 << 18)
     db = torch.from_numpy(sc["bounds"]).cuda()
     di = torch.from_numpy(sc["ids"].view(np.int32)).cuda()
-    pairs = dl.frame(sc["sys_bounds"], db, di, 1 << 18, None)
-    allp = dl.gather_pairs(pairs)
+    for _ in range(2):
+        pairs = ctx.frame(sc["sys_bounds"], db, di, 1 << 18, None)
+    allp = ctx.gather_pairs(pairs)
     if rank == 0:
         np.save(os.path.join(out_dir, "cfg2slice.npy"), allp)
+    ctx.close()
     dist.barrier()
     dist.destroy_process_group()
 
@@ -357,20 +419,22 @@ def test_nccl_frame_equals_oracle(bp, tmp_path):
     mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     from tests import dist_cpu_ops as dco
     for case in ("uniform3d", "big_objects3d", "skewed3d", "multibounds3d"):
-        got = np.load(os.path.join(str(tmp_path), "%s.npy" % case))
         want = dco.reference_pairs(case)
+        got = np.load(os.path.join(str(tmp_path), "ctx_%s.npy" % case))
         assert got.shape == want.shape and (got == want).all(), case
-    # with every shard deciding "dedup at the source" on its own, pairs whose canonical cell holds an
-    # inactive record are lost when a neighbouring shard suppresses its copy; the global decision (above) keeps them
-    lost = dco.reference_pairs("multibounds3d").shape[0] - np.load(os.path.join(str(tmp_path), "multibounds3d_local_decision.npy")).shape[0]
-    print("pairs lost without the global dedup decision: %d" % lost)
+        assert np.load(os.path.join(str(tmp_path), "ctx_%s.fused.npy" % case))[0] == 1
+    for frame in range(2):
+        got = np.load(os.path.join(str(tmp_path), "ctx_static_dynamic_%d.npy" % frame))
+        want = dco.reference_static_dynamic(frame)
+        assert got.shape == want.shape and (got == want).all(), ("ctx static+dynamic", frame)
+    # with every shard deciding "dedup at the source" on its own, pairs whose canonical cell holds an inactive
+    # record are lost when a neighbouring shard suppresses its copy; the global decision (asserted above) keeps them.  The run
+    # with the decision switched off is only recorded.
+    lost = dco.reference_pairs("multibounds3d").shape[0] - np.load(os.path.join(str(tmp_path), "ctx_multibounds3d_local_decision.npy")).shape[0]
+    print("bp_dist_frame: pairs lost without the global dedup decision: %d" % lost)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "dedup_decision.txt"), "w") as f:
         f.write("world=%d pairs lost with per-shard decision: %d (0 with the global decision: asserted)\n" % (world, lost))
-    for frame in range(2):
-        got = np.load(os.path.join(str(tmp_path), "static_dynamic_%d.npy" % frame))
-        want = dco.reference_static_dynamic(frame)
-        assert got.shape == want.shape and (got == want).all(), ("static+dynamic", frame)
     import importlib
     dbm = importlib.import_module("broadphase_rs_b200.dist_bench")
     o = co.OracleLayer(2, 4, 0)

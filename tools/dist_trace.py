@@ -19,8 +19,10 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 20)
 sc = dist_bench._scene_slice(bp, n, world, rank, 6)
-ops = bpd.CudaOps(bp, 2, 0, local)
-dl = bpd.DistLayer(ops, 2, trace=True)
+from broadphase_rs_b200 import _lib
+dl = dist_bench._context(bp, bpd, 2, local, n)
+dl.set_stream(torch.cuda.current_stream(local).cuda_stream)
+dl.set_option(_lib.DIST_OPT_TRACE, 1)   # bp_dist_frame synchronises and stamps every phase
 db = torch.from_numpy(sc["bounds"]).cuda()
 di = torch.from_numpy(sc["ids"].view(np.int32)).cuda()
 acc = {}
@@ -34,8 +36,6 @@ for r in range(world):
         print("rank %d objects/gpu=%d world=%d  total %.3f ms" % (rank, n, world, sum(acc.values())))
         print("   " + "  ".join("%s=%.3f" % (k, v) for k, v in acc.items()))
         print("   records local=%d owned=%d halo=%d raw=%d pairs=%d" % (dl.last["records_local"], dl.last["records_owned"], dl.last["halo"], dl.last["raw_pairs"], dl.last["pairs"]))
-        if rank == 0:
-            print("   record matrix", dl.last["record_matrix"].tolist(), "pair matrix", dl.last["pair_matrix"].tolist())
         sys.stdout.flush()
     dist.barrier()
 dist.barrier()
