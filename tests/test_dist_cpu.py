@@ -89,7 +89,7 @@ def test_ancestor_keys_and_splitters(bp):
 def test_sort_plan_from_tag_words(bp):
     """The receivers' sort plan from the senders' tag words: masks OR / AND over the sources, IDs ascending only if every
     source's are, the ID ranges follow each other in rank order and no halo copies arrived."""
-    from broadphase_rs_b200.dist import sort_plan
+    from tests.dist_protocol import sort_plan
     full = (1 << 64) - 1
     empty = [0, 0, full, full, full, 0, 1]
     a = [0xFF | (1 << 63), 0xF0F0, 0x1010, 0x01, 0, 99, 1]
