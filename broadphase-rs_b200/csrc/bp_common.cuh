@@ -231,6 +231,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shard of a key: the number of splitters <= v, over 15 ascending splitters in shared memory (unused ones = ~0: no key
+// reaches them).  Four dependent probes instead of fifteen comparisons.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t splitter_rank15(const uint64_t *sspl, uint64_t v) {
+    uint32_t lo = (sspl[7] <= v) ? 8u : 0u;
+    lo += (sspl[lo + 3] <= v) ? 4u : 0u;
+    lo += (sspl[lo + 1] <= v) ? 2u : 0u;
+    lo += (sspl[lo] <= v) ? 1u : 0u;
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
 // streaming loads: data that is read exactly once should not displace the look-back state in L1
 // ---------------------------------------------------------------------------------------------
 template <class T> __device__ __forceinline__ T ld_stream(const T *p) { return __ldcs(p); }

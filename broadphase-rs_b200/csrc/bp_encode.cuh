@@ -103,7 +103,15 @@ template <class T, class IdT, bool COUNT = false>
 __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs<T, IdT> a) {
     typedef typename T::key_t K;
     __shared__ uint32_t scount[COUNT ? 32 : 1];
+    __shared__ uint64_t sspl[COUNT ? ENCODE_MAX_SPLITTERS + 1 : 1];
     if (COUNT && threadIdx.x < 32) scount[threadIdx.x] = 0; // (published by the barriers below, long before its first use)
+    if (COUNT && threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < ENCODE_MAX_SPLITTERS; ++i) sspl[i] = a.count.spl[i]; // static indices: from the constant bank
+    }
+    // COUNT: records per home shard, one 8-bit field per shard in two packed words (a thread generates at most
+    // 8 cells x 4 objects = 32 records of a tile), reduced over the warp once per tile
+    unsigned long long pc0 = 0, pc1 = 0;
     constexpr int DIM = T::DIM;
     constexpr int FPO = 2 * DIM; // floats per object
     typedef EncodeSmem<T, IdT> S;
@@ -297,21 +305,16 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
                 if (a.cell_flags_out) a.cell_flags_out[gi] = (uint8_t)((ix ? 1u : 0u) | (iy ? 2u : 0u) | (iz ? 4u : 0u));
             }
             if constexpr (COUNT) {
-                // the threads of the warp that are still in the loop vote bucket by bucket; their first lane books the counts
-                const unsigned act = __activemask();
-                const unsigned leader = (unsigned)__ffs((int)act) - 1u;
                 const uint32_t ns = a.count.n_spl;
-                uint32_t home = 0;
-                for (uint32_t i = 0; i < ns; ++i) home += (a.count.spl[i] <= (uint64_t)key) ? 1u : 0u;
-                for (uint32_t b = 0; b <= ns; ++b) {
-                    const uint32_t c = (uint32_t)__popc(__ballot_sync(act, home == b));
-                    if (lane == leader && c) atomicAdd(&scount[b], c);
-                }
+                const uint32_t home = splitter_rank15(sspl, (uint64_t)key);
+                if (home < 8)
+                    pc0 += 1ull << (8 * home);
+                else
+                    pc1 += 1ull << (8 * (home - 8));
                 if (home < ns) { // common case: the cell ends before the next splitter -- one comparison
                     const uint64_t hi = (uint64_t)run_upper_key<T>(key);
-                    if (hi >= a.count.spl[home]) {
-                        uint32_t last = 0;
-                        for (uint32_t i = 0; i < ns; ++i) last += (a.count.spl[i] <= hi) ? 1u : 0u;
+                    if (hi >= sspl[home]) {
+                        const uint32_t last = splitter_rank15(sspl, hi);
                         for (uint32_t s2 = home + 1; s2 <= last; ++s2) atomicAdd(&scount[16 + s2], 1u); // rare
                     }
                 }
@@ -340,6 +343,10 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
         if (too_many) atomicOr(&a.result->too_many, 1u);
     }
     if constexpr (COUNT) {
+        for (uint32_t b = 0; b <= a.count.n_spl; ++b) { // (warp-uniform trip count; every thread is here)
+            const uint32_t c = warp_sum((uint32_t)((b < 8 ? pc0 >> (8 * b) : pc1 >> (8 * (b - 8))) & 0xffull));
+            if (lane == 0 && c) atomicAdd(&scount[b], c);
+        }
         __syncthreads();
         if (tid < 32 && scount[tid]) atomicAdd(&a.count.cnt[tid], scount[tid]);
     }

@@ -48,7 +48,7 @@ template <class K, class V, int THREADS, int ITEMS> struct ExchangeCfg {
     static constexpr int VPER = 16 / VSIZE;                                      // payloads per 16 bytes
     static constexpr size_t KEY_BYTES = ((size_t)(TILE + XCH_BUCKETS * KPER) * sizeof(K) + 15) / 16 * 16;
     static constexpr size_t VAL_BYTES = HAS_V ? ((size_t)(TILE + XCH_BUCKETS * VPER) * VSIZE + 15) / 16 * 16 : 0;
-    static constexpr size_t SMEM_BYTES = KEY_BYTES + VAL_BYTES + (size_t)(WARPS * XCH_BUCKETS + 8 * XCH_BUCKETS + 16) * sizeof(uint32_t);
+    static constexpr size_t SMEM_BYTES = KEY_BYTES + VAL_BYTES + (size_t)(WARPS * XCH_BUCKETS + 10 * XCH_BUCKETS + 16) * sizeof(uint32_t);
     static_assert(TILE < 65536, "ranks are packed in 16 bits");
 };
 
@@ -74,7 +74,8 @@ __device__ __forceinline__ void exchange_tile(const ExchangeArgs<K, V> &a, unsig
     uint32_t *kstart = gofs + NB;                                              // [NB] where the bucket's run starts in skeys
     uint32_t *vstart = kstart + NB;                                            // [NB] ... in svals
     uint64_t *sdst = (uint64_t *)(vstart + NB);                                // [2 * NB] kdst | vdst (8-byte aligned: 4 * NB words precede)
-    uint32_t *misc = (uint32_t *)(sdst + 2 * NB);                              // [0] tile, [1] poison
+    uint64_t *sspl = sdst + 2 * NB;                                            // [NB] splitters (unused ones ~0)
+    uint32_t *misc = (uint32_t *)(sspl + NB);                                  // [0] tile, [1] poison
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t tile_begin = (uint64_t)tile * TILE;
@@ -117,11 +118,7 @@ __device__ __forceinline__ void exchange_tile(const ExchangeArgs<K, V> &a, unsig
     uint32_t rd[ITEMS]; // low 16 bits: rank inside the (warp, bucket) group, high 16 bits: bucket
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
-        const uint64_t v = (uint64_t)key[k] >> a.shift;
-        uint32_t d = 0;
-#pragma unroll
-        for (int i = 0; i < MAX_SPLITTERS; ++i) // static indices: the splitters are read from the constant bank
-            if (i < (int)a.n_spl) d += (a.spl[i] <= v) ? 1u : 0u;
+        const uint32_t d = min(splitter_rank15(sspl, (uint64_t)key[k] >> a.shift), a.n_spl); // (an all-ones pad passes the ~0 fillers too)
         const unsigned m = match_bucket(d);
         uint32_t old = 0;
         if ((m & lt) == 0) old = atomicAdd(&wrow[d], (uint32_t)__popc(m)); // one shared atomic per group, in item order: stable
@@ -269,7 +266,8 @@ __global__ void __launch_bounds__(THREADS, MINB) exchange_pass_kernel(const Exch
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *whist = (uint32_t *)(smem_raw + Cfg::KEY_BYTES + Cfg::VAL_BYTES);
     uint64_t *sdst = (uint64_t *)(whist + WARPS * NB + 4 * NB);
-    uint32_t *misc = (uint32_t *)(sdst + 2 * NB);
+    uint64_t *sspl = sdst + 2 * NB;
+    uint32_t *misc = (uint32_t *)(sspl + NB);
 
     const unsigned tid = threadIdx.x;
     if (tid == 0) {
@@ -279,6 +277,7 @@ __global__ void __launch_bounds__(THREADS, MINB) exchange_pass_kernel(const Exch
         for (int b = 0; b < NB; ++b) { // static indices: straight from the constant bank
             sdst[b] = a.kdst[b];
             sdst[NB + b] = a.vdst[b];
+            sspl[b] = b < MAX_SPLITTERS ? a.spl[b < MAX_SPLITTERS ? b : 0] : ~0ull; // (the host pads unused splitters with ~0)
         }
     }
     for (int i = tid; i < WARPS * NB; i += THREADS) whist[i] = 0;

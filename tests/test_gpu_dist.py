@@ -184,7 +184,8 @@ def test_id_order_and_flagged_scatter(bp):
     """bp_layer_id_order reports what the receivers of a rank's records need; bp_dist_scatter_records_flagged ships the cell
     flags inside the IDs, and a shard sorted from such a buffer scans to the same pairs with no duplicate raw pair."""
     import torch
-    from broadphase_rs_b200.dist import _view, sort_plan
+    from broadphase_rs_b200.dist import _view
+    from tests.dist_protocol import sort_plan
     sc = bp.scenes.uniform_cubes(60_000, 4)
     L = bp.Layer(2, "u32")
     assert L.id_order() == ((1 << 64) - 1, 0, True)
@@ -237,7 +238,8 @@ def test_extend_count_rows_equals_the_separate_steps(bp):
     """bp_dist_extend_count_rows: the counts the encode kernel takes while it generates the records, and the tag words the
     row kernel reads from the extend's result block on the device, equal count_records + masks + id_order."""
     import torch
-    from broadphase_rs_b200.dist import _view, N_TAGS
+    from broadphase_rs_b200.dist import _view
+    from tests.dist_protocol import N_TAGS
     sc = bp.scenes.lognormal_cubes(150_000, 13)
     big = bp.scenes.uniform_cubes(64, 5, id_base=1_000_000, edge_factor=0.4 * 64 ** (1.0 / 3.0) * 0.9)  # halo copies exist
     bounds = np.concatenate([sc["bounds"], big["bounds"]])

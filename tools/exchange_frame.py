@@ -46,3 +46,32 @@ for rep in range(2):
     S.scatter_pairs(raw, nraw, aspl, [op.data_ptr() + 8 * int(poff[b]) for b in range(g)])
     torch.cuda.synchronize()
 print("records %d raw pairs %d buckets %d; launches: enc layer %d, shard layer %d" % (r, nraw, g, L.stats()["launches_total"], S.stats()["launches_total"]))
+
+# ---- cost of counting inside the encode (cached splitters): encode alone vs encode + per-shard counts ----
+rows = torch.zeros((2, 2 * g + 7), dtype=torch.int64, device=dev)
+
+
+def timed(fn, reps=5):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def plain():
+    L.clear()
+    L.extend_device(sc["sys_bounds"], db, di, n)
+    len(L)
+
+
+def counted():
+    L.extend_count_rows(sc["sys_bounds"], db, di, n, spl, True, [rows[0].data_ptr(), rows[1].data_ptr()])
+    len(L)
+
+
+print("encode %.3f ms, encode + counts for %d shards %.3f ms (%d objects)" % (timed(plain), g, timed(counted), n))
