@@ -305,3 +305,30 @@ impl LayerBuilder {
         Layer { handle, _marker: PhantomData }
     }
 }
+
+
+// ---- several GPUs: the sharded frame (include/bp.h "bp_dist_*"; no counterpart in the reference crate) -------------------------
+#[repr(C)]
+pub struct BpDist {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct BpDistConfig {
+    pub index_kind: i32,
+    pub min_depth: u32,
+    pub device: i32,
+    pub rank: i32,
+    pub world: i32,
+    pub record_capacity: usize,
+    pub pair_capacity: usize,
+}
+extern "C" {
+    pub fn bp_dist_create(cfg: *const BpDistConfig, out: *mut *mut BpDist) -> c_int;
+    pub fn bp_dist_destroy(ctx: *mut BpDist) -> c_int;
+    pub fn bp_dist_handle_bytes() -> usize;
+    pub fn bp_dist_export(ctx: *mut BpDist, out_blob: *mut u8) -> c_int;
+    pub fn bp_dist_connect(ctx: *mut BpDist, all_blobs: *const u8) -> c_int;
+    pub fn bp_dist_set_static(ctx: *mut BpDist, system_bounds: *const f32, d_bounds: *const f32, d_ids: *const c_void, n: usize) -> c_int;
+    pub fn bp_dist_frame(ctx: *mut BpDist, system_bounds: *const f32, d_bounds: *const f32, d_ids: *const c_void, n: usize,
+                         filter: *const BpFilter, out_d_pairs: *mut *const c_void, out_count: *mut usize) -> c_int;
+}
