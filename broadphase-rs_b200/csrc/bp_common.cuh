@@ -151,7 +151,9 @@ template <int THREADS, class T> __device__ __forceinline__ T block_exclusive_sum
 // already started: the spin below cannot deadlock.  It is still bounded (BP_SPIN_LIMIT polls) and
 // raises *err instead of hanging the GPU if that invariant is ever broken.
 // ---------------------------------------------------------------------------------------------
-#define BP_SPIN_LIMIT (1u << 22)
+// (2^26 polls, the later ones ~64 ns apart: seconds, so that a predecessor delayed by time-slicing (MPS, a debugger, preemption)
+// is waited for rather than reported -- ADVICE round 1; the kernels stay memory-safe on a time-out: offsets only shrink.)
+#define BP_SPIN_LIMIT (1u << 26)
 constexpr uint64_t LB_FLAG_AGG = 1ull << 62;
 constexpr uint64_t LB_FLAG_INC = 2ull << 62;
 constexpr uint64_t LB_VALUE_MASK = (1ull << 62) - 1;
@@ -185,7 +187,7 @@ __device__ __forceinline__ uint64_t lookback_exclusive(uint64_t *status, uint32_
                     s = LB_FLAG_INC;
                     break;
                 }
-                __nanosleep(20);
+                __nanosleep(spins > 4096 ? 64 : 20);
                 s = ld_volatile_u64(&status[idx]);
             }
         }

@@ -325,6 +325,9 @@ int post_mail(bp_layer *L, int box, const void *d_src, int nwords, unsigned int 
 int wait_mail(bp_layer *L, int box, unsigned int seq, void *dst, size_t bytes) {
     volatile Mailbox *mb = L->h_mail[box];
     for (unsigned int spins = 1; mb->seq != seq; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause(); // a polite spin: the sibling hyper-thread and the memory system are not hammered
+#endif
         if ((spins & 0xffffu) == 0) { // the stream must still be busy (or have just finished); anything else is an error
             const cudaError_t e = cudaStreamQuery(L->stream);
             if (e == cudaSuccess) {

@@ -223,6 +223,7 @@ __device__ __forceinline__ void lookback_round(const uint32_t *status, int NB, u
                         sb = RS_FLAG_INC;
                         break;
                     }
+                    if (spins > 4096) __nanosleep(64);
                     sb = ld_volatile_u32(ps);
                 } while ((sb >> 30) == 0);
             }

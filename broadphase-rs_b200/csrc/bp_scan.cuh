@@ -88,6 +88,7 @@ constexpr int RUNS_IPT = 8;
 constexpr int RUNS_TILE = RUNS_THREADS * RUNS_IPT;
 constexpr int EMIT_THREADS = 512;
 constexpr int EMIT_IPT = 8;
+constexpr int EMIT_MINB = 3; // CTAs per SM asked of the emission (latency-bound gathers: long_scoreboard 11 warps per issue slot at 2 CTAs)
 constexpr int EMIT_CHUNK = EMIT_THREADS * EMIT_IPT;
 
 struct ScanTotals {
@@ -440,7 +441,7 @@ template <class T> __device__ __forceinline__ bool canonical_cell(typename T::ke
 }
 
 template <class IdT, int FK, class T = IndexTraits<BP_INDEX64_3D>, bool DEDUP = false>
-__global__ void __launch_bounds__(EMIT_THREADS, 2) scan_emit_kernel(const EmitArgs<IdT> a) {
+__global__ void __launch_bounds__(EMIT_THREADS, EMIT_MINB) scan_emit_kernel(const EmitArgs<IdT> a) {
     constexpr bool WIDE = sizeof(IdT) == 8;
     constexpr int FLAG_SHIFT = 8 * sizeof(IdT) - 3;
     typedef EmitSmem<IdT> S;

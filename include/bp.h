@@ -18,7 +18,11 @@
  *  - Result pointers (records, pairs) are owned by the layer and stay valid until the next
  *    mutating call on it, like the `&'a Vec<(ID, ID)>` the reference returns.
  *  - There is no CPU fallback: without a CUDA device bp_layer_create fails with BP_ERR_CUDA.
- *  - Limits: fewer than 2^30 records per layer and fewer than 2^30 raw pairs per scan.
+ *  - Limits (BP_ERR_TOO_LARGE): fewer than 2^30 records per layer; a scan may visit fewer than 2^30 (ancestor, descendant)
+ *    record pairs -- about 46 000 objects sharing ONE cell, or a depth-0 cell, reach that -- and emits fewer than 2^30
+ *    raw pairs; an object may own at most 2^20 cells and 4095 per axis (only a min_depth far above its natural depth does
+ *    that; the reference warn!s and continues, src/geom.rs:299-301): the offending object is skipped, every other object
+ *    of the same extend call has been appended when the error is returned.
  */
 #ifndef BP_H
 #define BP_H
