@@ -35,7 +35,7 @@
 namespace {
 
 constexpr int MAX_WORLD = 16;
-constexpr int SAMPLES = 2048;        // keys every rank contributes to the splitter sample
+constexpr int SAMPLES = 8192;        // keys every rank contributes to the splitter sample (8 ranks: shard sizes within ~1 % of the mean)
 constexpr int N_TAGS = 7;            // id_or | fold bit, key_or, key_and, id_and, first ID, last ID, IDs ascending
 constexpr double REBALANCE_AT = 1.15; // cached splitters are dropped when the fullest shard exceeds the mean by this factor
 constexpr uint64_t FOLD_BIT = 1ull << 63;

@@ -1422,7 +1422,14 @@ template <int KIND, class IdT> struct Impl {
     static int partition_scatter(bp_layer *L, const PK *kin, const PV *vin, uint32_t n, const uint64_t *spl, int n_spl,
                                  uint32_t shift, const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst,
                                  const uint64_t *hvdst, const uint8_t *vflags = nullptr) {
-        constexpr int XT = 384, XI = 12, XMINB = 3;
+        // (256 x 12 x 5 and 256 x 16 x 4 CTAs/SM were measured too: 0.90 / 0.92 ms against 0.87 ms for 97.8 M records into 8 local buckets)
+        return exchange_launch<PK, PV, 384, 12, 3>(L, kin, vin, n, spl, n_spl, shift, kdst, vdst, hkdst, hvdst, vflags);
+    }
+
+    template <class PK, class PV, int XT, int XI, int XMINB>
+    static int exchange_launch(bp_layer *L, const PK *kin, const PV *vin, uint32_t n, const uint64_t *spl, int n_spl, uint32_t shift,
+                               const uint64_t *kdst, const uint64_t *vdst, const uint64_t *hkdst, const uint64_t *hvdst,
+                               const uint8_t *vflags) {
         typedef ExchangeCfg<PK, PV, XT, XI> Cfg;
         if (n == 0) return BP_OK;
         SplitterScatterDigit<PK> op; // (the halo copies below still go through the splitter functor)

@@ -19,6 +19,7 @@ sc = bp.scenes.uniform_cubes(n, 6)
 db = torch.from_numpy(sc["bounds"]).cuda()
 di = torch.from_numpy(sc["ids"].view(np.int32)).cuda()
 L = bp.Layer(2, "u32")
+L.set_stream(torch.cuda.current_stream().cuda_stream)   # so that torch's events bracket the layer's kernels
 dev = torch.device("cuda")
 for rep in range(2):
     L.clear()
@@ -75,3 +76,13 @@ def counted():
 
 
 print("encode %.3f ms, encode + counts for %d shards %.3f ms (%d objects)" % (timed(plain), g, timed(counted), n))
+
+# ---- the record exchange itself, all destinations local ----
+plain()
+kp, ip, r, _ = L.records_device()
+keys, ids = _view(kp, r, torch.int64, dev), _view(ip, r, torch.int32, dev)
+dk = [ok.data_ptr() + 8 * int(off[b]) for b in range(g)]
+dv = [oi.data_ptr() + 4 * int(off[b]) for b in range(g)]
+t = timed(lambda: L.scatter_records(keys, ids, r, spl, dk, dv, None, None, fold_cell_flags=True))
+print("record exchange, %d local destinations: %.3f ms for %d records = %.0f GB/s of algorithmic bytes (BP_EXCHANGE_TMA=%s)"
+      % (g, t, r, 24.0 * r / (t * 1e-3) / 1e9, os.environ.get("BP_EXCHANGE_TMA", "1")))
