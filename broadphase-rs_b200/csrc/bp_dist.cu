@@ -68,6 +68,43 @@ __global__ void dist_barrier_kernel(uint64_t *const *flag_arrays, int me, int g,
     }
 }
 
+// The barrier and, behind it, this rank's copy of a small matrix handed to the host through pinned, device-mapped memory:
+// the words, a system-scope fence, then a sequence number the host spins on.  (A cudaMemcpyAsync + cudaStreamSynchronize
+// per matrix cost ~15-20 us of idle GPU each, twice per frame -- what bp_layer's mailbox already avoids for its counts.)
+constexpr int MAIL_WORDS = 1024;
+struct DistMail {
+    uint64_t words[MAIL_WORDS];
+    uint32_t err;
+    uint32_t seq;
+};
+__global__ void dist_gather_kernel(uint64_t *const *flag_arrays, int me, int g, uint64_t epoch, int *err, const uint64_t *matrix,
+                                   int words, DistMail *mail, uint32_t seq) {
+    const int t = threadIdx.x;
+    if (t < g) {
+        __threadfence_system();
+        *((volatile uint64_t *)(flag_arrays[t] + me)) = epoch;
+        const volatile uint64_t *mine = (const volatile uint64_t *)(flag_arrays[me] + t);
+        uint32_t spins = 0;
+        while (*mine < epoch) {
+            if (++spins > SPIN_LIMIT) {
+                *err = 2;
+                break;
+            }
+            if (spins > 4096) __nanosleep(1000);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (int i = t; i < words; i += blockDim.x) mail->words[i] = ((const volatile uint64_t *)matrix)[i];
+    __threadfence_system();
+    __syncthreads();
+    if (t == 0) {
+        mail->err = (uint32_t)*err;
+        __threadfence_system();
+        *((volatile uint32_t *)&mail->seq) = seq;
+    }
+}
+
 // A regular sample of `n` 64-bit words (every stride-th, at most SAMPLES; the rest of the row is ~0 = "no sample"),
 // shifted right by `shift`, plus one trailing word, stored as this rank's row of every rank's sample matrix.
 struct RowPtrs {
@@ -106,6 +143,8 @@ struct bp_dist {
     uint64_t **d_flag_arrays = nullptr; // device array of g pointers
     int *d_err = nullptr;
     uint64_t epoch = 0;
+    DistMail *h_mail = nullptr, *d_mail = nullptr; // pinned + device-mapped: the count matrices come back through it
+    uint32_t mail_seq = 0;
     uint64_t *h_mat = nullptr; // pinned landing buffer for the matrices
     size_t h_mat_words = 0;
     // protocol state
@@ -191,8 +230,34 @@ int barrier(bp_dist *D) {
 
 // Barrier, then this rank's copy of a matrix (rows x cols 64-bit words at arena offset `off`) on the host.
 int gather(bp_dist *D, size_t off, int rows, int cols, const uint64_t **out) {
-    DTRY(barrier(D));
     const size_t words = (size_t)rows * cols;
+    if (words <= (size_t)MAIL_WORDS) { // the count matrices: barrier + hand-over in one kernel, the host spins on the mailbox
+        ++D->epoch;
+        const uint32_t seq = ++D->mail_seq;
+        dist_gather_kernel<<<1, 256, 0, D->stream>>>(D->d_flag_arrays, D->me, D->g, D->epoch, D->d_err, (const uint64_t *)(D->arena + off),
+                                                      (int)words, D->d_mail, seq);
+        DCU(D, cudaGetLastError());
+        volatile DistMail *mb = D->h_mail;
+        for (unsigned spins = 1; mb->seq != seq; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if ((spins & 0xffffu) == 0) { // the stream must still be busy; anything else is an error
+                const cudaError_t e = cudaStreamQuery(D->stream);
+                if (e == cudaSuccess) {
+                    if (mb->seq == seq) break;
+                    return fail(D, BP_ERR_INTERNAL, "the stream drained without posting the count matrix");
+                }
+                if (e != cudaErrorNotReady) return fail(D, BP_ERR_CUDA, "waiting for the count matrix: %s", cudaGetErrorString(e));
+            }
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        if (D->h_mail->err) return fail(D, BP_ERR_INTERNAL, "device barrier timed out (a peer never arrived)");
+        memcpy(D->h_mat, (const void *)D->h_mail->words, words * sizeof(uint64_t));
+        *out = D->h_mat;
+        return BP_OK;
+    }
+    DTRY(barrier(D));
     DCU(D, cudaMemcpyAsync(D->h_mat, D->arena + off, words * sizeof(uint64_t), cudaMemcpyDeviceToHost, D->stream));
     int herr = 0;
     DCU(D, cudaMemcpyAsync(&herr, D->d_err, sizeof(int), cudaMemcpyDeviceToHost, D->stream));
@@ -343,6 +408,9 @@ int bp_dist_create(const bp_dist_config *cfg, bp_dist **out) {
     if (cudaMemset(D->d_err, 0, sizeof(int)) != cudaSuccess) return bail(BP_ERR_CUDA);
     D->h_mat_words = (size_t)D->g * std::max<size_t>(SAMPLES + 1, D->row_rec);
     if (cudaMallocHost((void **)&D->h_mat, D->h_mat_words * sizeof(uint64_t)) != cudaSuccess) return bail(BP_ERR_OOM);
+    if (cudaHostAlloc((void **)&D->h_mail, sizeof(DistMail), cudaHostAllocMapped) != cudaSuccess) return bail(BP_ERR_OOM);
+    memset(D->h_mail, 0, sizeof(DistMail));
+    if (cudaHostGetDevicePointer((void **)&D->d_mail, D->h_mail, 0) != cudaSuccess) return bail(BP_ERR_CUDA);
     if (D->g == 1) { // a single rank is its own (only) peer
         D->peer[0] = D->arena;
         uint64_t *fa = (uint64_t *)(D->arena + D->off_flags);
@@ -366,6 +434,7 @@ int bp_dist_destroy(bp_dist *D) {
     if (D->d_flag_arrays) cudaFree(D->d_flag_arrays);
     if (D->d_err) cudaFree(D->d_err);
     if (D->h_mat) cudaFreeHost(D->h_mat);
+    if (D->h_mail) cudaFreeHost(D->h_mail);
     if (D->own_stream && D->stream) cudaStreamDestroy(D->stream);
     delete D;
     return BP_OK;

@@ -62,6 +62,7 @@ template <class T, class IdT> struct EncodeArgs {
     const IdT *prev_last_id; // last ID of the previous extend since the tail began (or null)
     IdT *next_last_id;
     int *err;
+    const uint32_t *lut;   // [2^ENCODE_LUT_BITS] Morton spread table of the layer's dimension (built once by the host)
     EncodeCount count; // used by encode_kernel<.., COUNT = true> only
 };
 
@@ -128,8 +129,9 @@ __global__ void __launch_bounds__(ENCODE_THREADS) encode_kernel(const EncodeArgs
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 
     if (tid == 0) *(uint32_t *)sred = atomicAdd(a.tile_counter, 1u);
-    // the spread table: entry v = bits of v moved to positions DIM * i
-    for (uint32_t v = tid; v < (1u << ENCODE_LUT_BITS); v += ENCODE_THREADS) slut[v] = (uint32_t)(DIM == 2 ? spread2(v) : spread3(v));
+    // the spread table (entry v = bits of v moved to positions DIM * i) is copied, not computed: 2^10 five-step mask
+    // cascades per 1024-object tile were 13 % of the kernel's instructions (profiles/r2_cfg5_frame_kernels.txt)
+    for (uint32_t v = tid; v < (1u << ENCODE_LUT_BITS); v += ENCODE_THREADS) slut[v] = a.lut[v];
     __syncthreads();
     const uint32_t tile = *(uint32_t *)sred;
     __syncthreads();

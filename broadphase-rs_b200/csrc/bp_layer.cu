@@ -145,6 +145,7 @@ struct bp_layer {
     // only holds encoded records moves them into the top 3 bits of the IDs (ids_flagged) so that they
     // travel with the records; any other mutation strips them again
     DevBuf cell_flags;
+    DevBuf spread_lut; // 2^10-entry Morton spread table of the layer's dimension (encode_kernel)
     bool flags_valid = true; // every record of the tree has its flags in cell_flags
     bool ids_flagged = false;
 
@@ -631,6 +632,7 @@ template <int KIND, class IdT> struct Impl {
         TRY(ensure(L, L->scratch, sbytes));
         CU(L, cudaMemsetAsync(L->scratch.p, 0, sbytes, L->stream));
         a.tile_counter = (uint32_t *)L->scratch.p;
+        a.lut = (const uint32_t *)L->spread_lut.p;
         a.status = (uint64_t *)((char *)L->scratch.p + 64);
         // result accumulators: sums 0, and-masks all ones
         ExtendResult init;
@@ -1813,6 +1815,13 @@ int bp_layer_create(const bp_layer_config *cfg, bp_layer **out) {
     if (cudaMalloc((void **)&L->d_err, sizeof(int)) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMalloc((void **)&L->d_last, 16) != cudaSuccess) return bail(BP_ERR_OOM);
     if (cudaMemsetAsync(L->d_err, 0, sizeof(int), L->stream) != cudaSuccess) return bail(BP_ERR_CUDA);
+    {
+        std::vector<uint32_t> lut((size_t)1 << ENCODE_LUT_BITS);
+        for (uint32_t v = 0; v < lut.size(); ++v) lut[v] = (uint32_t)(L->dim == 2 ? spread2(v) : spread3(v));
+        if (ensure(L, L->spread_lut, lut.size() * sizeof(uint32_t)) != BP_OK) return bail(BP_ERR_OOM);
+        if (cudaMemcpyAsync(L->spread_lut.p, lut.data(), lut.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, L->stream) != cudaSuccess)
+            return bail(BP_ERR_CUDA); // (pageable source: the copy has been staged when the call returns)
+    }
     if (cudaStreamSynchronize(L->stream) != cudaSuccess) return bail(BP_ERR_CUDA);
     *L->h_err = 0;
     if (cfg->index_capacity) {
@@ -1843,6 +1852,7 @@ int bp_layer_destroy(bp_layer *L) {
     }
     release(L->scratch);
     release(L->cell_flags);
+    release(L->spread_lut);
     release(L->stage_bounds);
     release(L->stage_ids);
     release(L->src_idx);
