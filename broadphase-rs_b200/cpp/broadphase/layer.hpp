@@ -224,4 +224,57 @@ public:
     }
 };
 
+// One scene spread over the GPUs of an NVLink domain, one DistFrame per rank (one process per GPU).  No counterpart in the
+// reference crate (single process): frame() is clear -> extend -> par_sort -> [merge(static)] -> par_scan_filtered
+// (src/layer.rs:84-165, 449-520) of the whole distributed scene, run by ONE C-ABI call (bp_dist_frame, csrc/bp_dist.cu).
+// The host brings its own transport for the one thing that has to travel at start-up: an all-gather of every rank's blob.
+template <class Index> class DistFrame {
+    bp_dist *h_ = nullptr;
+    void ck(int st) const {
+        if (st != BP_OK) throw Error(st, bp_dist_last_error(h_));
+    }
+
+public:
+    DistFrame(int rank, int world, int device, size_t record_capacity, size_t pair_capacity, uint32_t min_depth = 0) {
+        bp_dist_config c{};
+        c.index_kind = Index::KIND;
+        c.min_depth = min_depth;
+        c.device = device;
+        c.rank = rank;
+        c.world = world;
+        c.record_capacity = record_capacity;
+        c.pair_capacity = pair_capacity;
+        const int st = bp_dist_create(&c, &h_);
+        if (st != BP_OK) throw Error(st, "bp_dist_create");
+    }
+    DistFrame(const DistFrame &) = delete;
+    DistFrame &operator=(const DistFrame &) = delete;
+    ~DistFrame() { bp_dist_destroy(h_); }
+
+    // this rank's blob; all_gather the blobs of ranks 0 .. world-1 (MPI_Allgather, a socket, a file) and connect()
+    std::vector<unsigned char> export_blob() {
+        std::vector<unsigned char> b(bp_dist_handle_bytes());
+        ck(bp_dist_export(h_, b.data()));
+        return b;
+    }
+    void connect(const std::vector<unsigned char> &all_blobs) { ck(bp_dist_connect(h_, all_blobs.data())); }
+    void set_static(const Bounds<Index::DIM> &system_bounds, const float *d_bounds, const uint32_t *d_ids, size_t n) {
+        ck(bp_dist_set_static(h_, system_bounds.min, d_bounds, d_ids, n));
+    }
+    // -> this rank's slice of the globally sorted, duplicate-free (later, earlier) pair list: device pointer + length,
+    // valid until the next call (like the reference's borrowed &Vec<(ID, ID)>)
+    std::pair<const uint32_t *, size_t> frame(const Bounds<Index::DIM> &system_bounds, const float *d_bounds, const uint32_t *d_ids, size_t n,
+                                              const bp_filter *filter = nullptr) {
+        const void *pairs = nullptr;
+        size_t count = 0;
+        ck(bp_dist_frame(h_, system_bounds.min, d_bounds, d_ids, n, filter, &pairs, &count));
+        return {static_cast<const uint32_t *>(pairs), count};
+    }
+    bp_dist_info last_info() const {
+        bp_dist_info i;
+        bp_dist_last_info(h_, &i);
+        return i;
+    }
+};
+
 } // namespace broadphase

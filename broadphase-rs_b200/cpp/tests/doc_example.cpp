@@ -28,7 +28,11 @@ int main() {
         for (auto id : hit) std::printf(" %llu", (unsigned long long)id);
         std::printf("\n");
         const bool query_ok = hit.size() == 1 && hit[0] == 11;
-        return (scan_ok && query_ok) ? 0 : 1;
+        // the sharded frame with a world of one rank (the same C++ path that runs over NVLink with more): an empty frame
+        DistFrame<Index64_3D> dist(0, 1, -1, 1 << 16, 1 << 16);
+        const auto none = dist.frame(system_bounds, nullptr, nullptr, 0);
+        std::printf("dist frame pairs=%zu\n", none.second);
+        return (scan_ok && query_ok && none.second == 0) ? 0 : 1;
     } catch (const Error &e) {
         std::printf("error: %s\n", e.what());
         return e.status == BP_ERR_CUDA ? 77 : 2; // 77: no GPU here

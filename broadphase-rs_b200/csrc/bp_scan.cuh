@@ -13,14 +13,24 @@
 // filter(id_j, id_i) }.  (DESIGN.md has the proof; tests/test_oracle.py checks the closed form
 // against the literal stack sweep.)
 //
-// Kernels:
-//   scan_runs_kernel   one thread per record: galloping search for the end of its run, compaction of
-//                      the non-empty runs and exclusive scan of their lengths (single pass, two
-//                      decoupled look-back chains), plus the first source of every work chunk.
-//   scan_emit_kernel   one CTA per chunk of 2048 (ancestor, descendant) work items regardless of
-//                      how they are distributed over the runs; applies the filter functor, compacts
-//                      the surviving pairs (look-back) and writes them coalesced.
-//   pair_unique_kernel adjacent-difference dedup of the sorted pairs + final (later, earlier) layout.
+// Kernels (DESIGN.md section 4, K3 / K4):
+//   scan_runs_kernel    4096-record tiles, keys staged by one TMA bulk copy + a 32-key halo.  lcp[p] = whole levels on which
+//                       keys p and p+1 agree; the run of record i ends at the first p >= i with lcp[p] < depth_i, found from
+//                       per-depth bitmaps (a warp transposes the 32 x 32 bit matrix of `~0 << (lcp + 1)` columns) with two
+//                       find-first-set steps, no key comparisons; runs that leave the tile use the halo, very long ones a
+//                       warp-cooperative search.  Non-empty runs are compacted, their lengths prefix-summed; a tile takes
+//                       its range of (sources, work items) with ONE packed 64-bit atomicAdd (the order of the sources is
+//                       irrelevant: the pairs are sorted afterwards).
+//   scan_chunks_kernel  every 4096-work-item chunk boundary is claimed by the run that contains it.
+//   scan_emit_kernel    one CTA per chunk of 4096 (ancestor, descendant) work items however they are spread over the runs:
+//                       an owner table + running maximum gives every item its run, the items are handed out striped
+//                       (coalesced descendant loads, broadcast ancestor), the filter is a compile-time functor, with DEDUP
+//                       a pair is emitted from the canonical one of the cells two objects share only; survivors are staged
+//                       and written coalesced (slots by one atomicAdd per chunk; identity emission writes straight out).
+//   count_scan_kernel + pair_scatter_kernel   counting sort of the pairs by later ID while they fit L2 (dense u32 IDs).
+//   pair_finish_kernel  after the radix passes over the later ID: orders every (tiny) group of equal later IDs by the
+//                       earlier ID, removes duplicates, compacts in order (look-back), writes the final (later, earlier)
+//                       layout.  pair_unique_kernel: the adjacent-difference dedup behind the full-width fallback sort.
 #pragma once
 
 #include "bp_common.cuh"

@@ -42,6 +42,26 @@ def test_no_cpu_fallback(bp):
     assert e.value.status == 2
 
 
+def test_dist_context_arguments(bp):
+    """bp_dist_create validates its configuration before it touches a device; without one it fails like bp_layer_create."""
+    from broadphase_rs_b200._lib import DistConfig
+    L = bp.lib()
+    h = ctypes.c_void_p()
+    assert L.bp_dist_handle_bytes() >= 64                                    # a CUDA IPC handle + the layout check
+    assert L.bp_dist_create(None, ctypes.byref(h)) == 1
+    for cfg in (DistConfig(2, 0, -1, 0, 0, 1 << 10, 1 << 10),                # world 0
+                DistConfig(2, 0, -1, 0, 17, 1 << 10, 1 << 10),               # more than 16 ranks
+                DistConfig(2, 0, -1, 3, 2, 1 << 10, 1 << 10),                # rank outside the world
+                DistConfig(0, 0, -1, 0, 1, 1 << 10, 1 << 10)):               # Index32_2D: the sharded frame is for the 64-bit indices
+        assert L.bp_dist_create(ctypes.byref(cfg), ctypes.byref(h)) == 1 and not h.value
+    if bp.device_count() == 0:
+        cfg = DistConfig(2, 0, -1, 0, 1, 1 << 10, 1 << 10)
+        assert L.bp_dist_create(ctypes.byref(cfg), ctypes.byref(h)) == 2     # BP_ERR_CUDA: no CPU fallback
+    assert L.bp_dist_destroy(None) == 0
+    assert L.bp_dist_frame(None, None, None, None, 0, None, None, None) == 1
+    assert L.bp_dist_layer(None, 0) is None
+
+
 def test_invalid_arguments(bp):
     from broadphase_rs_b200._lib import LayerConfig
     L = bp.lib()
