@@ -9,9 +9,9 @@ SO_PATH = os.path.join(_HERE, "libbroadphase_b200.so")
 BP_OK = 0
 STATUS = {0: "BP_OK", 1: "BP_ERR_INVALID_ARG", 2: "BP_ERR_CUDA", 3: "BP_ERR_OOM", 4: "BP_ERR_TOO_LARGE",
           5: "BP_ERR_INTERNAL", 6: "BP_ERR_MISMATCH"}
-BP_K_COUNT = 12
+BP_K_COUNT = 13
 KERNEL_CLASSES = ["encode", "sort_hist", "sort_pass", "merge", "scan_runs", "scan_emit", "pair_hist", "pair_pass",
-                  "pair_unique", "misc", "query", "partition"]
+                  "pair_unique", "misc", "query", "partition", "sort_finish"]
 
 
 class BpError(RuntimeError):
@@ -121,6 +121,7 @@ SYMBOLS = {
     "bp_version": (_i, []),
     "bp_device_count": (_i, [_P(_i)]),
     "bp_plan_radix_passes": (_i, [_u64, _P(_u32), _P(_u32), _i]),
+    "bp_plan_sort_finish": (_i, [_u64, _u64, _P(_u64), _P(_u32)]),
 }
 
 _lib = None

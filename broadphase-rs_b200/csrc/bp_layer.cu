@@ -132,6 +132,7 @@ struct bp_layer {
     uint64_t id_first = 0, id_last = 0; // IDs of the first / last object extended since the last clear (bp_layer_id_order)
     uint64_t n_invalid = 0;
     uint64_t n_halo = 0; // records [0, n_halo) only act as ancestors in scan (multi-GPU halos)
+    uint64_t last_raw_pairs = 0; // raw pairs of the last scan that took the one-kernel path (sizes the next scan's output)
     // Layer::merge of a sorted layer into a sorted layer is deferred: the other layer's records are not copied behind ours,
     // the next sort merges the two runs straight out of the two layers' buffers (one read of the other tree instead of
     // copy + read).  Every other access to this layer's records, and every call that may change the other layer,
@@ -140,6 +141,9 @@ struct bp_layer {
     uint64_t lazy_n = 0;
     std::vector<bp_layer *> lazy_readers;   // layers holding a deferred merge from this one
     int radix_bits_cap = 0; // BP_RADIX_BITS (tuning aid): widest radix digit the sorts may use; 0 = no cap
+    uint64_t sort_finish_min = 1ull << 18; // record sorts of at least this many records may take the "top bits + finish" plan
+                                           // (it ends with a host round trip); BP_SORT_FINISH_MIN, 0 = never
+    uint32_t sort_finish_cooldown = 0;     // sorts to go before the plan is tried again after a group overflowed its window
     bool scan_dedup = true; // bp_layer_set_scan_dedup: the scan may emit every ID pair from its canonical shared cell only
     // dedup at the source: encode writes 3 cell flags per record (cell_flags); a full sort of a tree that
     // only holds encoded records moves them into the top 3 bits of the IDs (ids_flagged) so that they
@@ -356,7 +360,7 @@ void collect_profile(bp_layer *L) {
     static const bool timeline = getenv("BP_TIMELINE") != nullptr;
     if (timeline && !L->prof_events.empty()) {
         static const char *names[BP_K_COUNT] = {"encode", "sort_hist", "sort_pass", "merge", "scan_runs", "scan_emit",
-                                                "pair_hist", "pair_pass", "pair_unique", "misc", "query", "partition"};
+                                                "pair_hist", "pair_pass", "pair_unique", "misc", "query", "partition", "sort_finish"};
         float prev_end = 0.f;
         for (ProfEvent &pe : L->prof_events) {
             float t0 = 0.f, t1 = 0.f;
@@ -424,6 +428,36 @@ int plan_passes(uint64_t mask, RadixPlan &plan, int first = 0, int W = 8) {
     }
     plan.npasses = np;
     return np;
+}
+
+// "Top bits + finish" plan of a record sort (record_finish_kernel, bp_radix.cuh): radix passes over the highest varying key
+// bits only -- whole 8-bit passes, enough of them that a group of records agreeing on those bits is expected to hold at most
+// ~8 records (2^bits >= cnt / 8) -- and one finish pass that orders every group by the rest.  Taken when it replaces at
+// least two radix passes (the finish pass costs about one).  *top = the bits the radix passes sort on; records with equal
+// (key >> *gshift) form a group.
+bool plan_top_bits(uint64_t kmask, uint64_t cnt, uint64_t *top, uint32_t *gshift) {
+    const int nv = __builtin_popcountll(kmask);
+    RadixPlan full;
+    memset(&full, 0, sizeof full);
+    const int np_full = plan_passes(kmask, full, 0, 8);
+    if (np_full < 3 || cnt < 2) return false;
+    const int lg = 64 - __builtin_clzll(cnt - 1); // ceil(log2(cnt))
+    const int want = std::max(lg - 3, 8);
+    const int nbits = std::min(8 * ((want + 7) / 8), nv);
+    if (nbits >= nv) return false;
+    uint64_t m = kmask;
+    int low = 0;
+    for (int i = 0; i < nbits; ++i) {
+        low = 63 - __builtin_clzll(m);
+        m &= ~(1ull << low);
+    }
+    const uint64_t t = kmask & ~((1ull << low) - 1ull);
+    RadixPlan tp;
+    memset(&tp, 0, sizeof tp);
+    if (plan_passes(t, tp, 0, 8) + 2 > np_full) return false;
+    *top = t;
+    *gshift = (uint32_t)low;
+    return true;
 }
 
 // scratch layout for one radix sort: [hist 16*256 u32][counters 16 u32][status passes*tiles*256 u32]
@@ -739,10 +773,77 @@ template <int KIND, class IdT> struct Impl {
         bool in_alt2 = false;
         // (the flags can only ride along when the key passes are the first thing that touches the records)
         const uint8_t *vf = (fold_flags && !(need_id_passes && imask)) ? fold_flags + off : nullptr;
-        TRY((radix_sort<K, IdT>(L, k0, v0, k1, v1, (uint32_t)cnt, nullptr, kmask, BP_K_SORT_HIST, BP_K_SORT_PASS, &passes,
-                                &in_alt2, sizeof(K) + sizeof(IdT), vf, src_k, src_v)));
+        // Multi-depth scenes have 40-60 varying key bits but only ~log2(cnt) bits of position: radix passes over the top
+        // bits, then one finish pass that orders the (tiny) groups of records agreeing on them (plan_top_bits).
+        uint64_t top = 0;
+        uint32_t gshift = 0;
+        bool finish = false;
+        if (L->sort_finish_min && cnt >= L->sort_finish_min) {
+            if (L->sort_finish_cooldown)
+                --L->sort_finish_cooldown; // a recent sort met a group beyond the finish window: plain passes for a while
+            else
+                finish = plan_top_bits(kmask, cnt, &top, &gshift);
+        }
+        TRY((radix_sort<K, IdT>(L, k0, v0, k1, v1, (uint32_t)cnt, nullptr, finish ? top : kmask, BP_K_SORT_HIST, BP_K_SORT_PASS,
+                                &passes, &in_alt2, sizeof(K) + sizeof(IdT), vf, src_k, src_v)));
         if (flags_folded) *flags_folded = vf != nullptr && passes > 0;
         total_passes += passes;
+        if (finish && passes) {
+            RecordFinishArgs<K, IdT> fa;
+            fa.kin = in_alt2 ? k1 : k0;
+            fa.vin = in_alt2 ? v1 : v0;
+            fa.kout = in_alt2 ? k0 : k1;
+            fa.vout = in_alt2 ? v0 : v1;
+            fa.n = (uint32_t)cnt;
+            fa.gshift = gshift;
+            fa.big = &L->d_tot->pad;
+            // what orders a group: the varying bits below gshift, as one bit-field or two around their widest gap
+            const uint64_t lowmask = kmask & ((1ull << gshift) - 1ull);
+            int f0 = 0, l0 = 0, f1 = 0, l1 = 0;
+            if (lowmask) {
+                const int lo = __builtin_ctzll(lowmask), hi = 63 - __builtin_clzll(lowmask);
+                int gap_at = -1, gap_len = 0;
+                for (int b = lo, run = 0; b <= hi; ++b) {
+                    run = ((lowmask >> b) & 1ull) ? 0 : run + 1;
+                    if (run > gap_len) gap_len = run, gap_at = b - run + 1;
+                }
+                f0 = lo;
+                l0 = (gap_len ? gap_at : hi + 1) - lo;
+                if (gap_len) f1 = gap_at + gap_len, l1 = hi + 1 - f1;
+            }
+            fa.shift0 = (uint32_t)f0;
+            fa.bits0 = (uint32_t)l0;
+            fa.mask0 = l0 >= 32 ? 0xffffffffu : (1u << l0) - 1u;
+            fa.shift1 = (uint32_t)f1;
+            fa.mask1 = l1 >= 32 ? 0xffffffffu : (1u << l1) - 1u;
+            CU(L, cudaMemsetAsync(L->d_tot, 0, sizeof(ScanTotals), L->stream));
+            {
+                LaunchScope ls(L, BP_K_SORT_FINISH, 2.0 * (double)cnt * (sizeof(K) + sizeof(IdT)));
+                const uint32_t ftiles = (uint32_t)((cnt + RFIN_TILE - 1) / RFIN_TILE);
+                static const bool walk = getenv("BP_SORT_FINISH_WALK") && atoi(getenv("BP_SORT_FINISH_WALK")) != 0;
+                if (walk)
+                    record_finish_walk_kernel<K, IdT><<<ftiles, RFIN_THREADS, 0, L->stream>>>(fa);
+                else if (l0 + l1 <= 32)
+                    record_finish_kernel<K, IdT, uint32_t><<<ftiles, RFIN_THREADS, 0, L->stream>>>(fa);
+                else
+                    record_finish_kernel<K, IdT, uint64_t><<<ftiles, RFIN_THREADS, 0, L->stream>>>(fa);
+            }
+            TRY(check_launch(L, "record_finish_kernel"));
+            in_alt2 = !in_alt2;
+            TRY(fetch_totals(L));
+            if (L->h_tot->pad) {
+                // Some group is larger than the finish window (many records in one small region of space): those groups were
+                // copied through unchanged, so the buffer still is a stable permutation -- sort it the long way.
+                L->sort_finish_cooldown = 32;
+                K *fk0 = in_alt2 ? k1 : k0, *fk1 = in_alt2 ? k0 : k1;
+                IdT *fv0 = in_alt2 ? v1 : v0, *fv1 = in_alt2 ? v0 : v1;
+                bool in_alt3 = false;
+                TRY((radix_sort<K, IdT>(L, fk0, fv0, fk1, fv1, (uint32_t)cnt, nullptr, kmask, BP_K_SORT_HIST, BP_K_SORT_PASS,
+                                        &passes, &in_alt3, sizeof(K) + sizeof(IdT))));
+                total_passes += passes;
+                in_alt2 = in_alt2 != in_alt3;
+            }
+        }
         if (src_k && !passes) { // nothing to sort by: the records still have to arrive in the tree
             CU(L, cudaMemcpyAsync(k0, src_k, cnt * sizeof(K), cudaMemcpyDeviceToDevice, L->stream));
             CU(L, cudaMemcpyAsync(v0, src_v, cnt * sizeof(IdT), cudaMemcpyDeviceToDevice, L->stream));
@@ -888,6 +989,97 @@ template <int KIND, class IdT> struct Impl {
         return dedup ? emit_fk<true>(L, a, fk, chunks, bytes) : emit_fk<false>(L, a, fk, chunks, bytes);
     }
 
+    template <int FK, bool DEDUP> static int launch_groups(bp_layer *L, GroupScanArgs<K, IdT> &a, uint32_t tiles, double bytes) {
+        LaunchScope ls(L, BP_K_SCAN_EMIT, bytes);
+        scan_groups_kernel<K, IdT, FK, DEDUP><<<tiles, GRP_THREADS, 0, L->stream>>>(a);
+        return BP_OK;
+    }
+    template <bool DEDUP> static int groups_fk(bp_layer *L, GroupScanArgs<K, IdT> &a, int fk, uint32_t tiles, double bytes) {
+        switch (fk) {
+        case BP_FILTER_NONE: TRY((launch_groups<BP_FILTER_NONE, DEDUP>(L, a, tiles, bytes))); break;
+        case BP_FILTER_ID_PARITY: TRY((launch_groups<BP_FILTER_ID_PARITY, DEDUP>(L, a, tiles, bytes))); break;
+        case BP_FILTER_XOR_MASK: TRY((launch_groups<BP_FILTER_XOR_MASK, DEDUP>(L, a, tiles, bytes))); break;
+        case BP_FILTER_CATEGORY: TRY((launch_groups<BP_FILTER_CATEGORY, DEDUP>(L, a, tiles, bytes))); break;
+        case BP_FILTER_SPHERES: TRY((launch_groups<BP_FILTER_SPHERES, DEDUP>(L, a, tiles, bytes))); break;
+        default: return fail(L, BP_ERR_INVALID_ARG, "unknown filter kind %d", fk);
+        }
+        return check_launch(L, "scan_groups_kernel");
+    }
+
+    // The scan of a tree whose records all sit at one depth (scan_groups_kernel): 0 = done (*out_raw pairs in praw[0]),
+    // 1 = take the general path (a same-ID item or a crowded cell turned up), < 0 = -status.
+    static int scan_uniform(bp_layer *L, int fk, const FilterArgs &fa, uint64_t *out_raw) {
+        constexpr bool wide = sizeof(IdT) == 8;
+        const uint64_t R = L->n_records;
+        const uint32_t tiles = (uint32_t)((R + GRP_TILE - 1) / GRP_TILE);
+        const bool dedup = L->ids_flagged && L->n_halo == 0 && L->scan_dedup;
+        // the output is sized from the last scan of this layer (a frame loop: no second launch), else from the tree
+        uint64_t cap = std::max<uint64_t>(L->last_raw_pairs + L->last_raw_pairs / 8 + 4096, R / 2 + R / 4 + 4096);
+        cap = std::max<uint64_t>(cap, L->praw[0].cap / sizeof(uint64_t));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+#define BP_TRYN(expr)                  \
+    do {                               \
+        const int s__ = (expr);        \
+        if (s__ != BP_OK) return -s__; \
+    } while (0)
+            BP_TRYN(ensure(L, L->praw[0], cap * sizeof(uint64_t)));
+            if (wide) BP_TRYN(ensure(L, L->praw_b[0], cap * sizeof(uint64_t)));
+            BP_TRYN(ensure(L, L->scratch, 64));
+            if (cudaMemsetAsync(L->d_tot, 0, sizeof(ScanTotals), L->stream) != cudaSuccess ||
+                cudaMemsetAsync(L->scratch.p, 0, 64, L->stream) != cudaSuccess)
+                return -fail(L, BP_ERR_CUDA, "cudaMemsetAsync failed");
+            GroupScanArgs<K, IdT> ga;
+            ga.keys = keys(L, L->cur);
+            ga.ids = ids(L, L->cur);
+            ga.n = (uint32_t)R;
+            ga.id_mask = L->ids_flagged ? (IdT)((((IdT)1) << (8 * sizeof(IdT) - 3)) - 1) : (IdT) ~(IdT)0;
+            ga.first_owned = (uint32_t)std::min<uint64_t>(L->n_halo, R);
+            ga.out_packed = wide ? nullptr : (uint64_t *)L->praw[0].p;
+            ga.out_a = wide ? (uint64_t *)L->praw[0].p : nullptr;
+            ga.out_b = wide ? (uint64_t *)L->praw_b[0].p : nullptr;
+            ga.capacity = cap;
+            ga.pair_counter = (unsigned long long *)L->scratch.p;
+            ga.work_counter = (unsigned long long *)L->scratch.p + 1;
+            ga.later_count = nullptr;
+            L->pair_cnt_n = 0;
+            // (the counting sort of the pairs: same rule as the general path, on the capacity instead of the work-item count)
+            if (L->want_pair_counts && !wide && L->id_or < (1ull << 22) && cap <= (1ull << 22)) {
+                const int id_bits = 64 - (L->id_or ? __builtin_clzll(L->id_or) : 64);
+                const uint64_t M = std::max<uint64_t>(4, 1ull << id_bits);
+                BP_TRYN(ensure(L, L->pair_cnt, M * sizeof(uint32_t)));
+                if (cudaMemsetAsync(L->pair_cnt.p, 0, M * sizeof(uint32_t), L->stream) != cudaSuccess)
+                    return -fail(L, BP_ERR_CUDA, "cudaMemsetAsync failed");
+                ga.later_count = (uint32_t *)L->pair_cnt.p;
+                L->pair_cnt_n = M;
+            }
+            ga.totals = L->d_tot;
+            ga.filter = fa;
+            const double bytes = (double)R * (sizeof(K) + sizeof(IdT));
+            BP_TRYN(dedup ? groups_fk<true>(L, ga, fk, tiles, bytes) : groups_fk<false>(L, ga, fk, tiles, bytes));
+            if (cudaMemcpyAsync(&L->d_tot->n_raw_pairs, L->scratch.p, 8, cudaMemcpyDeviceToDevice, L->stream) != cudaSuccess ||
+                cudaMemcpyAsync(&L->d_tot->n_work, (char *)L->scratch.p + 8, 8, cudaMemcpyDeviceToDevice, L->stream) != cudaSuccess)
+                return -fail(L, BP_ERR_CUDA, "cudaMemcpyAsync failed");
+            BP_TRYN(fetch_totals(L));
+#undef BP_TRYN
+            if (L->h_tot->pad || L->h_tot->any_same_id) {
+                L->pair_cnt_n = 0;
+                return 1;
+            }
+            const uint64_t P = L->h_tot->n_raw_pairs;
+            if (P <= cap) {
+                L->stats.n_work_items = L->h_tot->n_work;
+                L->stats.n_raw_pairs = P;
+                L->stats.algo_bytes[BP_K_SCAN_EMIT] += (double)P * 2.0 * sizeof(IdT);
+                L->last_raw_pairs = P;
+                *out_raw = P;
+                return 0;
+            }
+            if (P > MAX_RECORDS) return -fail(L, BP_ERR_TOO_LARGE, "scan would emit %llu pairs (limit 2^30)", (unsigned long long)P);
+            cap = P; // the kernel counted everything it could not write: once more with room for it
+        }
+        return -fail(L, BP_ERR_INTERNAL, "uniform scan did not converge");
+    }
+
     static int fetch_totals(bp_layer *L) {
         unsigned int seq = 0;
         TRY(post_mail(L, 1, L->d_tot, (int)(sizeof(ScanTotals) / 8), &seq));
@@ -922,6 +1114,17 @@ template <int KIND, class IdT> struct Impl {
                 TRY(ensure(L, L->filter_table, f->n_table * row));
                 CU(L, cudaMemcpyAsync(L->filter_table.p, f->table, f->n_table * row, cudaMemcpyHostToDevice, L->stream));
                 fa.table = (const uint32_t *)L->filter_table.p;
+            }
+        }
+
+        // ---- every record at the same depth (no depth bit differs between two keys): one fused kernel ----
+        {
+            constexpr uint64_t DEPTH_FIELD = (1ull << T::DEPTH_BITS) - 1ull;
+            static const bool off = getenv("BP_SCAN_UNIFORM") && atoi(getenv("BP_SCAN_UNIFORM")) == 0; // tuning aid
+            if (!off && ((L->key_or & ~L->key_and) & DEPTH_FIELD) == 0) {
+                const int r = scan_uniform(L, fk, fa, out_raw);
+                if (r < 0) return -r;
+                if (r == 0) return BP_OK;
             }
         }
 
@@ -1041,7 +1244,7 @@ template <int KIND, class IdT> struct Impl {
 
     // Sorts the P_raw raw pairs in praw[0] (+ praw_b[0]) and removes duplicates into pout.
     static int finish_pairs(bp_layer *L, uint64_t P_raw) {
-        const bool wide = sizeof(IdT) == 8;
+        constexpr bool wide = sizeof(IdT) == 8;
         L->n_pairs = 0;
         L->stats.n_pairs = 0;
         L->stats.pair_sort_passes = 0;
@@ -1059,6 +1262,7 @@ template <int KIND, class IdT> struct Impl {
         uint64_t *b0 = wide ? (uint64_t *)L->praw_b[0].p : nullptr, *b1 = wide ? (uint64_t *)L->praw_b[1].p : nullptr;
         int passes = 0, total_passes = 0;
         bool in_alt = false;
+        uint32_t fin_gshift = 32; // pair_finish_kernel: one group per later ID
         if (L->pairs_grouped) {
             // (query, ID) pairs of a batched query: written query by query, only the order inside a group is open
         } else if (!wide && L->pair_cnt_n) {
@@ -1083,7 +1287,29 @@ template <int KIND, class IdT> struct Impl {
             L->pair_cnt_n = 0; // consumed
             in_alt = true;
         } else if (!wide) {
-            TRY((radix_sort<uint64_t, NoVal>(L, a0, (NoVal *)nullptr, a1, (NoVal *)nullptr, (uint32_t)P_raw, nullptr, imask << 32,
+            // The finish kernel orders whole packed pairs inside a group, so the lowest bits of the later ID need no radix
+            // pass of their own when leaving them out saves one: a group then holds the pairs of 2^drop later IDs -- taken
+            // while that is expected to be at most ~6 pairs (2^25 IDs, 49 M pairs: 3 passes over 24 bits instead of 4).
+            uint64_t lmask = imask & 0xffffffffull;
+            {
+                RadixPlan pl;
+                memset(&pl, 0, sizeof pl);
+                const int np_all = plan_passes(lmask << 32, pl, 0, 8);
+                const int nb = __builtin_popcountll(lmask);
+                uint64_t m = lmask;
+                for (int drop = 1; drop <= 3 && drop < nb && np_all >= 2; ++drop) {
+                    m &= m - 1; // without its lowest varying bit
+                    static const double max_group = getenv("BP_PAIR_DROP_MAX_GROUP") ? atof(getenv("BP_PAIR_DROP_MAX_GROUP")) : 6.0; // tuning aid
+                    if ((double)P_raw * (double)(1u << drop) > max_group * (double)(1ull << nb)) break;
+                    memset(&pl, 0, sizeof pl);
+                    if (plan_passes(m << 32, pl, 0, 8) < np_all) {
+                        lmask = m;
+                        fin_gshift = 32u + (uint32_t)__builtin_ctzll(m);
+                        break;
+                    }
+                }
+            }
+            TRY((radix_sort<uint64_t, NoVal>(L, a0, (NoVal *)nullptr, a1, (NoVal *)nullptr, (uint32_t)P_raw, nullptr, lmask << 32,
                                              BP_K_PAIR_HIST, BP_K_PAIR_PASS, &passes, &in_alt, 8)));
         } else {
             TRY((radix_sort<uint64_t, uint64_t>(L, a0, b0, a1, b1, (uint32_t)P_raw, nullptr, imask, BP_K_PAIR_HIST, BP_K_PAIR_PASS,
@@ -1104,6 +1330,7 @@ template <int KIND, class IdT> struct Impl {
             fa.in_a = wide ? a0 : nullptr;
             fa.in_b = b0;
             fa.n = (uint32_t)P_raw;
+            fa.gshift = fin_gshift;
             fa.out = (IdT *)L->pout.p;
             fa.tile_counter = (uint32_t *)L->scratch.p;
             fa.status = (uint64_t *)((char *)L->scratch.p + 64);
@@ -1111,7 +1338,14 @@ template <int KIND, class IdT> struct Impl {
             fa.err = L->d_err;
             {
                 LaunchScope ls(L, BP_K_PAIR_UNIQUE, (double)P_raw * 2.0 * sizeof(IdT));
-                pair_finish_kernel<IdT><<<ftiles, FIN_THREADS, 0, L->stream>>>(fa);
+                if constexpr (!wide) {
+                    if (fin_gshift != 32)
+                        pair_finish_kernel<IdT, true><<<ftiles, FIN_THREADS, 0, L->stream>>>(fa);
+                    else
+                        pair_finish_kernel<IdT, false><<<ftiles, FIN_THREADS, 0, L->stream>>>(fa);
+                } else {
+                    pair_finish_kernel<IdT, false><<<ftiles, FIN_THREADS, 0, L->stream>>>(fa);
+                }
             }
             TRY(check_launch(L, "pair_finish_kernel"));
             TRY(fetch_totals(L));
@@ -1755,6 +1989,15 @@ int bp_device_count(int *out) {
     return BP_OK;
 }
 
+int bp_plan_sort_finish(uint64_t varying_mask, uint64_t n_records, uint64_t *out_top_mask, uint32_t *out_group_shift) {
+    uint64_t top = 0;
+    uint32_t gshift = 0;
+    const bool yes = plan_top_bits(varying_mask, n_records, &top, &gshift);
+    if (out_top_mask) *out_top_mask = yes ? top : varying_mask;
+    if (out_group_shift) *out_group_shift = yes ? gshift : 0u;
+    return yes ? 1 : 0;
+}
+
 int bp_plan_radix_passes(uint64_t varying_mask, uint32_t *out_shift, uint32_t *out_bits, int max_passes) {
     RadixPlan plan;
     memset(&plan, 0, sizeof plan);
@@ -1793,6 +2036,7 @@ int bp_layer_create(const bp_layer_config *cfg, bp_layer **out) {
     L->min_depth = cfg->min_depth;
     memset(&L->stats, 0, sizeof L->stats);
     if (const char *e = getenv("BP_RADIX_BITS")) L->radix_bits_cap = atoi(e); // tuning aid: 8 = the 8-bit pass everywhere
+    if (const char *e = getenv("BP_SORT_FINISH_MIN")) L->sort_finish_min = strtoull(e, nullptr, 10);
     DeviceGuard g(dev);
     auto bail = [&](int st) {
         bp_layer_destroy(L);

@@ -524,6 +524,186 @@ __global__ void __launch_bounds__(THREADS, MINB) radix_pass_kernel(const RadixPa
         radix_pass_tile<K, V, Op, THREADS, ITEMS, false, RB>(a, smem_raw, tile, tile_n);
 }
 
+// ---- record finish: the low key bits, ordered group by group ------------------------------------------------
+// R records have only ~log2(R) bits of "position" in them: once a stable LSD sort has ordered the records by the TOP
+// ~log2(R) - 3 varying key bits, every group of records that agree on those bits is a handful of neighbours, and
+// ordering such a group by the remaining low bits is a few comparisons per record -- far cheaper than one more full
+// radix pass per 8 low bits (multi-depth scenes: 43-48 varying key bits = 6 passes; 3 passes + this kernel instead).
+// The same idea as pair_finish_kernel, without its compaction: the output position of a record is
+//      group start + #(records of the group that sort before it),
+// "before" = smaller key, or equal key and earlier in the input (the passes before were stable, so among equal keys the
+// input order is the order the tie-break wants -- ascending IDs, see Impl::sort_range).
+// A tile reads its records plus RFIN_HALO neighbours on either side; a group of more than RFIN_HALO records is "big" --
+// every one of its records can tell, whichever tile it is in -- and is copied through unchanged while `*big` is raised:
+// the output then still is a stable permutation of the input and the host runs the remaining radix passes over it.
+constexpr int RFIN_THREADS = 256;
+constexpr int RFIN_IPT = 8;
+constexpr int RFIN_TILE = RFIN_THREADS * RFIN_IPT;
+constexpr int RFIN_HALO = 256;
+constexpr int RFIN_WIN = RFIN_TILE + 2 * RFIN_HALO;   // window of a tile: its records + RFIN_HALO neighbours on either side
+constexpr int RFIN_WBITS = 12;                         // bits of a window position
+constexpr int RFIN_ROWS = RFIN_WIN / 32;               // words of the group-head bitmap
+static_assert(RFIN_HALO == RFIN_THREADS && RFIN_WIN <= (1 << RFIN_WBITS) && RFIN_HALO % 32 == 0, "window layout");
+
+template <class K, class V> struct RecordFinishArgs {
+    const K *kin;
+    const V *vin;
+    K *kout;
+    V *vout;
+    uint32_t n;
+    uint32_t gshift;   // records with equal (key >> gshift) form a group
+    unsigned int *big; // raised when a group exceeds RFIN_HALO records
+    // the varying key bits below gshift as one or two bit-fields, (key >> shift) & mask, the second stacked above the
+    // first's `bits0` bits -- what orders a group (used when they fit 32 - RFIN_WBITS bits)
+    uint32_t shift0, mask0, bits0, shift1, mask1;
+};
+
+// The plain form of the rule, kept as the executable statement of it (BP_SORT_FINISH_WALK=1 selects it): every record walks
+// its group in the staged keys.
+template <class K, class V>
+__global__ void __launch_bounds__(RFIN_THREADS) record_finish_walk_kernel(const RecordFinishArgs<K, V> a) {
+    __shared__ K sk[RFIN_WIN];
+    const unsigned tid = threadIdx.x;
+    const uint32_t t0 = blockIdx.x * (uint32_t)RFIN_TILE;
+    if (t0 >= a.n) return;
+    const uint32_t w0 = t0 >= (uint32_t)RFIN_HALO ? t0 - (uint32_t)RFIN_HALO : 0u;
+    const uint32_t w1 = (uint32_t)min((uint64_t)a.n, (uint64_t)t0 + RFIN_TILE + RFIN_HALO);
+    const uint32_t wn = w1 - w0;
+    for (uint32_t i = tid; i < wn; i += RFIN_THREADS) sk[i] = ld_stream(a.kin + w0 + i);
+    // the payloads of this thread's records: in flight while the keys settle (striped: coalesced)
+    V val[RFIN_IPT];
+#pragma unroll
+    for (int q = 0; q < RFIN_IPT; ++q) {
+        const uint32_t i = t0 + q * RFIN_THREADS + tid;
+        if (i < a.n) val[q] = ld_stream(a.vin + i);
+    }
+    __syncthreads();
+    const uint32_t gs = a.gshift;
+    bool any_big = false;
+#pragma unroll
+    for (int q = 0; q < RFIN_IPT; ++q) {
+        const uint32_t i = t0 + q * RFIN_THREADS + tid;
+        if (i >= a.n) break;
+        const uint32_t li = i - w0;
+        const K x = sk[li];
+        const K g = x >> gs;
+        uint32_t h = li, pos = 0;
+        while (h > 0 && li - h <= (uint32_t)RFIN_HALO) { // records of the group before this one: smaller or equal keys come first
+            const K y = sk[h - 1];
+            if ((y >> gs) != g) break;
+            --h;
+            pos += (y <= x) ? 1u : 0u;
+        }
+        uint32_t e = li + 1;
+        while (e < wn && e - li <= (uint32_t)RFIN_HALO) { // ... and after it: only strictly smaller keys come first
+            const K y = sk[e];
+            if ((y >> gs) != g) break;
+            pos += (y < x) ? 1u : 0u;
+            ++e;
+        }
+        // both ends seen <=> the neighbour on either side is a record of another group (or the array ends there)
+        const bool closed_l = h == 0 ? w0 == 0 : (sk[h - 1] >> gs) != g;
+        const bool closed_r = e == wn ? w1 == a.n : (sk[e] >> gs) != g;
+        const bool big = !closed_l || !closed_r || e - h > (uint32_t)RFIN_HALO;
+        any_big |= big;
+        const uint32_t out = big ? i : w0 + h + pos;
+        a.kout[out] = x;
+        a.vout[out] = val[q];
+    }
+    if (any_big) *a.big = 1u;
+}
+
+// The fast form.  No key is compared twice and no group boundary is searched for:
+//   * group heads ("my top bits differ from my predecessor's") go into a bitmap of the window, one ballot per 32 records;
+//     a record finds the start and the end of its group with a count-leading-zeros / find-first-set on that bitmap;
+//   * what orders a group is reduced to ONE word per record, C = the varying key bits below gshift squeezed together
+//     (config 3: 4 depth bits + 18 origin bits), so the rank of a record is the number of words of its group before it that
+//     are not larger plus the number after it that are smaller: one shared-memory load, one comparison, one add per member.
+// C is 32 bits when those bits fit (two bit-fields around their widest gap), else the low gshift bits as they are.
+// INNER: every position of the window is a record (all tiles but those at the two ends of the array).
+template <class K, class V, class C, bool INNER>
+__device__ __forceinline__ void record_finish_tile(const RecordFinishArgs<K, V> &a, C *sc, uint32_t *heads, const uint32_t t0) {
+    constexpr int SLOTS = RFIN_WIN / RFIN_THREADS; // window positions per thread: slot j of thread t is position j * THREADS + t
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const int32_t n = (int32_t)a.n;
+    const int32_t wb = (int32_t)t0 - RFIN_HALO; // index of window position 0 (negative at the start of the array: empty positions)
+    const uint32_t gs = a.gshift;
+    K kk[SLOTS];
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) { // all the loads first: one memory round trip for the window
+        const int32_t g = wb + j * RFIN_THREADS + (int32_t)tid;
+        kk[j] = (INNER || (g >= 0 && g < n)) ? ld_stream(a.kin + g) : (K)0;
+    }
+    V val[RFIN_IPT];
+#pragma unroll
+    for (int q = 0; q < RFIN_IPT; ++q) {
+        const int32_t g = (int32_t)t0 + q * RFIN_THREADS + (int32_t)tid;
+        if (INNER || g < n) val[q] = ld_stream(a.vin + g);
+    }
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+        const uint32_t w = j * RFIN_THREADS + tid;
+        const int32_t g = wb + (int32_t)w;
+        const K k = kk[j];
+        K prev = __shfl_up_sync(BP_FULL_MASK, k, 1);
+        if (lane == 0 && (INNER || (g > 0 && g < n))) prev = a.kin[g - 1];
+        // a head: the first record, a record whose predecessor belongs to another group, and the position after the last record
+        bool head = ((k ^ prev) >> gs) != 0;
+        if (!INNER) head = (g >= 0 && g < n) ? (g == 0 || head) : g == n;
+        const uint32_t hb = __ballot_sync(BP_FULL_MASK, head);
+        if (lane == 0) heads[j * (RFIN_THREADS / 32) + warp] = hb;
+        if constexpr (sizeof(C) == 4)
+            sc[w] = (C)(((uint32_t)(k >> a.shift0) & a.mask0) | (((uint32_t)(k >> a.shift1) & a.mask1) << a.bits0));
+        else
+            sc[w] = (C)((uint64_t)k & (gs >= 64 ? ~0ull : (1ull << gs) - 1ull));
+    }
+    __syncthreads();
+    bool any_big = false;
+#pragma unroll
+    for (int q = 0; q < RFIN_IPT; ++q) {
+        const uint32_t w = (q + 1) * RFIN_THREADS + tid;
+        const int32_t g = wb + (int32_t)w;
+        if (!INNER && g >= n) break;
+        const uint32_t r = w >> 5, b = w & 31u;
+        // start of the group: the last head at or before w
+        uint32_t m = heads[r] & (0xffffffffu >> (31u - b));
+        int rr = (int)r;
+        while (m == 0 && rr > 0 && (int)r - rr <= RFIN_HALO / 32) m = heads[--rr];
+        // end of the group: the first head after w
+        uint32_t m2 = heads[r] & ((0xfffffffeu << b));
+        int re = (int)r;
+        while (m2 == 0 && re + 1 < RFIN_ROWS && re - (int)r <= RFIN_HALO / 32) m2 = heads[++re];
+        const uint32_t hs = (uint32_t)rr * 32u + 31u - (uint32_t)__clz((int)m);
+        const uint32_t he = (uint32_t)re * 32u + (uint32_t)__ffs((int)m2) - 1u;
+        const bool big = m == 0 || m2 == 0 || he - hs > (uint32_t)RFIN_HALO;
+        int32_t out = g;
+        if (!big) {
+            const C mine = sc[w];
+            uint32_t cnt = 0;
+            // (left to the compiler's 8-way unrolling: `#pragma unroll 1` was measured slower, 1.04 against 0.90 ms at config 3)
+            for (uint32_t j = hs; j < w; ++j) cnt += sc[j] <= mine ? 1u : 0u;     // before it: smaller or equal words come first (stable)
+            for (uint32_t j = w + 1; j < he; ++j) cnt += sc[j] < mine ? 1u : 0u;  // after it: only smaller ones
+            out = wb + (int32_t)(hs + cnt);
+        }
+        any_big |= big;
+        a.kout[out] = kk[q + 1];
+        a.vout[out] = val[q];
+    }
+    if (any_big) *a.big = 1u;
+}
+
+template <class K, class V, class C>
+__global__ void __launch_bounds__(RFIN_THREADS, 4) record_finish_kernel(const RecordFinishArgs<K, V> a) {
+    __shared__ C sc[RFIN_WIN];
+    __shared__ uint32_t heads[RFIN_ROWS + 1];
+    const uint32_t t0 = blockIdx.x * (uint32_t)RFIN_TILE;
+    if (t0 >= a.n) return;
+    if (t0 >= (uint32_t)RFIN_HALO && (uint64_t)t0 + RFIN_TILE + RFIN_HALO <= (uint64_t)a.n)
+        record_finish_tile<K, V, C, true>(a, sc, heads, t0);
+    else
+        record_finish_tile<K, V, C, false>(a, sc, heads, t0);
+}
+
 // ---- bucket counts for a splitter partition (one read of the keys) --------------------------------------
 // With HALO (records of a multi-GPU shard exchange): a record whose cell reaches past later splitters is an
 // ancestor of records other shards will own, so it is also counted as a halo copy for each of those

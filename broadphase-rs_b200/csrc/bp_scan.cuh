@@ -635,6 +635,202 @@ __global__ void __launch_bounds__(EMIT_THREADS, EMIT_MINB) scan_emit_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// scan_groups_kernel -- the whole sweep of scan_impl (src/layer.rs:550-573) in ONE kernel for trees whose records all
+// sit at the same depth (uniform object sizes: BASELINE configs 2, 4, 5 -- the host sees it in the varying-bit mask of
+// the keys: no depth bit differs).  Then cell(i) contains cell(j) iff key_i == key_j, so the stack at record j holds
+// exactly the earlier records with j's key: the run of equal keys that ends at j.  No run search, no list of sources, no
+// work-item chunks, no gathers: a tile stages the IDs of its records (+ GRP_HALO records before it), marks the first
+// record of every equal-key group in a bitmap (one ballot per 32 records), and every record pairs itself with the
+// records between the head of its group and itself -- counted first (one atomicAdd per tile hands out the output range),
+// then written.  Same filter functors, same dedup at the source (equal depths: the pair is canonical iff the two records'
+// cell flags share no axis), same-ID items only detected (the host then takes the general path with its inactive-record
+// passes), records below first_owned only act as ancestors.  A group of more than GRP_HALO records (a crowded cell)
+// raises `pad`: general path as well.  Output past `capacity` is counted, not written: the host grows the buffer and
+// runs the kernel again (it sizes the buffer from the last scan, so a steady frame loop never does).
+// ---------------------------------------------------------------------------------------------
+constexpr int GRP_THREADS = 256;
+constexpr int GRP_IPT = 8;
+constexpr int GRP_TILE = GRP_THREADS * GRP_IPT;
+constexpr int GRP_HALO = GRP_THREADS;            // one more window slot per thread
+constexpr int GRP_WIN = GRP_TILE + GRP_HALO;
+constexpr int GRP_ROWS = GRP_WIN / 32;
+constexpr int GRP_STAGE = 2048;                  // pairs a tile stages for coalesced stores (more than that: written directly)
+
+template <class K, class IdT> struct GroupScanArgs {
+    const K *keys;  // sorted tree keys, all of one depth
+    const IdT *ids; // sorted tree IDs (cell flags in their top 3 bits when id_mask != ~0)
+    uint32_t n;
+    IdT id_mask;
+    uint32_t first_owned;
+    uint64_t *out_packed; // u32 IDs: (later << 32) | earlier
+    uint64_t *out_a;      // u64 IDs: later
+    uint64_t *out_b;      //          earlier
+    uint64_t capacity;
+    unsigned long long *pair_counter; // zeroed: pairs emitted
+    unsigned long long *work_counter; // zeroed: (ancestor, descendant) record pairs visited
+    uint32_t *later_count;            // optional, zeroed: pairs per later ID (counting sort of the pairs)
+    ScanTotals *totals;               // any_same_id, pad
+    FilterArgs filter;
+};
+
+template <class K, class IdT, int FK, bool DEDUP>
+__global__ void __launch_bounds__(GRP_THREADS) scan_groups_kernel(const GroupScanArgs<K, IdT> a) {
+    constexpr bool WIDE = sizeof(IdT) == 8;
+    constexpr int FLAG_SHIFT = 8 * sizeof(IdT) - 3;
+    constexpr int SLOTS = GRP_WIN / GRP_THREADS;
+    __shared__ IdT sid[GRP_WIN];
+    constexpr int STAGE_N = WIDE ? GRP_STAGE / 2 : GRP_STAGE; // (u64 IDs stage two words per pair)
+    __shared__ uint64_t stage[GRP_STAGE];
+    __shared__ uint32_t heads[GRP_ROWS];
+    __shared__ uint32_t sscratch[GRP_THREADS / 32 + 2];
+    __shared__ unsigned long long sbase;
+    __shared__ uint32_t swork;
+    const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t t0 = blockIdx.x * (uint32_t)GRP_TILE;
+    if (t0 >= a.n) return;
+    const int32_t n = (int32_t)a.n;
+    const int32_t wb = (int32_t)t0 - GRP_HALO; // record index of window position 0
+    if (tid == 0) swork = 0;
+#pragma unroll
+    for (int j = 0; j < SLOTS; ++j) {
+        const uint32_t p = j * GRP_THREADS + tid;
+        const int32_t g = wb + (int32_t)p;
+        const bool valid = g >= 0 && g < n;
+        const K k = valid ? ld_stream(a.keys + g) : (K)0;
+        K prev = __shfl_up_sync(BP_FULL_MASK, k, 1);
+        if (lane == 0 && valid && g > 0) prev = a.keys[g - 1];
+        const bool head = valid && (g == 0 || k != prev);
+        const uint32_t hb = __ballot_sync(BP_FULL_MASK, head);
+        if (lane == 0) heads[j * (GRP_THREADS / 32) + warp] = hb;
+        sid[p] = valid ? ld_stream(a.ids + g) : (IdT)0;
+    }
+    __syncthreads();
+
+    // one work item: the earlier record at window position i under the later record (raw ID rj, owned or not)
+    bool same_seen = false;
+    auto emits = [&](IdT rj, uint32_t i, bool owned) -> bool {
+        const IdT ri = sid[i];
+        const IdT id_i = ri & a.id_mask, id_j = rj & a.id_mask;
+        if (id_i == id_j) {
+            same_seen = true;
+            return false;
+        }
+        bool e = owned && FilterFn<FK>::pass(a.filter, id_j, id_i);
+        if (DEDUP) e = e && ((uint32_t)(ri >> FLAG_SHIFT) & (uint32_t)(rj >> FLAG_SHIFT)) == 0u;
+        return e;
+    };
+
+    // ---- count: head of every record's group, its work items, the pairs it will emit ------------------------
+    // The verdict on every work item is kept as one bit (groups of up to 33 records: always, in practice), so the
+    // write pass below visits the surviving pairs only and evaluates nothing twice.
+    uint32_t hs[GRP_IPT], em[GRP_IPT];
+    uint32_t mine = 0, work = 0, longq = 0; // longq bit q: more than 32 ancestors, evaluated again when written
+    bool big = false;
+#pragma unroll
+    for (int q = 0; q < GRP_IPT; ++q) {
+        const uint32_t p = (q + 1) * GRP_THREADS + tid;
+        const int32_t g = wb + (int32_t)p;
+        hs[q] = p;
+        em[q] = 0;
+        if (g >= n) continue;
+        const uint32_t r = p >> 5, b = p & 31u;
+        uint32_t m = heads[r] & (0xffffffffu >> (31u - b));
+        int rr = (int)r;
+        while (m == 0 && rr > 0 && (int)r - rr <= GRP_HALO / 32) m = heads[--rr];
+        const uint32_t h = (uint32_t)rr * 32u + 31u - (uint32_t)__clz((int)m);
+        if (m == 0 || p - h > (uint32_t)GRP_HALO) { // the group starts before the window: not for this kernel
+            big = true;
+            continue;
+        }
+        if (h == p) continue; // the first record of its group: no ancestor
+        hs[q] = h;
+        work += p - h;
+        const IdT rj = sid[p];
+        const bool owned = (uint32_t)g >= a.first_owned;
+        if (p - h <= 32u) {
+            uint32_t bits = 0;
+#pragma unroll 1
+            for (uint32_t i = h; i < p; ++i) bits |= (emits(rj, i, owned) ? 1u : 0u) << (i - h);
+            em[q] = bits;
+            mine += (uint32_t)__popc(bits);
+        } else {
+            longq |= 1u << q;
+#pragma unroll 1
+            for (uint32_t i = h; i < p; ++i) mine += emits(rj, i, owned) ? 1u : 0u;
+        }
+    }
+    if (same_seen) a.totals->any_same_id = 1u;
+    if (big) a.totals->pad = 1u;
+    work = warp_sum(work);
+    if (lane == 0 && work) atomicAdd(&swork, work);
+    uint32_t tile_pairs;
+    const uint32_t ex = block_exclusive_sum<GRP_THREADS, uint32_t>(mine, sscratch, &tile_pairs);
+    if (tid == 0) {
+        sbase = tile_pairs ? atomicAdd(a.pair_counter, (unsigned long long)tile_pairs) : 0ull;
+        if (swork) atomicAdd(a.work_counter, (unsigned long long)swork);
+    }
+    __syncthreads();
+    if (tile_pairs == 0) return;
+
+    // ---- write: every surviving pair into this thread's part of the tile's output range, through a staging buffer
+    // (coalesced stores) whenever the tile's pairs fit it -----------------------------------------------------------
+    const bool staged = tile_pairs <= (uint32_t)STAGE_N;
+    const uint64_t base = sbase;
+    uint32_t slot = ex;
+    auto put = [&](IdT id_j, IdT id_i) {
+        if (staged) {
+            if (WIDE) {
+                stage[slot] = (uint64_t)id_j;
+                stage[STAGE_N + slot] = (uint64_t)id_i;
+            } else {
+                stage[slot] = ((uint64_t)id_j << 32) | (uint64_t)id_i;
+            }
+        } else if (base + slot < a.capacity) {
+            if (WIDE) {
+                a.out_a[base + slot] = (uint64_t)id_j; // (later, earlier) -- src/layer.rs:567
+                a.out_b[base + slot] = (uint64_t)id_i;
+            } else {
+                a.out_packed[base + slot] = ((uint64_t)id_j << 32) | (uint64_t)id_i;
+            }
+        }
+        ++slot;
+        if (a.later_count) atomicAdd(a.later_count + (size_t)id_j, 1u);
+    };
+#pragma unroll
+    for (int q = 0; q < GRP_IPT; ++q) {
+        const uint32_t p = (q + 1) * GRP_THREADS + tid;
+        if (hs[q] == p) continue;
+        const IdT rj = sid[p];
+        const IdT id_j = rj & a.id_mask;
+        if (!(longq & (1u << q))) {
+            uint32_t bits = em[q];
+            while (bits) {
+                const uint32_t i = hs[q] + (uint32_t)__ffs((int)bits) - 1u;
+                bits &= bits - 1u;
+                put(id_j, sid[i] & a.id_mask);
+            }
+        } else {
+            const bool owned = (uint32_t)(wb + (int32_t)p) >= a.first_owned;
+#pragma unroll 1
+            for (uint32_t i = hs[q]; i < p; ++i)
+                if (emits(rj, i, owned)) put(id_j, sid[i] & a.id_mask);
+        }
+    }
+    if (staged) {
+        __syncthreads();
+        for (uint32_t i = tid; i < tile_pairs; i += GRP_THREADS) {
+            if (base + i >= a.capacity) break;
+            if (WIDE) {
+                a.out_a[base + i] = stage[i];
+                a.out_b[base + i] = stage[STAGE_N + i];
+            } else {
+                a.out_packed[base + i] = stage[i];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Counting sort of the raw pairs by their later ID -- the first half of `collisions.sort_unstable()`
 // (src/layer.rs:473, :516) when the IDs are dense 32-bit numbers (the usual 0..N): scan_emit_kernel
 // counts the pairs of every later ID as it emits them, one exclusive scan over the ID range turns the
@@ -835,6 +1031,9 @@ template <class IdT> struct FinishArgs {
     const uint64_t *in_a;      // u64 IDs: later IDs (sorted) ...
     const uint64_t *in_b;      //          ... and their partners
     uint32_t n;
+    uint32_t gshift;        // u32 IDs: pairs with equal (packed >> gshift) form a group; 32 = one group per later ID, more when
+                            // the radix passes left the lowest bits of the later ID to this kernel (a group then holds a few
+                            // later IDs and is ordered by the whole packed pair)
     IdT *out;               // [2 * n] (later, earlier) interleaved
     uint64_t *status;       // look-back, one per tile, zeroed
     uint32_t *tile_counter; // zeroed
@@ -846,9 +1045,12 @@ template <class IdT> struct FinishArgs {
 // earlier ID (#smaller + #equal-before); the group is rewritten in that order in a second shared buffer,
 // where duplicates are adjacent, so dedup + ordered compaction + coalesced stores are the usual
 // adjacent-difference / scan / look-back.
-template <class IdT>
+// LOWBITS (u32 IDs): a group is the pairs with equal (packed >> gshift), gshift > 32 -- a few later IDs -- ordered by the
+// whole packed pair; otherwise a group is one later ID (the high word), ordered by the earlier ID (the low word).
+template <class IdT, bool LOWBITS = false>
 __global__ void __launch_bounds__(FIN_THREADS) pair_finish_kernel(const FinishArgs<IdT> a) {
     constexpr bool WIDE = sizeof(IdT) == 8;
+    static_assert(!(WIDE && LOWBITS), "u64 IDs are grouped by the later ID");
     constexpr int FIN_TILE = FinCfg<IdT>::TILE, FIN_WIN = FinCfg<IdT>::WIN, FIN_IPT = FinCfg<IdT>::IPT;
     constexpr uint64_t HOLE = ~0ull; // marks window slots this tile does not own
     __shared__ uint64_t sa[FIN_WIN + 1];            // packed pair, or later ID (+1: the element after the window, for the overflow test)
@@ -878,35 +1080,36 @@ __global__ void __launch_bounds__(FIN_THREADS) pair_finish_kernel(const FinishAr
         if (WIDE) tb[i] = HOLE; // (max, max) is not a pair, so both halves equal to HOLE can only be a hole
     }
     // does the first group of the window continue a group of the previous tile?
-    const uint64_t prev = t0 > 0 ? (WIDE ? a.in_a[t0 - 1] : (a.in_packed[t0 - 1] >> 32)) : 0;
+    const uint32_t gs = LOWBITS ? a.gshift : 32u;
+    const uint64_t prev = t0 > 0 ? (WIDE ? a.in_a[t0 - 1] : (a.in_packed[t0 - 1] >> gs)) : 0;
     __syncthreads();
-    const bool cont0 = t0 > 0 && prev == (WIDE ? sa[0] : (sa[0] >> 32));
+    const bool cont0 = t0 > 0 && prev == (WIDE ? sa[0] : (sa[0] >> gs));
 
     // ---- one walk per element: head of its group, stable position inside the group ------------------
 #pragma unroll 1
     for (uint32_t i = tid; i < win_n; i += FIN_THREADS) {
         const uint64_t x = sa[i];
-        const uint64_t la = WIDE ? x : (x >> 32);
-        const uint64_t eb = WIDE ? sb[i] : (x & 0xffffffffull);
+        const uint64_t la = WIDE ? x : (x >> gs);
+        const uint64_t eb = WIDE ? sb[i] : (LOWBITS ? x : (x & 0xffffffffull)); // what orders the group: the earlier ID, or the whole packed pair
         uint32_t h = i, pos = 0;
-        while (h > 0) { // elements before i in the group: smaller or equal earlier IDs come first (stable)
+        while (h > 0) { // elements before i in the group: smaller or equal ones come first (stable)
             const uint64_t y = sa[h - 1];
-            if ((WIDE ? y : (y >> 32)) != la) break;
+            if ((WIDE ? y : (y >> gs)) != la) break;
             --h;
-            pos += ((WIDE ? sb[h] : (y & 0xffffffffull)) <= eb) ? 1u : 0u;
+            pos += ((WIDE ? sb[h] : (LOWBITS ? y : (y & 0xffffffffull))) <= eb) ? 1u : 0u;
         }
         if (h >= tile_n || (h == 0 && cont0)) continue; // the group belongs to a neighbouring tile
         uint32_t e = i + 1;
         while (e < win_n) { // elements after i: only strictly smaller ones come first
             const uint64_t y = sa[e];
-            if ((WIDE ? y : (y >> 32)) != la) break;
-            pos += ((WIDE ? sb[e] : (y & 0xffffffffull)) < eb) ? 1u : 0u;
+            if ((WIDE ? y : (y >> gs)) != la) break;
+            pos += ((WIDE ? sb[e] : (LOWBITS ? y : (y & 0xffffffffull))) < eb) ? 1u : 0u;
             ++e;
         }
         // an owned group that runs past the window cannot be finished here
-        if (e == win_n && more && (WIDE ? sa[win_n] : (sa[win_n] >> 32)) == la) a.totals->pad = 1u;
+        if (e == win_n && more && (WIDE ? sa[win_n] : (sa[win_n] >> gs)) == la) a.totals->pad = 1u;
         ta[h + pos] = x;
-        if (WIDE) tb[h + pos] = eb;
+        if (WIDE) tb[h + pos] = sb[i];
     }
     __syncthreads();
 

@@ -470,6 +470,16 @@ def plan_radix_passes(mask):
     return out
 
 
+def plan_sort_finish(mask, n_records):
+    """The "top bits + finish" plan of a record sort (bp_plan_sort_finish): None when the plain radix plan is kept, else
+    (top_mask, group_shift): radix passes over top_mask, then one pass that orders the groups of equal key >> group_shift."""
+    top = ctypes.c_uint64()
+    gs = ctypes.c_uint32()
+    if not lib().bp_plan_sort_finish(mask, n_records, ctypes.byref(top), ctypes.byref(gs)):
+        return None
+    return top.value, gs.value
+
+
 def device_count():
     n = ctypes.c_int()
     st = lib().bp_device_count(ctypes.byref(n))

@@ -104,7 +104,8 @@ enum {
     BP_K_MISC = 9,      /* small helpers (histogram scans, masks, gathers) */
     BP_K_QUERY = 10,    /* batched box / ray queries: hierarchy descent (count pass + write pass) */
     BP_K_PARTITION = 11, /* multi-GPU: splitter counts + the partition pass that stores into the peers' receive buffers */
-    BP_K_COUNT = 12
+    BP_K_SORT_FINISH = 12, /* record sort: the pass that orders the low key bits group by group after radix passes over the top bits */
+    BP_K_COUNT = 13
 };
 
 typedef struct bp_stats {
@@ -385,6 +386,15 @@ int bp_device_count(int *out_count);
  * bit-fields: the low half-words of out_shift[i] / out_bits[i] describe the first field, the high
  * half-words the second (bits == 0: absent), stacked above the first. */
 int bp_plan_radix_passes(uint64_t varying_mask, uint32_t *out_shift, uint32_t *out_bits, int max_passes);
+
+/* The "top bits + finish" plan of a record sort, exposed for tests: n_records records whose keys differ in the bits
+ * of varying_mask.  Returns 1 and writes the bits the radix passes sort on (*out_top_mask) and the shift that defines a
+ * finish group (records with equal key >> *out_group_shift) when the plan replaces at least two radix passes, else 0:
+ * R records only carry ~log2(R) bits of position, so after a stable sort on the top log2(R) - 3 varying bits (rounded up
+ * to whole 8-bit passes) every group of records agreeing on them is a handful of neighbours, ordered by one more pass
+ * (record_finish_kernel) however many low bits remain.  Replaces the tail of `tree.par_sort_unstable()`,
+ * src/layer.rs:149, :162 -- a total order, so the result is the same sequence. */
+int bp_plan_sort_finish(uint64_t varying_mask, uint64_t n_records, uint64_t *out_top_mask, uint32_t *out_group_shift);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -130,3 +131,58 @@ def test_scene_recipes_are_deterministic(bp):
     assert (c["bounds"][:, 3:] >= c["bounds"][:, :3]).all() and (c["bounds"][:, 3:] <= 1.0).all()
     d = bp.scenes.example_circles(1000, 1)
     assert d["kind"] == 0 and d["min_depth"] == 4 and d["bounds"].shape == (1000, 4)
+
+
+def test_sort_finish_planner(bp):
+    """Which record sorts take "radix passes over the top bits + one finish pass" (bp_plan_sort_finish)."""
+    plan = bp.plan_sort_finish
+    origin = lambda nbits: ((1 << nbits) - 1) << (5 + 57 - nbits)     # the top origin bits of an Index64_3D key
+    # config 3: 4 depth bits + 39 origin bits, 87 M records -> 24 top bits in 3 passes (+ finish) instead of 6 passes
+    mask = 0xF | origin(39)
+    top, gs = plan(mask, 87_322_146)
+    assert top == origin(24) and gs == 62 - 24 and len(bp.plan_radix_passes(top)) == 3
+    # the same keys, 2.7 M records (the test-sized config 3): 19 bits wanted, whole passes -> again 24 bits
+    assert plan(mask, 2_700_000) == (origin(24), 38)
+    # config-5 shape: 27 varying bits, 146 M records want 25 bits -> every pass is needed, plain plan
+    assert plan(origin(27), 146_536_534) is None
+    # config 2: 21 bits in 3 passes: nothing to save
+    assert plan(origin(21), 3_554_446) is None
+    # all 62 bits, 1 M records: 17 bits wanted -> 3 passes (24 bits) instead of 8
+    top, gs = plan((1 << 62) - 1, 1 << 20)
+    assert top == ((1 << 24) - 1) << 38 and gs == 38
+    # a plan that would save a single pass is not worth the finish pass
+    assert plan(origin(32), 1 << 20) is None      # 4 passes against 3 + finish
+    assert plan(origin(33), 1 << 20) is not None  # 5 passes against 3 + finish
+    # scattered varying bits: the group shift is the lowest of the bits sorted on
+    mask = 0x8000_0000_0000_0000 | (0xFFFF_FFFF << 20) | 0xFF
+    top, gs = plan(mask, 1 << 12)                  # 9 bits wanted -> 16 bits
+    assert bin(top).count("1") == 16 and top & mask == top and top >> gs << gs == top and (mask >> gs << gs) == top
+    assert plan(0, 100) is None and plan(0xFF, 1) is None and plan((1 << 62) - 1, 0) is None
+
+
+def test_finish_model_orders_groups():
+    """The ordering rule of the finish kernels on windows small enough to hit every edge: tile boundaries inside groups,
+    groups at the array ends, groups of exactly / just over the window -- tests/finish_model.py."""
+    from tests.finish_model import record_finish
+    rng = np.random.Generator(np.random.Philox(5))
+    for trial in range(60):
+        n = int(rng.integers(1, 400))
+        gshift = int(rng.integers(2, 7))
+        halo, tile = int(rng.integers(2, 12)), int(rng.integers(4, 40))
+        ngroups = max(1, int(rng.integers(1, max(2, n // max(1, int(rng.integers(1, 14)))))))
+        keys = (rng.integers(0, ngroups, n).astype(np.uint64) << np.uint64(gshift)) | rng.integers(0, 1 << gshift, n).astype(np.uint64)
+        order = np.argsort(keys >> np.uint64(gshift), kind="stable")           # what the radix passes leave behind
+        pre = keys[order]
+        out, big = record_finish(pre, gshift, halo, tile)
+        assert sorted(out.tolist()) == list(range(n))                             # a permutation, big groups or not
+        res = np.empty(n, dtype=np.uint64)
+        src = np.empty(n, dtype=np.int64)
+        res[out] = pre
+        src[out] = order
+        want = np.argsort(keys, kind="stable")
+        sizes = np.unique(pre >> np.uint64(gshift), return_counts=True)[1]
+        assert big == bool((sizes > halo).any())
+        if not big:
+            assert (src == want).all()                                            # = the stable sort by the whole key
+        else:   # big groups stay as they were: still stable, the remaining passes finish the job
+            assert (src[np.argsort(res, kind="stable")] == want).all()
