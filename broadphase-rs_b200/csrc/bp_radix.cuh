@@ -658,12 +658,16 @@ __device__ __forceinline__ void record_finish_tile(const RecordFinishArgs<K, V> 
             sc[w] = (C)((uint64_t)k & (gs >= 64 ? ~0ull : (1ull << gs) - 1ull));
     }
     __syncthreads();
+    // The members of a group are visited by DISTANCE, d = 1 .. (the largest extent of a group around any of the warp's 32
+    // records): the same trip count for every lane (one REDUX), lane l looking at positions w - d and w + d -- consecutive
+    // lanes, consecutive words.  (A loop per thread over its own group made the warp run through every lane's loop
+    // structure in turn: 164 thread instructions per record, 85 % issue-bound, profiles/r2_finish_kernel.txt.)
     bool any_big = false;
 #pragma unroll
     for (int q = 0; q < RFIN_IPT; ++q) {
         const uint32_t w = (q + 1) * RFIN_THREADS + tid;
         const int32_t g = wb + (int32_t)w;
-        if (!INNER && g >= n) break;
+        const bool live = INNER || g < n;
         const uint32_t r = w >> 5, b = w & 31u;
         // start of the group: the last head at or before w
         uint32_t m = heads[r] & (0xffffffffu >> (31u - b));
@@ -675,19 +679,23 @@ __device__ __forceinline__ void record_finish_tile(const RecordFinishArgs<K, V> 
         while (m2 == 0 && re + 1 < RFIN_ROWS && re - (int)r <= RFIN_HALO / 32) m2 = heads[++re];
         const uint32_t hs = (uint32_t)rr * 32u + 31u - (uint32_t)__clz((int)m);
         const uint32_t he = (uint32_t)re * 32u + (uint32_t)__ffs((int)m2) - 1u;
-        const bool big = m == 0 || m2 == 0 || he - hs > (uint32_t)RFIN_HALO;
-        int32_t out = g;
-        if (!big) {
-            const C mine = sc[w];
-            uint32_t cnt = 0;
-            // (left to the compiler's 8-way unrolling: `#pragma unroll 1` was measured slower, 1.04 against 0.90 ms at config 3)
-            for (uint32_t j = hs; j < w; ++j) cnt += sc[j] <= mine ? 1u : 0u;     // before it: smaller or equal words come first (stable)
-            for (uint32_t j = w + 1; j < he; ++j) cnt += sc[j] < mine ? 1u : 0u;  // after it: only smaller ones
-            out = wb + (int32_t)(hs + cnt);
+        const bool big = live && (m == 0 || m2 == 0 || he - hs > (uint32_t)RFIN_HALO);
+        const uint32_t nb = (live && !big) ? w - hs : 0u;      // members before this record ...
+        const uint32_t na = (live && !big) ? he - 1u - w : 0u; // ... and after it
+        const uint32_t dmax = __reduce_max_sync(BP_FULL_MASK, max(nb, na));
+        const C mine = sc[w];
+        uint32_t cnt = 0;
+        for (uint32_t d = 1; d <= dmax; ++d) { // (w - d >= 0 and w + d < RFIN_WIN: d <= RFIN_HALO)
+            const C cb = sc[w - d], ca = sc[w + d];
+            cnt += (d <= nb && cb <= mine) ? 1u : 0u; // before it: smaller or equal words come first (stable)
+            cnt += (d <= na && ca < mine) ? 1u : 0u;  // after it: only smaller ones
         }
         any_big |= big;
-        a.kout[out] = kk[q + 1];
-        a.vout[out] = val[q];
+        if (live) {
+            const int32_t out = big ? g : wb + (int32_t)(hs + cnt);
+            a.kout[out] = kk[q + 1];
+            a.vout[out] = val[q];
+        }
     }
     if (any_big) *a.big = 1u;
 }

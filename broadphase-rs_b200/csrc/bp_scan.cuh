@@ -673,101 +673,90 @@ template <class K, class IdT> struct GroupScanArgs {
     FilterArgs filter;
 };
 
-template <class K, class IdT, int FK, bool DEDUP>
-__global__ void __launch_bounds__(GRP_THREADS) scan_groups_kernel(const GroupScanArgs<K, IdT> a) {
+// INNER: every position of the window is a record (all tiles but the first and the last few).
+// The walk over a record's ancestors is a loop over the DISTANCE d = 1 .. (largest ancestor count in the warp), the same
+// trip count for all 32 lanes (one REDUX), lane l looking at position p - d: consecutive lanes, consecutive shared-memory
+// words.  A loop per thread over its own ancestors made the warp execute every lane's loop structure one after the
+// other (7.2 warp instructions per record, 76 % issue-bound; profiles/r2_scan_groups.txt).
+template <class K, class IdT, int FK, bool DEDUP, bool INNER>
+__device__ __forceinline__ void scan_groups_tile(const GroupScanArgs<K, IdT> &a, IdT *sid, uint64_t *stage, uint32_t *heads,
+                                                 uint32_t *sscratch, unsigned long long *sbase, uint32_t *swork, const uint32_t t0) {
     constexpr bool WIDE = sizeof(IdT) == 8;
     constexpr int FLAG_SHIFT = 8 * sizeof(IdT) - 3;
     constexpr int SLOTS = GRP_WIN / GRP_THREADS;
-    __shared__ IdT sid[GRP_WIN];
     constexpr int STAGE_N = WIDE ? GRP_STAGE / 2 : GRP_STAGE; // (u64 IDs stage two words per pair)
-    __shared__ uint64_t stage[GRP_STAGE];
-    __shared__ uint32_t heads[GRP_ROWS];
-    __shared__ uint32_t sscratch[GRP_THREADS / 32 + 2];
-    __shared__ unsigned long long sbase;
-    __shared__ uint32_t swork;
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t t0 = blockIdx.x * (uint32_t)GRP_TILE;
-    if (t0 >= a.n) return;
     const int32_t n = (int32_t)a.n;
     const int32_t wb = (int32_t)t0 - GRP_HALO; // record index of window position 0
-    if (tid == 0) swork = 0;
+    if (tid == 0) *swork = 0;
 #pragma unroll
     for (int j = 0; j < SLOTS; ++j) {
         const uint32_t p = j * GRP_THREADS + tid;
         const int32_t g = wb + (int32_t)p;
-        const bool valid = g >= 0 && g < n;
+        const bool valid = INNER || (g >= 0 && g < n);
         const K k = valid ? ld_stream(a.keys + g) : (K)0;
         K prev = __shfl_up_sync(BP_FULL_MASK, k, 1);
-        if (lane == 0 && valid && g > 0) prev = a.keys[g - 1];
-        const bool head = valid && (g == 0 || k != prev);
+        if (lane == 0 && valid && (INNER || g > 0)) prev = a.keys[g - 1];
+        const bool head = valid && ((!INNER && g == 0) || k != prev);
         const uint32_t hb = __ballot_sync(BP_FULL_MASK, head);
         if (lane == 0) heads[j * (GRP_THREADS / 32) + warp] = hb;
         sid[p] = valid ? ld_stream(a.ids + g) : (IdT)0;
     }
     __syncthreads();
 
-    // one work item: the earlier record at window position i under the later record (raw ID rj, owned or not)
-    bool same_seen = false;
-    auto emits = [&](IdT rj, uint32_t i, bool owned) -> bool {
-        const IdT ri = sid[i];
-        const IdT id_i = ri & a.id_mask, id_j = rj & a.id_mask;
-        if (id_i == id_j) {
-            same_seen = true;
-            return false;
-        }
-        bool e = owned && FilterFn<FK>::pass(a.filter, id_j, id_i);
-        if (DEDUP) e = e && ((uint32_t)(ri >> FLAG_SHIFT) & (uint32_t)(rj >> FLAG_SHIFT)) == 0u;
-        return e;
-    };
-
-    // ---- count: head of every record's group, its work items, the pairs it will emit ------------------------
-    // The verdict on every work item is kept as one bit (groups of up to 33 records: always, in practice), so the
-    // write pass below visits the surviving pairs only and evaluates nothing twice.
-    uint32_t hs[GRP_IPT], em[GRP_IPT];
-    uint32_t mine = 0, work = 0, longq = 0; // longq bit q: more than 32 ancestors, evaluated again when written
-    bool big = false;
+    // ---- count: every record's ancestors (the records between the head of its group and itself), the verdict on each
+    // kept as one bit (up to 32 of them: always, in practice; beyond that they are evaluated again when written) ------
+    uint32_t cnt[GRP_IPT], em[GRP_IPT];
+    uint32_t mine = 0, work = 0;
+    bool big = false, same_seen = false;
 #pragma unroll
     for (int q = 0; q < GRP_IPT; ++q) {
         const uint32_t p = (q + 1) * GRP_THREADS + tid;
         const int32_t g = wb + (int32_t)p;
-        hs[q] = p;
-        em[q] = 0;
-        if (g >= n) continue;
         const uint32_t r = p >> 5, b = p & 31u;
         uint32_t m = heads[r] & (0xffffffffu >> (31u - b));
         int rr = (int)r;
         while (m == 0 && rr > 0 && (int)r - rr <= GRP_HALO / 32) m = heads[--rr];
-        const uint32_t h = (uint32_t)rr * 32u + 31u - (uint32_t)__clz((int)m);
-        if (m == 0 || p - h > (uint32_t)GRP_HALO) { // the group starts before the window: not for this kernel
+        uint32_t c = p - ((uint32_t)rr * 32u + 31u - (uint32_t)__clz((int)m));
+        if (!INNER && g >= n) {
+            c = 0;
+        } else if (m == 0 || c > (uint32_t)GRP_HALO) { // the group starts before the window: not for this kernel
             big = true;
-            continue;
+            c = 0;
         }
-        if (h == p) continue; // the first record of its group: no ancestor
-        hs[q] = h;
-        work += p - h;
+        cnt[q] = c;
+        work += c;
         const IdT rj = sid[p];
+        const IdT id_j = rj & a.id_mask;
+        const uint32_t fj = (uint32_t)(rj >> FLAG_SHIFT);
         const bool owned = (uint32_t)g >= a.first_owned;
-        if (p - h <= 32u) {
-            uint32_t bits = 0;
-#pragma unroll 1
-            for (uint32_t i = h; i < p; ++i) bits |= (emits(rj, i, owned) ? 1u : 0u) << (i - h);
-            em[q] = bits;
-            mine += (uint32_t)__popc(bits);
-        } else {
-            longq |= 1u << q;
-#pragma unroll 1
-            for (uint32_t i = h; i < p; ++i) mine += emits(rj, i, owned) ? 1u : 0u;
+        const uint32_t dmax = __reduce_max_sync(BP_FULL_MASK, c);
+        uint32_t bits = 0;
+        for (uint32_t d = 1; d <= dmax; ++d) {
+            const IdT ri = sid[p - d]; // (d <= dmax <= GRP_HALO <= p: inside the window for every lane)
+            const IdT id_i = ri & a.id_mask;
+            const bool live = d <= c;
+            const bool same = id_i == id_j;
+            same_seen |= live && same;
+            bool e = live && !same && owned && FilterFn<FK>::pass(a.filter, id_j, id_i);
+            if (DEDUP) e = e && ((uint32_t)(ri >> FLAG_SHIFT) & fj) == 0u;
+            if (d <= 32u)
+                bits |= (e ? 1u : 0u) << (d - 1u);
+            else
+                mine += e ? 1u : 0u;
         }
+        em[q] = bits;
+        mine += (uint32_t)__popc(bits);
     }
     if (same_seen) a.totals->any_same_id = 1u;
     if (big) a.totals->pad = 1u;
     work = warp_sum(work);
-    if (lane == 0 && work) atomicAdd(&swork, work);
+    if (lane == 0 && work) atomicAdd(swork, work);
     uint32_t tile_pairs;
     const uint32_t ex = block_exclusive_sum<GRP_THREADS, uint32_t>(mine, sscratch, &tile_pairs);
     if (tid == 0) {
-        sbase = tile_pairs ? atomicAdd(a.pair_counter, (unsigned long long)tile_pairs) : 0ull;
-        if (swork) atomicAdd(a.work_counter, (unsigned long long)swork);
+        *sbase = tile_pairs ? atomicAdd(a.pair_counter, (unsigned long long)tile_pairs) : 0ull;
+        if (*swork) atomicAdd(a.work_counter, (unsigned long long)*swork);
     }
     __syncthreads();
     if (tile_pairs == 0) return;
@@ -775,7 +764,7 @@ __global__ void __launch_bounds__(GRP_THREADS) scan_groups_kernel(const GroupSca
     // ---- write: every surviving pair into this thread's part of the tile's output range, through a staging buffer
     // (coalesced stores) whenever the tile's pairs fit it -----------------------------------------------------------
     const bool staged = tile_pairs <= (uint32_t)STAGE_N;
-    const uint64_t base = sbase;
+    const uint64_t base = *sbase;
     uint32_t slot = ex;
     auto put = [&](IdT id_j, IdT id_i) {
         if (staged) {
@@ -799,21 +788,26 @@ __global__ void __launch_bounds__(GRP_THREADS) scan_groups_kernel(const GroupSca
 #pragma unroll
     for (int q = 0; q < GRP_IPT; ++q) {
         const uint32_t p = (q + 1) * GRP_THREADS + tid;
-        if (hs[q] == p) continue;
+        if (cnt[q] == 0) continue;
         const IdT rj = sid[p];
         const IdT id_j = rj & a.id_mask;
-        if (!(longq & (1u << q))) {
-            uint32_t bits = em[q];
-            while (bits) {
-                const uint32_t i = hs[q] + (uint32_t)__ffs((int)bits) - 1u;
-                bits &= bits - 1u;
-                put(id_j, sid[i] & a.id_mask);
-            }
-        } else {
+        uint32_t bits = em[q];
+        while (bits) {
+            const uint32_t d = (uint32_t)__ffs((int)bits);
+            bits &= bits - 1u;
+            put(id_j, sid[p - d] & a.id_mask);
+        }
+        if (cnt[q] > 32u) { // (a crowded cell of up to GRP_HALO records)
             const bool owned = (uint32_t)(wb + (int32_t)p) >= a.first_owned;
+            const uint32_t fj = (uint32_t)(rj >> FLAG_SHIFT);
 #pragma unroll 1
-            for (uint32_t i = hs[q]; i < p; ++i)
-                if (emits(rj, i, owned)) put(id_j, sid[i] & a.id_mask);
+            for (uint32_t d = 33; d <= cnt[q]; ++d) {
+                const IdT ri = sid[p - d];
+                const IdT id_i = ri & a.id_mask;
+                bool e = id_i != id_j && owned && FilterFn<FK>::pass(a.filter, id_j, id_i);
+                if (DEDUP) e = e && ((uint32_t)(ri >> FLAG_SHIFT) & fj) == 0u;
+                if (e) put(id_j, id_i);
+            }
         }
     }
     if (staged) {
@@ -828,6 +822,22 @@ __global__ void __launch_bounds__(GRP_THREADS) scan_groups_kernel(const GroupSca
             }
         }
     }
+}
+
+template <class K, class IdT, int FK, bool DEDUP>
+__global__ void __launch_bounds__(GRP_THREADS) scan_groups_kernel(const GroupScanArgs<K, IdT> a) {
+    __shared__ IdT sid[GRP_WIN];
+    __shared__ uint64_t stage[GRP_STAGE];
+    __shared__ uint32_t heads[GRP_ROWS];
+    __shared__ uint32_t sscratch[GRP_THREADS / 32 + 2];
+    __shared__ unsigned long long sbase;
+    __shared__ uint32_t swork;
+    const uint32_t t0 = blockIdx.x * (uint32_t)GRP_TILE;
+    if (t0 >= a.n) return;
+    if (t0 >= (uint32_t)GRP_HALO + 1u && (uint64_t)t0 + GRP_TILE <= (uint64_t)a.n)
+        scan_groups_tile<K, IdT, FK, DEDUP, true>(a, sid, stage, heads, sscratch, &sbase, &swork, t0);
+    else
+        scan_groups_tile<K, IdT, FK, DEDUP, false>(a, sid, stage, heads, sscratch, &sbase, &swork, t0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1060,6 +1070,9 @@ __global__ void __launch_bounds__(FIN_THREADS) pair_finish_kernel(const FinishAr
     __shared__ uint32_t sscratch[FIN_THREADS / 32 + 2];
     __shared__ uint64_t sbase;
     __shared__ uint32_t stile;
+    constexpr int FIN_ROWS = FIN_WIN / 32;
+    __shared__ uint32_t heads[FIN_ROWS];
+    static_assert(FIN_WIN % FIN_THREADS == 0, "whole rows of the head bitmap");
 
     const unsigned tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) stile = atomicAdd(a.tile_counter, 1u);
@@ -1085,31 +1098,56 @@ __global__ void __launch_bounds__(FIN_THREADS) pair_finish_kernel(const FinishAr
     __syncthreads();
     const bool cont0 = t0 > 0 && prev == (WIDE ? sa[0] : (sa[0] >> gs));
 
-    // ---- one walk per element: head of its group, stable position inside the group ------------------
+    // ---- group heads of the window as a bitmap (one ballot per 32 elements) -----------------------------------
+    auto grp = [&](uint64_t y) -> uint64_t { return WIDE ? y : (y >> gs); };
+#pragma unroll
+    for (int k = 0; k < FIN_IPT; ++k) {
+        const uint32_t i = k * FIN_THREADS + tid;
+        bool head = false;
+        if (i < win_n) head = i == 0 ? !cont0 : grp(sa[i]) != grp(sa[i - 1]);
+        const uint32_t hb = __ballot_sync(BP_FULL_MASK, head);
+        if (lane == 0) heads[k * (FIN_THREADS / 32) + warp] = hb;
+    }
+    __syncthreads();
+
+    // ---- per element: the ends of its group from the bitmap, then its stable position inside the group: the number of
+    // members before it that are not larger + the number after it that are smaller.  The members are visited by
+    // DISTANCE, d = 1 .. (largest extent of a group around any of the warp's 32 elements): one trip count for all lanes (a
+    // REDUX), lane l looking at elements i - d and i + d -- consecutive lanes, consecutive words.
 #pragma unroll 1
-    for (uint32_t i = tid; i < win_n; i += FIN_THREADS) {
-        const uint64_t x = sa[i];
-        const uint64_t la = WIDE ? x : (x >> gs);
-        const uint64_t eb = WIDE ? sb[i] : (LOWBITS ? x : (x & 0xffffffffull)); // what orders the group: the earlier ID, or the whole packed pair
-        uint32_t h = i, pos = 0;
-        while (h > 0) { // elements before i in the group: smaller or equal ones come first (stable)
-            const uint64_t y = sa[h - 1];
-            if ((WIDE ? y : (y >> gs)) != la) break;
-            --h;
-            pos += ((WIDE ? sb[h] : (LOWBITS ? y : (y & 0xffffffffull))) <= eb) ? 1u : 0u;
-        }
-        if (h >= tile_n || (h == 0 && cont0)) continue; // the group belongs to a neighbouring tile
-        uint32_t e = i + 1;
-        while (e < win_n) { // elements after i: only strictly smaller ones come first
-            const uint64_t y = sa[e];
-            if ((WIDE ? y : (y >> gs)) != la) break;
-            pos += ((WIDE ? sb[e] : (LOWBITS ? y : (y & 0xffffffffull))) < eb) ? 1u : 0u;
-            ++e;
-        }
+    for (int k = 0; k < FIN_IPT; ++k) {
+        const uint32_t i = k * FIN_THREADS + tid;
+        const bool live = i < win_n;
+        const uint32_t r = i >> 5, b = i & 31u;
+        uint32_t m = heads[r] & (0xffffffffu >> (31u - b));
+        int rr = (int)r;
+        while (m == 0 && rr > 0) m = heads[--rr];
+        const uint32_t hs = (uint32_t)rr * 32u + 31u - (uint32_t)__clz((int)m);
+        uint32_t m2 = heads[r] & (0xfffffffeu << b);
+        int re = (int)r;
+        while (m2 == 0 && re + 1 < FIN_ROWS) m2 = heads[++re];
+        const uint32_t he = m2 ? (uint32_t)re * 32u + (uint32_t)__ffs((int)m2) - 1u : win_n; // no head after it: up to the end of the window
+        // owned: the group starts in this tile (m == 0: it continues a group of the previous tile)
+        const bool owned = live && m != 0 && hs < tile_n;
+        const uint64_t x = sa[live ? i : 0u];
         // an owned group that runs past the window cannot be finished here
-        if (e == win_n && more && (WIDE ? sa[win_n] : (sa[win_n] >> gs)) == la) a.totals->pad = 1u;
-        ta[h + pos] = x;
-        if (WIDE) tb[h + pos] = sb[i];
+        if (owned && he == win_n && more && grp(sa[win_n]) == grp(x)) a.totals->pad = 1u;
+        const uint32_t nb = owned ? i - hs : 0u, na = owned ? he - 1u - i : 0u;
+        const uint32_t dmax = __reduce_max_sync(BP_FULL_MASK, max(nb, na));
+        // what orders the group: the earlier ID, or the whole packed pair
+        const uint64_t eb = WIDE ? sb[live ? i : 0u] : (LOWBITS ? x : (x & 0xffffffffull));
+        uint32_t pos = 0;
+        for (uint32_t d = 1; d <= dmax; ++d) {
+            const uint32_t jb = i - min(d, i), ja = min(i + d, (uint32_t)FIN_WIN);
+            const uint64_t ob = WIDE ? sb[jb] : (LOWBITS ? sa[jb] : (sa[jb] & 0xffffffffull));
+            const uint64_t oa = WIDE ? sb[ja] : (LOWBITS ? sa[ja] : (sa[ja] & 0xffffffffull));
+            pos += (d <= nb && ob <= eb) ? 1u : 0u; // before it: smaller or equal ones come first (stable)
+            pos += (d <= na && oa < eb) ? 1u : 0u;  // after it: only strictly smaller ones
+        }
+        if (owned) {
+            ta[hs + pos] = x;
+            if (WIDE) tb[hs + pos] = sb[i];
+        }
     }
     __syncthreads();
 
