@@ -20,6 +20,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
     "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
     "--shared", "-cudart", "shared",
+    "--threads", "2",   # the two translation units side by side
 ]
 
 

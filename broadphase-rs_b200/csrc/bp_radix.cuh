@@ -257,13 +257,16 @@ __device__ __forceinline__ void lookback_round(const uint32_t *status, int NB, u
     t -= B;
 }
 
-// RB = digit width in bits: NB = 2^RB bins.  The 256 threads that own the digits (publish, look-back, digit offsets) own
-// DPT = NB / 256 consecutive digits each; above 8 bits the per-warp digit counters are packed 16-bit halves (a warp ranks
-// 32 * ITEMS < 2^16 keys), so the shared-memory footprint -- and with it 3 CTAs per SM -- stays that of the 8-bit pass.
+// RB = digit width in bits: NB = 2^RB bins.  The OWN = min(NB, 256) threads that own the digits (publish, look-back, digit
+// offsets) own DPT = NB / OWN consecutive digits each; above 8 bits the per-warp digit counters are packed 16-bit halves (a
+// warp ranks 32 * ITEMS < 2^16 keys), so the shared-memory footprint -- and with it 3 CTAs per SM -- stays that of the 8-bit
+// pass.  Below 8 bits (a sort whose passes need not be full: 27 varying bits = 4 x 7) a pass votes once less per key and its
+// digit runs are twice as long.
 template <class K, class V, int THREADS, int ITEMS, int RB = 8> struct RadixPassCfg {
     static constexpr bool HAS_V = !std::is_same<V, NoVal>::value;
     static constexpr int NB = 1 << RB;
-    static constexpr int DPT = NB / 256;
+    static constexpr int OWN = NB < 256 ? NB : 256;
+    static constexpr int DPT = NB / OWN;
     static constexpr bool PACK = RB > 8;
     static constexpr int TILE = THREADS * ITEMS;
     static constexpr int WARPS = THREADS / 32;
@@ -271,8 +274,8 @@ template <class K, class V, int THREADS, int ITEMS, int RB = 8> struct RadixPass
     static constexpr size_t STAGE_BYTES = (size_t)TILE * ELEM;
     static constexpr size_t WHIST_WORDS = (size_t)WARPS * NB / (PACK ? 2 : 1);
     static constexpr size_t SMEM_BYTES = STAGE_BYTES + (WHIST_WORDS + 2 * NB + 16) * sizeof(uint32_t);
-    static_assert(RB >= 8 && RB <= RADIX_MAX_BITS, "digit width");
-    static_assert(THREADS >= 256 && THREADS % 32 == 0, "256 threads own the digits");
+    static_assert(RB >= 5 && RB <= RADIX_MAX_BITS, "digit width");
+    static_assert(THREADS >= 256 && THREADS % 32 == 0, "up to 256 threads own the digits");
     static_assert(TILE < 65536, "ranks are packed in 16 bits");
 };
 
@@ -281,7 +284,7 @@ template <class K, class V, class Op, int THREADS, int ITEMS, bool FULL, int RB>
 __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a, unsigned char *smem_raw, const uint32_t tile,
                                                 const uint32_t tile_n) {
     typedef RadixPassCfg<K, V, THREADS, ITEMS, RB> Cfg;
-    constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS, NB = Cfg::NB, DPT = Cfg::DPT;
+    constexpr int TILE = Cfg::TILE, WARPS = Cfg::WARPS, NB = Cfg::NB, DPT = Cfg::DPT, OWN = Cfg::OWN;
     constexpr bool HAS_V = Cfg::HAS_V, PACK = Cfg::PACK;
 
     unsigned char *stage = smem_raw;
@@ -347,10 +350,10 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
     __syncthreads();
 
     // ---- per digit: exclusive scan over the warps, publish the tile count ----------------------------
-    const unsigned d0 = tid * DPT; // first of this thread's digits (tid < 256)
+    const unsigned d0 = tid * DPT; // first of this thread's digits (tid < OWN)
     uint32_t count_full[DPT];
     uint32_t incl = 0, mine = 0;
-    if (tid < 256) {
+    if (tid < (unsigned)OWN) {
         if constexpr (PACK) { // two digits per word: the packed halves add independently (a tile holds < 2^16 keys)
 #pragma unroll
             for (int j = 0; j < DPT / 2; ++j) {
@@ -387,7 +390,7 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
         if (lane == 31) misc[1 + warp] = incl;
     }
     __syncthreads();
-    if (tid < 256) {
+    if (tid < (unsigned)OWN) {
         uint32_t off = incl - mine;
         for (unsigned w = 0; w < warp; ++w) off += misc[1 + w];
 #pragma unroll
@@ -432,7 +435,7 @@ __device__ __forceinline__ void radix_pass_tile(const RadixPassArgs<K, V, Op> &a
     }
 
     // ---- look back: global offset of every digit run of this tile ------------------------------------
-    if (tid < 256) {
+    if (tid < (unsigned)OWN) {
         uint32_t excl[DPT];
 #pragma unroll
         for (int j = 0; j < DPT; ++j) excl[j] = 0;

@@ -179,6 +179,14 @@ int main(int argc, char **argv) {
     if (!only || strstr("kv " #T "x" #I " minb" #B " rb" #RBITS, only))                                  \
     run<uint64_t, uint32_t, T, I, B, RBITS>("kv " #T "x" #I " minb" #B " rb" #RBITS, k0, v0, k1, v1, n, mask, scratch, scratch_bytes, d_err, d_chk)
     RUNB(384, 12, 3, 8);
+    RUNB(384, 12, 3, 7);
+    RUNB(384, 12, 3, 6);
+    RUNB(384, 14, 3, 7);
+    RUNB(384, 16, 3, 7);
+    RUNB(512, 12, 2, 7);
+    RUNB(256, 16, 4, 7);
+    RUNB(384, 12, 4, 7);
+    if (argc > 4) return 0;
     RUNB(384, 12, 3, 9);
     RUNB(384, 12, 3, 10);
     RUNB(384, 12, 2, 9);
