@@ -6,7 +6,8 @@ import json
 import sys
 
 CLASS = [("encode_kernel", "encode"), ("radix_hist_kernel", "hist"), ("radix_pass_kernel", "pass"), ("scan_runs_kernel", "scan_runs"),
-         ("scan_emit_kernel", "scan_emit"), ("pair_finish_kernel", "pair_unique"), ("pair_unique_kernel", "pair_unique"),
+         ("scan_emit_kernel", "scan_emit"), ("scan_groups_kernel", "scan_emit"), ("record_finish", "sort_finish"),
+         ("pair_finish_kernel", "pair_unique"), ("pair_unique_kernel", "pair_unique"),
          ("merge_tiles_kernel", "merge"), ("exchange_pass_kernel", "partition"), ("partition_hist_kernel", "partition")]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
