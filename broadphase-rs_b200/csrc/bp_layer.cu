@@ -1924,6 +1924,12 @@ int resolve_pending(bp_layer *L, bool keep_lazy) {
     TRY(wait_mail(L, 0, L->pending_seq, L->h_res, sizeof(ExtendResult)));
     L->pending = false;
     const ExtendResult &r = *L->h_res;
+    // An object that wants more cells than the encoder enumerates (only a min_depth far above its natural depth does that;
+    // the reference warn!s and heap-allocates, src/geom.rs:299-301): the extend call is rejected as a whole -- nothing it
+    // wrote lies inside the tree, whose length, flags and masks stay what they were before the call.
+    if (r.too_many)
+        return fail(L, BP_ERR_TOO_LARGE, "an object of the last extend wanted more than 2^20 cells (min_depth too high for its size): "
+                                          "the call was rejected, the tree is unchanged");
     L->n_invalid += r.n_invalid;
     L->stats.n_invalid = L->n_invalid;
     L->tail_has_last = true;
@@ -1948,7 +1954,6 @@ int resolve_pending(bp_layer *L, bool keep_lazy) {
         L->id_and &= r.id_and;
     }
     L->stats.n_records = L->n_records;
-    if (r.too_many) return fail(L, BP_ERR_TOO_LARGE, "an object wanted more than 2^20 cells (min_depth too high for its size); it was skipped");
     if (r.total_records > room) return fail(L, BP_ERR_INTERNAL, "record capacity exceeded");
     return BP_OK;
 }

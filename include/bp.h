@@ -21,8 +21,9 @@
  *  - Limits (BP_ERR_TOO_LARGE): fewer than 2^30 records per layer; a scan may visit fewer than 2^30 (ancestor, descendant)
  *    record pairs -- about 46 000 objects sharing ONE cell, or a depth-0 cell, reach that -- and emits fewer than 2^30
  *    raw pairs; an object may own at most 2^20 cells and 4095 per axis (only a min_depth far above its natural depth does
- *    that; the reference warn!s and continues, src/geom.rs:299-301): the offending object is skipped, every other object
- *    of the same extend call has been appended when the error is returned.
+ *    that; the reference warn!s and continues, src/geom.rs:299-301): the extend call that contains such an object is
+ *    rejected as a whole -- the error comes back from that call or from the next call on the layer, whose tree is what
+ *    it was before the rejected call.
  */
 #ifndef BP_H
 #define BP_H

@@ -576,3 +576,30 @@ def test_config3_full_size_properties(bp):
     pall = g.par_scan()
     sub = pall[((pall[:, 0] ^ pall[:, 1]) & 1) == 1]
     assert sub.shape == p1.shape and (sub == p1).all()
+
+
+def test_oversized_object_rejects_the_whole_extend(bp):
+    """An object that wants more than 2^20 cells (min_depth far above its natural depth; the reference warn!s and
+    heap-allocates, src/geom.rs:299-301) is a documented limit of the encoder: the extend call is rejected as a whole with
+    BP_ERR_TOO_LARGE and the tree is what it was before the call."""
+    sc = bp.scenes.uniform_cubes(5_000, 61)
+    g = bp.LayerBuilder().with_min_depth(8).build(2, "u32")
+    o = co.OracleLayer(2, 4, 8)
+    g.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    o.extend(sc["sys_bounds"], sc["bounds"], sc["ids"])
+    n_before = len(g)
+    assert n_before == len(o)
+    more = bp.scenes.uniform_cubes(1_000, 62, id_base=5_000)
+    bad = more["bounds"].copy()
+    bad[500] = np.array([0.1, 0.1, 0.1, 0.62, 0.62, 0.62], dtype=np.float32)   # 134^3 cells at depth 8
+    with pytest.raises(bp.BpError) as e:
+        g.extend(sc["sys_bounds"], bad, more["ids"])
+        len(g)                                                                   # (the error may only surface at the next call)
+    assert e.value.status == 4
+    assert len(g) == n_before
+    _assert_records_equal(g, o)
+    _assert_pairs_equal(g.par_scan(), o.par_scan())
+    g.extend(more["sys_bounds"], more["bounds"], more["ids"])                    # the layer goes on as if nothing had happened
+    o.extend(more["sys_bounds"], more["bounds"], more["ids"])
+    _assert_pairs_equal(g.par_scan(), o.par_scan())
+    _assert_records_equal(g, o)

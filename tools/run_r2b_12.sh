@@ -1,0 +1,3 @@
+set -x
+python -m pytest tests -q -m gpu 2>&1 | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
