@@ -107,6 +107,7 @@ SYMBOLS = {
     "bp_dist_last_error": (ctypes.c_char_p, [_vp]),
     "bp_layer_set_halo": (_i, [_vp, _sz]),
     "bp_layer_set_scan_dedup": (_i, [_vp, _i]),
+    "bp_layer_set_pair_later_fixed": (_i, [_vp, _u64]),
     "bp_layer_scan_raw_device": (_i, [_vp, _P(Filter), _P(_vp), _P(_sz)]),
     "bp_layer_unique_pairs_device": (_i, [_vp, _vp, _sz, _u64, _P(_vp), _P(_sz)]),
     "bp_layer_len": (_i, [_vp, _P(_sz)]),

@@ -19,33 +19,58 @@ NVCC_FLAGS = [
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
     "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-    "--shared", "-cudart", "shared",
-    "--threads", "2",   # the two translation units side by side
 ]
+LINK_FLAGS = ["--shared", "-cudart", "shared"]
+OBJ_DIR = os.path.join(HERE, "_build")   # one object per translation unit (git- and gpurun-ignored): an edit of bp_dist.cu
+                                         # does not recompile the four-minute bp_layer.cu
+
+
+def _deps(src):
+    return [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def _obj(src):
+    return os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
 
 
 def needs_build():
-    if not os.path.exists(SO):
-        return True
-    t = os.path.getmtime(SO)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return _stale(SO, [d for s in SOURCES for d in _deps(s)])
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        [os.path.join(CSRC, s) for s in SOURCES] + ["-o", SO]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    jobs = []
+    for src in SOURCES:   # the translation units side by side
+        if force or _stale(_obj(src), _deps(src)):
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", _obj(src)]
+            jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = []
+    for src, p in jobs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            failed.append(src)
+    if failed:
+        raise RuntimeError("nvcc failed compiling " + ", ".join(failed))
+    r = subprocess.run([nvcc] + NVCC_FLAGS + LINK_FLAGS + [_obj(s) for s in SOURCES] + ["-o", SO], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libbroadphase_b200.so")
+        raise RuntimeError("nvcc failed linking libbroadphase_b200.so")
     return SO
 
 
 if __name__ == "__main__":
-    build(force=True, verbose="-v" in sys.argv)
+    build(force="-f" in sys.argv, verbose="-v" in sys.argv)
     print(SO)

@@ -121,6 +121,11 @@ __global__ void sample_rows_kernel(const uint64_t *src, uint64_t n, uint64_t str
     for (int r = 0; r < g; ++r) rows.p[r][i] = v;
 }
 
+bool snap_splitters() { // BP_DIST_SNAP_SPLITTERS=0: plain quantiles (measurement aid)
+    static const bool on = !(getenv("BP_DIST_SNAP_SPLITTERS") && atoi(getenv("BP_DIST_SNAP_SPLITTERS")) == 0);
+    return on;
+}
+
 double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -271,13 +276,46 @@ void row_addresses(const bp_dist *D, size_t off, int row_words, uint64_t *out) {
     for (int r = 0; r < D->g; ++r) out[r] = (uint64_t)(uintptr_t)(D->peer[r] + off + (size_t)D->me * row_words * sizeof(uint64_t));
 }
 
-// parts-1 ascending splitters at the quantiles of a sample (identical on every rank because the gathered sample is)
+int bit_length(uint64_t v) { return v ? 64 - __builtin_clzll(v) : 0; }
+
+// parts-1 ascending splitters at the quantiles of a sample (identical on every rank because the gathered sample is).
+// A splitter may be ANY value -- it only decides the balance -- so each one is moved to the roundest value (most trailing
+// zero bits) whose sample rank stays within 1/32 of a shard's size of its quantile: the keys of a shard [lower, upper) share
+// every bit above the highest one in which `lower` and `upper - 1` differ, and with round splitters those are the top
+// log2(parts) bits or so, which the shard's sort then never looks at (shard_fixed_bits below; 8 shards of a 30-bit scene:
+// 27 varying bits = four 7-bit passes instead of four 8-bit ones).
 void choose_splitters(std::vector<uint64_t> &s, int parts, uint64_t *out) {
     std::sort(s.begin(), s.end());
-    for (int i = 1; i < parts; ++i) out[i - 1] = s.empty() ? ~0ull : s[std::min(s.size() - 1, (size_t)i * s.size() / parts)];
+    const size_t m = s.size(), slack = snap_splitters() ? m / (size_t)parts / 32 : 0;
+    for (int i = 1; i < parts; ++i) {
+        if (m == 0) {
+            out[i - 1] = ~0ull;
+            continue;
+        }
+        const size_t t = std::min(m - 1, (size_t)i * m / parts);
+        uint64_t v = s[t];
+        if (slack) { // (slack < the distance between two quantiles: the windows of neighbouring splitters never overlap)
+            const uint64_t lo = s[t - std::min(t, slack)], hi = s[std::min(m - 1, t + slack)];
+            if (lo < hi) v = hi & (~0ull << (bit_length(lo ^ hi) - 1)); // in (lo, hi]: hi without the bits below the first difference
+        }
+        out[i - 1] = v;
+    }
 }
 
-int bit_length(uint64_t v) { return v ? 64 - __builtin_clzll(v) : 0; }
+// The bits every key of shard `me` is known to share, from its two splitters alone: *fixed = their positions, *value = the
+// bits themselves (both inside `top`'s width and above).  A key v belongs to shard d iff splitters[d-1] <= v < splitters[d]
+// (splitter_rank15, bp_common.cuh).
+void shard_fixed_bits(const uint64_t *splitters, int parts, int me, uint64_t top, uint64_t *fixed, uint64_t *value) {
+    *fixed = 0;
+    *value = 0;
+    const uint64_t lo = me > 0 ? splitters[me - 1] : 0;
+    if ((me < parts - 1 && splitters[me] <= lo) || lo > top) return; // an empty shard (or splitters of an empty sample)
+    const uint64_t hi = me < parts - 1 ? std::min(splitters[me] - 1, top) : top; // top = the largest value a key can have
+    const int b = bit_length(lo ^ hi); // bits [b, 64) agree between the two ends, hence in everything between them
+    if (b >= 64) return;
+    *fixed = ~0ull << b;
+    *value = lo & *fixed;
+}
 
 double imbalance(const uint64_t *col_sums, int g) {
     double sum = 0, mx = 0;
@@ -648,6 +686,12 @@ int bp_dist_frame(bp_dist *D, const float *sysb, const float *d_bounds, const vo
         prev_last = have_prev ? std::max(prev_last, last) : last;
         have_prev = true;
     }
+    if (g > 1 && halo_in == 0 && snap_splitters()) { // (halo copies lie below my lower splitter)
+        uint64_t fixed, value;
+        shard_fixed_bits(D->splitters, g, me, p_key_or ? ~0ull >> (64 - bit_length(p_key_or)) : 0, &fixed, &value);
+        p_key_or &= ~fixed | value;
+        p_key_and |= value;
+    }
     const uint64_t plan_id_or = id_bits;
     id_bits |= D->static_id_bits;
     D->id_mask |= (1ull << std::max(1, bit_length(id_bits))) - 1; // IDs seen since the splitters were cached
@@ -748,6 +792,11 @@ int bp_dist_frame(bp_dist *D, const float *sysb, const float *d_bounds, const vo
     mark(); // pair_exchange
     const void *pairs = nullptr;
     size_t n_pairs = 0;
+    if (g > 1 && snap_splitters()) { // the later IDs of my slice lie between two pair splitters: their top bits need no radix pass
+        uint64_t fixed, value;
+        shard_fixed_bits(D->pair_splitters, g, me, D->id_mask & 0xffffffffull, &fixed, &value);
+        LTRY(D, D->shard, bp_layer_set_pair_later_fixed(D->shard, fixed & 0xffffffffull));
+    }
     LTRY(D, D->shard, bp_layer_unique_pairs_inplace_device(D->shard, D->arena + D->off_rp, precv[me], D->id_mask, &pairs, &n_pairs));
     I.pairs = n_pairs;
     mark(); // unique

@@ -184,6 +184,7 @@ struct bp_layer {
     size_t h_offsets_cap = 0;
     void *pairs_src = nullptr;     // finish_pairs: the raw pairs live here instead of praw[0] (bp_layer_unique_pairs_inplace_device)
     bool pairs_grouped = false;    // finish_pairs: the raw pairs are already grouped by their first ID, in order
+    uint64_t pair_later_fixed = 0; // bp_layer_set_pair_later_fixed: bits of the later ID that agree in every pair of the next call
     DevBuf pair_cnt;               // pairs per later ID (counting sort of the pairs; dense 32-bit IDs only)
     bool want_pair_counts = false; // the caller of scan_raw will finish the pairs itself (scan), not hand them out raw
     uint64_t pair_cnt_n = 0;       // > 0: the last emission counted its pairs per later ID into pair_cnt[0, pair_cnt_n)
@@ -1305,7 +1306,7 @@ template <int KIND, class IdT> struct Impl {
             // The finish kernel orders whole packed pairs inside a group, so the lowest bits of the later ID need no radix
             // pass of their own when leaving them out saves one: a group then holds the pairs of 2^drop later IDs -- taken
             // while that is expected to be at most ~6 pairs (2^25 IDs, 49 M pairs: 3 passes over 24 bits instead of 4).
-            uint64_t lmask = imask & 0xffffffffull;
+            uint64_t lmask = imask & 0xffffffffull & ~L->pair_later_fixed;
             {
                 RadixPlan pl;
                 memset(&pl, 0, sizeof pl);
@@ -2466,6 +2467,12 @@ int bp_layer_set_scan_dedup(bp_layer *L, int enabled) {
     return BP_OK;
 }
 
+int bp_layer_set_pair_later_fixed(bp_layer *L, uint64_t fixed_bits) {
+    if (!L) return BP_ERR_INVALID_ARG;
+    L->pair_later_fixed = fixed_bits;
+    return BP_OK;
+}
+
 int bp_layer_scan_raw_device(bp_layer *L, const bp_filter *f, const void **out_raw, size_t *out_count) {
     if (!L) return BP_ERR_INVALID_ARG;
     if (L->id_bytes != 4) return fail(L, BP_ERR_INVALID_ARG, "raw pairs are exposed for 32-bit IDs only");
@@ -2512,6 +2519,7 @@ static int unique_pairs_impl(bp_layer *L, const void *d_raw, size_t n, uint64_t 
     CU(L, cudaMemsetAsync(L->d_tot, 0, sizeof(ScanTotals), L->stream));
     const int st = do_finish_pairs(L, n);
     L->pairs_src = nullptr;
+    L->pair_later_fixed = 0; // (one call only)
     L->id_or = keep_or;
     L->id_and = keep_and;
     TRY(st);

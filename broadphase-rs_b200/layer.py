@@ -276,6 +276,9 @@ class Layer:
     def set_scan_dedup(self, enabled):
         self._ck(lib().bp_layer_set_scan_dedup(self._h, int(enabled)))
 
+    def set_pair_later_fixed(self, fixed_bits):
+        self._ck(lib().bp_layer_set_pair_later_fixed(self._h, int(fixed_bits)))
+
     def scan_raw_device(self, flt=None):
         """Raw (filtered, unsorted, duplicate-carrying) packed pairs: (device pointer, count)."""
         f = None if flt is None else flt._c()

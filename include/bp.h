@@ -313,6 +313,10 @@ int bp_layer_scan_raw_device(bp_layer *layer, const bp_filter *filter, const voi
  * (later, earlier) layout.  id_mask: OR of all bits in which two IDs may differ (0: use the layer's own). */
 int bp_layer_unique_pairs_device(bp_layer *layer, const void *d_raw, size_t n, uint64_t id_mask, const void **out_d_pairs,
                                  size_t *out_count);
+/* What the caller knows about the pairs of the NEXT bp_layer_unique_pairs_*_device call: the bits of fixed_bits (bits 0-31)
+ * have the same value in the later ID of every pair -- a shard's slice of a range partition on the later ID lies between
+ * two splitters -- so the pair sort spends no radix pass on them.  Forgotten after that call; 0 = nothing known. */
+int bp_layer_set_pair_later_fixed(bp_layer *layer, uint64_t fixed_bits);
 /* The same without the staging copy: d_raw itself is one side of the sort's ping-pong (its contents are destroyed). */
 int bp_layer_unique_pairs_inplace_device(bp_layer *layer, void *d_raw, size_t n, uint64_t id_mask, const void **out_d_pairs,
                                          size_t *out_count);

@@ -174,6 +174,17 @@ class CpuOpsProduct(CpuOps):
     def sort_tags(self):
         return list(self._tags)
 
+    def set_pair_later_fixed(self, fixed, value):
+        self._later_fixed = (fixed & 0xFFFFFFFF, value & 0xFFFFFFFF)
+
+    def unique_pairs(self, raw, id_mask):
+        fixed, value = getattr(self, "_later_fixed", (0, 0))  # CHECKED against the pairs that arrived, like the sort plan
+        self._later_fixed = (0, 0)
+        later = _u64(raw) >> np.uint64(32)
+        assert ((later & np.uint64(fixed)) == np.uint64(value)).all(), "a later ID outside the bits its shard is said to share"
+        self.later_fixed_bits = getattr(self, "later_fixed_bits", []) + [bin(fixed).count("1")]
+        return super().unique_pairs(raw, id_mask)
+
     def count_records_matrix(self, keys, splitters, tags):
         counts, halo = self.count_records(keys, splitters)
         row = torch.tensor([_s64(v) for v in counts + halo + list(tags)], dtype=torch.int64)

@@ -38,20 +38,49 @@ def ancestor_keys(kind, key):
 
 
 def choose_splitters(sample, parts):
-    """parts-1 ascending splitters at the quantiles of a (host, uint64) sample; identical on every
-    rank because the gathered sample is."""
+    """parts-1 ascending splitters at the quantiles of a (host, uint64) sample; identical on every rank because the
+    gathered sample is.  Any value is a valid splitter (it only decides the balance), so each one is moved to the roundest
+    value (most trailing zero bits) whose sample rank stays within 1/32 of a shard's size of its quantile: the keys of a
+    shard then share their top bits (shard_fixed_bits) and the shard's sort never looks at them."""
     s = np.sort(np.asarray(sample, dtype=np.uint64))
-    if s.shape[0] == 0:
+    m = s.shape[0]
+    if m == 0:
         return np.full(parts - 1, U64_MAX, dtype=np.uint64)
-    q = [s[min(s.shape[0] - 1, (i * s.shape[0]) // parts)] for i in range(1, parts)]
+    slack = m // parts // 32
+    q = []
+    for i in range(1, parts):
+        t = min(m - 1, (i * m) // parts)
+        v = int(s[t])
+        if slack:
+            lo, hi = int(s[t - min(t, slack)]), int(s[min(m - 1, t + slack)])
+            if lo < hi:  # in (lo, hi]: hi without the bits below the first one in which the two differ
+                v = hi & ~((1 << ((lo ^ hi).bit_length() - 1)) - 1)
+        q.append(v)
     return np.asarray(q, dtype=np.uint64)
 
 
-def sort_plan(tags, id_or, n_halo):
+def shard_fixed_bits(splitters, me, top=0xFFFFFFFFFFFFFFFF):
+    """(fixed, value): the bit positions every key of shard `me` is known to share, from its two splitters alone, and the
+    bits themselves.  A key v belongs to shard d iff splitters[d-1] <= v < splitters[d]; `top` = the largest possible key."""
+    parts = len(splitters) + 1
+    full = 0xFFFFFFFFFFFFFFFF
+    lo = int(splitters[me - 1]) if me > 0 else 0
+    if (me < parts - 1 and int(splitters[me]) <= lo) or lo > top:
+        return 0, 0  # an empty shard
+    hi = min(int(splitters[me]) - 1, top) if me < parts - 1 else top
+    b = (lo ^ hi).bit_length()
+    fixed = (full << b) & full
+    return fixed, lo & fixed
+
+
+def sort_plan(tags, id_or, n_halo, shard=None):
     """(key_or, key_and, id_or, id_and, ids_ascending) for the sort of a receive buffer, from the tag words every source
     sent with its counts (N_TAGS per source: id_or | fold bit, key_or, key_and, id_and, first ID, last ID, ascending).
     The buffer holds the sources' chunks in rank order, each a stable partition of the source's records: its IDs ascend
-    iff every source's do, the sources' ID ranges follow each other in rank order, and no (unordered) halo copies came."""
+    iff every source's do, the sources' ID ranges follow each other in rank order, and no (unordered) halo copies came.
+    shard = (splitters, me) of the receiving shard: without halo copies (they lie below the lower splitter) every key
+    carries the bits the shard's two ends share (shard_fixed_bits; the last shard ends at the largest key the sources' OR
+    allows), whatever the sources' masks say about their whole key sets."""
     full = 0xFFFFFFFFFFFFFFFF
     key_or, key_and, id_and = 0, full, full
     ascending, prev_last = n_halo == 0, -1
@@ -64,6 +93,10 @@ def sort_plan(tags, id_or, n_halo):
             continue
         ascending = ascending and bool(asc) and first >= prev_last
         prev_last = max(prev_last, last)
+    if n_halo == 0 and shard is not None and len(shard[0]):
+        fixed, value = shard_fixed_bits(shard[0], shard[1], (1 << key_or.bit_length()) - 1)
+        key_or &= ~fixed | value
+        key_and |= value
     return key_or, key_and, id_or, id_and, ascending
 
 
@@ -213,7 +246,7 @@ class DistLayer:
             flagged = flagged and bool(t[0] >> 63)  # every rank can: the cell flags ride in the IDs across the exchange
             id_bits |= t[0] & ~(1 << 63)
         if product:
-            plan = sort_plan(tags, id_bits, n_halo)
+            plan = sort_plan(tags, id_bits, n_halo, (splitters, me))
         id_bits |= self._static_id_bits
         self._id_mask |= (1 << max(1, id_bits.bit_length())) - 1  # IDs seen since the splitters were cached
         mark("counts")
@@ -264,6 +297,8 @@ class DistLayer:
         mark("pair_counts")
         rp = ops.exchange_pairs(raw, a_splitters, pm)
         mark("pair_exchange")
+        if g > 1 and hasattr(ops, "set_pair_later_fixed"):  # my later IDs lie between two pair splitters: no radix pass on their top bits
+            ops.set_pair_later_fixed(*shard_fixed_bits(a_splitters, me, self._id_mask))
         pairs = ops.unique_pairs(rp, self._id_mask)
         mark("unique")
 

@@ -76,7 +76,8 @@ def test_ancestor_keys_and_splitters(bp):
     for d, a in enumerate(anc):
         assert a & 31 == d and co.overlaps(2, a, key)
     s = bpd.choose_splitters(np.arange(1000, dtype=np.uint64), 4)
-    assert list(s) == [250, 500, 750]
+    assert list(s) == [256, 496, 752]  # the roundest values within 1000 / 4 / 32 = 7 sample ranks of the quantiles 250, 500, 750
+    assert list(bpd.choose_splitters(np.arange(100, dtype=np.uint64), 4)) == [25, 50, 75]  # too small a sample to move anything
     assert list(bpd.choose_splitters(np.zeros(0, dtype=np.uint64), 4)) == [2**64 - 1] * 3
     # run_upper_key: the cell of `key` at depth 5 spans the low 3*(19-5) origin bits + the depth field
     assert bpd.run_upper_key(2, key) == key | ((1 << (5 + 3 * 14)) - 1)
@@ -84,6 +85,50 @@ def test_ancestor_keys_and_splitters(bp):
     m_halo = np.array([[0, 3], [0, 0]])
     assert bpd.chunk_offsets(m_own, m_halo, 0) == ([0, 0], [5, 1])
     assert bpd.chunk_offsets(m_own, m_halo, 1) == ([5, 4], [7, 11])
+
+
+def test_round_splitters_and_the_bits_a_shard_shares(bp):
+    """Splitters snapped to round values stay ascending and within the slack of their quantiles; shard_fixed_bits is true
+    of every key that the shard rule (#splitters <= key) sends to the shard, for keys AND for 32-bit later IDs."""
+    from tests import dist_protocol as bpd
+    rng = np.random.Generator(np.random.Philox(5))
+    full = (1 << 64) - 1
+    for trial in range(60):
+        parts = int(rng.integers(2, 17))
+        bits = int(rng.integers(4, 65))
+        m = int(rng.integers(1, 40000))
+        sample = rng.integers(0, 1 << bits, size=m, dtype=np.uint64, endpoint=False) if bits < 64 else rng.integers(0, full, size=m, dtype=np.uint64, endpoint=True)
+        if trial % 5 == 0:  # heavy duplicates
+            sample = sample >> np.uint64(max(0, bits - 3)) << np.uint64(max(0, bits - 3))
+        top = (1 << int(np.bitwise_or.reduce(sample)).bit_length()) - 1  # what the product knows: the sources' OR
+        spl = bpd.choose_splitters(sample, parts)
+        assert spl.shape == (parts - 1,) and (np.diff(spl.astype(object)) >= 0).all()
+        srt = np.sort(sample)
+        slack = m // parts // 32
+        for i, v in enumerate(spl, start=1):
+            t = min(m - 1, i * m // parts)
+            assert int(srt[max(0, t - slack)]) <= int(v) <= int(srt[min(m - 1, t + slack)])
+        shard = np.searchsorted(spl, sample, side="right")
+        for d in range(parts):
+            fixed, value = bpd.shard_fixed_bits(spl, d, top)
+            mine = sample[shard == d]
+            assert value & ~fixed == 0
+            assert ((mine & np.uint64(fixed)) == np.uint64(value)).all(), (trial, d)
+    # uniform keys, power-of-two shards, a sample large enough that the octant boundaries fall inside the windows: every
+    # shard shares its top log2(parts) bits (8 shards of the 62-bit keys: 3 bits less to sort on, each)
+    sample = rng.integers(0, 1 << 62, size=1 << 19, dtype=np.uint64)
+    for parts in (2, 4, 8, 16):
+        spl = bpd.choose_splitters(sample, parts)
+        assert [int(v) for v in spl] == [i << (62 - parts.bit_length() + 1) for i in range(1, parts)]
+        for d in range(parts):
+            fixed, value = bpd.shard_fixed_bits(spl, d, (1 << 62) - 1)
+            assert fixed == full & ~((1 << (62 - parts.bit_length() + 1)) - 1) and value == d << (62 - parts.bit_length() + 1)
+    # degenerate splitters: empty shards share nothing, the last shard's upper end is `top`
+    assert bpd.shard_fixed_bits(np.array([8, 8, 16], dtype=np.uint64), 1, 31) == (0, 0)
+    assert bpd.shard_fixed_bits(np.array([8, 8, 16], dtype=np.uint64), 2, 31) == (full & ~7, 8)
+    assert bpd.shard_fixed_bits(np.array([8, 8, 16], dtype=np.uint64), 3, 31) == (full & ~15, 16)
+    assert bpd.shard_fixed_bits(np.array([8, 8, 16], dtype=np.uint64), 0, 31) == (full & ~7, 0)
+    assert bpd.shard_fixed_bits(np.array([full] * 3, dtype=np.uint64), 0) == (0, 0)  # splitters of an empty sample: everything in shard 0
 
 
 def test_sort_plan_from_tag_words(bp):
@@ -101,6 +146,12 @@ def test_sort_plan_from_tag_words(bp):
     assert sort_plan([a, b[:6] + [0]], 0x1FF, 0)[4] is False  # a source whose own IDs do not ascend
     assert sort_plan([a, [0x1FF, 0, full, full, 99, 250, 1]], 0x1FF, 0)[4] is True   # equal IDs may meet at the seam
     assert sort_plan([empty, empty], 0, 0) == (0, full, 0, full, True)
+    # the receiving shard's keys share the bits its two splitters share -- unless halo copies (below the lower splitter) came
+    spl = np.array([0x3000, 0x4000, 0xC000], dtype=np.uint64)
+    assert sort_plan([a, b], 0x1FF, 0, (spl, 1))[:2] == (0x3FFF, 0x3000)   # [0x3000, 0x4000): the top 4 of 16 bits are 0011
+    assert sort_plan([a, b], 0x1FF, 2, (spl, 1))[:2] == (0xFFFF, 0)
+    assert sort_plan([a, b], 0x1FF, 0, (spl, 3))[:2] == (0xFFFF, 0xC000)   # the last shard ends at the sources' largest possible key
+    assert sort_plan([a, b], 0x1FF, 0, (spl, 0))[:2] == (0x3FFF, 0)
 
 
 def test_scatter_destinations_equal_the_per_destination_sums(bp):

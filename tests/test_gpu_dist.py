@@ -63,6 +63,33 @@ def test_partition_pairs_and_unique(bp):
     assert (got[:, 0].astype(np.uint64) == want >> np.uint64(32)).all() and (got[:, 1].astype(np.uint64) == (want & np.uint64(0xFFFFFFFF))).all()
 
 
+def test_pair_sort_skips_the_later_id_bits_a_slice_shares(bp):
+    """bp_layer_set_pair_later_fixed: a shard's slice of the range partition on the later ID lies between two splitters, so
+    the top bits of its later IDs are the same in every pair and the pair sort needs no radix pass for them -- fewer passes,
+    the same result; the hint is forgotten after one call."""
+    import torch
+    from broadphase_rs_b200.dist import _view
+    rng = np.random.Generator(np.random.Philox(19))
+    n = 600_000
+    a = (rng.integers(0, 1 << 22, size=n).astype(np.uint64)) | np.uint64(5 << 22)   # later IDs of the slice [5 << 22, 6 << 22)
+    b = rng.integers(0, 1 << 25, size=n).astype(np.uint64)
+    raw = (a << np.uint64(32)) | b
+    raw[::7] = raw[3::7][:raw[::7].shape[0]]  # duplicates
+    want = np.unique(raw)
+    L = bp.Layer(2, "u32")
+    passes = []
+    for fixed in (0, 0xFFFFFFFF & ~((1 << 22) - 1), 0):
+        d = torch.from_numpy(raw.view(np.int64).copy()).cuda()
+        if fixed:
+            L.set_pair_later_fixed(fixed)
+        ptr, cnt = L.unique_pairs_inplace_device(d, n, (1 << 28) - 1)  # 28 ID bits: 4 passes; 22 in the slice: 3
+        got = _view(ptr, 2 * cnt, torch.int32, torch.device("cuda")).cpu().numpy().view(np.uint32).reshape(cnt, 2)
+        assert cnt == want.shape[0]
+        assert (got[:, 0].astype(np.uint64) == want >> np.uint64(32)).all() and (got[:, 1].astype(np.uint64) == (want & np.uint64(0xFFFFFFFF))).all()
+        passes.append(L.stats()["pair_sort_passes"])
+    assert passes[1] < passes[0] and passes[2] == passes[0], passes
+
+
 def test_lookup_ranges_and_halo_scan(bp):
     import torch
     sc, k, i = _records(bp, 100_000, 5)
@@ -405,6 +432,9 @@ def _nccl_worker(rank, world, port, out_dir):
     for _ in range(2):
         pairs = ctx.frame(sc["sys_bounds"], db, di, 1 << 18, None)
     allp = ctx.gather_pairs(pairs)
+    st = ctx.layers()[1].stats()
+    with open(os.path.join(out_dir, "cfg2slice_passes_%d.txt" % rank), "w") as f:  # (recorded: round splitters save passes)
+        f.write("rank %d of %d: %d records, sort passes %d, pair sort passes %d\n" % (rank, world, st["n_records"], st["sort_passes"], st["pair_sort_passes"]))
     if rank == 0:
         np.save(os.path.join(out_dir, "cfg2slice.npy"), allp)
     ctx.close()
@@ -446,3 +476,6 @@ def test_nccl_frame_equals_oracle(bp, tmp_path):
     want = o.par_scan().astype(np.uint32)
     got = np.load(os.path.join(str(tmp_path), "cfg2slice.npy"))
     assert got.shape == want.shape and (got == want).all()
+    with open(os.path.join(ROOT, "gpurun_out", "dist_passes.txt"), "w") as f:
+        for r in range(world):
+            f.write(open(os.path.join(str(tmp_path), "cfg2slice_passes_%d.txt" % r)).read())
