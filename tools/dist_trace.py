@@ -31,11 +31,38 @@ for it in range(8):
     if it >= 3:
         for k, v in dl.last["phases_ms"].items():
             acc[k] = acc.get(k, 0.0) + v / 5
+# the result of the last frame against the bench's own record of this scene (profiles/*_bench_n<world>.json, parity.timed_shape):
+# pair count, order-sensitive hash of the concatenated slices, strict increase inside and across the slices
+pairs = dl.frame(sc["sys_bounds"], db, di, n, None)
+cnt = torch.tensor([pairs.shape[0]], dtype=torch.int64, device=db.device)
+cnts = [torch.empty_like(cnt) for _ in range(world)]
+dist.all_gather(cnts, cnt)
+cnts = [int(c.item()) for c in cnts]
+h = torch.tensor([dist_bench._i64(dist_bench.pair_hash(pairs, sum(cnts[:rank])))], dtype=torch.int64, device=db.device)
+edge = torch.zeros(4, dtype=torch.int64, device=db.device)
+if pairs.shape[0]:
+    edge[:2] = pairs[0].to(torch.int64) & 0xFFFFFFFF
+    edge[2:] = pairs[-1].to(torch.int64) & 0xFFFFFFFF
+edges = [torch.empty_like(edge) for _ in range(world)]
+dist.all_gather(edges, edge)
+inc, prev = dist_bench._strictly_increasing(pairs), None
+for r in range(world):
+    if cnts[r]:
+        e = [int(x) for x in edges[r].tolist()]
+        inc = inc and (prev is None or prev < (e[0], e[1]))
+        prev = (e[2], e[3])
+incf = torch.tensor([1 if inc else 0], dtype=torch.int64, device=db.device)
+dist.all_reduce(incf, op=dist.ReduceOp.MIN)
+dist.all_reduce(h, op=dist.ReduceOp.SUM)
+if rank == 0:
+    print("check: objects=%d pairs=%d hash=%016x sorted_unique_global=%s" % (n * world, sum(cnts), int(h.item()) & ((1 << 64) - 1), bool(incf.item())))
 for r in range(world):
     if rank == r:
         print("rank %d objects/gpu=%d world=%d  total %.3f ms" % (rank, n, world, sum(acc.values())))
         print("   " + "  ".join("%s=%.3f" % (k, v) for k, v in acc.items()))
         print("   records local=%d owned=%d halo=%d raw=%d pairs=%d" % (dl.last["records_local"], dl.last["records_owned"], dl.last["halo"], dl.last["raw_pairs"], dl.last["pairs"]))
+        st = dl.layers()[1].stats()
+        print("   shard sort passes=%d pair sort passes=%d" % (st["sort_passes"], st["pair_sort_passes"]))
         sys.stdout.flush()
     dist.barrier()
 dist.barrier()
