@@ -10,9 +10,10 @@ from ._lib import BpError, lib
 lib()  # fail loudly, at import time, if the CUDA library is missing
 
 from .layer import (FILTER_CATEGORY, FILTER_SPHERES, FILTER_ID_PARITY, FILTER_NONE, FILTER_XOR_MASK, PICK_AABB, PICK_SPHERE, Index32_2D,  # noqa: E402
-                    Index64_2D, Index64_3D, Layer, LayerBuilder, ScanFilter, device_count, plan_radix_passes, plan_sort_finish)
+                    Index64_2D, Index64_3D, Layer, LayerBuilder, ScanFilter, device_count, plan_dist_shard_bits,
+                    plan_dist_splitters, plan_radix_passes, plan_sort_finish)
 from . import scenes  # noqa: E402
 
 __all__ = ["Layer", "LayerBuilder", "ScanFilter", "Index32_2D", "Index64_2D", "Index64_3D", "BpError",
            "FILTER_NONE", "FILTER_ID_PARITY", "FILTER_XOR_MASK", "FILTER_CATEGORY", "FILTER_SPHERES", "PICK_SPHERE", "PICK_AABB", "device_count",
-           "plan_radix_passes", "plan_sort_finish", "scenes", "lib"]
+           "plan_radix_passes", "plan_sort_finish", "plan_dist_splitters", "plan_dist_shard_bits", "scenes", "lib"]

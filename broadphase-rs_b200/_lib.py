@@ -123,6 +123,8 @@ SYMBOLS = {
     "bp_device_count": (_i, [_P(_i)]),
     "bp_plan_radix_passes": (_i, [_u64, _P(_u32), _P(_u32), _i]),
     "bp_plan_sort_finish": (_i, [_u64, _u64, _P(_u64), _P(_u32)]),
+    "bp_dist_plan_splitters": (_i, [_P(_u64), _sz, _i, _P(_u64)]),
+    "bp_dist_plan_shard_bits": (_i, [_P(_u64), _i, _i, _u64, _P(_u64), _P(_u64)]),
 }
 
 _lib = None

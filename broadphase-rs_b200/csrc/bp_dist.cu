@@ -284,9 +284,9 @@ int bit_length(uint64_t v) { return v ? 64 - __builtin_clzll(v) : 0; }
 // every bit above the highest one in which `lower` and `upper - 1` differ, and with round splitters those are the top
 // log2(parts) bits or so, which the shard's sort then never looks at (shard_fixed_bits below; 8 shards of a 30-bit scene:
 // 27 varying bits = four 7-bit passes instead of four 8-bit ones).
-void choose_splitters(std::vector<uint64_t> &s, int parts, uint64_t *out) {
-    std::sort(s.begin(), s.end());
-    const size_t m = s.size(), slack = snap_splitters() ? m / (size_t)parts / 32 : 0;
+void choose_splitters(uint64_t *s, size_t m, int parts, uint64_t *out) {
+    std::sort(s, s + m);
+    const size_t slack = snap_splitters() ? m / (size_t)parts / 32 : 0;
     for (int i = 1; i < parts; ++i) {
         if (m == 0) {
             out[i - 1] = ~0ull;
@@ -301,6 +301,7 @@ void choose_splitters(std::vector<uint64_t> &s, int parts, uint64_t *out) {
         out[i - 1] = v;
     }
 }
+void choose_splitters(std::vector<uint64_t> &s, int parts, uint64_t *out) { choose_splitters(s.data(), s.size(), parts, out); }
 
 // The bits every key of shard `me` is known to share, from its two splitters alone: *fixed = their positions, *value = the
 // bits themselves (both inside `top`'s width and above).  A key v belongs to shard d iff splitters[d-1] <= v < splitters[d]
@@ -400,6 +401,19 @@ int exchange_records(bp_dist *D, const void *d_keys, const void *d_ids, uint64_t
 extern "C" {
 
 size_t bp_dist_handle_bytes(void) { return sizeof(Blob); }
+
+int bp_dist_plan_splitters(uint64_t *sample, size_t n, int parts, uint64_t *out_splitters) {
+    if ((n && !sample) || parts < 1 || parts > MAX_WORLD || (parts > 1 && !out_splitters)) return BP_ERR_INVALID_ARG;
+    choose_splitters(sample, n, parts, out_splitters);
+    return BP_OK;
+}
+
+int bp_dist_plan_shard_bits(const uint64_t *splitters, int parts, int shard, uint64_t top, uint64_t *out_fixed, uint64_t *out_value) {
+    if (parts < 1 || parts > MAX_WORLD || shard < 0 || shard >= parts || (parts > 1 && !splitters) || !out_fixed || !out_value)
+        return BP_ERR_INVALID_ARG;
+    shard_fixed_bits(splitters, parts, shard, top, out_fixed, out_value);
+    return BP_OK;
+}
 
 int bp_dist_create(const bp_dist_config *cfg, bp_dist **out) {
     if (!cfg || !out) return BP_ERR_INVALID_ARG;

@@ -483,6 +483,28 @@ def plan_sort_finish(mask, n_records):
     return top.value, gs.value
 
 
+def plan_dist_splitters(sample, parts):
+    """parts - 1 splitters of the sharded frame from a gathered key sample (bp_dist_plan_splitters; host only)."""
+    s = np.ascontiguousarray(np.asarray(sample, dtype=np.uint64)).copy()  # (sorted in place by the library)
+    out = np.zeros(max(parts - 1, 1), dtype=np.uint64)
+    st = lib().bp_dist_plan_splitters(s.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), s.shape[0], parts,
+                                      out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)))
+    if st != 0:
+        raise BpError(st, "bp_dist_plan_splitters")
+    return out[:parts - 1]
+
+
+def plan_dist_shard_bits(splitters, shard, top=0xFFFFFFFFFFFFFFFF):
+    """(fixed, value): the key bits every record of `shard` shares, from its two splitters (bp_dist_plan_shard_bits)."""
+    spl = np.ascontiguousarray(np.asarray(splitters, dtype=np.uint64))
+    fixed, value = ctypes.c_uint64(), ctypes.c_uint64()
+    st = lib().bp_dist_plan_shard_bits(spl.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), spl.shape[0] + 1, shard, top,
+                                       ctypes.byref(fixed), ctypes.byref(value))
+    if st != 0:
+        raise BpError(st, "bp_dist_plan_shard_bits")
+    return fixed.value, value.value
+
+
 def device_count():
     n = ctypes.c_int()
     st = lib().bp_device_count(ctypes.byref(n))

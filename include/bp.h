@@ -401,6 +401,16 @@ int bp_plan_radix_passes(uint64_t varying_mask, uint32_t *out_shift, uint32_t *o
  * src/layer.rs:149, :162 -- a total order, so the result is the same sequence. */
 int bp_plan_sort_finish(uint64_t varying_mask, uint64_t n_records, uint64_t *out_top_mask, uint32_t *out_group_shift);
 
+/* Host-side planning of the sharded frame, exposed for tests (no device involved).  bp_dist_plan_splitters: parts - 1
+ * ascending splitters from a gathered key sample (the array is sorted in place) -- the sample quantiles, each moved to the
+ * roundest value (most trailing zero bits) whose sample rank stays within 1/32 of a shard's size.  A key v belongs to shard
+ * d iff splitters[d-1] <= v < splitters[d], so every key of a shard carries the bits its two ends share:
+ * bp_dist_plan_shard_bits writes their positions (*out_fixed) and values (*out_value) for shard `shard`, `top` being the
+ * largest key that can occur (the last shard's upper end) -- the bits the shard's record sort, and the pair sort of its
+ * slice of the later IDs, never look at. */
+int bp_dist_plan_splitters(uint64_t *sample, size_t n, int parts, uint64_t *out_splitters);
+int bp_dist_plan_shard_bits(const uint64_t *splitters, int parts, int shard, uint64_t top, uint64_t *out_fixed, uint64_t *out_value);
+
 #ifdef __cplusplus
 }
 #endif

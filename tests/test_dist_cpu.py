@@ -131,6 +131,32 @@ def test_round_splitters_and_the_bits_a_shard_shares(bp):
     assert bpd.shard_fixed_bits(np.array([full] * 3, dtype=np.uint64), 0) == (0, 0)  # splitters of an empty sample: everything in shard 0
 
 
+def test_product_splitter_planner_equals_the_model(bp):
+    """The C++ planner of bp_dist_frame (bp_dist_plan_splitters / bp_dist_plan_shard_bits: host code, no device needed)
+    against tests/dist_protocol.py on random samples -- duplicates, tiny samples, every shard count, 64- and 32-bit tops."""
+    from tests import dist_protocol as bpd
+    rng = np.random.Generator(np.random.Philox(23))
+    full = (1 << 64) - 1
+    for trial in range(200):
+        parts = int(rng.integers(1, 17))
+        bits = int(rng.integers(1, 65))
+        m = int(rng.integers(0, 5000)) if trial % 3 else int(rng.integers(0, 40))
+        hi = full if bits == 64 else (1 << bits) - 1
+        sample = rng.integers(0, hi, size=m, dtype=np.uint64, endpoint=True)
+        if trial % 4 == 0 and m:
+            sample = sample[rng.integers(0, max(1, m // 50), size=m)]  # few distinct values
+        want = bpd.choose_splitters(sample, parts)
+        got = bp.plan_dist_splitters(sample, parts)
+        assert got.shape == want.shape and (got == want).all(), (trial, parts, m)
+        top = [full, 0xFFFFFFFF, (1 << max(1, int(np.bitwise_or.reduce(sample)).bit_length())) - 1 if m else 0][trial % 3]
+        for d in range(parts):
+            assert bp.plan_dist_shard_bits(want, d, top) == bpd.shard_fixed_bits(want, d, top), (trial, d, [hex(int(v)) for v in want], hex(top))
+    with pytest.raises(bp.BpError):
+        bp.plan_dist_splitters(np.zeros(4, dtype=np.uint64), 17)
+    with pytest.raises(bp.BpError):
+        bp.plan_dist_shard_bits(np.zeros(3, dtype=np.uint64), 4)
+
+
 def test_sort_plan_from_tag_words(bp):
     """The receivers' sort plan from the senders' tag words: masks OR / AND over the sources, IDs ascending only if every
     source's are, the ID ranges follow each other in rank order and no halo copies arrived."""
