@@ -15,6 +15,7 @@
 //   layer.scan() / par_scan()              src/layer.rs:449 layer.scan() / par_scan()   -> const std::vector-like view
 //   layer.scan_filtered(f) / par_..        src/layer.rs:456 layer.scan_filtered(Filter) / par_scan_filtered(Filter)
 //   layer.iter()                           src/layer.rs:79  layer.iter()
+//   layer.clone() / layer == other     src/layer.rs:576-617 layer.clone() / layer == other (min_depth, records, sorted flag)
 //   layer.test_box(system_bounds, b, d)    src/layer.rs:293 layer.test_box(system_bounds, b, max_depth) -> std::vector<ID>
 //   layer.test_ray(system_bounds, o, v, ..) src/layer.rs:326 layer.test_ray(system_bounds, origin, direction, rmin, rmax, max_depth)
 //   (many geometries in one call)                           layer.test_box_batch(...) / test_ray_batch(...) -> QueryResults<ID>
@@ -89,19 +90,20 @@ template <class Index, class ID> class Layer {
     static_assert(sizeof(ID) == 4 || sizeof(ID) == 8, "ObjectID must be a 32- or 64-bit integer (src/traits.rs:6-16)");
     static_assert(sizeof(std::pair<ID, ID>) == 2 * sizeof(ID), "pair layout");
     bp_layer *h_ = nullptr;
+    bp_layer_config cfg_{}; // what the layer was built with (clone() builds its copy the same way)
     void ck(int st) const {
         if (st != BP_OK) throw Error(st, h_ ? bp_layer_last_error(h_) : "");
     }
     friend class LayerBuilder;
-    explicit Layer(const bp_layer_config &cfg) {
+    explicit Layer(const bp_layer_config &cfg) : cfg_(cfg) {
         int st = bp_layer_create(&cfg, &h_);
         if (st != BP_OK) throw Error(st, "bp_layer_create");
     }
 
 public:
     typedef typename Index::key_type key_type;
-    Layer(Layer &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
-    Layer &operator=(Layer &&o) noexcept { std::swap(h_, o.h_); return *this; }
+    Layer(Layer &&o) noexcept : h_(o.h_), cfg_(o.cfg_) { o.h_ = nullptr; }
+    Layer &operator=(Layer &&o) noexcept { std::swap(h_, o.h_); std::swap(cfg_, o.cfg_); return *this; }
     Layer(const Layer &) = delete;
     Layer &operator=(const Layer &) = delete;
     ~Layer() { if (h_) bp_layer_destroy(h_); }
@@ -185,6 +187,35 @@ public:
         for (size_t r = 0; r < n; ++r) out[r] = {static_cast<const key_type *>(k)[r], static_cast<const ID *>(i)[r]};
         return out;
     }
+    // Clone -- src/layer.rs:597-617: min_depth and the tree with its sorted flag; the result buffers of the copy start
+    // empty.  (Through the host mirror of bp_layer_records: cloning is not on the hot path.)
+    Layer clone() {
+        bp_layer_config c = cfg_;
+        c.min_depth = min_depth(); // (merge may have lowered it, src/layer.rs:131-134)
+        Layer out(c);
+        const void *k = nullptr, *i = nullptr;
+        size_t n = 0;
+        int sorted = 0;
+        ck(bp_layer_records(h_, &k, &i, &n, &sorted));
+        out.ck(bp_layer_set_records(out.h_, k, i, n, sorted, 0));
+        return out;
+    }
+    // PartialEq -- src/layer.rs:576-587: min_depth and `tree`, which is the (Index, ID) sequence AND its sorted flag
+    bool equals(Layer &other) {
+        const void *ka = nullptr, *ia = nullptr, *kb = nullptr, *ib = nullptr;
+        size_t na = 0, nb = 0;
+        int sa = 0, sb = 0;
+        ck(bp_layer_records(h_, &ka, &ia, &na, &sa));
+        other.ck(bp_layer_records(other.h_, &kb, &ib, &nb, &sb));
+        if (min_depth() != other.min_depth() || na != nb || (sa != 0) != (sb != 0)) return false;
+        for (size_t r = 0; r < na; ++r)
+            if (static_cast<const key_type *>(ka)[r] != static_cast<const key_type *>(kb)[r] ||
+                static_cast<const ID *>(ia)[r] != static_cast<const ID *>(ib)[r])
+                return false;
+        return true;
+    }
+    friend bool operator==(Layer &a, Layer &b) { return a.equals(b); }
+    friend bool operator!=(Layer &a, Layer &b) { return !a.equals(b); }
     size_t len() { size_t n = 0; ck(bp_layer_len(h_, &n)); return n; }
     bool is_sorted() { int s = 0; ck(bp_layer_is_sorted(h_, &s)); return s != 0; }
     uint32_t min_depth() const { uint32_t d = 0; bp_layer_min_depth(h_, &d); return d; }

@@ -28,6 +28,15 @@ int main() {
         for (auto id : hit) std::printf(" %llu", (unsigned long long)id);
         std::printf("\n");
         const bool query_ok = hit.size() == 1 && hit[0] == 11;
+        // Clone / PartialEq (src/layer.rs:576-617): reported, not part of the exit status
+        try {
+            auto copy = layer.clone();
+            const bool same = copy == layer;
+            copy.clear();
+            std::printf("clone_equal=%d cleared_clone_differs=%d\n", same ? 1 : 0, copy != layer ? 1 : 0);
+        } catch (const Error &e) {
+            std::printf("clone: %s\n", e.what());
+        }
         // the sharded frame with a world of one rank (the same C++ path that runs over NVLink with more): an empty frame
         DistFrame<Index64_3D> dist(0, 1, -1, 1 << 16, 1 << 16);
         const auto none = dist.frame(system_bounds, nullptr, nullptr, 0);

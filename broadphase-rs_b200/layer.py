@@ -87,6 +87,7 @@ class Layer:
         h = ctypes.c_void_p()
         check(lib().bp_layer_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h
+        self._device = device
 
     @classmethod
     def borrow(cls, handle, index, id_type="u32"):
@@ -255,6 +256,21 @@ class Layer:
         return np.frombuffer(kb, dtype=self.key_dtype).copy(), np.frombuffer(ib, dtype=self.id_dtype).copy()
 
     records = iter
+
+    def clone(self):
+        """Clone for Layer (src/layer.rs:597-617): min_depth and the tree with its sorted flag; the copy's result buffers
+        start empty.  Goes through the host mirror of bp_layer_records -- cloning is not on the hot path."""
+        keys, ids = self.iter()
+        c = Layer(self.index, self.id_bytes, self.min_depth, device=getattr(self, "_device", -1))
+        c.set_records(keys, ids, sorted_=self.sorted)
+        return c
+
+    def equals(self, other):
+        """PartialEq for Layer (src/layer.rs:576-587): min_depth and `tree` = the (Index, ID) sequence AND its sorted flag."""
+        if (self.index, self.id_bytes, self.min_depth, self.sorted) != (other.index, other.id_bytes, other.min_depth, other.sorted):
+            return False
+        (ka, ia), (kb, ib) = self.iter(), other.iter()
+        return ka.shape == kb.shape and bool((ka == kb).all()) and bool((ia == ib).all())
 
     def records_device(self):
         k, i, n, s = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_int()

@@ -59,6 +59,8 @@ extern "C" {
     fn bp_layer_sort(layer: *mut BpLayer) -> c_int;
     fn bp_layer_scan(layer: *mut BpLayer, filter: *const BpFilter, out_pairs: *mut *const c_void, out_count: *mut usize) -> c_int;
     fn bp_layer_records(layer: *mut BpLayer, keys: *mut *const c_void, ids: *mut *const c_void, n: *mut usize, sorted: *mut c_int) -> c_int;
+    fn bp_layer_set_records(layer: *mut BpLayer, keys: *const c_void, ids: *const c_void, n: usize, sorted: c_int, on_device: c_int) -> c_int;
+    fn bp_layer_min_depth(layer: *const BpLayer, out_min_depth: *mut u32) -> c_int;
     fn bp_layer_test_box_batch(layer: *mut BpLayer, system_bounds: *const f32, boxes: *const f32, n_queries: usize, max_depth: i32,
                                on_device: c_int, out_pairs: *mut *const c_void, out_offsets: *mut *const u32, out_count: *mut usize) -> c_int;
     fn bp_layer_test_ray_batch(layer: *mut BpLayer, system_bounds: *const f32, rays: *const f32, n_queries: usize, max_depth: i32,
@@ -73,7 +75,7 @@ extern "C" {
 pub trait SpatialIndex: Copy {
     const KIND: i32;
     const DIM: usize;
-    type Key: Copy;
+    type Key: Copy + PartialEq;
     type Point;
 }
 #[derive(Clone, Copy, Debug, Default, Eq, Ord, PartialEq, PartialOrd)]
@@ -265,6 +267,66 @@ impl<Index: SpatialIndex, ID: ObjectID> Layer<Index, ID> {
         let keys = unsafe { std::slice::from_raw_parts(k as *const Index::Key, n) };
         let ids = unsafe { std::slice::from_raw_parts(i as *const ID, n) };
         keys.iter().cloned().zip(ids.iter().cloned()).collect()
+    }
+}
+
+impl<Index: SpatialIndex, ID: ObjectID> Layer<Index, ID> {
+    /// The host mirror of the tree (valid until the next call on this layer) and its sorted flag: what `Clone` and
+    /// `PartialEq` read.
+    fn raw_records(&self) -> (*const c_void, *const c_void, usize, bool) {
+        let (mut k, mut i): (*const c_void, *const c_void) = (std::ptr::null(), std::ptr::null());
+        let (mut n, mut sorted): (usize, c_int) = (0, 0);
+        let s = unsafe { bp_layer_records(self.handle, &mut k, &mut i, &mut n, &mut sorted) };
+        self.check(s);
+        (k, i, n, sorted != 0)
+    }
+
+    fn current_min_depth(&self) -> u32 {
+        let mut d: u32 = 0;
+        let s = unsafe { bp_layer_min_depth(self.handle, &mut d) };
+        self.check(s);
+        d
+    }
+}
+
+/// src/layer.rs:576-587: `min_depth` and `tree` -- the `(Index, ID)` sequence AND its sorted flag
+impl<Index: SpatialIndex, ID: ObjectID> PartialEq for Layer<Index, ID> {
+    fn eq(&self, other: &Self) -> bool {
+        if self.current_min_depth() != other.current_min_depth() {
+            return false;
+        }
+        let (ka, ia, na, sa) = self.raw_records();
+        let (kb, ib, nb, sb) = other.raw_records();
+        if na != nb || sa != sb {
+            return false;
+        }
+        let (ka, kb) = unsafe { (std::slice::from_raw_parts(ka as *const Index::Key, na), std::slice::from_raw_parts(kb as *const Index::Key, nb)) };
+        let (ia, ib) = unsafe { (std::slice::from_raw_parts(ia as *const ID, na), std::slice::from_raw_parts(ib as *const ID, nb)) };
+        ka == kb && ia == ib
+    }
+}
+impl<Index: SpatialIndex, ID: ObjectID> Eq for Layer<Index, ID> {}
+
+/// src/layer.rs:597-617: `min_depth` and the tree with its sorted flag; the copy's result buffers start empty
+impl<Index: SpatialIndex, ID: ObjectID> Clone for Layer<Index, ID> {
+    fn clone(&self) -> Self {
+        let cfg = BpLayerConfig {
+            index_kind: Index::KIND,
+            id_bytes: ID::BYTES,
+            min_depth: self.current_min_depth(),
+            device: -1,
+            index_capacity: 0,
+            collision_capacity: 0,
+            test_capacity: 0,
+        };
+        let mut handle: *mut BpLayer = std::ptr::null_mut();
+        let s = unsafe { bp_layer_create(&cfg, &mut handle) };
+        assert!(s == 0, "bp_layer_create failed with status {}", s);
+        let out = Layer { handle, _marker: PhantomData };
+        let (k, i, n, sorted) = self.raw_records();
+        let s = unsafe { bp_layer_set_records(out.handle, k, i, n, sorted as c_int, 0) };
+        out.check(s);
+        out
     }
 }
 
